@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — filter-steps/s of the batched 1-point-RANSAC EKF-SLAM filter step on B200.
+
+Contract: ``python bench.py --gpus N --steps K --warmup W`` (under torchrun for N>1) prints ONE
+JSON line from rank 0.  A "step" is one pass of the whole filter step (mc/mono_slam.m:56-74:
+predict -> h/H/S -> matcher gate -> 1-point RANSAC -> li update -> rescue -> hi update) over a
+batch of independent Monte-Carlo filters; workload = BASELINE.json configs[2]: N=100 inverse-depth
+features, 4096 filters per GPU (weak scaling: every rank owns its own 4096 filters, no data-path
+collective; NCCL only gathers per-filter statistics after the timed region).
+
+  value  = filter-steps/s with the frame inputs already resident in HBM (kernel path only)
+  e2e    = the same through the host-buffer C-ABI call (ekfslam_step_host): per step the frame's
+           candidate pixels + flags + RANSAC uniforms go host->device from pinned memory and the
+           new camera/feature state x_k_k, the inlier flags and the step statistics come back.
+  roofline / cpu_baseline: see DESIGN.md §Measurement.
+
+``--impl reference`` times the CPU oracle port of the reference (the reference itself is MATLAB
+and cannot run here: no Octave/MATLAB in the image) on the host cores, on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "filter-steps/s at N=100 features, batch 4096 filters"
+UNIT = "filter-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="filters per GPU")
+    ap.add_argument("--features", type=int, default=100)
+    ap.add_argument("--fixed-hyp", type=int, default=0, help="0 = reference adaptive rule; >0 = fixed budget")
+    ap.add_argument("--n-u", type=int, default=0, help="uniforms per frame (default 64 adaptive / fixed-hyp)")
+    ap.add_argument("--p-outlier", type=float, default=0.2)
+    ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="filters in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic work (SURVEY.md §8d / BASELINE.md §4), per filter
+# ------------------------------------------------------------------------------------------
+def algorithmic_work(n, N, m, hyps, k_li, k_hi):
+    upd_b = sum(2 * n * n + 2 * n * k for k in (k_li, k_hi))
+    nbytes = 8.0 * (52 * n + 2 * (n + 201 * N) + n * n + upd_b)
+    upd_f = sum(n * n * k + n * k * k + k ** 3 / 3.0 + 26 * n * k + 26 * k * k for k in (k_li, k_hi))
+    flops = 676.0 * n + 3504.0 * N + hyps * (56.0 * n + 200.0 * m) + upd_f
+    return nbytes, flops
+
+
+def read_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "fp64_tflops": 37.0,
+             "fp64_src": "nominal (no measurement found)"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                peaks["hbm_gbs"] = float(json.load(f)["hbm_gbs"])
+            peaks["hbm_src"] = "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    p = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                d = json.load(f)
+            peaks["fp64_tflops"] = float(max(d["dfma_tflops"], d["dmma_m8n8k4_tflops"]))
+            peaks["fp64_src"] = "measured (profiles/fp64_peak.json, tools/microbench_fp64.cu)"
+        except Exception:
+            pass
+    return peaks
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(s[3 + i].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    """Runs `steps` reference steps of one filter with the numpy oracle; returns seconds."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import ekf_oracle as O
+    from tests import helpers as H
+    x0, P0, types, zcs, hass, us, fixed, warm = job
+    cam = O.initialize_cam()
+    filt = H.oracle_filter(x0, P0)
+    feats = H.oracle_features(types)
+    t_acc = 0.0
+    for t in range(len(zcs)):
+        t0 = time.perf_counter()
+        filt, feats, _ = H.oracle_step(filt, feats, cam, zcs[t], hass[t], us[t], fixed)
+        if t >= warm:
+            t_acc += time.perf_counter() - t0
+    return t_acc
+
+
+def cpu_reference_rate(args, n_filters, steps, warm, procs):
+    """filter-steps/s of the CPU oracle over `n_filters` filters x `steps` timed steps on `procs` processes."""
+    import multiprocessing as mp
+    import ekf_slam_b200.synth as synth
+    n_u = args.n_u or (args.fixed_hyp if args.fixed_hyp > 0 else 64)
+    seq = synth.SynthSequence(B=n_filters, N=args.features, T=warm + steps, seed=args.seed,
+                              p_outlier=args.p_outlier, n_u=n_u)
+    x0, P0, types = seq.initial_state()
+    jobs = []
+    for b in range(n_filters):
+        jobs.append((x0[b], P0[b], types[b], [seq.zc[t, b] for t in range(1, warm + steps + 1)],
+                     [seq.has[t, b] for t in range(1, warm + steps + 1)],
+                     [seq.U[b, t, :n_u] for t in range(1, warm + steps + 1)], args.fixed_hyp, warm))
+    t0 = time.perf_counter()
+    if procs > 1:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(procs) as pool:
+            pool.map(_cpu_worker, jobs)
+    else:
+        for j in jobs:
+            _cpu_worker(j)
+    wall = time.perf_counter() - t0
+    # the warm-up steps of each filter run inside `wall`; scale to the timed share
+    timed_share = steps / float(steps + warm)
+    return n_filters * steps / (wall * timed_share), wall
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    procs = max(1, min(cores, 64))
+    nf = args.cpu_sample or procs
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    rate, wall = cpu_reference_rate(args, nf, steps, warm, procs)
+    sample = "%d filters x %d steps (+%d warm-up) of the same synthetic workload, numpy oracle, %d processes" % (
+        nf, steps, warm, procs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / rate,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "cfg3: N=%d inverse-depth features, batch %d Monte-Carlo filters (CPU arm runs a "
+                               "bounded sample)" % (args.features, args.batch),
+                   "ransac": "adaptive (reference rule)" if args.fixed_hyp <= 0 else "fixed %d" % args.fixed_hyp,
+                   "reference_runtime": "GNU Octave / MATLAB absent in this image: CPU oracle port (oracle/ekf_oracle.py)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ekf_slam_b200 as pkg
+    import ekf_slam_b200.synth as synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+
+    K, W, N = args.steps, args.warmup, args.features
+    B = args.batch if args.scaling == "weak" else max(1, args.batch // world)
+    n = 13 + 6 * N
+    n_u = args.n_u or (args.fixed_hyp if args.fixed_hyp > 0 else 64)
+    T = W + 2 * K
+    t_setup = time.perf_counter()
+    seq = synth.SynthSequence(B=B, N=N, T=T, seed=args.seed, b_offset=rank * B, p_outlier=args.p_outlier, n_u=n_u)
+    bank = pkg.FilterBank(B, N, n, device=local_rank)
+    stream = torch.cuda.current_stream(dev)
+    bank.set_stream(stream.cuda_stream)
+    bank.set_params(fixed_hyp=args.fixed_hyp)
+    chunk = 256
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        x0, P0, types = seq.initial_state(b0, nb)
+        bank.upload_feature_types(types, b0=b0)
+        bank.upload_state(x0, P0, b0=b0)
+        del x0, P0
+    # frame inputs: pinned host copies (e2e arm) and HBM-resident copies (device arm)
+    fl_np = (seq.has * pkg.F_CAND).astype(np.uint8)
+    zc_pin = torch.from_numpy(seq.zc).pin_memory()
+    fl_pin = torch.from_numpy(fl_np).pin_memory()
+    u_pin = torch.from_numpy(np.ascontiguousarray(np.transpose(seq.U, (1, 0, 2)))).pin_memory()   # [T+1,B,n_u]
+    zc_dev = zc_pin.to(dev)
+    fl_dev = fl_pin.to(dev)
+    u_dev = u_pin.to(dev)
+    torch.cuda.synchronize(dev)
+    t_setup = time.perf_counter() - t_setup
+
+    def bind(t):
+        bank.bind_frame(zc_dev[t].data_ptr(), fl_dev[t].data_ptr(), u_dev[t].data_ptr(), n_u)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- warm-up (also lets the covariances fill in) -------------------------------------
+    for t in range(1, W + 1):
+        bind(t)
+        bank.step(reset=True, match_mode=1)
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: device-resident inputs ----------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    bank.enable_timing(True)
+    l0 = bank.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize(dev)
+    ev0.record(stream)
+    for t in range(W + 1, W + K + 1):
+        bind(t)
+        bank.step(reset=True, match_mode=1)
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+    launches = bank.launch_count - l0
+    ktimes = bank.kernel_times()
+    bank.enable_timing(False)
+    stats = bank.download_stats()
+    bank.unbind_frame()
+
+    # ---- timed region: end to end through the host-buffer call ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        x_out = torch.empty((B, n), dtype=torch.float64).pin_memory()
+        f_out = torch.empty((B, N), dtype=torch.uint8).pin_memory()
+        s_out = torch.empty((B, 8), dtype=torch.int32).pin_memory()
+        zc_h, fl_h, u_h = zc_pin.numpy(), fl_pin.numpy(), u_pin.numpy()
+        xo, fo, so = x_out.numpy(), f_out.numpy(), s_out.numpy()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for t in range(W + K + 1, W + 2 * K + 1):
+            bank.step_host(zc_h[t], fl_h[t], u_h[t], match_mode=1, x_out=xo, flags_out=fo, stats_out=so)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        h2d = zc_h[1].nbytes + fl_h[1].nbytes + u_h[1].nbytes
+        d2h = xo.nbytes + fo.nbytes + so.nbytes
+        e2e = (ms_e2e, h2d, d2h)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    # ---- reduce over ranks (max time), gather per-filter statistics over NCCL ---------------
+    tvec = torch.tensor([ms_dev, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
+    svec = torch.tensor([float(stats["n_li"].sum()), float(stats["n_hi"].sum()), float(stats["n_ic"].sum()),
+                         float(stats["ransac_iters"].sum()), float(stats["ransac_scored"].sum()),
+                         float((stats["status"] != 0).sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(svec, op=dist.ReduceOp.SUM)
+    ms_dev, ms_e2e = float(tvec[0]), float(tvec[1])
+    tot_filters = B * world
+    mean = lambda i: float(svec[i]) / tot_filters  # noqa: E731
+
+    if rank == 0:
+        peaks = read_peaks()
+        value = tot_filters * K / (ms_dev * 1e-3)
+        k_li, k_hi = 2 * mean(0), 2 * mean(1)
+        m, hyps = mean(2), mean(3)
+        nbytes, flops = algorithmic_work(n, N, m, hyps, k_li, k_hi)
+        # dominant kernel = the covariance downdate P -= W'W (two launches per step: li and hi)
+        kt = {k: v for k, v in ktimes.items() if v[1] > 0}
+        tot_k_ms = sum(v[0] for v in kt.values())
+        top = max(kt.items(), key=lambda kv: kv[1][0])
+        dd_ms, dd_cnt = kt.get("k_downdate", (0.0, 0))
+        # per launch (whole batch B): flops n^2 k (lower triangle, FMA = 2), bytes 2 n^2 * 8
+        dd_flops_per_step = B * sum(n * n * k for k in (k_li, k_hi))
+        dd_bytes_per_step = B * 2 * (2 * n * n * 8.0)
+        dd_s_per_step = (dd_ms * 1e-3) / K if dd_cnt else float("nan")
+        dd_tf = dd_flops_per_step / dd_s_per_step / 1e12
+        dd_gbs = dd_bytes_per_step / dd_s_per_step / 1e9
+        t_fp = dd_flops_per_step / (peaks["fp64_tflops"] * 1e12)
+        t_hbm = dd_bytes_per_step / (peaks["hbm_gbs"] * 1e9)
+        if t_fp >= t_hbm:
+            roof = {"bound": "tensor", "achieved": dd_tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
+                    "frac": dd_tf / peaks["fp64_tflops"], "traffic": None,
+                    "peak_source": "fp64 " + peaks["fp64_src"]}
+        else:
+            roof = {"bound": "hbm", "achieved": dd_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": dd_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": "hbm " + peaks["hbm_src"]}
+        roof.update({"kernel": "k_downdate", "kernel_share_of_step": dd_ms / tot_k_ms if tot_k_ms else None,
+                     "kernel_ms_per_launch": dd_ms / dd_cnt if dd_cnt else None, "launches_timed": dd_cnt,
+                     "algorithmic_flops_per_launch": dd_flops_per_step / 2.0,
+                     "algorithmic_bytes_per_launch": dd_bytes_per_step / 2.0,
+                     "hbm_gbs_achieved": dd_gbs, "fp64_tflops_achieved": dd_tf})
+        step_roof = {"bytes_per_filter_step": nbytes, "flops_per_filter_step": flops,
+                     "hbm_frac_of_step": (nbytes * tot_filters * K / world / (ms_dev * 1e-3)) / (peaks["hbm_gbs"] * 1e9),
+                     "fp64_frac_of_step": (flops * tot_filters * K / world / (ms_dev * 1e-3)) / (peaks["fp64_tflops"] * 1e12)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg3: N=%d inverse-depth features (n=%d), batch %d Monte-Carlo filters per GPU, "
+                                   "synthetic point-field sequence, p_outlier=%.2f" % (N, n, B, args.p_outlier),
+                       "global_batch": tot_filters,
+                       "ransac": "adaptive (reference rule)" if args.fixed_hyp <= 0 else "fixed %d" % args.fixed_hyp,
+                       "parallelism": "filters sharded across ranks, no data-path collective",
+                       "l2": "inputs larger than L2 (covariances %.1f GB per GPU vs 126 MB L2)" % (B * n * n * 8 / 1e9),
+                       "mean_matches": m, "mean_li_inliers": mean(0), "mean_hi_inliers": mean(1),
+                       "mean_hypotheses_drawn": hyps, "mean_hypotheses_scored": mean(4),
+                       "filters_with_status_flags": int(svec[5]), "setup_s": t_setup},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "step_roofline": step_roof,
+            "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])},
+            "top_kernel": top[0],
+            "ransac_hyps_per_s": {"drawn": hyps * tot_filters * K / (ms_dev * 1e-3),
+                                  "scored": mean(4) * tot_filters * K / (ms_dev * 1e-3),
+                                  "kernel_only_drawn": (hyps * B * K / (kt["k_ransac"][0] * 1e-3)) if "k_ransac" in kt else None},
+            "clocks": sampler.summary(),
+        }
+        if e2e:
+            line["e2e"] = {"value": tot_filters * K / (ms_e2e * 1e-3), "unit": UNIT,
+                           "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
+                           "ms_per_step": ms_e2e / K,
+                           "note": "covariances stay resident on the device between frames (filter state, like the "
+                                   "reference's persistent `filter` struct); per-frame inputs/outputs cross PCIe"}
+        if not args.no_cpu_baseline:
+            cores = 1
+            nf = args.cpu_sample or 2
+            rate, wall = cpu_reference_rate(args, nf, 2, 1, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d filters x 2 steps (+1 warm-up) of the same workload, numpy oracle "
+                                              "(oracle/ekf_oracle.py), single process, %.1f s" % (nf, wall)}
+        print(json.dumps(line), flush=True)
+    bank.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,260 @@
+"""FilterBank — B independent EKF-SLAM filters resident on one B200.
+
+Thin, typed wrapper over the C ABI (include/ekfslam.h).  All arrays crossing this boundary
+are host numpy arrays (C-contiguous); device memory belongs to the context.  The batched
+layout is structure-of-arrays: ``x [B, n_max]``, ``P [B, n_max, n_max]``, per-feature fields
+``[B, N_max, ...]`` (see the header for the exact shapes).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(a.shape)))
+    return a
+
+
+class FilterBank:
+    def __init__(self, B, N_max, n_max=None, device=0, camera=None, params=None):
+        self.lib = L.load()
+        n_max = int(n_max if n_max is not None else 13 + 6 * N_max)
+        h = C.c_void_p()
+        L.check(self.lib.ekfslam_create(C.byref(h), int(device), int(B), int(N_max), n_max))
+        self._h = h
+        self.B, self.N, self.n_max, self.device = int(B), int(N_max), n_max, int(device)
+        ld = C.c_int()
+        L.check(self.lib.ekfslam_dims(self._h, None, None, None, C.byref(ld)))
+        self.ld = ld.value
+        self.camera = L.Camera()
+        self.lib.ekfslam_default_camera(C.byref(self.camera))
+        self.params = L.Params()
+        self.lib.ekfslam_default_params(C.byref(self.params))
+        if camera is not None:
+            self.set_camera(camera)
+        if params is not None:
+            self.set_params(**params)
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ekfslam_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- configuration --------------------------------------------------------------------
+    def set_camera(self, cam):
+        """cam: any object with the fields of mc/initialize_cam.m (k1,k2,Cx,Cy,f,dx,dy,nRows,nCols)."""
+        for name, _ in L.Camera._fields_:
+            setattr(self.camera, name, getattr(cam, name))
+        L.check(self.lib.ekfslam_set_camera(self._h, C.byref(self.camera)))
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise KeyError(k)
+            setattr(self.params, k, v)
+        L.check(self.lib.ekfslam_set_params(self._h, C.byref(self.params)))
+
+    def set_stream(self, cuda_stream):
+        L.check(self.lib.ekfslam_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        L.check(self.lib.ekfslam_synchronize(self._h))
+
+    @property
+    def device_bytes(self):
+        return int(self.lib.ekfslam_device_bytes(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.ekfslam_launch_count(self._h))
+
+    def device_ptr(self, name):
+        return self.lib.ekfslam_device_ptr(self._h, name.encode())
+
+    # -- measurement hooks ------------------------------------------------------------------
+    def enable_timing(self, on=True):
+        L.check(self.lib.ekfslam_enable_timing(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{kernel name: (accumulated ms, launches)} since timing was (re-)enabled."""
+        out = {}
+        for slot in range(self.lib.ekfslam_kernel_count()):
+            name = C.create_string_buffer(64)
+            ms = C.c_double()
+            cnt = C.c_int64()
+            L.check(self.lib.ekfslam_kernel_time(self._h, slot, name, 64, C.byref(ms), C.byref(cnt)))
+            out[name.value.decode()] = (ms.value, cnt.value)
+        return out
+
+    def bind_frame(self, d_zc, d_fl, d_u, n_u):
+        """Device pointers (ints) of caller-owned frame buffers; see ekfslam_bind_frame."""
+        L.check(self.lib.ekfslam_bind_frame(self._h, C.c_void_p(d_zc), C.c_void_p(d_fl), C.c_void_p(d_u), int(n_u)))
+
+    def unbind_frame(self):
+        L.check(self.lib.ekfslam_unbind_frame(self._h))
+
+    # -- filter struct <-> device ---------------------------------------------------------
+    def upload_state(self, x=None, P=None, nstate=None, which=0, b0=0):
+        nb = None
+        for a in (x, P, nstate):
+            if a is not None:
+                nb = len(a)
+        if nb is None:
+            return
+        xx = None if x is None else _c(x, np.float64, (nb, self.n_max))
+        PP = None if P is None else _c(P, np.float64, (nb, self.n_max, self.n_max))
+        ns = None if nstate is None else _c(nstate, np.int32, (nb,))
+        L.check(self.lib.ekfslam_upload_state(self._h, b0, nb, which, _ptr(xx), _ptr(PP), _ptr(ns)))
+
+    def download_state(self, which=0, b0=0, nb=None, want_P=True):
+        nb = self.B - b0 if nb is None else nb
+        x = np.empty((nb, self.n_max))
+        P = np.empty((nb, self.n_max, self.n_max)) if want_P else None
+        ns = np.empty(nb, dtype=np.int32)
+        L.check(self.lib.ekfslam_download_state(self._h, b0, nb, which, _ptr(x), _ptr(P), _ptr(ns)))
+        return x, P, ns
+
+    # -- features_info <-> device ---------------------------------------------------------
+    def upload_feature_types(self, types, nfeat=None, b0=0):
+        types = _c(types, np.uint8)
+        nb = types.shape[0]
+        if types.shape != (nb, self.N):
+            raise ValueError("types must be [nb, N_max]")
+        if nfeat is None:
+            nfeat = (types != 0).sum(axis=1)
+        nfeat = _c(nfeat, np.int32, (nb,))
+        L.check(self.lib.ekfslam_upload_feature_types(self._h, b0, nb, _ptr(types), _ptr(nfeat)))
+
+    def upload_matches(self, z, flags, b0=0):
+        z = _c(z, np.float64)
+        nb = z.shape[0]
+        z = _c(z, np.float64, (nb, self.N, 2))
+        flags = _c(flags, np.uint8, (nb, self.N))
+        L.check(self.lib.ekfslam_upload_matches(self._h, b0, nb, _ptr(z), _ptr(flags)))
+
+    def upload_candidates(self, zc, has, b0=0):
+        zc = _c(zc, np.float64)
+        nb = zc.shape[0]
+        zc = _c(zc, np.float64, (nb, self.N, 2))
+        has = _c(has, np.uint8, (nb, self.N))
+        L.check(self.lib.ekfslam_upload_candidates(self._h, b0, nb, _ptr(zc), _ptr(has)))
+
+    def upload_uniforms(self, u, b0=0):
+        u = _c(u, np.float64)
+        if u.ndim != 2:
+            raise ValueError("u must be [nb, n_u]")
+        L.check(self.lib.ekfslam_upload_uniforms(self._h, b0, u.shape[0], _ptr(u), u.shape[1]))
+
+    def upload_features(self, h=None, Hc=None, S=None, z=None, flags=None, b0=0):
+        nb = None
+        for a in (h, Hc, S, z, flags):
+            if a is not None:
+                nb = len(a)
+        if nb is None:
+            return
+        h = None if h is None else _c(h, np.float64, (nb, self.N, 2))
+        Hc = None if Hc is None else _c(Hc, np.float64, (nb, self.N, 2, 13))
+        S = None if S is None else _c(S, np.float64, (nb, self.N, 2, 2))
+        z = None if z is None else _c(z, np.float64, (nb, self.N, 2))
+        flags = None if flags is None else _c(flags, np.uint8, (nb, self.N))
+        L.check(self.lib.ekfslam_upload_features(self._h, b0, nb, _ptr(h), _ptr(Hc), _ptr(S), _ptr(z), _ptr(flags)))
+
+    def download_features(self, b0=0, nb=None):
+        nb = self.B - b0 if nb is None else nb
+        out = dict(h=np.empty((nb, self.N, 2)), Hc=np.empty((nb, self.N, 2, 13)), S=np.empty((nb, self.N, 2, 2)),
+                   z=np.empty((nb, self.N, 2)), flags=np.empty((nb, self.N), dtype=np.uint8),
+                   offs=np.empty((nb, self.N), dtype=np.int32), counters=np.empty((nb, self.N, 2), dtype=np.int32))
+        L.check(self.lib.ekfslam_download_features(self._h, b0, nb, _ptr(out["h"]), _ptr(out["Hc"]), _ptr(out["S"]),
+                                                   _ptr(out["z"]), _ptr(out["flags"]), _ptr(out["offs"]),
+                                                   _ptr(out["counters"])))
+        return out
+
+    def download_flags(self, b0=0, nb=None):
+        nb = self.B - b0 if nb is None else nb
+        flags = np.empty((nb, self.N), dtype=np.uint8)
+        L.check(self.lib.ekfslam_download_features(self._h, b0, nb, None, None, None, None, _ptr(flags), None, None))
+        return flags
+
+    def download_stats(self, b0=0, nb=None):
+        nb = self.B - b0 if nb is None else nb
+        st = np.empty((nb, len(L.STATS_FIELDS)), dtype=np.int32)
+        L.check(self.lib.ekfslam_download_stats(self._h, b0, nb, _ptr(st)))
+        return {k: st[:, i].copy() for i, k in enumerate(L.STATS_FIELDS)}
+
+    # -- stages (names follow the reference functions they replace) --------------------------
+    def begin_frame(self):
+        L.check(self.lib.ekfslam_begin_frame(self._h))
+
+    def ekf_prediction(self):
+        L.check(self.lib.ekfslam_predict(self._h))
+
+    def measure(self, which=1):
+        L.check(self.lib.ekfslam_measure(self._h, which))
+
+    def features(self, which=1, parts=3):
+        L.check(self.lib.ekfslam_features(self._h, which, parts))
+
+    def hp(self, need=L.F_HAS_H, forbid=0):
+        L.check(self.lib.ekfslam_hp(self._h, need, forbid))
+
+    def innovation(self):
+        L.check(self.lib.ekfslam_innovation(self._h))
+
+    def gate(self):
+        L.check(self.lib.ekfslam_gate(self._h))
+
+    def apply_matches(self):
+        L.check(self.lib.ekfslam_apply_matches(self._h))
+
+    def ransac_hypotheses(self):
+        L.check(self.lib.ekfslam_ransac(self._h))
+
+    def ekf_update_li_inliers(self):
+        L.check(self.lib.ekfslam_update_li(self._h))
+
+    def rescue_hi_inliers(self):
+        L.check(self.lib.ekfslam_rescue(self._h))
+
+    def ekf_update_hi_inliers(self):
+        L.check(self.lib.ekfslam_update_hi(self._h))
+
+    def update_masked(self, mask, which_prior):
+        L.check(self.lib.ekfslam_update_masked(self._h, mask, which_prior))
+
+    def step(self, reset=True, match_mode=1):
+        """One filter step on resident data (mc/mono_slam.m:56-74)."""
+        L.check(self.lib.ekfslam_step(self._h, 1 if reset else 0, match_mode))
+
+    def step_host(self, zc, fl, u, match_mode=1, x_out=None, flags_out=None, stats_out=None):
+        """The per-frame call with HOST buffers (pinned buffers make the copies asynchronous).
+        zc [B,N,2] f64, fl [B,N] u8, u [B,n_u] f64; outputs are written in place if given."""
+        for a, dt in ((zc, np.float64), (fl, np.uint8), (u, np.float64)):
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("step_host takes C-contiguous arrays of the exact dtype (no hidden copies)")
+        if zc.shape != (self.B, self.N, 2) or fl.shape != (self.B, self.N) or u.shape[0] != self.B:
+            raise ValueError("step_host: bad shapes")
+        L.check(self.lib.ekfslam_step_host(self._h, match_mode, _ptr(zc), _ptr(fl), _ptr(u), u.shape[1],
+                                           _ptr(x_out), _ptr(flags_out), _ptr(stats_out)))

@@ -1,0 +1,688 @@
+// C ABI of libekfslam.so (include/ekfslam.h): context management, host<->device marshalling
+// of the reference's `filter` / `features_info` structs, and the stage sequencing of the
+// filter step.  Host logic only — every arithmetic stage is a CUDA kernel; there is no CPU
+// fallback (a missing device is an error).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <climits>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(EKFSLAM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorName(_e) + \
+                                              " (" + cudaGetErrorString(_e) + ")");           \
+    } while (0)
+
+#define NEED_CTX(c)                                                     \
+    do {                                                                \
+        if (!(c)) return fail(EKFSLAM_ERR_INVALID, "null context");     \
+        CK(cudaSetDevice((c)->device));                                 \
+    } while (0)
+
+// ---- per-kernel timing ---------------------------------------------------------------------
+struct KTimer {
+    struct Rec { cudaEvent_t a, b; int slot; };
+    std::vector<Rec> pending;
+    std::vector<cudaEvent_t> pool;
+    double ms[KT_COUNT];
+    long long count[KT_COUNT];
+    cudaEvent_t cur[KT_COUNT];
+};
+
+static cudaEvent_t kt_event(KTimer* t) {
+    if (!t->pool.empty()) { cudaEvent_t e = t->pool.back(); t->pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void kt_begin(ekfslam_ctx* c, int slot) {
+    KTimer* t = c->timer;
+    t->cur[slot] = kt_event(t);
+    cudaEventRecord(t->cur[slot], c->stream);
+}
+
+void kt_end(ekfslam_ctx* c, int slot) {
+    KTimer* t = c->timer;
+    KTimer::Rec r;
+    r.a = t->cur[slot]; r.b = kt_event(t); r.slot = slot;
+    cudaEventRecord(r.b, c->stream);
+    t->pending.push_back(r);
+}
+
+static void kt_collect(ekfslam_ctx* c) {
+    KTimer* t = c->timer;
+    if (!t) return;
+    for (auto& r : t->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { t->ms[r.slot] += ms; t->count[r.slot]++; }
+        t->pool.push_back(r.a);
+        t->pool.push_back(r.b);
+    }
+    t->pending.clear();
+}
+
+static const char* KT_NAMES[KT_COUNT] = {"k_begin_frame", "k_predict", "k_features", "k_hp", "k_innov", "k_ransac",
+                                         "k_upd_S", "k_chol", "k_w", "k_xupd", "k_downdate", "k_symmetrize",
+                                         "k_add_features"};
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count, int64_t* total) {
+    const size_t bytes = count * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)p, bytes ? bytes : 1);
+    if (e == cudaSuccess) {
+        *total += (int64_t)bytes;
+        e = cudaMemset(*p, 0, bytes ? bytes : 1);
+    }
+    return e;
+}
+
+extern "C" {
+
+const char* ekfslam_last_error(void) { return g_err.c_str(); }
+int ekfslam_version(void) { return 100; }
+
+int ekfslam_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void ekfslam_default_camera(ekfslam_camera* cam) {
+    // mc/initialize_cam.m:3-10
+    const double d = 0.0112;
+    cam->k1 = 6.333e-2; cam->k2 = 1.390e-2;
+    cam->Cx = 1.7945 / d; cam->Cy = 1.4433 / d;
+    cam->f = 2.1735; cam->dx = d; cam->dy = d;
+    cam->nRows = 240; cam->nCols = 320;
+}
+
+void ekfslam_default_params(ekfslam_params* p) {
+    p->std_a = 0.007; p->std_alpha = 0.007; p->std_z = 1.0;  // mc/mono_slam.m:29-31
+    p->delta_t = 1.0;                                         // mc/predict_state_and_covariance.m:5
+    p->chi2_gate = 5.9915;                                    // mc/rescue_hi_inliers.m:3
+    p->p_spurious_free = 0.99;                                // mc/ransac_hypotheses.m:3
+    p->max_hyp = 1000;                                        // mc/ransac_hypotheses.m:9
+    p->fixed_hyp = 0;
+}
+
+static void set_devcam(ekfslam_ctx* c, const ekfslam_camera* cam) {
+    DevCam& d = c->cam;
+    d.k1 = cam->k1; d.k2 = cam->k2; d.Cx = cam->Cx; d.Cy = cam->Cy; d.f = cam->f; d.dx = cam->dx; d.dy = cam->dy;
+    d.fku = cam->f * (1.0 / cam->dx);  // f*ku, ku = 1/dx (mc/compute_hypothesis_support_fast.m:35-38)
+    d.fkv = cam->f * (1.0 / cam->dy);
+    d.nRows = (double)cam->nRows; d.nCols = (double)cam->nCols;
+}
+
+// mc/ransac_hypotheses.m:40-41 tabulated with the HOST libm for every (num_IC_matches, support):
+//   epsilon = 1 - support/nIC;  n_hyp = ceil(log(1-p)/log(1-(1-epsilon)))
+// Ratios such as support/nIC = 0.9 sit on an integer boundary of the ceil(); evaluating the two
+// log() calls with the same libm as the CPU oracle keeps the hypothesis count identical.
+static void build_nhyp_table(std::vector<int32_t>& tab, int N, double p) {
+    tab.assign((size_t)(N + 1) * (N + 2) / 2, 0);
+    const double num = std::log(1.0 - p);
+    for (int nic = 1; nic <= N; ++nic)
+        for (int s = 0; s <= nic; ++s) {
+            const double epsilon = 1.0 - ((double)s / (double)nic);
+            const double den = 1.0 - (1.0 - epsilon);
+            double v;
+            if (den <= 0.0) v = 0.0;  // log(0) = -Inf -> ceil(-0) = 0
+            else {
+                const double lden = std::log(den);
+                v = (lden == 0.0) ? (double)INT_MAX : std::ceil(num / lden);
+            }
+            if (!(v < (double)INT_MAX)) v = (double)INT_MAX;
+            if (v < 0.0) v = 0.0;
+            tab[EKF_TRI(nic, s)] = (int32_t)v;
+        }
+}
+
+int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
+    if (!out) return fail(EKFSLAM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (B <= 0 || N_max <= 0 || n_max < EKF_XV) return fail(EKFSLAM_ERR_INVALID, "B, N_max must be > 0 and n_max >= 13");
+    if (B > 65535) return fail(EKFSLAM_ERR_INVALID, "B must be <= 65535 per context");
+    if (n_max > EKF_XV + 6 * N_max) return fail(EKFSLAM_ERR_INVALID, "n_max exceeds 13 + 6*N_max");
+    const int ndev = ekfslam_device_count();
+    if (ndev <= 0) return fail(EKFSLAM_ERR_NODEVICE, "no CUDA device visible: libekfslam has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(EKFSLAM_ERR_INVALID, "device index out of range");
+    CK(cudaSetDevice(device));
+    ekfslam_ctx* c = new (std::nothrow) ekfslam_ctx();
+    if (!c) return fail(EKFSLAM_ERR_NOMEM, "host allocation failed");
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    DevView& v = c->v;
+    v.B = B; v.N = N_max; v.nmax = n_max;
+    v.ld = (n_max + 7) & ~7;
+    v.kmax = 2 * N_max;
+    v.n_u = 0;
+    c->u_cap = 0;
+    const size_t Bz = (size_t)B;
+#define DA(ptr, count)                                                                           \
+    do {                                                                                         \
+        cudaError_t _e = dalloc(&(ptr), (count), &c->bytes);                                     \
+        if (_e != cudaSuccess) {                                                                 \
+            std::string m = std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(_e);       \
+            ekfslam_destroy(c);                                                                  \
+            return fail(_e == cudaErrorMemoryAllocation ? EKFSLAM_ERR_NOMEM : EKFSLAM_ERR_CUDA, m); \
+        }                                                                                        \
+    } while (0)
+    DA(v.x, Bz * v.ld);
+    DA(v.xp, Bz * v.ld);
+    DA(v.P, Bz * v.nmax * v.ld);
+    DA(v.G, Bz * v.kmax * v.ld);
+    DA(v.W, Bz * v.kmax * v.ld);
+    DA(v.Sb, Bz * v.kmax * v.kmax);
+    DA(v.Li, Bz * v.kmax * v.kmax);
+    DA(v.yv, Bz * v.kmax);
+    DA(v.jn, Bz * 16);
+    DA(v.h, Bz * v.N * 2);
+    DA(v.Hc, Bz * v.N * EKF_HSTRIDE);
+    DA(v.S, Bz * v.N * 4);
+    DA(v.z, Bz * v.N * 2);
+    DA(v.zc, Bz * v.N * 2);
+    DA(v.ftype, Bz * v.N);
+    DA(v.flags, Bz * v.N);
+    DA(v.mflags, Bz * v.N);
+    DA(v.foff, Bz * v.N);
+    DA(v.nstate, Bz);
+    DA(v.nfeat, Bz);
+    DA(v.counters, Bz * v.N * 2);
+    DA(v.sel, Bz * v.N);
+    DA(v.ksel, Bz);
+    DA(v.stats, Bz);
+    DA(v.nhyp_tab, (size_t)(v.N + 1) * (v.N + 2) / 2);
+#undef DA
+    ekfslam_camera cam;
+    ekfslam_default_camera(&cam);
+    set_devcam(c, &cam);
+    ekfslam_default_params(&c->prm);
+    std::vector<int32_t> tab;
+    build_nhyp_table(tab, v.N, c->prm.p_spurious_free);
+    cudaError_t e = cudaMemcpy(v.nhyp_tab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        ekfslam_destroy(c);
+        return fail(EKFSLAM_ERR_CUDA, std::string("context init: ") + cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return EKFSLAM_OK;
+}
+
+int ekfslam_destroy(ekfslam_ctx* c) {
+    if (!c) return EKFSLAM_OK;
+    cudaSetDevice(c->device);
+    if (c->own_zc) { c->v.zc = c->own_zc; c->v.mflags = c->own_mflags; c->v.u = c->own_u; c->own_zc = nullptr; }
+    DevView& v = c->v;
+    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
+                    v.flags, v.mflags, v.foff, v.nstate, v.nfeat, v.counters, v.sel, v.ksel, v.stats, v.nhyp_tab};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->timer) {
+        cudaStreamSynchronize(c->stream);
+        kt_collect(c);
+        for (cudaEvent_t e : c->timer->pool) cudaEventDestroy(e);
+        delete c->timer;
+        c->timer = nullptr;
+    }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->pin) cudaFreeHost(c->pin);
+    delete c;
+    return EKFSLAM_OK;
+}
+
+int ekfslam_set_stream(ekfslam_ctx* c, void* s) {
+    NEED_CTX(c);
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return EKFSLAM_OK;
+}
+
+int ekfslam_set_camera(ekfslam_ctx* c, const ekfslam_camera* cam) {
+    NEED_CTX(c);
+    if (!cam) return fail(EKFSLAM_ERR_INVALID, "cam is null");
+    if (!(cam->dx > 0) || !(cam->dy > 0) || cam->nRows <= 0 || cam->nCols <= 0)
+        return fail(EKFSLAM_ERR_INVALID, "camera: dx, dy, nRows, nCols must be positive");
+    set_devcam(c, cam);
+    return EKFSLAM_OK;
+}
+
+int ekfslam_set_params(ekfslam_ctx* c, const ekfslam_params* p) {
+    NEED_CTX(c);
+    if (!p) return fail(EKFSLAM_ERR_INVALID, "params is null");
+    if (p->max_hyp <= 0 || p->fixed_hyp < 0 || !(p->p_spurious_free > 0 && p->p_spurious_free < 1))
+        return fail(EKFSLAM_ERR_INVALID, "params: max_hyp > 0, fixed_hyp >= 0, 0 < p_spurious_free < 1");
+    const bool retab = p->p_spurious_free != c->prm.p_spurious_free;
+    c->prm = *p;
+    if (retab) {
+        std::vector<int32_t> tab;
+        build_nhyp_table(tab, c->v.N, p->p_spurious_free);
+        CK(cudaMemcpyAsync(c->v.nhyp_tab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return EKFSLAM_OK;
+}
+
+int ekfslam_synchronize(ekfslam_ctx* c) {
+    NEED_CTX(c);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return EKFSLAM_OK;
+}
+
+int ekfslam_dims(const ekfslam_ctx* c, int* B, int* N_max, int* n_max, int* ld) {
+    if (!c) return fail(EKFSLAM_ERR_INVALID, "null context");
+    if (B) *B = c->v.B;
+    if (N_max) *N_max = c->v.N;
+    if (n_max) *n_max = c->v.nmax;
+    if (ld) *ld = c->v.ld;
+    return EKFSLAM_OK;
+}
+
+int ekfslam_enable_timing(ekfslam_ctx* c, int on) {
+    NEED_CTX(c);
+    CK(cudaStreamSynchronize(c->stream));
+    if (on && !c->timer) {
+        c->timer = new KTimer();
+        memset(c->timer->ms, 0, sizeof(c->timer->ms));
+        memset(c->timer->count, 0, sizeof(c->timer->count));
+    } else if (on && c->timer) {
+        kt_collect(c);
+        memset(c->timer->ms, 0, sizeof(c->timer->ms));
+        memset(c->timer->count, 0, sizeof(c->timer->count));
+    } else if (!on && c->timer) {
+        kt_collect(c);
+        for (cudaEvent_t e : c->timer->pool) cudaEventDestroy(e);
+        delete c->timer;
+        c->timer = nullptr;
+    }
+    return EKFSLAM_OK;
+}
+
+int ekfslam_kernel_count(void) { return KT_COUNT; }
+
+int ekfslam_kernel_time(ekfslam_ctx* c, int slot, char* name, int name_cap, double* ms, int64_t* launches) {
+    NEED_CTX(c);
+    if (slot < 0 || slot >= KT_COUNT) return fail(EKFSLAM_ERR_INVALID, "kernel slot out of range");
+    if (!c->timer) return fail(EKFSLAM_ERR_STATE, "timing is not enabled");
+    CK(cudaStreamSynchronize(c->stream));
+    kt_collect(c);
+    if (name && name_cap > 0) { strncpy(name, KT_NAMES[slot], name_cap - 1); name[name_cap - 1] = 0; }
+    if (ms) *ms = c->timer->ms[slot];
+    if (launches) *launches = c->timer->count[slot];
+    return EKFSLAM_OK;
+}
+
+int ekfslam_bind_frame(ekfslam_ctx* c, const void* d_zc, const void* d_fl, const void* d_u, int n_u) {
+    NEED_CTX(c);
+    if (!d_zc || !d_fl || !d_u || n_u <= 0) return fail(EKFSLAM_ERR_INVALID, "bind_frame: null pointer or n_u <= 0");
+    if (!c->own_zc) { c->own_zc = c->v.zc; c->own_mflags = c->v.mflags; c->own_u = c->v.u; c->own_n_u = c->v.n_u; }
+    c->v.zc = (double*)d_zc; c->v.mflags = (uint8_t*)d_fl; c->v.u = (double*)d_u; c->v.n_u = n_u;
+    return EKFSLAM_OK;
+}
+
+int ekfslam_unbind_frame(ekfslam_ctx* c) {
+    NEED_CTX(c);
+    if (c->own_zc) {
+        c->v.zc = c->own_zc; c->v.mflags = c->own_mflags; c->v.u = c->own_u; c->v.n_u = c->own_n_u;
+        c->own_zc = nullptr; c->own_mflags = nullptr; c->own_u = nullptr;
+    }
+    return EKFSLAM_OK;
+}
+
+int64_t ekfslam_device_bytes(const ekfslam_ctx* c) { return c ? c->bytes : 0; }
+int64_t ekfslam_launch_count(const ekfslam_ctx* c) { return c ? c->launches : 0; }
+
+static int check_range(const ekfslam_ctx* c, int b0, int nb) {
+    if (b0 < 0 || nb <= 0 || b0 + nb > c->v.B) return fail(EKFSLAM_ERR_INVALID, "filter range [b0, b0+nb) out of bounds");
+    return EKFSLAM_OK;
+}
+
+// ---- filter struct <-> device ------------------------------------------------------------
+int ekfslam_upload_state(ekfslam_ctx* c, int b0, int nb, int which, const double* x, const double* P,
+                         const int32_t* nstate) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    DevView& v = c->v;
+    if (nstate) {
+        for (int i = 0; i < nb; ++i)
+            if (nstate[i] < EKF_XV || nstate[i] > v.nmax) return fail(EKFSLAM_ERR_INVALID, "nstate out of [13, n_max]");
+        CK(cudaMemcpyAsync(v.nstate + b0, nstate, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (x) {
+        double* dst = (which ? v.xp : v.x) + (size_t)b0 * v.ld;
+        CK(cudaMemcpy2DAsync(dst, sizeof(double) * v.ld, x, sizeof(double) * v.nmax, sizeof(double) * v.nmax, nb,
+                             cudaMemcpyHostToDevice, c->stream));
+    }
+    if (P) {
+        // host: nb matrices of n_max x n_max (ld n_max); device rows padded to ld (padding stays zero)
+        double* dst = v.P + (size_t)b0 * v.nmax * v.ld;
+        CK(cudaMemcpy2DAsync(dst, sizeof(double) * v.ld, P, sizeof(double) * v.nmax, sizeof(double) * v.nmax,
+                             (size_t)nb * v.nmax, cudaMemcpyHostToDevice, c->stream));
+        launch_symmetrize(c, b0, nb);  // lower triangle is authoritative (see k_symmetrize)
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_download_state(ekfslam_ctx* c, int b0, int nb, int which, double* x, double* P, int32_t* nstate) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    DevView& v = c->v;
+    if (nstate) CK(cudaMemcpyAsync(nstate, v.nstate + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (x) {
+        const double* src = (which ? v.xp : v.x) + (size_t)b0 * v.ld;
+        CK(cudaMemcpy2DAsync(x, sizeof(double) * v.nmax, src, sizeof(double) * v.ld, sizeof(double) * v.nmax, nb,
+                             cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (P) {
+        const double* src = v.P + (size_t)b0 * v.nmax * v.ld;
+        CK(cudaMemcpy2DAsync(P, sizeof(double) * v.nmax, src, sizeof(double) * v.ld, sizeof(double) * v.nmax,
+                             (size_t)nb * v.nmax, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+// ---- features_info <-> device --------------------------------------------------------------
+int ekfslam_upload_feature_types(ekfslam_ctx* c, int b0, int nb, const uint8_t* type, const int32_t* nfeat) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!type || !nfeat) return fail(EKFSLAM_ERR_INVALID, "type / nfeat is null");
+    DevView& v = c->v;
+    std::vector<int32_t> off((size_t)nb * v.N, 0), ns(nb);
+    for (int i = 0; i < nb; ++i) {
+        if (nfeat[i] < 0 || nfeat[i] > v.N) return fail(EKFSLAM_ERR_INVALID, "nfeat out of [0, N_max]");
+        int pos = EKF_XV;  // mc/calculate_Hi_inverse_depth.m:22 (index_of_insertion, 0-based)
+        for (int f = 0; f < nfeat[i]; ++f) {
+            const uint8_t t = type[(size_t)i * v.N + f];
+            if (t != EKFSLAM_FEAT_INVERSEDEPTH && t != EKFSLAM_FEAT_CARTESIAN)
+                return fail(EKFSLAM_ERR_INVALID, "feature type must be 1 (inversedepth) or 2 (cartesian)");
+            off[(size_t)i * v.N + f] = pos;
+            pos += (t == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+        }
+        if (pos > v.nmax) return fail(EKFSLAM_ERR_INVALID, "features do not fit in n_max");
+        ns[i] = pos;
+    }
+    const size_t o = (size_t)b0 * v.N;
+    CK(cudaMemcpyAsync(v.ftype + o, type, (size_t)nb * v.N, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(v.foff + o, off.data(), sizeof(int32_t) * nb * v.N, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(v.nfeat + b0, nfeat, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(v.nstate + b0, ns.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(v.flags + o, 0, (size_t)nb * v.N, c->stream));
+    CK(cudaMemsetAsync(v.mflags + o, 0, (size_t)nb * v.N, c->stream));
+    CK(cudaMemsetAsync(v.counters + 2 * o, 0, sizeof(int32_t) * 2 * nb * v.N, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+static int upload_zc(ekfslam_ctx* c, int b0, int nb, const double* z, const uint8_t* fl, bool sync) {
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
+    DevView& v = c->v;
+    const size_t o = (size_t)b0 * v.N;
+    if (z) CK(cudaMemcpyAsync(v.zc + 2 * o, z, sizeof(double) * 2 * nb * v.N, cudaMemcpyHostToDevice, c->stream));
+    if (fl) CK(cudaMemcpyAsync(v.mflags + o, fl, (size_t)nb * v.N, cudaMemcpyHostToDevice, c->stream));
+    if (sync) CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_upload_matches(ekfslam_ctx* c, int b0, int nb, const double* z, const uint8_t* flags) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!z || !flags) return fail(EKFSLAM_ERR_INVALID, "z / flags is null");
+    return upload_zc(c, b0, nb, z, flags, true);
+}
+
+int ekfslam_upload_candidates(ekfslam_ctx* c, int b0, int nb, const double* zc, const uint8_t* has) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!zc || !has) return fail(EKFSLAM_ERR_INVALID, "zc / has is null");
+    // normalise any non-zero byte to the CAND bit
+    std::vector<uint8_t> fl((size_t)nb * c->v.N);
+    for (size_t i = 0; i < fl.size(); ++i) fl[i] = has[i] ? EKFSLAM_F_CAND : 0;
+    return upload_zc(c, b0, nb, zc, fl.data(), true);
+}
+
+static int ensure_u(ekfslam_ctx* c, int n_u) {
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
+    DevView& v = c->v;
+    if (n_u > c->u_cap) {
+        if (v.u) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(v.u)); v.u = nullptr; }
+        CK(cudaMalloc((void**)&v.u, sizeof(double) * (size_t)v.B * n_u));
+        CK(cudaMemsetAsync(v.u, 0, sizeof(double) * (size_t)v.B * n_u, c->stream));
+        c->bytes += (int64_t)sizeof(double) * v.B * (n_u - c->u_cap);
+        c->u_cap = n_u;
+    }
+    return EKFSLAM_OK;
+}
+
+int ekfslam_upload_uniforms(ekfslam_ctx* c, int b0, int nb, const double* u, int n_u) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!u || n_u <= 0) return fail(EKFSLAM_ERR_INVALID, "u is null or n_u <= 0");
+    DevView& v = c->v;
+    if (n_u != v.n_u && !(b0 == 0 && nb == v.B) && v.n_u != 0)
+        return fail(EKFSLAM_ERR_INVALID, "changing n_u requires uploading all B filters at once");
+    if (int r = ensure_u(c, n_u)) return r;
+    v.n_u = n_u;
+    CK(cudaMemcpyAsync(v.u + (size_t)b0 * n_u, u, sizeof(double) * (size_t)nb * n_u, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_download_features(ekfslam_ctx* c, int b0, int nb, double* h, double* Hc, double* S, double* z,
+                              uint8_t* flags, int32_t* offs, int32_t* counters) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    DevView& v = c->v;
+    const size_t o = (size_t)b0 * v.N, cnt = (size_t)nb * v.N;
+    if (h) CK(cudaMemcpyAsync(h, v.h + 2 * o, sizeof(double) * 2 * cnt, cudaMemcpyDeviceToHost, c->stream));
+    if (Hc) CK(cudaMemcpyAsync(Hc, v.Hc + EKF_HSTRIDE * o, sizeof(double) * EKF_HSTRIDE * cnt, cudaMemcpyDeviceToHost, c->stream));
+    if (S) CK(cudaMemcpyAsync(S, v.S + 4 * o, sizeof(double) * 4 * cnt, cudaMemcpyDeviceToHost, c->stream));
+    if (z) CK(cudaMemcpyAsync(z, v.z + 2 * o, sizeof(double) * 2 * cnt, cudaMemcpyDeviceToHost, c->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, v.flags + o, cnt, cudaMemcpyDeviceToHost, c->stream));
+    if (offs) CK(cudaMemcpyAsync(offs, v.foff + o, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, c->stream));
+    if (counters) CK(cudaMemcpyAsync(counters, v.counters + 2 * o, sizeof(int32_t) * 2 * cnt, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_upload_features(ekfslam_ctx* c, int b0, int nb, const double* h, const double* Hc, const double* S,
+                            const double* z, const uint8_t* flags) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    DevView& v = c->v;
+    const size_t o = (size_t)b0 * v.N, cnt = (size_t)nb * v.N;
+    if (h) CK(cudaMemcpyAsync(v.h + 2 * o, h, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, c->stream));
+    if (Hc) CK(cudaMemcpyAsync(v.Hc + EKF_HSTRIDE * o, Hc, sizeof(double) * EKF_HSTRIDE * cnt, cudaMemcpyHostToDevice, c->stream));
+    if (S) CK(cudaMemcpyAsync(v.S + 4 * o, S, sizeof(double) * 4 * cnt, cudaMemcpyHostToDevice, c->stream));
+    if (z) CK(cudaMemcpyAsync(v.z + 2 * o, z, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, c->stream));
+    if (flags) CK(cudaMemcpyAsync(v.flags + o, flags, cnt, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_download_stats(ekfslam_ctx* c, int b0, int nb, ekfslam_stats* stats) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!stats) return fail(EKFSLAM_ERR_INVALID, "stats is null");
+    CK(cudaMemcpyAsync(stats, c->v.stats + b0, sizeof(ekfslam_stats) * nb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+// ---- stages ---------------------------------------------------------------------------------
+#define LAUNCHED()                                                                                     \
+    do {                                                                                               \
+        cudaError_t _e = cudaGetLastError();                                                           \
+        if (_e != cudaSuccess) return fail(EKFSLAM_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    } while (0)
+
+int ekfslam_begin_frame(ekfslam_ctx* c) {
+    NEED_CTX(c);
+    launch_begin_frame(c);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_predict(ekfslam_ctx* c) {
+    NEED_CTX(c);
+    launch_predict(c);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_features(ekfslam_ctx* c, int which, int parts) {
+    NEED_CTX(c);
+    if (parts < 1 || parts > 3) return fail(EKFSLAM_ERR_INVALID, "parts must be 1 (h), 2 (H) or 3 (both)");
+    launch_features(c, which ? 1 : 0, parts);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_hp(ekfslam_ctx* c, int need, int forbid) {
+    NEED_CTX(c);
+    launch_hp(c, need, forbid);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_innovation(ekfslam_ctx* c) {
+    NEED_CTX(c);
+    launch_innov(c, 0);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_measure(ekfslam_ctx* c, int which) {
+    NEED_CTX(c);
+    launch_features(c, which ? 1 : 0, 3);
+    launch_hp(c, EKFSLAM_F_HAS_H, 0);
+    launch_innov(c, 0);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+// mode: 1 = gate the staged candidates, 2 = apply the staged explicit matches
+static int gate_mode(ekfslam_ctx* c, int mode) {
+    launch_innov(c, mode);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_gate(ekfslam_ctx* c) {
+    NEED_CTX(c);
+    return gate_mode(c, 1);
+}
+
+int ekfslam_apply_matches(ekfslam_ctx* c) {
+    NEED_CTX(c);
+    return gate_mode(c, 2);
+}
+
+int ekfslam_ransac(ekfslam_ctx* c) {
+    NEED_CTX(c);
+    if (c->v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "ransac: no uniform stream uploaded (ekfslam_upload_uniforms)");
+    launch_ransac(c);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_update_masked(ekfslam_ctx* c, int mask, int which_prior) {
+    NEED_CTX(c);
+    if (!(mask & 0xff)) return fail(EKFSLAM_ERR_INVALID, "empty mask");
+    launch_update(c, mask, which_prior ? 1 : 0);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_update_li(ekfslam_ctx* c) { return ekfslam_update_masked(c, EKFSLAM_F_LI, 1); }
+
+int ekfslam_rescue(ekfslam_ctx* c) {
+    NEED_CTX(c);
+    launch_features(c, 0, 3);                            // h, H of ALL features at x_k_k (:6-7)
+    launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);  // G rows of the candidates (IC && !LI)
+    launch_innov(c, 3);                                 // chi2 gate -> HI (:11-20)
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_update_hi(ekfslam_ctx* c) { return ekfslam_update_masked(c, EKFSLAM_F_HI, 0); }
+
+int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
+    NEED_CTX(c);
+    if (match_mode < 0 || match_mode > 2) return fail(EKFSLAM_ERR_INVALID, "match_mode must be 0, 1 or 2");
+    if (c->v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "step: no uniform stream uploaded");
+    if (reset) launch_begin_frame(c);
+    launch_predict(c);
+    launch_features(c, 1, 3);
+    launch_hp(c, EKFSLAM_F_HAS_H, 0);
+    launch_innov(c, 0);
+    if (match_mode) launch_innov(c, match_mode);
+    launch_ransac(c);
+    launch_update(c, EKFSLAM_F_LI, 1);
+    launch_features(c, 0, 3);
+    launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);
+    launch_innov(c, 3);
+    launch_update(c, EKFSLAM_F_HI, 0);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_step_host(ekfslam_ctx* c, int match_mode, const double* zc, const uint8_t* fl, const double* u, int n_u,
+                      double* x_out, uint8_t* flags_out, ekfslam_stats* stats_out) {
+    NEED_CTX(c);
+    if (match_mode != 1 && match_mode != 2) return fail(EKFSLAM_ERR_INVALID, "match_mode must be 1 (gate) or 2 (explicit)");
+    if (!zc || !fl || !u || n_u <= 0) return fail(EKFSLAM_ERR_INVALID, "zc / flags / u is null or n_u <= 0");
+    DevView& v = c->v;
+    if (int r = ensure_u(c, n_u)) return r;
+    v.n_u = n_u;
+    if (int r = upload_zc(c, 0, v.B, zc, fl, false)) return r;
+    CK(cudaMemcpyAsync(v.u, u, sizeof(double) * (size_t)v.B * n_u, cudaMemcpyHostToDevice, c->stream));
+    if (int r = ekfslam_step(c, 1, match_mode)) return r;
+    if (x_out)
+        CK(cudaMemcpy2DAsync(x_out, sizeof(double) * v.nmax, v.x, sizeof(double) * v.ld, sizeof(double) * v.nmax, v.B,
+                             cudaMemcpyDeviceToHost, c->stream));
+    if (flags_out) CK(cudaMemcpyAsync(flags_out, v.flags, (size_t)v.B * v.N, cudaMemcpyDeviceToHost, c->stream));
+    if (stats_out) CK(cudaMemcpyAsync(stats_out, v.stats, sizeof(ekfslam_stats) * v.B, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_add_features(ekfslam_ctx* c, int b0, int nb, const double* uvd, const uint8_t* add, double std_pxl,
+                         double initial_rho, double std_rho) {
+    NEED_CTX(c);
+    (void)b0; (void)nb; (void)uvd; (void)add; (void)std_pxl; (void)initial_rho; (void)std_rho;
+    return fail(EKFSLAM_ERR_STATE, "ekfslam_add_features: not built yet (SURVEY §8f rank 1)");
+}
+
+void* ekfslam_device_ptr(ekfslam_ctx* c, const char* name) {
+    if (!c || !name) return nullptr;
+    DevView& v = c->v;
+    struct { const char* n; void* p; } tab[] = {
+        {"x", v.x}, {"xp", v.xp}, {"P", v.P}, {"G", v.G}, {"W", v.W}, {"h", v.h}, {"Hc", v.Hc}, {"S", v.S},
+        {"z", v.z}, {"zc", v.zc}, {"flags", v.flags}, {"mflags", v.mflags}, {"u", v.u}, {"stats", v.stats},
+        {"Sb", v.Sb}, {"Li", v.Li}, {"yv", v.yv}};
+    for (auto& e : tab)
+        if (!strcmp(e.n, name)) return e.p;
+    return nullptr;
+}
+
+}  // extern "C"

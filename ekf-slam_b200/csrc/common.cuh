@@ -1,0 +1,97 @@
+// Internal definitions shared by the kernels and the C ABI (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ekfslam.h"
+
+#define EKF_XV 13        // camera state size, mc/fv.m:3-6
+#define EKF_HC 13        // compact Jacobian columns: 7 (r,q) + 6 (feature block)
+#define EKF_HSTRIDE 26   // doubles per feature in Hc: 2 rows x 13
+
+struct DevCam {
+    double k1, k2, Cx, Cy, f, dx, dy;
+    double fku, fkv;  // f*(1/dx), f*(1/dy) in the reference's evaluation order
+    double nRows, nCols;
+};
+
+// Everything a kernel needs; passed by value.
+struct DevView {
+    int B, N, nmax, ld;   // ld = leading dimension (doubles) of x rows, P rows, G/W rows
+    int kmax;             // 2*N
+    int n_u;              // uniforms per filter
+    double* x;            // [B][ld]      x_k_k
+    double* xp;           // [B][ld]      x_k_km1
+    double* P;            // [B][nmax][ld] covariance (single buffer, updated in place)
+    double* G;            // [B][kmax][ld] rows 2i,2i+1 = H_i * P
+    double* W;            // [B][kmax][ld] W = inv(L) * G_sel
+    double* Sb;           // [B][kmax][kmax] stacked innovation covariance / its Cholesky factor
+    double* Li;           // [B][kmax][kmax] inverse of the Cholesky factor
+    double* yv;           // [B][kmax]     inv(L)*(z-h)
+    double* jn;           // [B][16]       normJac(q+) of the running update
+    double* h;            // [B][N][2]
+    double* Hc;           // [B][N][26]
+    double* S;            // [B][N][4]
+    double* z;            // [B][N][2]
+    double* zc;           // [B][N][2]  candidates for the gate
+    double* u;            // [B][n_u]
+    uint8_t* ftype;       // [B][N]
+    uint8_t* flags;       // [B][N]
+    uint8_t* mflags;      // [B][N]  staged match / candidate flags of the current frame
+    int32_t* foff;        // [B][N]
+    int32_t* nstate;      // [B]
+    int32_t* nfeat;       // [B]
+    int32_t* counters;    // [B][N][2]
+    int32_t* sel;         // [B][N]   selected feature list of the running update
+    int32_t* ksel;        // [B]      number of selected features
+    int32_t* nhyp_tab;    // [(N+1)(N+2)/2] adaptive hypothesis count, host libm (see abi.cu)
+    ekfslam_stats* stats; // [B]
+};
+
+// per-kernel timing (ekfslam_enable_timing): every launch is bracketed by an event pair
+enum {
+    KT_BEGIN_FRAME = 0, KT_PREDICT, KT_FEATURES, KT_HP, KT_INNOV, KT_RANSAC, KT_UPD_S, KT_CHOL, KT_W, KT_XUPD,
+    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_COUNT
+};
+struct KTimer;
+
+struct ekfslam_ctx {
+    int device;
+    KTimer* timer;
+    DevView v;
+    DevCam cam;
+    ekfslam_params prm;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    int64_t bytes;
+    int64_t launches;
+    int stage;  // call-order tracking
+    // pinned staging
+    void* pin;
+    size_t pin_bytes;
+    int u_cap;
+    // the context's own frame buffers while caller-owned ones are bound (ekfslam_bind_frame)
+    double* own_zc; uint8_t* own_mflags; double* own_u; int own_n_u;
+};
+
+#define EKF_TRI(nic, s) (((nic) * ((nic) + 1)) / 2 + (s))
+
+// timing hooks (abi.cu): no-ops unless timing is enabled
+void kt_begin(ekfslam_ctx* c, int slot);
+void kt_end(ekfslam_ctx* c, int slot);
+struct KScope {
+    ekfslam_ctx* c; int slot;
+    KScope(ekfslam_ctx* c_, int s_) : c(c_), slot(s_) { if (c->timer) kt_begin(c, slot); }
+    ~KScope() { if (c->timer) kt_end(c, slot); c->launches++; }
+};
+
+// launchers (defined in the kernel .cu files)
+void launch_begin_frame(ekfslam_ctx* c);
+void launch_predict(ekfslam_ctx* c);
+void launch_features(ekfslam_ctx* c, int which, int parts);  // parts: 1 = h, 2 = H, 3 = both
+void launch_hp(ekfslam_ctx* c, int need, int forbid);  // G rows for features with (flags&need)==need && !(flags&forbid)
+void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gate / explicit matches / rescue gate
+void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
+void launch_ransac(ekfslam_ctx* c);
+void launch_update(ekfslam_ctx* c, int mask, int which_prior);
+void launch_add_features(ekfslam_ctx* c, int b0, int nb, const double* d_uvd, const uint8_t* d_add,
+                         double std_pxl, double rho0, double std_rho);

@@ -1,0 +1,432 @@
+// Per-frame bookkeeping, state/covariance prediction, measurement prediction + analytic
+// Jacobians, G = H*P row products and per-feature innovation covariances.
+#include "model.cuh"
+
+// ---------------------------------------------------------------------------------------
+// mc/update_features_info.m:4-18 — one thread per (filter, feature)
+// ---------------------------------------------------------------------------------------
+__global__ void k_begin_frame(DevView v) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= v.B * v.N) return;
+    const int b = t / v.N, i = t - b * v.N;
+    if (i >= v.nfeat[b]) return;
+    const uint8_t f = v.flags[t];
+    if (f & EKFSLAM_F_HAS_H) v.counters[2 * t] += 1;
+    if (f & (EKFSLAM_F_LI | EKFSLAM_F_HI)) v.counters[2 * t + 1] += 1;
+    v.flags[t] = f & EKFSLAM_F_CAND;  // a staged candidate survives the reset, everything else clears
+}
+
+void launch_begin_frame(ekfslam_ctx* c) {
+    const int tot = c->v.B * c->v.N;
+    KScope ks(c, KT_BEGIN_FRAME);
+    k_begin_frame<<<(tot + 255) / 256, 256, 0, c->stream>>>(c->v);
+}
+
+// ---------------------------------------------------------------------------------------
+// mc/predict_state_and_covariance.m:3-27.  One block per filter.  The covariance is updated in
+// place: F differs from the identity only in rows 0-6 (r and q), so only rows/columns 0-6 of P
+// change:  P[0:13,j] <- F P[0:13,j]  and  Pxx <- F Pxx F' + Q.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_predict(DevView v, ekfslam_params prm) {
+    const int b = blockIdx.x;
+    const int n = v.nstate[b];
+    const int ld = v.ld;
+    double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    const double* __restrict__ x = v.x + (size_t)b * ld;
+    double* __restrict__ xp = v.xp + (size_t)b * ld;
+
+    __shared__ double F[13][13];
+    __shared__ double Q[13][13];
+    __shared__ double Pxx[13][13];
+    __shared__ double T[13][13];
+    __shared__ double Fqq[4][4], Fqw[4][3];
+
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 169; e += blockDim.x) {
+        const int r = e / 13, cc = e - r * 13;
+        Pxx[r][cc] = P[(size_t)r * ld + cc];
+        F[r][cc] = (r == cc) ? 1.0 : 0.0;
+        Q[r][cc] = 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double dt = prm.delta_t;
+        const double q0 = x[3], qx = x[4], qy = x[5], qz = x[6];
+        const double wx = x[10], wy = x[11], wz = x[12];
+        // mc/v2q.m:10-16 with quaternions(v_n, theta) = [cos(theta/2), sin(theta/2) v_n]
+        const double ax = wx * dt, ay = wy * dt, az = wz * dt;
+        const double theta = sqrt(ax * ax + ay * ay + az * az);
+        double p0 = 1.0, px = 0.0, py = 0.0, pz = 0.0;
+        if (!(theta < 2.220446049250313e-16)) {
+            const double sh = sin(theta / 2.0);
+            p0 = cos(theta / 2.0);
+            px = sh * (ax / theta); py = sh * (ay / theta); pz = sh * (az / theta);
+        }
+        // mc/fv.m:43-46, mc/qprod.m:8
+        xp[0] = x[0] + x[7] * dt; xp[1] = x[1] + x[8] * dt; xp[2] = x[2] + x[9] * dt;
+        xp[3] = q0 * p0 - (qx * px + qy * py + qz * pz);
+        xp[4] = (q0 * px + p0 * qx) + (qy * pz - qz * py);
+        xp[5] = (q0 * py + p0 * qy) + (qz * px - qx * pz);
+        xp[6] = (q0 * pz + p0 * qz) + (qx * py - qy * px);
+        for (int k = 7; k < 13; ++k) xp[k] = x[k];
+        // mc/dfv_by_dxv.m:9 — dq3_by_dq2(qwt)
+        Fqq[0][0] = p0; Fqq[0][1] = -px; Fqq[0][2] = -py; Fqq[0][3] = -pz;
+        Fqq[1][0] = px; Fqq[1][1] = p0;  Fqq[1][2] = pz;  Fqq[1][3] = -py;
+        Fqq[2][0] = py; Fqq[2][1] = -pz; Fqq[2][2] = p0;  Fqq[2][3] = px;
+        Fqq[3][0] = pz; Fqq[3][1] = py;  Fqq[3][2] = -px; Fqq[3][3] = p0;
+        // mc/dqomegadt_by_domega.m:6-48
+        const double om = sqrt(wx * wx + wy * wy + wz * wz);
+        const double sn = sin(om * dt / 2.0), cs = cos(om * dt / 2.0);
+        const double w[3] = {wx, wy, wz};
+        double dq[4][3];
+        for (int a = 0; a < 3; ++a) {
+            dq[0][a] = (-dt / 2.0) * (w[a] / om) * sn;
+            for (int c2 = 0; c2 < 3; ++c2) {
+                if (a == c2)
+                    dq[1 + a][c2] = (dt / 2.0) * w[a] * w[a] / (om * om) * cs +
+                                    (1.0 / om) * (1.0 - w[a] * w[a] / (om * om)) * sn;
+                else
+                    dq[1 + a][c2] = (w[a] * w[c2] / (om * om)) * ((dt / 2.0) * cs - (1.0 / om) * sn);
+            }
+        }
+        // dq3_by_dq1(qOld) (missing in the reference; left-multiplication matrix of qOld)
+        const double L[4][4] = {{q0, -qx, -qy, -qz}, {qx, q0, -qz, qy}, {qy, qz, q0, -qx}, {qz, -qy, qx, q0}};
+        for (int r = 0; r < 4; ++r)
+            for (int c2 = 0; c2 < 3; ++c2) {
+                double s = 0.0;
+                for (int k = 0; k < 4; ++k) s += L[r][k] * dq[k][c2];
+                Fqw[r][c2] = s;
+            }
+        for (int r = 0; r < 4; ++r) {
+            for (int c2 = 0; c2 < 4; ++c2) F[3 + r][3 + c2] = Fqq[r][c2];
+            for (int c2 = 0; c2 < 3; ++c2) F[3 + r][10 + c2] = Fqw[r][c2];
+        }
+        for (int r = 0; r < 3; ++r) F[r][7 + r] = dt;
+        // mc/func_Q.m:15-28: Q = G Pn G', G = [dt*I 0; 0 M; I 0; 0 I], Pn = diag(la*I3, aa*I3)
+        const double la = (prm.std_a * dt) * (prm.std_a * dt);
+        const double aa = (prm.std_alpha * dt) * (prm.std_alpha * dt);
+        for (int r = 0; r < 3; ++r) {
+            Q[r][r] = dt * la * dt;
+            Q[r][7 + r] = dt * la;
+            Q[7 + r][r] = la * dt;
+            Q[7 + r][7 + r] = la;
+            Q[10 + r][10 + r] = aa;
+        }
+        for (int r = 0; r < 4; ++r) {
+            for (int c2 = 0; c2 < 4; ++c2) {
+                double s = 0.0;
+                for (int k = 0; k < 3; ++k) s += Fqw[r][k] * aa * Fqw[c2][k];
+                Q[3 + r][3 + c2] = s;
+            }
+            for (int c2 = 0; c2 < 3; ++c2) {
+                Q[3 + r][10 + c2] = Fqw[r][c2] * aa;
+                Q[10 + c2][3 + r] = aa * Fqw[r][c2];
+            }
+        }
+    }
+    // features are static: x_k_km1(14:end) = x_k_k(14:end)
+    for (int j = 13 + tid; j < n; j += blockDim.x) xp[j] = x[j];
+    __syncthreads();
+
+    // cross-covariance panel
+    for (int j = 13 + tid; j < n; j += blockDim.x) {
+        double c[13];
+#pragma unroll
+        for (int r = 0; r < 13; ++r) c[r] = P[(size_t)r * ld + j];
+        double o[7];
+        const double dt = prm.delta_t;
+        o[0] = c[0] + dt * c[7]; o[1] = c[1] + dt * c[8]; o[2] = c[2] + dt * c[9];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            o[3 + r] = Fqq[r][0] * c[3] + Fqq[r][1] * c[4] + Fqq[r][2] * c[5] + Fqq[r][3] * c[6] +
+                       Fqw[r][0] * c[10] + Fqw[r][1] * c[11] + Fqw[r][2] * c[12];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            P[(size_t)r * ld + j] = o[r];
+            P[(size_t)j * ld + r] = o[r];
+        }
+    }
+    // camera block: T = F Pxx ; Pxx' = T F' + Q, stored symmetric
+    for (int e = tid; e < 169; e += blockDim.x) {
+        const int r = e / 13, cc = e - r * 13;
+        double s = 0.0;
+        for (int k = 0; k < 13; ++k) s += F[r][k] * Pxx[k][cc];
+        T[r][cc] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < 169; e += blockDim.x) {
+        const int r = e / 13, cc = e - r * 13;
+        if (cc > r) continue;
+        double s = 0.0;
+        for (int k = 0; k < 13; ++k) s += T[r][k] * F[cc][k];
+        s += Q[r][cc];
+        P[(size_t)r * ld + cc] = s;
+        P[(size_t)cc * ld + r] = s;
+    }
+}
+
+void launch_predict(ekfslam_ctx* c) {
+    KScope ks(c, KT_PREDICT);
+    k_predict<<<c->v.B, 128, 0, c->stream>>>(c->v, c->prm);
+}
+
+// ---------------------------------------------------------------------------------------
+// mc/predict_camera_measurements.m:8-28 + mc/calculate_derivatives.m:6-28.
+// One thread per (filter, feature).  h is only overwritten when the feature is visible at this
+// state (a stale h from earlier in the frame survives, and H is then linearised at that stale
+// pixel — mc/predict_camera_measurements.m:14-16, mc/calculate_Hi_inverse_depth.m:3).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_features(DevView v, DevCam cam, int which, int parts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= v.B * v.N) return;
+    const int b = t / v.N, i = t - b * v.N;
+    if (i >= v.nfeat[b]) return;
+    const int type = v.ftype[t];
+    if (type == EKFSLAM_FEAT_NONE) return;
+    const double* __restrict__ x = (which ? v.xp : v.x) + (size_t)b * v.ld;
+    double xv[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) xv[k] = x[k];
+    double R[9];
+    q2r_dev(xv + 3, R);
+    const int off = v.foff[t];
+    double y[6];
+    const int w = (type == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) y[k] = (k < w) ? x[off + k] : 0.0;
+
+    uint8_t f = v.flags[t];
+    double hu = 0.0, hv = 0.0;
+    if ((parts & 1) && predict_h_dev(cam, xv, R, y, type, hu, hv)) {
+        v.h[2 * t] = hu; v.h[2 * t + 1] = hv;
+        f |= EKFSLAM_F_HAS_H;
+        v.flags[t] = f;
+    } else if (f & EKFSLAM_F_HAS_H) {
+        hu = v.h[2 * t]; hv = v.h[2 * t + 1];
+    }
+    if ((parts & 2) && (f & EKFSLAM_F_HAS_H)) {
+        double Hc[EKF_HSTRIDE];
+        jacobian_dev(cam, xv, R, y, type, hu, hv, Hc);
+        double* dst = v.Hc + (size_t)t * EKF_HSTRIDE;
+#pragma unroll
+        for (int k = 0; k < EKF_HSTRIDE; ++k) dst[k] = Hc[k];
+    }
+}
+
+void launch_features(ekfslam_ctx* c, int which, int parts) {
+    const int tot = c->v.B * c->v.N;
+    KScope ks(c, KT_FEATURES);
+    k_features<<<(tot + 127) / 128, 128, 0, c->stream>>>(c->v, c->cam, which, parts);
+}
+
+// ---------------------------------------------------------------------------------------
+// G = H * P for the selected features: rows 2i, 2i+1 of G are H_i (2 x n, 13 non-zero columns)
+// times P.  P is symmetric, so row a of G is a combination of 13 ROWS of P, read coalesced.
+// grid = (column chunks of 256, B); each thread owns two adjacent columns.
+// A feature is selected iff (flags & need) == need && (flags & forbid) == 0.
+// This single pass over P feeds S_i (mc/search_IC_matches.m:8), every 1-point RANSAC gain
+// K = P H_i' inv(S_i) (mc/ransac_hypotheses.m:24-25) and P H' of the update (mc/update.m:8-9).
+// ---------------------------------------------------------------------------------------
+#define HP_CHUNK 64
+__global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid) {
+    const int b = blockIdx.y;
+    const int n = v.nstate[b];
+    const int ld = v.ld;
+    const int c0 = (blockIdx.x * 128 + threadIdx.x) * 2;
+    if (blockIdx.x * 256 >= n) return;
+    const int nf = v.nfeat[b];
+    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
+
+    __shared__ double sH[HP_CHUNK][EKF_HSTRIDE];
+    __shared__ int sOff[HP_CHUNK];
+    __shared__ int sIdx[HP_CHUNK];
+    __shared__ int sW[HP_CHUNK];
+    __shared__ int sCnt;
+
+    const bool active = c0 < ld && c0 < n;
+    double2 pc[7];
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r) pc[r] = *reinterpret_cast<const double2*>(P + (size_t)r * ld + c0);
+    }
+    for (int f0 = 0; f0 < nf; f0 += HP_CHUNK) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cnt = 0;
+            const int f1 = min(nf, f0 + HP_CHUNK);
+            for (int i = f0; i < f1; ++i) {
+                const int t = b * v.N + i;
+                const uint8_t fl = v.flags[t];
+                const int ty = v.ftype[t];
+                if (ty != EKFSLAM_FEAT_NONE && (fl & need) == need && (fl & forbid) == 0) {
+                    sIdx[cnt] = i; sOff[cnt] = v.foff[t]; sW[cnt] = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+                    ++cnt;
+                }
+            }
+            sCnt = cnt;
+        }
+        __syncthreads();
+        const int cnt = sCnt;
+        for (int e = threadIdx.x; e < cnt * EKF_HSTRIDE; e += blockDim.x) {
+            const int s = e / EKF_HSTRIDE, k = e - s * EKF_HSTRIDE;
+            sH[s][k] = v.Hc[((size_t)b * v.N + sIdx[s]) * EKF_HSTRIDE + k];
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int s = 0; s < cnt; ++s) {
+            const double* Hs = sH[s];
+            double2 g0 = make_double2(0.0, 0.0), g1 = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                g0.x += Hs[r] * pc[r].x; g0.y += Hs[r] * pc[r].y;
+                g1.x += Hs[EKF_HC + r] * pc[r].x; g1.y += Hs[EKF_HC + r] * pc[r].y;
+            }
+            const int off = sOff[s];
+            const int w = sW[s];
+            const double* Pr = P + (size_t)off * ld + c0;
+            if (w == 6) {
+                double2 pf[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) pf[r] = *reinterpret_cast<const double2*>(Pr + (size_t)r * ld);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    g0.x += Hs[7 + r] * pf[r].x; g0.y += Hs[7 + r] * pf[r].y;
+                    g1.x += Hs[EKF_HC + 7 + r] * pf[r].x; g1.y += Hs[EKF_HC + 7 + r] * pf[r].y;
+                }
+            } else {
+                double2 pf[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) pf[r] = *reinterpret_cast<const double2*>(Pr + (size_t)r * ld);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    g0.x += Hs[7 + r] * pf[r].x; g0.y += Hs[7 + r] * pf[r].y;
+                    g1.x += Hs[EKF_HC + 7 + r] * pf[r].x; g1.y += Hs[EKF_HC + 7 + r] * pf[r].y;
+                }
+            }
+            const int i = sIdx[s];
+            *reinterpret_cast<double2*>(G + (size_t)(2 * i) * ld + c0) = g0;
+            *reinterpret_cast<double2*>(G + (size_t)(2 * i + 1) * ld + c0) = g1;
+        }
+    }
+}
+
+void launch_hp(ekfslam_ctx* c, int need, int forbid) {
+    dim3 grid((c->v.nmax + 255) / 256, c->v.B);
+    KScope ks(c, KT_HP);
+    k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid);
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-feature 2x2 innovation covariance from G, and the match gates.  One thread per feature.
+//   mode 0: S_i = H_i P H_i' + R_i for every predicted feature (mc/search_IC_matches.m:6-10)
+//   mode 1: synthetic matcher gate (mc/matching.m:16,38) on candidates  -> z, HAS_Z, IC
+//   mode 2: explicit matches (what mc/matching.m:52-53 would have written) -> z, HAS_Z, IC
+//   mode 3: rescue gate (mc/rescue_hi_inliers.m:11-20): S_i = H_i P H_i' (no R) for IC && !LI,
+//           nu' inv(S_i) nu < chi2 -> HI.  S is not stored (it is a local in the reference).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_innov(DevView v, ekfslam_params prm, int mode) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= v.B * v.N) return;
+    const int b = t / v.N, i = t - b * v.N;
+    if (i >= v.nfeat[b]) return;
+    const int type = v.ftype[t];
+    if (type == EKFSLAM_FEAT_NONE) return;
+    uint8_t f = v.flags[t];
+    if (mode == 2) {
+        const uint8_t m = v.mflags[t] & (EKFSLAM_F_HAS_Z | EKFSLAM_F_IC);
+        if (m) {
+            v.z[2 * t] = v.zc[2 * t]; v.z[2 * t + 1] = v.zc[2 * t + 1];
+            v.flags[t] = f | m;
+        }
+        return;
+    }
+    if (!(f & EKFSLAM_F_HAS_H)) return;
+    if (mode == 1 && !(v.mflags[t] & EKFSLAM_F_CAND)) return;
+    if (mode == 3 && !((f & EKFSLAM_F_IC) && !(f & EKFSLAM_F_LI))) return;
+
+    double s00, s01, s10, s11;
+    if (mode == 1) {
+        s00 = v.S[4 * t]; s01 = v.S[4 * t + 1]; s10 = v.S[4 * t + 2]; s11 = v.S[4 * t + 3];
+    } else {
+        const int ld = v.ld;
+        const double* __restrict__ g0 = v.G + ((size_t)b * v.kmax + 2 * i) * ld;
+        const double* __restrict__ g1 = g0 + ld;
+        const double* __restrict__ H = v.Hc + (size_t)t * EKF_HSTRIDE;
+        const int off = v.foff[t];
+        const int w = (type == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+        s00 = s01 = s10 = s11 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const double a0 = g0[k], a1 = g1[k], h0 = H[k], h1 = H[EKF_HC + k];
+            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
+        }
+        for (int k = 0; k < w; ++k) {
+            const double a0 = g0[off + k], a1 = g1[off + k], h0 = H[7 + k], h1 = H[EKF_HC + 7 + k];
+            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
+        }
+        if (mode == 0) {  // + R_i = eye(2), mc/add_feature_to_info_vector.m:32
+            s00 += 1.0; s11 += 1.0;
+            v.S[4 * t] = s00; v.S[4 * t + 1] = s01; v.S[4 * t + 2] = s10; v.S[4 * t + 3] = s11;
+            return;
+        }
+    }
+    const double zu = (mode == 1) ? v.zc[2 * t] : v.z[2 * t];
+    const double zv = (mode == 1) ? v.zc[2 * t + 1] : v.z[2 * t + 1];
+    const double n0 = zu - v.h[2 * t], n1 = zv - v.h[2 * t + 1];
+    const double det = s00 * s11 - s01 * s10;
+    // nu' inv(S) nu with inv(S) = [s11 -s01; -s10 s00]/det
+    const double d2 = (n0 * (s11 * n0 - s01 * n1) + n1 * (-s10 * n0 + s00 * n1)) / det;
+    if (mode == 1) {
+        // all(eig(S) < 100): the larger eigenvalue of the 2x2
+        const double tr = s00 + s11;
+        const double disc = sqrt((s00 - s11) * (s00 - s11) + 4.0 * s01 * s10);
+        const double lmax = 0.5 * (tr + disc);
+        if (lmax < 100.0 && d2 < prm.chi2_gate) {
+            v.z[2 * t] = zu; v.z[2 * t + 1] = zv;
+            v.flags[t] = f | EKFSLAM_F_HAS_Z | EKFSLAM_F_IC;
+        }
+    } else {  // mode 3
+        if (d2 < prm.chi2_gate) f |= EKFSLAM_F_HI; else f &= ~EKFSLAM_F_HI;
+        v.flags[t] = f;
+    }
+}
+
+void launch_innov(ekfslam_ctx* c, int mode) {
+    const int tot = c->v.B * c->v.N;
+    KScope ks(c, KT_INNOV);
+    k_innov<<<(tot + 127) / 128, 128, 0, c->stream>>>(c->v, c->prm, mode);
+}
+
+// ---------------------------------------------------------------------------------------
+// Mirror the lower triangle of freshly uploaded covariances into the upper one.  The kernels
+// read P by rows and write tiles together with their transposes, which assumes an exactly
+// symmetric P; a host matrix such as J P J' is only symmetric to rounding.
+// ---------------------------------------------------------------------------------------
+__global__ void k_symmetrize(DevView v, int b0) {
+    const int b = b0 + blockIdx.y;
+    const int n = v.nstate[b];
+    const int ld = v.ld;
+    double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    __shared__ double tile[32][33];
+    const int ti = blockIdx.x / ((v.nmax + 31) / 32), tj = blockIdx.x % ((v.nmax + 31) / 32);
+    if (tj > ti) return;
+    const int i0 = ti * 32, j0 = tj * 32;
+    if (i0 >= n) return;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int gi = i0 + r, gj = j0 + threadIdx.x;
+        tile[r][threadIdx.x] = (gi < n && gj < n) ? P[(size_t)gi * ld + gj] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int gj = j0 + r, gi = i0 + threadIdx.x;  // writes P[gj][gi] = tile[gi-i0][gj-j0]
+        if (gi < n && gj < n && gi > gj) P[(size_t)gj * ld + gi] = tile[threadIdx.x][r];
+    }
+}
+
+void launch_symmetrize(ekfslam_ctx* c, int b0, int nb) {
+    const int nt = (c->v.nmax + 31) / 32;
+    dim3 grid(nt * nt, nb), block(32, 8);
+    KScope ks(c, KT_SYMMETRIZE);
+    k_symmetrize<<<grid, block, 0, c->stream>>>(c->v, b0);
+}

@@ -1,0 +1,184 @@
+// 1-point RANSAC (mc/ransac_hypotheses.m:3-47) — one thread block per filter.
+//
+// A hypothesis is fully determined by the feature it draws: xi = x + P H_p' inv(S_p) (z_p - h_p)
+// (:22-26).  Rows 2p, 2p+1 of G = H*P (k_hp) are exactly (P H_p')', so
+//     xi = x + g0 * G[2p,:] + g1 * G[2p+1,:],   [g0 g1]' = inv(S_p) (z_p - h_p).
+// Hypotheses are scored warp-parallel in rounds of RW draws: warp w scores draw i0+w unless the
+// drawn feature was already scored (its support is memoised — a repeated draw reproduces the
+// same xi bit for bit).  Each lane re-projects matched features at xi
+// (mc/compute_hypothesis_support_fast.m) and the inlier count is a ballot/popc reduction.
+// After each round thread 0 replays the reference's sequential loop over those draws:
+// "first strictly greater support wins" (:37), the adaptive hypothesis count (:40-41, from a
+// host-libm table), the n_hyp==0 break (:42) and the i>n_hyp break (:45).
+#include "model.cuh"
+
+#define RANSAC_WARPS 8
+#define RANSAC_THREADS (RANSAC_WARPS * 32)
+
+__global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(DevView v, DevCam cam, ekfslam_params prm) {
+    extern __shared__ unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    const int n = v.nstate[b];
+    const int nf = v.nfeat[b];
+    const int N = v.N;
+    const int ld = v.ld;
+    const int nwords = (N + 31) / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // shared layout
+    double* xs = reinterpret_cast<double*>(smem_raw);              // [ld]
+    double* zs = xs + ld;                                          // [N][2] z of matched list entries
+    int* mlist = reinterpret_cast<int*>(zs + 2 * N);               // [N] matched (HAS_Z) feature indices
+    int* moff = mlist + N;                                         // [N] state offset of matched entries
+    int* mtype = moff + N;                                         // [N]
+    int* iclist = mtype + N;                                       // [N] IC feature indices
+    int* memo = iclist + N;                                        // [N] support per feature, -1 = unscored
+    unsigned* rmask = reinterpret_cast<unsigned*>(memo + N);       // [RW][nwords]
+    unsigned* bestmask = rmask + RANSAC_WARPS * nwords;            // [nwords]
+    __shared__ int s_nm, s_nic, s_done, s_best, s_roundbest, s_nhyp, s_iters, s_scored, s_status;
+    __shared__ int rpos[RANSAC_WARPS], rsup[RANSAC_WARPS];
+
+    const double* __restrict__ xp = v.xp + (size_t)b * ld;
+    const double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
+    const uint8_t* __restrict__ fl = v.flags + (size_t)b * N;
+
+    for (int j = tid; j < n; j += blockDim.x) xs[j] = xp[j];
+    for (int j = tid; j < N; j += blockDim.x) memo[j] = -1;
+    for (int j = tid; j < nwords; j += blockDim.x) bestmask[j] = 0u;
+    if (tid == 0) {
+        int nm = 0, nic = 0;
+        for (int i = 0; i < nf; ++i) {
+            const uint8_t f = fl[i];
+            if (f & EKFSLAM_F_HAS_Z) {
+                mlist[nm] = i; moff[nm] = v.foff[b * N + i]; mtype[nm] = v.ftype[b * N + i];
+                zs[2 * nm] = v.z[2 * (b * N + i)]; zs[2 * nm + 1] = v.z[2 * (b * N + i) + 1];
+                ++nm;
+            }
+            if (f & EKFSLAM_F_IC) iclist[nic++] = i;
+        }
+        s_nm = nm; s_nic = nic; s_done = (nic == 0); s_best = 0; s_roundbest = -1; s_nhyp = prm.max_hyp; s_iters = 0; s_scored = 0;
+        s_status = 0;
+    }
+    __syncthreads();
+    const int nm = s_nm, nic = s_nic;
+    const int n_loop = (prm.fixed_hyp > 0) ? prm.fixed_hyp : prm.max_hyp;
+    const double thr = prm.std_z;
+    const double* __restrict__ ub = v.u + (size_t)b * v.n_u;
+
+    for (int i0 = 0; !s_done; i0 += RANSAC_WARPS) {
+        // ---- which feature does draw i0+warp select?  (mc/select_random_match.m:12-16)
+        const int it = i0 + warp;  // 0-based draw index
+        int pos = -1;
+        if (it < n_loop && it < v.n_u) {
+            int r = (int)floor(ub[it] * (double)nic);
+            r = min(r, nic - 1);
+            pos = iclist[r];
+        }
+        if (lane == 0) { rpos[warp] = pos; rsup[warp] = -1; }
+        __syncthreads();
+        bool score = (pos >= 0) && (memo[pos] < 0);
+        for (int w2 = 0; w2 < warp && score; ++w2)
+            if (rpos[w2] == pos) score = false;
+        if (score) {
+            // ---- 1-match state update (mc/ransac_hypotheses.m:22-26), only the entries needed
+            const size_t t = (size_t)b * N + pos;
+            const double s00 = v.S[4 * t], s01 = v.S[4 * t + 1], s10 = v.S[4 * t + 2], s11 = v.S[4 * t + 3];
+            const double n0 = v.z[2 * t] - v.h[2 * t], n1 = v.z[2 * t + 1] - v.h[2 * t + 1];
+            const double det = s00 * s11 - s01 * s10;
+            const double g0 = (s11 * n0 - s01 * n1) / det;
+            const double g1 = (-s10 * n0 + s00 * n1) / det;
+            const double* __restrict__ Ga = G + (size_t)(2 * pos) * ld;
+            const double* __restrict__ Gb = Ga + ld;
+            double c7[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) c7[k] = xs[k] + (Ga[k] * g0 + Gb[k] * g1);
+            double R[9];
+            q2r_dev(c7 + 3, R);
+            int support = 0;
+            for (int j0 = 0; j0 < nm; j0 += 32) {
+                const int j = j0 + lane;
+                bool inl = false;
+                if (j < nm) {
+                    const int off = moff[j];
+                    const int ty = mtype[j];
+                    const int w = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+                    double y[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+                        y[k] = (k < w) ? xs[off + k] + (Ga[off + k] * g0 + Gb[off + k] * g1) : 0.0;
+                    const double res = support_residual_dev(cam, c7, R, y, ty, zs[2 * j], zs[2 * j + 1]);
+                    inl = res < thr;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, inl);
+                support += __popc(m);
+                if (lane == 0) rmask[warp * nwords + (j0 >> 5)] = m;
+            }
+            if (lane == 0) rsup[warp] = support;
+        }
+        __syncthreads();
+        // ---- sequential replay of the reference loop over this round's draws
+        if (tid == 0) {
+            int best = s_best, bestw = -1, iters = s_iters, scored = s_scored, done = 0, status = s_status;
+            int nh = s_nhyp;
+            const bool adaptive = prm.fixed_hyp <= 0;
+            for (int w2 = 0; w2 < RANSAC_WARPS; ++w2) {
+                const int i1 = i0 + w2 + 1;  // 1-based loop counter of the reference
+                if (i1 > n_loop) { done = 1; break; }               // for i = 1:n_hyp ran out
+                if (i1 > v.n_u) { status |= 1; done = 1; break; }   // uniform stream exhausted
+                const int p = rpos[w2];
+                iters = i1;
+                int sup = memo[p];
+                if (sup < 0) { sup = rsup[w2]; memo[p] = sup; ++scored; }
+                if (sup > best) {                                    // :37
+                    best = sup; bestw = w2;
+                    if (adaptive) {
+                        nh = v.nhyp_tab[EKF_TRI(nic, min(sup, nic))];  // :40-41
+                        if (nh == 0) { done = 1; break; }              // :42
+                    }
+                }
+                if (adaptive && i1 > nh) { done = 1; break; }        // :45
+            }
+            s_best = best; s_iters = iters; s_scored = scored; s_status = status; s_nhyp = nh;
+            s_roundbest = bestw;
+            s_done = done;
+        }
+        __syncthreads();
+        const int bw = s_roundbest;
+        if (bw >= 0)
+            for (int j = tid; j < nwords; j += blockDim.x) bestmask[j] = rmask[bw * nwords + j];
+        __syncthreads();
+    }
+
+    // ---- mc/set_as_most_supported_hypothesis.m:6-27 (only if some hypothesis had support > 0)
+    if (s_best > 0) {
+        for (int j = tid; j < nm; j += blockDim.x) {
+            const int i = mlist[j];
+            const bool inl = (bestmask[j >> 5] >> (j & 31)) & 1u;
+            uint8_t f = v.flags[(size_t)b * N + i];
+            f = inl ? (f | EKFSLAM_F_LI) : (f & ~EKFSLAM_F_LI);
+            v.flags[(size_t)b * N + i] = f;
+        }
+    }
+    if (tid == 0) {
+        ekfslam_stats& st = v.stats[b];
+        st.n_ic = nic; st.ransac_iters = s_iters; st.ransac_scored = s_scored; st.max_support = s_best;
+        st.status = s_status; st.n_li = 0; st.n_hi = 0; st.reserved = 0;
+    }
+}
+
+static size_t ransac_smem_bytes(const DevView& v) {
+    const int nwords = (v.N + 31) / 32;
+    return sizeof(double) * (v.ld + 2 * v.N) + sizeof(int) * (5 * v.N) +
+           sizeof(unsigned) * ((RANSAC_WARPS + 1) * nwords) + 16;
+}
+
+void launch_ransac(ekfslam_ctx* c) {
+    const size_t sm = ransac_smem_bytes(c->v);
+    static size_t configured = 0;
+    if (sm > 48 * 1024 && sm > configured) {
+        cudaFuncSetAttribute(k_ransac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        configured = sm;
+    }
+    KScope ks(c, KT_RANSAC);
+    k_ransac<<<c->v.B, RANSAC_THREADS, sm, c->stream>>>(c->v, c->cam, c->prm);
+}

@@ -1,0 +1,493 @@
+// EKF update of mc/update.m:3-32 for the features selected by a flag mask
+// (mc/ekf_update_li_inliers.m:8-21, mc/ekf_update_hi_inliers.m:8-21), batched over filters.
+//
+// With G = H P (rows of the selected features, from k_hp) and S = G_sel H_sel' + I = L L':
+//     K (z-h) = G_sel' inv(S) nu = W' y,      W = inv(L) G_sel,  y = inv(L) nu
+//     K S K'  = G_sel' inv(S) G_sel = W' W
+// so  x+ = x + W' y  and  P+ = P - W' W  (exactly symmetric, so the reference's
+// 0.5 P + 0.5 P' (:14) is the identity here), followed by the quaternion normalisation
+// Jacobian (:18-24) fused into the epilogue of the covariance downdate.
+//
+// Kernels: k_upd_S (select + stack S, nu) -> k_chol (blocked Cholesky, inv(L), y) ->
+//          k_w (W = inv(L) G_sel, triangular GEMM) -> k_xupd (x+, q normalisation, normJac) ->
+//          k_downdate (P -= W'W on 64x64 tiles of the lower triangle, mirrored).
+#include "model.cuh"
+
+#define NB 16
+
+// ---------------------------------------------------------------------------------------
+// select + S + nu.  One block per filter.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_prior) {
+    const int b = blockIdx.x;
+    const int N = v.N, ld = v.ld, kmax = v.kmax;
+    const int nf = v.nfeat[b];
+    const int tid = threadIdx.x;
+    __shared__ int s_k;
+    int* __restrict__ sel = v.sel + (size_t)b * N;
+    if (tid == 0) {
+        int cnt = 0;
+        for (int i = 0; i < nf; ++i)
+            if (v.ftype[b * N + i] != EKFSLAM_FEAT_NONE && (v.flags[(size_t)b * N + i] & mask)) sel[cnt++] = i;
+        v.ksel[b] = cnt;
+        s_k = cnt;
+        if (mask & EKFSLAM_F_LI) v.stats[b].n_li = cnt;
+        if (mask & EKFSLAM_F_HI) v.stats[b].n_hi = cnt;
+    }
+    __syncthreads();
+    const int ns = s_k;
+    const int k = 2 * ns;
+    if (which_prior == 1) {  // x_k_k starts from x_k_km1 (also the pass-through of mc/update.m:28)
+        const int n = v.nstate[b];
+        for (int j = tid; j < n; j += blockDim.x) v.x[(size_t)b * ld + j] = v.xp[(size_t)b * ld + j];
+    }
+    if (k == 0) return;
+    const double* __restrict__ G = v.G + (size_t)b * kmax * ld;
+    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    // lower triangle, feature-pair granularity: (fa >= fb) -> 2x2 block
+    const int npair = ns * (ns + 1) / 2;
+    for (int e = tid; e < npair; e += blockDim.x) {
+        // unrank e -> (fa, fb), fa >= fb
+        int fa = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while ((fa + 1) * (fa + 2) / 2 <= e) ++fa;
+        while (fa * (fa + 1) / 2 > e) --fa;
+        const int fb = e - fa * (fa + 1) / 2;
+        const int ia = sel[fa], ib = sel[fb];
+        const size_t tb = (size_t)b * N + ib;
+        const double* __restrict__ H = v.Hc + tb * EKF_HSTRIDE;
+        const int off = v.foff[tb];
+        const int w = (v.ftype[tb] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+        const double* __restrict__ g0 = G + (size_t)(2 * ia) * ld;
+        const double* __restrict__ g1 = g0 + ld;
+        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const double a0 = g0[c], a1 = g1[c], h0 = H[c], h1 = H[EKF_HC + c];
+            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
+        }
+        for (int c = 0; c < w; ++c) {
+            const double a0 = g0[off + c], a1 = g1[off + c], h0 = H[7 + c], h1 = H[EKF_HC + 7 + c];
+            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
+        }
+        if (fa == fb) { s00 += 1.0; s11 += 1.0; }  // R = eye(length(z)), mc/ekf_update_li_inliers.m:18
+        S[(size_t)(2 * fa) * kmax + 2 * fb] = s00;
+        S[(size_t)(2 * fa) * kmax + 2 * fb + 1] = s01;      // (for fa == fb this upper entry is never read)
+        S[(size_t)(2 * fa + 1) * kmax + 2 * fb] = s10;
+        S[(size_t)(2 * fa + 1) * kmax + 2 * fb + 1] = s11;
+    }
+    double* __restrict__ yv = v.yv + (size_t)b * kmax;
+    for (int a = tid; a < k; a += blockDim.x) {
+        const size_t t = (size_t)b * N + sel[a >> 1];
+        yv[a] = v.z[2 * t + (a & 1)] - v.h[2 * t + (a & 1)];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Blocked right-looking Cholesky S = L L' (lower, in place), X = inv(L), y <- X nu.
+// One block per filter, panels of NB columns.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chol(DevView v) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    const int k = 2 * v.ksel[b];
+    if (k == 0) return;
+    const int kmax = v.kmax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
+    double* D = sm;                       // [NB][NB+1] diagonal block factor
+    double* Di = D + NB * (NB + 1);       // [NB][NB+1] its inverse
+    double* Pn = Di + NB * (NB + 1);      // [kmax][NB+1] panel below the diagonal block / row panel
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = 0;
+
+    for (int j0 = 0; j0 < k; j0 += NB) {
+        const int nb = min(NB, k - j0);
+        for (int e = tid; e < NB * NB; e += blockDim.x) {
+            const int r = e / NB, c = e - r * NB;
+            D[r * (NB + 1) + c] = (r < nb && c <= r) ? S[(size_t)(j0 + r) * kmax + j0 + c] : 0.0;
+            Di[r * (NB + 1) + c] = 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // unblocked Cholesky of the nb x nb block, lane = row
+            for (int c = 0; c < nb; ++c) {
+                if (lane == c) {
+                    const double d = D[c * (NB + 1) + c];
+                    if (!(d > 0.0)) s_bad = 1;
+                    D[c * (NB + 1) + c] = sqrt(d);
+                }
+                __syncwarp();
+                const double dc = D[c * (NB + 1) + c];
+                if (lane > c && lane < nb) D[lane * (NB + 1) + c] /= dc;
+                __syncwarp();
+                if (lane > c && lane < nb) {
+                    const double lic = D[lane * (NB + 1) + c];
+                    for (int j = c + 1; j <= lane; ++j) D[lane * (NB + 1) + j] -= lic * D[j * (NB + 1) + c];
+                }
+                __syncwarp();
+            }
+            // inverse of the triangular block, lane = column
+            if (lane < nb) {
+                const int c = lane;
+                Di[c * (NB + 1) + c] = 1.0 / D[c * (NB + 1) + c];
+                for (int i = c + 1; i < nb; ++i) {
+                    double s = 0.0;
+                    for (int t = c; t < i; ++t) s += D[i * (NB + 1) + t] * Di[t * (NB + 1) + c];
+                    Di[i * (NB + 1) + c] = -s / D[i * (NB + 1) + i];
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < nb * nb; e += blockDim.x) {
+            const int r = e / nb, c = e - r * nb;
+            if (c <= r) {
+                S[(size_t)(j0 + r) * kmax + j0 + c] = D[r * (NB + 1) + c];
+                X[(size_t)(j0 + r) * kmax + j0 + c] = Di[r * (NB + 1) + c];
+            }
+        }
+        // panel: L[i][j0+c] = sum_{t<=c} S[i][j0+t] * Di[c][t]
+        const int i1 = j0 + nb;
+        for (int i = i1 + tid; i < k; i += blockDim.x) {
+            double row[NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) row[t] = (t < nb) ? S[(size_t)i * kmax + j0 + t] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int t = 0; t <= c; ++t) s += row[t] * Di[c * (NB + 1) + t];
+                if (c < nb) {
+                    S[(size_t)i * kmax + j0 + c] = s;
+                    Pn[(i - i1) * (NB + 1) + c] = s;
+                }
+            }
+        }
+        __syncthreads();
+        // trailing update of the lower triangle: S[i][c] -= sum_t Pn[i][t] Pn[c][t]
+        const int m = k - i1;
+        if (m > 0) {
+            const int mt = (m + 3) / 4;  // 4x4 micro tiles
+            const int ntile = mt * (mt + 1) / 2;
+            for (int e = tid; e < ntile; e += blockDim.x) {
+                int ti = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+                while (ti * (ti + 1) / 2 > e) --ti;
+                const int tj = e - ti * (ti + 1) / 2;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+                for (int t = 0; t < nb; ++t) {
+                    double ra[4], rc[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int ia = ti * 4 + a, ic = tj * 4 + a;
+                        ra[a] = (ia < m) ? Pn[ia * (NB + 1) + t] : 0.0;
+                        rc[a] = (ic < m) ? Pn[ic * (NB + 1) + t] : 0.0;
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[a][c] += ra[a] * rc[c];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int ia = ti * 4 + a, ic = tj * 4 + c;
+                        if (ia < m && ic <= ia) S[(size_t)(i1 + ia) * kmax + i1 + ic] -= acc[a][c];
+                    }
+            }
+        }
+        __syncthreads();
+    }
+
+    // X = inv(L), block row by block row:  X[I][0:I0] = -Di_I * ( L[I][0:I0] * X[0:I0][0:I0] )
+    for (int I0 = NB; I0 < k; I0 += NB) {
+        const int nb = min(NB, k - I0);
+        // stage the row panel L[I0..I0+nb)[0..I0) (transposed: Pn[t][r]) and Di of this block
+        for (int e = tid; e < nb * I0; e += blockDim.x) {
+            const int r = e / I0, t = e - r * I0;
+            Pn[t * (NB + 1) + r] = S[(size_t)(I0 + r) * kmax + t];
+        }
+        for (int e = tid; e < NB * NB; e += blockDim.x) {
+            const int r = e / NB, c = e - r * NB;
+            Di[r * (NB + 1) + c] = (r < nb && c <= r) ? X[(size_t)(I0 + r) * kmax + I0 + c] : 0.0;
+        }
+        __syncthreads();
+        for (int c = tid; c < I0; c += blockDim.x) {
+            double y[NB];
+#pragma unroll
+            for (int r = 0; r < NB; ++r) y[r] = 0.0;
+            for (int t = c; t < I0; ++t) {
+                const double xv = X[(size_t)t * kmax + c];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) y[r] += Pn[t * (NB + 1) + r] * xv;
+            }
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j <= r; ++j) s += Di[r * (NB + 1) + j] * y[j];
+                if (r < nb) X[(size_t)(I0 + r) * kmax + c] = -s;
+            }
+        }
+        __syncthreads();
+    }
+    // y = X nu (in place through shared memory)
+    double* nu = Pn;
+    double* __restrict__ yv = v.yv + (size_t)b * kmax;
+    for (int a = tid; a < k; a += blockDim.x) nu[a] = yv[a];
+    __syncthreads();
+    for (int a = tid; a < k; a += blockDim.x) {
+        double s = 0.0;
+        for (int t = 0; t <= a; ++t) s += X[(size_t)a * kmax + t] * nu[t];
+        yv[a] = s;
+    }
+    if (tid == 0 && s_bad) atomicOr(&v.stats[b].status, 2);
+}
+
+// ---------------------------------------------------------------------------------------
+// 64x64x16 register-tiled fp64 multiply-accumulate on shared-memory panels that are both
+// "k-major":  acc[i][j] += sum_t As[t][i] * Bs[t][j].   256 threads, 4x4 per thread.
+// ---------------------------------------------------------------------------------------
+#define TM 64
+#define TK 16
+#define TPAD 68  // row stride of the shared panels (doubles)
+
+__device__ __forceinline__ void tile_mac(const double* As, const double* Bs, int ty, int tx, double acc[4][4]) {
+#pragma unroll
+    for (int t = 0; t < TK; ++t) {
+        const double2 a01 = *reinterpret_cast<const double2*>(As + t * TPAD + ty * 4);
+        const double2 a23 = *reinterpret_cast<const double2*>(As + t * TPAD + ty * 4 + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(Bs + t * TPAD + tx * 4);
+        const double2 b23 = *reinterpret_cast<const double2*>(Bs + t * TPAD + tx * 4 + 2);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double bb[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * bb[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// W = X * G_sel  (X lower triangular k x k, G_sel = the selected rows of G, k x n).
+// grid = (column tiles, row tiles, B).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_w(DevView v) {
+    const int b = blockIdx.z;
+    const int k = 2 * v.ksel[b];
+    const int a0 = blockIdx.y * TM;
+    if (a0 >= k) return;
+    const int n = v.nstate[b];
+    const int c0 = blockIdx.x * TM;
+    if (c0 >= n) return;
+    const int ld = v.ld, kmax = v.kmax;
+    const double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
+    const double* __restrict__ G = v.G + (size_t)b * kmax * ld;
+    double* __restrict__ W = v.W + (size_t)b * kmax * ld;
+    const int* __restrict__ sel = v.sel + (size_t)b * v.N;
+
+    __shared__ __align__(16) double As[TK * TPAD];  // As[t][i] = X[a0+i][t0+t]
+    __shared__ __align__(16) double Bs[TK * TPAD];  // Bs[t][j] = G[row(t0+t)][c0+j]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    const int tend = min(k, a0 + TM);  // X[a][t] = 0 for t > a
+    for (int t0 = 0; t0 < tend; t0 += TK) {
+        for (int e = tid; e < TK * TM; e += blockDim.x) {
+            const int i = e / TK, t = e - i * TK;  // consecutive threads walk along t (contiguous in X)
+            const int a = a0 + i, tt = t0 + t;
+            As[t * TPAD + i] = (a < k && tt <= a) ? X[(size_t)a * kmax + tt] : 0.0;
+        }
+        for (int e = tid; e < TK * TM; e += blockDim.x) {
+            const int t = e / TM, j = e - t * TM;
+            const int tt = t0 + t;
+            double val = 0.0;
+            if (tt < k && c0 + j < ld) {
+                const int row = 2 * sel[tt >> 1] + (tt & 1);
+                val = G[(size_t)row * ld + c0 + j];
+            }
+            Bs[t * TPAD + j] = val;
+        }
+        __syncthreads();
+        tile_mac(As, Bs, ty, tx, acc);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int a = a0 + ty * 4 + i;
+        if (a >= k) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + tx * 4 + j;
+            if (c < ld) W[(size_t)a * ld + c] = (c < n) ? acc[i][j] : 0.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// x+ = x + W' y ; normJac(q+) (mc/normJac.m) ; q+ <- q+/|q+| (mc/update.m:12,18,24).
+// One block per filter.  The 4x4 Jacobian goes to the tail of the filter's yv scratch.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_xupd(DevView v, double* jn_out) {
+    const int b = blockIdx.x;
+    const int k = 2 * v.ksel[b];
+    if (k == 0) return;
+    const int n = v.nstate[b];
+    const int ld = v.ld, kmax = v.kmax;
+    const double* __restrict__ W = v.W + (size_t)b * kmax * ld;
+    const double* __restrict__ yv = v.yv + (size_t)b * kmax;
+    double* __restrict__ x = v.x + (size_t)b * ld;
+    extern __shared__ double ys[];
+    for (int a = threadIdx.x; a < k; a += blockDim.x) ys[a] = yv[a];
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double s = 0.0;
+        for (int a = 0; a < k; ++a) s += W[(size_t)a * ld + j] * ys[a];
+        x[j] += s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double r = x[3], qx = x[4], qy = x[5], qz = x[6];
+        const double nn = r * r + qx * qx + qy * qy + qz * qz;
+        const double sc = 1.0 / (nn * sqrt(nn));  // (.)^(-3/2)
+        double* J = jn_out + (size_t)b * 16;
+        J[0] = sc * (qx * qx + qy * qy + qz * qz); J[1] = sc * (-r * qx); J[2] = sc * (-r * qy); J[3] = sc * (-r * qz);
+        J[4] = sc * (-qx * r); J[5] = sc * (r * r + qy * qy + qz * qz); J[6] = sc * (-qx * qy); J[7] = sc * (-qx * qz);
+        J[8] = sc * (-qy * r); J[9] = sc * (-qy * qx); J[10] = sc * (r * r + qx * qx + qz * qz); J[11] = sc * (-qy * qz);
+        J[12] = sc * (-qz * r); J[13] = sc * (-qz * qx); J[14] = sc * (-qz * qy); J[15] = sc * (r * r + qx * qx + qy * qy);
+        const double nrm = sqrt(nn);
+        x[3] = r / nrm; x[4] = qx / nrm; x[5] = qy / nrm; x[6] = qz / nrm;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// P <- Jn (P - W' W) Jn'  on 64x64 tiles of the lower triangle, each tile also stored transposed.
+// grid = (lower-triangle tile index, B).  Jn = blkdiag(I3, normJac(q+), I): it only touches
+// columns 3-6 (tiles of tile-column 0) and rows 3-6 (tile (0,0)).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_downdate(DevView v, const double* __restrict__ jn_all) {
+    const int b = blockIdx.y;
+    const int k = 2 * v.ksel[b];
+    if (k == 0) return;
+    const int n = v.nstate[b];
+    // unrank tile index -> (ti >= tj)
+    const int e = blockIdx.x;
+    int ti = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+    while (ti * (ti + 1) / 2 > e) --ti;
+    const int tj = e - ti * (ti + 1) / 2;
+    const int i0 = ti * TM, j0 = tj * TM;
+    if (i0 >= n) return;
+    const int ld = v.ld, kmax = v.kmax;
+    const double* __restrict__ W = v.W + (size_t)b * kmax * ld;
+    double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+
+    __shared__ __align__(16) double buf[TM * (TM + 1)];  // panels during the k loop, then the C tile
+    double* As = buf;
+    double* Bs = buf + TK * TPAD;
+    double (*Ct)[TM + 1] = reinterpret_cast<double (*)[TM + 1]>(buf);
+    __shared__ double Jn[16];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    if (tid < 16) Jn[tid] = jn_all[(size_t)b * 16 + tid];
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    for (int t0 = 0; t0 < k; t0 += TK) {
+        for (int q = tid; q < TK * TM; q += blockDim.x) {
+            const int t = q / TM, j = q - t * TM;
+            const int tt = t0 + t;
+            // columns beyond n inside ld hold zeros in W (k_w), beyond ld are never touched
+            As[t * TPAD + j] = (tt < k && i0 + j < ld) ? W[(size_t)tt * ld + i0 + j] : 0.0;
+            Bs[t * TPAD + j] = (tt < k && j0 + j < ld) ? W[(size_t)tt * ld + j0 + j] : 0.0;
+        }
+        __syncthreads();
+        tile_mac(As, Bs, ty, tx, acc);
+        __syncthreads();
+    }
+    // C = P_tile - acc, staged in shared memory
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = ty * 4 + i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = tx * 4 + j;
+            const int gi = i0 + r, gj = j0 + c;
+            double val = 0.0;
+            if (gi < n && gj < n) val = P[(size_t)gi * ld + gj] - acc[i][j];
+            Ct[r][c] = val;
+        }
+    }
+    __syncthreads();
+    if (tj == 0) {
+        // columns 3..6 <- [c3 c4 c5 c6] * Jn'   (every row of the tile)
+        if (tid < TM) {
+            const int r = tid;
+            const double c3 = Ct[r][3], c4 = Ct[r][4], c5 = Ct[r][5], c6 = Ct[r][6];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                Ct[r][3 + a] = c3 * Jn[a * 4 + 0] + c4 * Jn[a * 4 + 1] + c5 * Jn[a * 4 + 2] + c6 * Jn[a * 4 + 3];
+        }
+        __syncthreads();
+        if (ti == 0) {
+            // rows 3..6 <- Jn * [r3; r4; r5; r6]   (every column of tile (0,0))
+            if (tid < TM) {
+                const int c = tid;
+                const double r3 = Ct[3][c], r4 = Ct[4][c], r5 = Ct[5][c], r6 = Ct[6][c];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    Ct[3 + a][c] = Jn[a * 4 + 0] * r3 + Jn[a * 4 + 1] * r4 + Jn[a * 4 + 2] * r5 + Jn[a * 4 + 3] * r6;
+            }
+            __syncthreads();
+            // keep tile (0,0) exactly symmetric after the two one-sided products (lower -> upper)
+            for (int q = tid; q < TM * TM; q += blockDim.x) {
+                const int r = q / TM, c = q - r * TM;
+                if (c > r) Ct[r][c] = Ct[c][r];
+            }
+            __syncthreads();
+        }
+    }
+    // store the tile and its mirror image
+    for (int q = tid; q < TM * TM; q += blockDim.x) {
+        const int r = q / TM, c = q - r * TM;
+        const int gi = i0 + r, gj = j0 + c;
+        if (gi < n && gj < n) P[(size_t)gi * ld + gj] = Ct[r][c];
+    }
+    if (ti != tj) {
+        for (int q = tid; q < TM * TM; q += blockDim.x) {
+            const int c = q / TM, r = q - c * TM;  // consecutive threads walk along r -> contiguous in P'
+            const int gi = i0 + r, gj = j0 + c;
+            if (gi < n && gj < n) P[(size_t)gj * ld + gi] = Ct[r][c];
+        }
+    }
+}
+
+void launch_update(ekfslam_ctx* c, int mask, int which_prior) {
+    DevView& v = c->v;
+    cudaStream_t st = c->stream;
+    { KScope ks(c, KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior); }
+    const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
+    static size_t chol_cfg = 0;
+    if (chol_sm > 48 * 1024 && chol_sm > chol_cfg) {
+        cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_sm);
+        chol_cfg = chol_sm;
+    }
+    { KScope ks(c, KT_CHOL); k_chol<<<v.B, 256, chol_sm, st>>>(v); }
+    dim3 gw((v.nmax + TM - 1) / TM, (v.kmax + TM - 1) / TM, v.B);
+    { KScope ks(c, KT_W); k_w<<<gw, 256, 0, st>>>(v); }
+    { KScope ks(c, KT_XUPD); k_xupd<<<v.B, 256, sizeof(double) * v.kmax, st>>>(v, v.jn); }
+    const int nt = (v.nmax + TM - 1) / TM;
+    dim3 gd(nt * (nt + 1) / 2, v.B);
+    { KScope ks(c, KT_DOWNDATE); k_downdate<<<gd, 256, 0, st>>>(v, v.jn); }
+}

@@ -1,0 +1,139 @@
+"""CUDA path vs the CPU oracle on identical seeded inputs, through the C ABI.
+
+Bar (BASELINE.json north_star): inlier sets and feature indices bit-exact, state and
+covariance within 1e-9 relative.  Checked teacher-forced (every step restarted from the oracle's
+state) and free-running (device state carried across frames).
+"""
+import numpy as np
+import pytest
+
+from oracle import ekf_oracle as O
+from tests import helpers as T
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ekf():
+    import ekf_slam_b200 as pkg
+    import ekf_slam_b200.synth as synth
+    return pkg, synth
+
+
+def _run_sequence(ekf, B, N, frames, seed, fixed=0, n_u=64, p_outlier=0.2, teacher_forced=False, cart=None):
+    pkg, synth = ekf
+    seq = synth.SynthSequence(B=B, N=N, T=frames, seed=seed, p_outlier=p_outlier, n_u=n_u)
+    x0, P0, types = seq.initial_state()
+    n_max = 13 + 6 * N
+    if cart:
+        xs, Ps, ts = [], [], []
+        for b in range(B):
+            xb, Pb, tb = synth.convert_to_cartesian(x0[b], P0[b], types[b], cart)
+            xs.append(np.pad(xb, (0, n_max - len(xb))))
+            Ps.append(np.pad(Pb, ((0, n_max - len(xb)), (0, n_max - len(xb)))))
+            ts.append(tb)
+        x0, P0, types = np.stack(xs), np.stack(Ps), np.stack(ts)
+    cam = O.initialize_cam()
+    bank = pkg.FilterBank(B, N, n_max)
+    bank.set_params(fixed_hyp=fixed)
+    bank.upload_feature_types(types)
+    bank.upload_state(x0, P0)
+    _, _, nstate = bank.download_state(want_P=False)
+    filts = [T.oracle_filter(x0[b, :nstate[b]], P0[b, :nstate[b], :nstate[b]]) for b in range(B)]
+    feats = [T.oracle_features(types[b]) for b in range(B)]
+    worst = dict(x=0.0, P=0.0)
+    totals = dict(li=0, hi=0, ic=0, iters=0)
+    for t in range(1, frames + 1):
+        zc, has = seq.frame(t)
+        u = seq.uniforms(t, n_u)
+        if teacher_forced and t > 1:
+            xs = np.zeros((B, n_max))
+            Ps = np.zeros((B, n_max, n_max))
+            for b in range(B):
+                xs[b, :nstate[b]] = filts[b].x_k_k
+                Ps[b, :nstate[b], :nstate[b]] = filts[b].p_k_k
+            bank.upload_state(xs, Ps)
+        bank.upload_candidates(zc, has)
+        bank.upload_uniforms(u)
+        bank.step(reset=True, match_mode=1)
+        xg, Pg, _ = bank.download_state()
+        fg = bank.download_flags()
+        st = bank.download_stats()
+        for b in range(B):
+            filts[b], feats[b], info = T.oracle_step(filts[b], feats[b], cam, zc[b], has[b], u[b], fixed)
+            n = nstate[b]
+            fo = T.oracle_flags(feats[b], N)
+            mask = T.F_HAS_H | T.F_HAS_Z | T.F_IC | T.F_LI | T.F_HI
+            assert np.array_equal(fg[b] & mask, fo), "flag mismatch: frame %d filter %d" % (t, b)
+            assert st["ransac_iters"][b] == info["iterations"], (t, b)
+            assert st["status"][b] == 0
+            ex = T.rel_err(xg[b, :n], filts[b].x_k_k)
+            eP = T.rel_err(Pg[b, :n, :n], filts[b].p_k_k)
+            worst["x"] = max(worst["x"], ex)
+            worst["P"] = max(worst["P"], eP)
+            assert ex < TOL and eP < TOL, "frame %d filter %d: x %.2e P %.2e" % (t, b, ex, eP)
+            assert np.array_equal(Pg[b], Pg[b].T)
+            totals["li"] += int(st["n_li"][b])
+            totals["hi"] += int(st["n_hi"][b])
+            totals["ic"] += int(st["n_ic"][b])
+            totals["iters"] += int(st["ransac_iters"][b])
+    bank.close()
+    return worst, totals
+
+
+def test_teacher_forced_small(ekf):
+    worst, tot = _run_sequence(ekf, B=4, N=12, frames=6, seed=100, teacher_forced=True)
+    assert tot["li"] > 0 and tot["ic"] > 0
+
+
+def test_free_running_small(ekf):
+    worst, tot = _run_sequence(ekf, B=4, N=12, frames=8, seed=200)
+    assert tot["li"] > 0
+
+
+def test_free_running_n40(ekf):
+    """BASELINE config 1 shape (~40 features), adaptive RANSAC."""
+    worst, tot = _run_sequence(ekf, B=3, N=40, frames=6, seed=300)
+    assert tot["hi"] >= 0 and tot["li"] > 40
+
+
+def test_n100_fixed_256(ekf):
+    """BASELINE config 2 shape: N=100, 256 hypotheses per frame."""
+    worst, tot = _run_sequence(ekf, B=2, N=100, frames=3, seed=400, fixed=256, n_u=256)
+    assert tot["iters"] == 2 * 3 * 256
+
+
+def test_heavy_outliers(ekf):
+    worst, tot = _run_sequence(ekf, B=3, N=30, frames=5, seed=500, p_outlier=0.5, n_u=200)
+    assert tot["li"] > 0
+
+
+def test_mixed_cartesian(ekf):
+    """BASELINE config 5 shape: mixed inverse-depth / Cartesian maps."""
+    worst, tot = _run_sequence(ekf, B=3, N=20, frames=5, seed=600, cart=[0, 3, 4, 9, 15, 19])
+    assert tot["li"] > 0
+
+
+def test_no_matches_is_passthrough(ekf):
+    pkg, synth = ekf
+    seq = synth.SynthSequence(B=2, N=8, T=2, seed=7)
+    x0, P0, types = seq.initial_state()
+    bank = pkg.FilterBank(2, 8)
+    bank.upload_feature_types(types)
+    bank.upload_state(x0, P0)
+    zc, has = seq.frame(1)
+    bank.upload_candidates(zc, np.zeros_like(has))   # no candidate at all
+    bank.upload_uniforms(seq.uniforms(1, 16))
+    bank.step()
+    xg, Pg, _ = bank.download_state()
+    st = bank.download_stats()
+    assert (st["n_ic"] == 0).all() and (st["n_li"] == 0).all() and (st["ransac_iters"] == 0).all()
+    cam = O.initialize_cam()
+    for b in range(2):
+        f = T.oracle_filter(x0[b], P0[b])
+        f, _ = O.ekf_prediction(f, [])
+        assert T.rel_err(xg[b], f.x_k_km1) < 1e-12
+        assert T.rel_err(Pg[b], f.p_k_km1) < 1e-12
+    bank.close()

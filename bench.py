@@ -233,7 +233,10 @@ def main():
     t_setup = time.perf_counter()
     seq = synth.SynthSequence(B=B, N=N, T=T, seed=args.seed, b_offset=rank * B, p_outlier=args.p_outlier, n_u=n_u)
     bank = pkg.FilterBank(B, N, n, device=local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated non-default stream shared by torch (events) and the library (kernels, copies)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     bank.set_stream(stream.cuda_stream)
     bank.set_params(fixed_hyp=args.fixed_hyp)
     chunk = 256

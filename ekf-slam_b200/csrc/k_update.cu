@@ -236,6 +236,11 @@ __global__ void __launch_bounds__(256) k_chol(DevView v) {
         }
         __syncthreads();
     }
+    // explicit zeros above the diagonal of X: k_w streams X panels with cp.async and does not mask
+    for (int e = tid; e < k * k; e += blockDim.x) {
+        const int r = e / k, c = e - r * k;
+        if (c > r) X[(size_t)r * kmax + c] = 0.0;
+    }
     // y = X nu (in place through shared memory)
     double* nu = Pn;
     double* __restrict__ yv = v.yv + (size_t)b * kmax;
@@ -250,34 +255,35 @@ __global__ void __launch_bounds__(256) k_chol(DevView v) {
 }
 
 // ---------------------------------------------------------------------------------------
-// 64x64x16 register-tiled fp64 multiply-accumulate on shared-memory panels that are both
-// "k-major":  acc[i][j] += sum_t As[t][i] * Bs[t][j].   256 threads, 4x4 per thread.
+// fp64 tensor-core building blocks.  mma.sync m8n8k4 f64 (SASS DMMA.8x8x4) fragment layout, lane
+// l, g = l>>2, q = l&3:  A[g][q],  B[q][g],  C[g][2q], C[g][2q+1].
+// Both GEMMs below use 64x64 block tiles, 8 warps in a 2x4 grid, 32x16 per warp (4x2 DMMA tiles),
+// K panels of 16 staged through a 3-deep cp.async (LDGSTS) ring.
 // ---------------------------------------------------------------------------------------
 #define TM 64
 #define TK 16
-#define TPAD 68  // row stride of the shared panels (doubles)
+#define TPAD 68    // row stride (doubles) of a K-major panel [TK][64]: stride % 16 == 4 -> conflict-free frags
+#define APAD 20    // row stride of a row-major A panel [64][TK]: same property
+#define NSTAGE 3
 
-__device__ __forceinline__ void tile_mac(const double* As, const double* Bs, int ty, int tx, double acc[4][4]) {
-#pragma unroll
-    for (int t = 0; t < TK; ++t) {
-        const double2 a01 = *reinterpret_cast<const double2*>(As + t * TPAD + ty * 4);
-        const double2 a23 = *reinterpret_cast<const double2*>(As + t * TPAD + ty * 4 + 2);
-        const double2 b01 = *reinterpret_cast<const double2*>(Bs + t * TPAD + tx * 4);
-        const double2 b23 = *reinterpret_cast<const double2*>(Bs + t * TPAD + tx * 4 + 2);
-        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-        const double bb[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * bb[j];
-    }
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src, int src_bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------------------------------
-// W = X * G_sel  (X lower triangular k x k, G_sel = the selected rows of G, k x n).
-// grid = (column tiles, row tiles, B).
+// W = X * G_sel  (X = inv(L) lower triangular k x k with an explicitly zeroed upper triangle,
+// G_sel = the selected rows of G, k x n).  grid = (column tiles, row tiles, B).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_w(DevView v) {
+__global__ void __launch_bounds__(256, 3) k_w(DevView v) {
+    extern __shared__ __align__(16) double dsm[];
     const int b = blockIdx.z;
     const int k = 2 * v.ksel[b];
     const int a0 = blockIdx.y * TM;
@@ -291,44 +297,79 @@ __global__ void __launch_bounds__(256) k_w(DevView v) {
     double* __restrict__ W = v.W + (size_t)b * kmax * ld;
     const int* __restrict__ sel = v.sel + (size_t)b * v.N;
 
-    __shared__ __align__(16) double As[TK * TPAD];  // As[t][i] = X[a0+i][t0+t]
-    __shared__ __align__(16) double Bs[TK * TPAD];  // Bs[t][j] = G[row(t0+t)][c0+j]
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    double acc[4][4];
+    double* As = dsm;                           // [NSTAGE][64][APAD]   As[i][t] = X[a0+i][t0+t]
+    double* Bs = dsm + NSTAGE * TM * APAD;      // [NSTAGE][TK][TPAD]   Bs[t][j] = G[row(t0+t)][c0+j]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
+
+    const int tend = min(k, a0 + TM);  // X[a][t] = 0 for t > a
+    const int nk = (tend + TK - 1) / TK;
+    auto load_stage = [&](int st, int t0) {
+        double* as = As + st * TM * APAD;
+        double* bs = Bs + st * TK * TPAD;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int ch = tid + 256 * j;          // 512 chunks of 2 doubles
+            {   // A: 64 rows x 8 chunks
+                const int r = ch >> 3, cc = (ch & 7) * 2;
+                const bool ok = (a0 + r < k) && (t0 + cc < k);
+                cp_async16(as + r * APAD + cc, ok ? X + (size_t)(a0 + r) * kmax + t0 + cc : X, ok ? 16 : 0);
+            }
+            {   // B: 16 rows x 32 chunks
+                const int r = ch >> 5, cc = (ch & 31) * 2;
+                const int tt = t0 + r;
+                const bool ok = (tt < k) && (c0 + cc < ld);
+                const double* src = G;
+                if (ok) src = G + (size_t)(2 * sel[tt >> 1] + (tt & 1)) * ld + c0 + cc;
+                cp_async16(bs + r * TPAD + cc, src, ok ? 16 : 0);
+            }
+        }
+    };
+    double acc[4][2][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    const int tend = min(k, a0 + TM);  // X[a][t] = 0 for t > a
-    for (int t0 = 0; t0 < tend; t0 += TK) {
-        for (int e = tid; e < TK * TM; e += blockDim.x) {
-            const int i = e / TK, t = e - i * TK;  // consecutive threads walk along t (contiguous in X)
-            const int a = a0 + i, tt = t0 + t;
-            As[t * TPAD + i] = (a < k && tt <= a) ? X[(size_t)a * kmax + tt] : 0.0;
-        }
-        for (int e = tid; e < TK * TM; e += blockDim.x) {
-            const int t = e / TM, j = e - t * TM;
-            const int tt = t0 + t;
-            double val = 0.0;
-            if (tt < k && c0 + j < ld) {
-                const int row = 2 * sel[tt >> 1] + (tt & 1);
-                val = G[(size_t)row * ld + c0 + j];
-            }
-            Bs[t * TPAD + j] = val;
-        }
-        __syncthreads();
-        tile_mac(As, Bs, ty, tx, acc);
-        __syncthreads();
-    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int a = a0 + ty * 4 + i;
+    for (int st = 0; st < NSTAGE - 1; ++st) {
+        if (st < nk) load_stage(st, st * TK);
+        cp_async_commit();
+    }
+    for (int it = 0; it < nk; ++it) {
+        cp_async_wait<NSTAGE - 2>();
+        __syncthreads();
+        if (it + NSTAGE - 1 < nk) load_stage((it + NSTAGE - 1) % NSTAGE, (it + NSTAGE - 1) * TK);
+        cp_async_commit();
+        const double* as = As + (it % NSTAGE) * TM * APAD;
+        const double* bs = Bs + (it % NSTAGE) * TK * TPAD;
+#pragma unroll
+        for (int k4 = 0; k4 < TK / 4; ++k4) {
+            double af[4], bf[2];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) af[mt] = as[(wr * 32 + mt * 8 + g) * APAD + k4 * 4 + q];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) bf[nt] = bs[(k4 * 4 + q) * TPAD + wc * 16 + nt * 8 + g];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int a = a0 + wr * 32 + mt * 8 + g;
         if (a >= k) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c0 + tx * 4 + j;
-            if (c < ld) W[(size_t)a * ld + c] = (c < n) ? acc[i][j] : 0.0;
+        for (int nt = 0; nt < 2; ++nt) {
+            const int c = c0 + wc * 16 + nt * 8 + 2 * q;
+            if (c < ld) {  // ld is even: c+1 < ld as well; the padding columns [n, ld) are kept zero
+                double2 o;
+                o.x = (c < n) ? acc[mt][nt][0] : 0.0;
+                o.y = (c + 1 < n) ? acc[mt][nt][1] : 0.0;
+                *reinterpret_cast<double2*>(W + (size_t)a * ld + c) = o;
+            }
         }
     }
 }
@@ -372,9 +413,11 @@ __global__ void __launch_bounds__(256) k_xupd(DevView v, double* jn_out) {
 // ---------------------------------------------------------------------------------------
 // P <- Jn (P - W' W) Jn'  on 64x64 tiles of the lower triangle, each tile also stored transposed.
 // grid = (lower-triangle tile index, B).  Jn = blkdiag(I3, normJac(q+), I): it only touches
-// columns 3-6 (tiles of tile-column 0) and rows 3-6 (tile (0,0)).
+// columns 3-6 (tiles of tile-column 0) and rows 3-6 (tile (0,0)).  The P tile is prefetched into
+// the accumulator layout before the K loop so its HBM latency hides behind the DMMA work.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_downdate(DevView v, const double* __restrict__ jn_all) {
+__global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __restrict__ jn_all) {
+    extern __shared__ __align__(16) double dsm[];
     const int b = blockIdx.y;
     const int k = 2 * v.ksel[b];
     if (k == 0) return;
@@ -391,42 +434,87 @@ __global__ void __launch_bounds__(256) k_downdate(DevView v, const double* __res
     const double* __restrict__ W = v.W + (size_t)b * kmax * ld;
     double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
 
-    __shared__ __align__(16) double buf[TM * (TM + 1)];  // panels during the k loop, then the C tile
-    double* As = buf;
-    double* Bs = buf + TK * TPAD;
-    double (*Ct)[TM + 1] = reinterpret_cast<double (*)[TM + 1]>(buf);
+    const bool diag = (ti == tj);
+    double* As = dsm;                            // [NSTAGE][TK][TPAD]  As[t][i] = W[t0+t][i0+i]
+    double* Bs = dsm + NSTAGE * TK * TPAD;       // [NSTAGE][TK][TPAD]  Bs[t][j] = W[t0+t][j0+j]
+    double (*Ct)[TM + 1] = reinterpret_cast<double (*)[TM + 1]>(dsm);  // C tile, aliases the ring afterwards
     __shared__ double Jn[16];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
     if (tid < 16) Jn[tid] = jn_all[(size_t)b * 16 + tid];
-    double acc[4][4];
+
+    // prefetch this thread's part of the P tile (accumulator layout)
+    double pf[4][2][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int gi = i0 + wr * 32 + mt * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
+            double2 val = make_double2(0.0, 0.0);
+            if (gi < n && gj < ld) val = *reinterpret_cast<const double2*>(P + (size_t)gi * ld + gj);
+            pf[mt][nt][0] = val.x; pf[mt][nt][1] = val.y;
+        }
+    }
+    const int nk = (k + TK - 1) / TK;
+    auto load_stage = [&](int st, int t0) {
+        double* as = As + st * TK * TPAD;
+        double* bs = Bs + st * TK * TPAD;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int ch = tid + 256 * j;  // 16 rows x 32 chunks of 2 doubles
+            const int r = ch >> 5, cc = (ch & 31) * 2;
+            const int tt = t0 + r;
+            const bool oka = (tt < k) && (i0 + cc < ld);
+            cp_async16(as + r * TPAD + cc, oka ? W + (size_t)tt * ld + i0 + cc : W, oka ? 16 : 0);
+            if (!diag) {
+                const bool okb = (tt < k) && (j0 + cc < ld);
+                cp_async16(bs + r * TPAD + cc, okb ? W + (size_t)tt * ld + j0 + cc : W, okb ? 16 : 0);
+            }
+        }
+    };
+    double acc[4][2][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int t0 = 0; t0 < k; t0 += TK) {
-        for (int q = tid; q < TK * TM; q += blockDim.x) {
-            const int t = q / TM, j = q - t * TM;
-            const int tt = t0 + t;
-            // columns beyond n inside ld hold zeros in W (k_w), beyond ld are never touched
-            As[t * TPAD + j] = (tt < k && i0 + j < ld) ? W[(size_t)tt * ld + i0 + j] : 0.0;
-            Bs[t * TPAD + j] = (tt < k && j0 + j < ld) ? W[(size_t)tt * ld + j0 + j] : 0.0;
-        }
-        __syncthreads();
-        tile_mac(As, Bs, ty, tx, acc);
-        __syncthreads();
+#pragma unroll
+    for (int st = 0; st < NSTAGE - 1; ++st) {
+        if (st < nk) load_stage(st, st * TK);
+        cp_async_commit();
     }
-    // C = P_tile - acc, staged in shared memory
+    for (int it = 0; it < nk; ++it) {
+        cp_async_wait<NSTAGE - 2>();
+        __syncthreads();
+        if (it + NSTAGE - 1 < nk) load_stage((it + NSTAGE - 1) % NSTAGE, (it + NSTAGE - 1) * TK);
+        cp_async_commit();
+        const double* as = As + (it % NSTAGE) * TK * TPAD;
+        const double* bs = diag ? as : Bs + (it % NSTAGE) * TK * TPAD;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = ty * 4 + i;
+        for (int k4 = 0; k4 < TK / 4; ++k4) {
+            double af[4], bf[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = tx * 4 + j;
-            const int gi = i0 + r, gj = j0 + c;
-            double val = 0.0;
-            if (gi < n && gj < n) val = P[(size_t)gi * ld + gj] - acc[i][j];
-            Ct[r][c] = val;
+            for (int mt = 0; mt < 4; ++mt) af[mt] = as[(k4 * 4 + q) * TPAD + wr * 32 + mt * 8 + g];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) bf[nt] = bs[(k4 * 4 + q) * TPAD + wc * 16 + nt * 8 + g];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // every warp is done with the ring: reuse it as the C tile
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int r = wr * 32 + mt * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int cc = wc * 16 + nt * 8 + 2 * q;
+            const bool rin = (i0 + r < n);
+            Ct[r][cc] = (rin && j0 + cc < n) ? pf[mt][nt][0] - acc[mt][nt][0] : 0.0;
+            Ct[r][cc + 1] = (rin && j0 + cc + 1 < n) ? pf[mt][nt][1] - acc[mt][nt][1] : 0.0;
         }
     }
     __syncthreads();
@@ -450,23 +538,26 @@ __global__ void __launch_bounds__(256) k_downdate(DevView v, const double* __res
                     Ct[3 + a][c] = Jn[a * 4 + 0] * r3 + Jn[a * 4 + 1] * r4 + Jn[a * 4 + 2] * r5 + Jn[a * 4 + 3] * r6;
             }
             __syncthreads();
-            // keep tile (0,0) exactly symmetric after the two one-sided products (lower -> upper)
-            for (int q = tid; q < TM * TM; q += blockDim.x) {
-                const int r = q / TM, c = q - r * TM;
-                if (c > r) Ct[r][c] = Ct[c][r];
-            }
-            __syncthreads();
         }
     }
+    if (diag) {
+        // keep diagonal tiles exactly symmetric (lower -> upper): the tensor-core summation order of
+        // C[i][j] and C[j][i] is not guaranteed to be identical, nor are the two one-sided Jn products
+        for (int qd = tid; qd < TM * TM; qd += blockDim.x) {
+            const int r = qd / TM, c = qd - r * TM;
+            if (c > r) Ct[r][c] = Ct[c][r];
+        }
+        __syncthreads();
+    }
     // store the tile and its mirror image
-    for (int q = tid; q < TM * TM; q += blockDim.x) {
-        const int r = q / TM, c = q - r * TM;
+    for (int qd = tid; qd < TM * TM; qd += blockDim.x) {
+        const int r = qd / TM, c = qd - r * TM;
         const int gi = i0 + r, gj = j0 + c;
         if (gi < n && gj < n) P[(size_t)gi * ld + gj] = Ct[r][c];
     }
-    if (ti != tj) {
-        for (int q = tid; q < TM * TM; q += blockDim.x) {
-            const int c = q / TM, r = q - c * TM;  // consecutive threads walk along r -> contiguous in P'
+    if (!diag) {
+        for (int qd = tid; qd < TM * TM; qd += blockDim.x) {
+            const int c = qd / TM, r = qd - c * TM;  // consecutive threads walk along r -> contiguous in P'
             const int gi = i0 + r, gj = j0 + c;
             if (gi < n && gj < n) P[(size_t)gj * ld + gi] = Ct[r][c];
         }
@@ -485,9 +576,17 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior) {
     }
     { KScope ks(c, KT_CHOL); k_chol<<<v.B, 256, chol_sm, st>>>(v); }
     dim3 gw((v.nmax + TM - 1) / TM, (v.kmax + TM - 1) / TM, v.B);
-    { KScope ks(c, KT_W); k_w<<<gw, 256, 0, st>>>(v); }
+    const size_t w_sm = sizeof(double) * NSTAGE * (TM * APAD + TK * TPAD);
+    const size_t dd_sm = sizeof(double) * (size_t)max(2 * NSTAGE * TK * TPAD, TM * (TM + 1));
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w_sm);
+        cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dd_sm);
+        attr_done = true;
+    }
+    { KScope ks(c, KT_W); k_w<<<gw, 256, w_sm, st>>>(v); }
     { KScope ks(c, KT_XUPD); k_xupd<<<v.B, 256, sizeof(double) * v.kmax, st>>>(v, v.jn); }
     const int nt = (v.nmax + TM - 1) / TM;
     dim3 gd(nt * (nt + 1) / 2, v.B);
-    { KScope ks(c, KT_DOWNDATE); k_downdate<<<gd, 256, 0, st>>>(v, v.jn); }
+    { KScope ks(c, KT_DOWNDATE); k_downdate<<<gd, 256, dd_sm, st>>>(v, v.jn); }
 }

@@ -193,6 +193,7 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     DA(v.Li, Bz * v.kmax * v.kmax);
     DA(v.yv, Bz * v.kmax);
     DA(v.jn, Bz * 16);
+    DA(v.cv, Bz * v.kmax);
     DA(v.h, Bz * v.N * 2);
     DA(v.Hc, Bz * v.N * EKF_HSTRIDE);
     DA(v.S, Bz * v.N * 4);
@@ -232,7 +233,7 @@ int ekfslam_destroy(ekfslam_ctx* c) {
     cudaSetDevice(c->device);
     if (c->own_zc) { c->v.zc = c->own_zc; c->v.mflags = c->own_mflags; c->v.u = c->own_u; c->own_zc = nullptr; }
     DevView& v = c->v;
-    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
+    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
                     v.flags, v.mflags, v.foff, v.nstate, v.nfeat, v.counters, v.sel, v.ksel, v.stats, v.nhyp_tab};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -28,6 +28,7 @@ struct DevView {
     double* Li;           // [B][kmax][kmax] inverse of the Cholesky factor
     double* yv;           // [B][kmax]     inv(L)*(z-h)
     double* jn;           // [B][16]       normJac(q+) of the running update
+    double* cv;           // [B][kmax]     inv(S)*(z-h) = inv(L)' * yv
     double* h;            // [B][N][2]
     double* Hc;           // [B][N][26]
     double* S;            // [B][N][4]

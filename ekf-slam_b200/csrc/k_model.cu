@@ -252,19 +252,29 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid) {
     }
     for (int f0 = 0; f0 < nf; f0 += HP_CHUNK) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int cnt = 0;
-            const int f1 = min(nf, f0 + HP_CHUNK);
-            for (int i = f0; i < f1; ++i) {
-                const int t = b * v.N + i;
-                const uint8_t fl = v.flags[t];
-                const int ty = v.ftype[t];
-                if (ty != EKFSLAM_FEAT_NONE && (fl & need) == need && (fl & forbid) == 0) {
-                    sIdx[cnt] = i; sOff[cnt] = v.foff[t]; sW[cnt] = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
-                    ++cnt;
+        if (threadIdx.x < 32) {
+            // warp 0 compacts the selected features of this chunk (ballot + prefix popcount)
+            int base = 0;
+#pragma unroll
+            for (int h2 = 0; h2 < HP_CHUNK / 32; ++h2) {
+                const int i = f0 + h2 * 32 + threadIdx.x;
+                bool selq = false;
+                int ty = 0, of = 0;
+                if (i < nf) {
+                    const int t = b * v.N + i;
+                    const uint8_t fl = v.flags[t];
+                    ty = v.ftype[t];
+                    of = v.foff[t];
+                    selq = (ty != EKFSLAM_FEAT_NONE) && ((fl & need) == need) && ((fl & forbid) == 0);
                 }
+                const unsigned m = __ballot_sync(0xffffffffu, selq);
+                if (selq) {
+                    const int slot = base + __popc(m & ((1u << threadIdx.x) - 1u));
+                    sIdx[slot] = i; sOff[slot] = of; sW[slot] = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+                }
+                base += __popc(m);
             }
-            sCnt = cnt;
+            if (threadIdx.x == 0) sCnt = base;
         }
         __syncthreads();
         const int cnt = sCnt;

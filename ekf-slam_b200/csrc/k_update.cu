@@ -9,7 +9,7 @@
 // Jacobian (:18-24) fused into the epilogue of the covariance downdate.
 //
 // Kernels: k_upd_S (select + stack S, nu) -> k_chol (blocked Cholesky, inv(L), y) ->
-//          k_w (W = inv(L) G_sel, triangular GEMM) -> k_xupd (x+, q normalisation, normJac) ->
+//          k_w (W = inv(L) G_sel, triangular GEMM; also x+, q normalisation, normJac) ->
 //          k_downdate (P -= W'W on 64x64 tiles of the lower triangle, mirrored).
 #include "model.cuh"
 
@@ -251,6 +251,16 @@ __global__ void __launch_bounds__(256) k_chol(DevView v) {
         for (int t = 0; t <= a; ++t) s += X[(size_t)a * kmax + t] * nu[t];
         yv[a] = s;
     }
+    __syncthreads();
+    // cv = X' y = inv(S) nu  (the state update is x+ = x + G_sel' cv, accumulated inside k_w)
+    for (int a = tid; a < k; a += blockDim.x) nu[a] = yv[a];
+    __syncthreads();
+    double* __restrict__ cv = v.cv + (size_t)b * kmax;
+    for (int t = tid; t < k; t += blockDim.x) {
+        double s = 0.0;
+        for (int a = t; a < k; ++a) s += X[(size_t)a * kmax + t] * nu[a];
+        cv[t] = s;
+    }
     if (tid == 0 && s_bad) atomicOr(&v.stats[b].status, 2);
 }
 
@@ -299,8 +309,15 @@ __global__ void __launch_bounds__(256, 3) k_w(DevView v) {
 
     double* As = dsm;                           // [NSTAGE][64][APAD]   As[i][t] = X[a0+i][t0+t]
     double* Bs = dsm + NSTAGE * TM * APAD;      // [NSTAGE][TK][TPAD]   Bs[t][j] = G[row(t0+t)][c0+j]
+    double* cs = Bs + NSTAGE * TK * TPAD;       // [kmax]               inv(S) nu
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
+    // The last row tile streams every selected row of G for its 64 columns, so it also accumulates
+    // the state update  x+ = x + G_sel' inv(S) nu  (mc/update.m:12) for those columns.
+    const bool xrole = (a0 + TM >= k);
+    if (xrole)
+        for (int t = tid; t < k; t += blockDim.x) cs[t] = v.cv[(size_t)b * kmax + t];
+    double xacc = 0.0;
 
     const int tend = min(k, a0 + TM);  // X[a][t] = 0 for t > a
     const int nk = (tend + TK - 1) / TK;
@@ -343,6 +360,10 @@ __global__ void __launch_bounds__(256, 3) k_w(DevView v) {
         cp_async_commit();
         const double* as = As + (it % NSTAGE) * TM * APAD;
         const double* bs = Bs + (it % NSTAGE) * TK * TPAD;
+        if (xrole && tid < TM) {
+            const int tmax = min(TK, k - it * TK);
+            for (int t = 0; t < tmax; ++t) xacc += bs[t * TPAD + tid] * cs[it * TK + t];
+        }
 #pragma unroll
         for (int k4 = 0; k4 < TK / 4; ++k4) {
             double af[4], bf[2];
@@ -372,41 +393,26 @@ __global__ void __launch_bounds__(256, 3) k_w(DevView v) {
             }
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------
-// x+ = x + W' y ; normJac(q+) (mc/normJac.m) ; q+ <- q+/|q+| (mc/update.m:12,18,24).
-// One block per filter.  The 4x4 Jacobian goes to the tail of the filter's yv scratch.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_xupd(DevView v, double* jn_out) {
-    const int b = blockIdx.x;
-    const int k = 2 * v.ksel[b];
-    if (k == 0) return;
-    const int n = v.nstate[b];
-    const int ld = v.ld, kmax = v.kmax;
-    const double* __restrict__ W = v.W + (size_t)b * kmax * ld;
-    const double* __restrict__ yv = v.yv + (size_t)b * kmax;
-    double* __restrict__ x = v.x + (size_t)b * ld;
-    extern __shared__ double ys[];
-    for (int a = threadIdx.x; a < k; a += blockDim.x) ys[a] = yv[a];
-    __syncthreads();
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        double s = 0.0;
-        for (int a = 0; a < k; ++a) s += W[(size_t)a * ld + j] * ys[a];
-        x[j] += s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double r = x[3], qx = x[4], qy = x[5], qz = x[6];
-        const double nn = r * r + qx * qx + qy * qy + qz * qz;
-        const double sc = 1.0 / (nn * sqrt(nn));  // (.)^(-3/2)
-        double* J = jn_out + (size_t)b * 16;
-        J[0] = sc * (qx * qx + qy * qy + qz * qz); J[1] = sc * (-r * qx); J[2] = sc * (-r * qy); J[3] = sc * (-r * qz);
-        J[4] = sc * (-qx * r); J[5] = sc * (r * r + qy * qy + qz * qz); J[6] = sc * (-qx * qy); J[7] = sc * (-qx * qz);
-        J[8] = sc * (-qy * r); J[9] = sc * (-qy * qx); J[10] = sc * (r * r + qx * qx + qz * qz); J[11] = sc * (-qy * qz);
-        J[12] = sc * (-qz * r); J[13] = sc * (-qz * qx); J[14] = sc * (-qz * qy); J[15] = sc * (r * r + qx * qx + qy * qy);
-        const double nrm = sqrt(nn);
-        x[3] = r / nrm; x[4] = qx / nrm; x[5] = qy / nrm; x[6] = qz / nrm;
+    if (xrole) {
+        double* __restrict__ x = v.x + (size_t)b * ld;
+        if (tid < TM && c0 + tid < n) x[c0 + tid] += xacc;
+        if (c0 == 0) {
+            // this block owns state entries 0..63: normJac(q+) (mc/normJac.m) from the un-normalised
+            // quaternion, then q+ <- q+/|q+|  (mc/update.m:18,24)
+            __syncthreads();
+            if (tid == 0) {
+                const double r = x[3], qx = x[4], qy = x[5], qz = x[6];
+                const double nn = r * r + qx * qx + qy * qy + qz * qz;
+                const double sc = 1.0 / (nn * sqrt(nn));  // (.)^(-3/2)
+                double* J = v.jn + (size_t)b * 16;
+                J[0] = sc * (qx * qx + qy * qy + qz * qz); J[1] = sc * (-r * qx); J[2] = sc * (-r * qy); J[3] = sc * (-r * qz);
+                J[4] = sc * (-qx * r); J[5] = sc * (r * r + qy * qy + qz * qz); J[6] = sc * (-qx * qy); J[7] = sc * (-qx * qz);
+                J[8] = sc * (-qy * r); J[9] = sc * (-qy * qx); J[10] = sc * (r * r + qx * qx + qz * qz); J[11] = sc * (-qy * qz);
+                J[12] = sc * (-qz * r); J[13] = sc * (-qz * qx); J[14] = sc * (-qz * qy); J[15] = sc * (r * r + qx * qx + qy * qy);
+                const double nrm = sqrt(nn);
+                x[3] = r / nrm; x[4] = qx / nrm; x[5] = qy / nrm; x[6] = qz / nrm;
+            }
+        }
     }
 }
 
@@ -478,6 +484,9 @@ __global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    // a warp whose 32x16 sub-tile lies strictly above the diagonal (diagonal tiles) or entirely
+    // outside the n x n matrix has nothing to compute
+    const bool warp_active = !(diag && wc * 16 > wr * 32 + 31) && (i0 + wr * 32 < n) && (j0 + wc * 16 < n);
 
 #pragma unroll
     for (int st = 0; st < NSTAGE - 1; ++st) {
@@ -489,10 +498,13 @@ __global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __
         __syncthreads();
         if (it + NSTAGE - 1 < nk) load_stage((it + NSTAGE - 1) % NSTAGE, (it + NSTAGE - 1) * TK);
         cp_async_commit();
+        if (!warp_active) continue;
         const double* as = As + (it % NSTAGE) * TK * TPAD;
         const double* bs = diag ? as : Bs + (it % NSTAGE) * TK * TPAD;
+        const int k4n = min(TK / 4, (k - it * TK + 3) >> 2);  // the tail panel stops at k (rounded to 4)
 #pragma unroll
         for (int k4 = 0; k4 < TK / 4; ++k4) {
+            if (k4 >= k4n) break;
             double af[4], bf[2];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) af[mt] = as[(k4 * 4 + q) * TPAD + wr * 32 + mt * 8 + g];
@@ -505,6 +517,45 @@ __global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __
         }
     }
     cp_async_wait<0>();
+    if (tj != 0) {
+        // common case (no quaternion rows/columns in the tile): store P - W'W and its mirror image
+        // straight from the accumulator fragments.  Per warp store, lanes with equal q cover 64 B runs.
+        if (!warp_active) return;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int gi = i0 + wr * 32 + mt * 8 + g;
+            if (gi >= n) continue;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
+                const double c0 = pf[mt][nt][0] - acc[mt][nt][0];
+                const double c1 = pf[mt][nt][1] - acc[mt][nt][1];
+                if (!diag) {
+                    if (gj + 1 < n) {
+                        *reinterpret_cast<double2*>(P + (size_t)gi * ld + gj) = make_double2(c0, c1);
+                        P[(size_t)gj * ld + gi] = c0;
+                        P[(size_t)(gj + 1) * ld + gi] = c1;
+                    } else if (gj < n) {
+                        P[(size_t)gi * ld + gj] = c0;
+                        P[(size_t)gj * ld + gi] = c0;
+                    }
+                } else {
+                    // diagonal tile: the lower triangle is authoritative, the upper one its mirror
+                    if (gj <= gi && gj < n) {
+                        P[(size_t)gi * ld + gj] = c0;
+                        if (gj < gi) P[(size_t)gj * ld + gi] = c0;
+                    }
+                    if (gj + 1 <= gi && gj + 1 < n) {
+                        P[(size_t)gi * ld + gj + 1] = c1;
+                        if (gj + 1 < gi) P[(size_t)(gj + 1) * ld + gi] = c1;
+                    }
+                }
+            }
+        }
+        return;
+    }
+    // tile column 0 holds state columns 3..6 (the quaternion): go through shared memory for the
+    // normalisation Jacobian products
     __syncthreads();  // every warp is done with the ring: reuse it as the C tile
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
@@ -518,31 +569,34 @@ __global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __
         }
     }
     __syncthreads();
-    if (tj == 0) {
-        // columns 3..6 <- [c3 c4 c5 c6] * Jn'   (every row of the tile)
-        if (tid < TM) {
-            const int r = tid;
-            const double c3 = Ct[r][3], c4 = Ct[r][4], c5 = Ct[r][5], c6 = Ct[r][6];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-                Ct[r][3 + a] = c3 * Jn[a * 4 + 0] + c4 * Jn[a * 4 + 1] + c5 * Jn[a * 4 + 2] + c6 * Jn[a * 4 + 3];
+    if (diag) {
+        // tile (0,0): warps above the diagonal skipped their part -> mirror the lower triangle first
+        for (int qd = tid; qd < TM * TM; qd += blockDim.x) {
+            const int r = qd / TM, c = qd - r * TM;
+            if (c > r) Ct[r][c] = Ct[c][r];
         }
         __syncthreads();
-        if (ti == 0) {
-            // rows 3..6 <- Jn * [r3; r4; r5; r6]   (every column of tile (0,0))
-            if (tid < TM) {
-                const int c = tid;
-                const double r3 = Ct[3][c], r4 = Ct[4][c], r5 = Ct[5][c], r6 = Ct[6][c];
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    Ct[3 + a][c] = Jn[a * 4 + 0] * r3 + Jn[a * 4 + 1] * r4 + Jn[a * 4 + 2] * r5 + Jn[a * 4 + 3] * r6;
-            }
-            __syncthreads();
-        }
     }
+    // columns 3..6 <- [c3 c4 c5 c6] * Jn'   (every row of the tile)
+    if (tid < TM) {
+        const int r = tid;
+        const double c3 = Ct[r][3], c4 = Ct[r][4], c5 = Ct[r][5], c6 = Ct[r][6];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            Ct[r][3 + a] = c3 * Jn[a * 4 + 0] + c4 * Jn[a * 4 + 1] + c5 * Jn[a * 4 + 2] + c6 * Jn[a * 4 + 3];
+    }
+    __syncthreads();
     if (diag) {
-        // keep diagonal tiles exactly symmetric (lower -> upper): the tensor-core summation order of
-        // C[i][j] and C[j][i] is not guaranteed to be identical, nor are the two one-sided Jn products
+        // rows 3..6 <- Jn * [r3; r4; r5; r6]   (every column of tile (0,0))
+        if (tid < TM) {
+            const int c = tid;
+            const double r3 = Ct[3][c], r4 = Ct[4][c], r5 = Ct[5][c], r6 = Ct[6][c];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                Ct[3 + a][c] = Jn[a * 4 + 0] * r3 + Jn[a * 4 + 1] * r4 + Jn[a * 4 + 2] * r5 + Jn[a * 4 + 3] * r6;
+        }
+        __syncthreads();
+        // the two one-sided products are symmetric only to rounding: lower -> upper once more
         for (int qd = tid; qd < TM * TM; qd += blockDim.x) {
             const int r = qd / TM, c = qd - r * TM;
             if (c > r) Ct[r][c] = Ct[c][r];
@@ -576,16 +630,15 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior) {
     }
     { KScope ks(c, KT_CHOL); k_chol<<<v.B, 256, chol_sm, st>>>(v); }
     dim3 gw((v.nmax + TM - 1) / TM, (v.kmax + TM - 1) / TM, v.B);
-    const size_t w_sm = sizeof(double) * NSTAGE * (TM * APAD + TK * TPAD);
+    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax);
     const size_t dd_sm = sizeof(double) * (size_t)max(2 * NSTAGE * TK * TPAD, TM * (TM + 1));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static size_t attr_done = 0;
+    if (attr_done < w_sm) {
         cudaFuncSetAttribute(k_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w_sm);
         cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dd_sm);
-        attr_done = true;
+        attr_done = w_sm;
     }
     { KScope ks(c, KT_W); k_w<<<gw, 256, w_sm, st>>>(v); }
-    { KScope ks(c, KT_XUPD); k_xupd<<<v.B, 256, sizeof(double) * v.kmax, st>>>(v, v.jn); }
     const int nt = (v.nmax + TM - 1) / TM;
     dim3 gd(nt * (nt + 1) / 2, v.B);
     { KScope ks(c, KT_DOWNDATE); k_downdate<<<gd, 256, dd_sm, st>>>(v, v.jn); }

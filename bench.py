@@ -127,64 +127,42 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on host cores
+# CPU arm: the oracle port on host cores (oracle/ekf_oracle.c, OpenMP over filters)
 # ------------------------------------------------------------------------------------------
-def _cpu_worker(job):
-    """Runs `steps` reference steps of one filter with the numpy oracle; returns seconds."""
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    from oracle import ekf_oracle as O
-    from tests import helpers as H
-    x0, P0, types, zcs, hass, us, fixed, warm = job
-    cam = O.initialize_cam()
-    filt = H.oracle_filter(x0, P0)
-    feats = H.oracle_features(types)
-    t_acc = 0.0
-    for t in range(len(zcs)):
-        t0 = time.perf_counter()
-        filt, feats, _ = H.oracle_step(filt, feats, cam, zcs[t], hass[t], us[t], fixed)
-        if t >= warm:
-            t_acc += time.perf_counter() - t0
-    return t_acc
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def cpu_reference_rate(args, n_filters, steps, warm, procs):
-    """filter-steps/s of the CPU oracle over `n_filters` filters x `steps` timed steps on `procs` processes."""
-    import multiprocessing as mp
+def cpu_reference_rate(args, n_filters, steps, warm, threads):
+    """filter-steps/s of the C oracle: `n_filters` filters x `steps` timed steps on `threads` threads."""
     import ekf_slam_b200.synth as synth
+    from oracle import c_oracle
     n_u = args.n_u or (args.fixed_hyp if args.fixed_hyp > 0 else 64)
     seq = synth.SynthSequence(B=n_filters, N=args.features, T=warm + steps, seed=args.seed,
                               p_outlier=args.p_outlier, n_u=n_u)
-    x0, P0, types = seq.initial_state()
-    jobs = []
-    for b in range(n_filters):
-        jobs.append((x0[b], P0[b], types[b], [seq.zc[t, b] for t in range(1, warm + steps + 1)],
-                     [seq.has[t, b] for t in range(1, warm + steps + 1)],
-                     [seq.U[b, t, :n_u] for t in range(1, warm + steps + 1)], args.fixed_hyp, warm))
-    t0 = time.perf_counter()
-    if procs > 1:
-        ctx = mp.get_context("fork")
-        with ctx.Pool(procs) as pool:
-            pool.map(_cpu_worker, jobs)
-    else:
-        for j in jobs:
-            _cpu_worker(j)
-    wall = time.perf_counter() - t0
-    # the warm-up steps of each filter run inside `wall`; scale to the timed share
-    timed_share = steps / float(steps + warm)
-    return n_filters * steps / (wall * timed_share), wall
+    x, P, types = seq.initial_state()
+    nfeat = np.full(n_filters, args.features, dtype=np.int32)
+    wall = 0.0
+    for t in range(1, warm + steps + 1):
+        zc = np.ascontiguousarray(seq.zc[t])
+        has = np.ascontiguousarray(seq.has[t])
+        u = seq.uniforms(t, n_u)
+        t0 = time.perf_counter()
+        c_oracle.step_batch(x, P, types, nfeat, zc, has, u, fixed_hyp=args.fixed_hyp, nthreads=threads)
+        if t > warm:
+            wall += time.perf_counter() - t0
+    return n_filters * steps / wall, wall
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    procs = max(1, min(cores, 64))
-    nf = args.cpu_sample or procs
-    steps = max(1, min(args.steps, 3))
-    warm = 1
-    rate, wall = cpu_reference_rate(args, nf, steps, warm, procs)
-    sample = "%d filters x %d steps (+%d warm-up) of the same synthetic workload, numpy oracle, %d processes" % (
-        nf, steps, warm, procs)
+    threads = max(1, min(host_cores(), 256))
+    nf = args.cpu_sample or min(16 * threads, 2048)
+    steps, warm = max(1, args.steps), max(1, min(args.warmup, 3))
+    rate, wall = cpu_reference_rate(args, nf, steps, warm, threads)
+    sample = ("%d filters x %d timed steps (+%d warm-up) of the same synthetic workload, C restatement "
+              "oracle/ekf_oracle.c, OpenMP %d threads, %.1f s" % (nf, steps, warm, threads, wall))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / rate,
@@ -193,8 +171,9 @@ def run_reference(args, rank):
         "config": {"workload": "cfg3: N=%d inverse-depth features, batch %d Monte-Carlo filters (CPU arm runs a "
                                "bounded sample)" % (args.features, args.batch),
                    "ransac": "adaptive (reference rule)" if args.fixed_hyp <= 0 else "fixed %d" % args.fixed_hyp,
-                   "reference_runtime": "GNU Octave / MATLAB absent in this image: CPU oracle port (oracle/ekf_oracle.py)"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+                   "reference_runtime": "GNU Octave / MATLAB absent in this image: C port of the reference "
+                                        "(oracle/ekf_oracle.c) on all host cores"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -317,16 +296,15 @@ def main():
     sampler.join(timeout=2)
 
     # ---- reduce over ranks (max time), gather per-filter statistics over NCCL ---------------
-    tvec = torch.tensor([ms_dev, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
-    svec = torch.tensor([float(stats["n_li"].sum()), float(stats["n_hi"].sum()), float(stats["n_ic"].sum()),
-                         float(stats["ransac_iters"].sum()), float(stats["ransac_scored"].sum()),
-                         float((stats["status"] != 0).sum())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(svec, op=dist.ReduceOp.SUM)
-    ms_dev, ms_e2e = float(tvec[0]), float(tvec[1])
+    import ekf_slam_b200.sharding as sharding
+    ms_dev = sharding.max_over_ranks(ms_dev, device=dev)
+    ms_e2e = sharding.max_over_ranks(e2e[0] if e2e else 0.0, device=dev)
     tot_filters = B * world
-    mean = lambda i: float(svec[i]) / tot_filters  # noqa: E731
+    allst = sharding.gather_stats(stats, n_filters_total=tot_filters, device=dev)
+    svec = [float(allst["n_li"].sum()), float(allst["n_hi"].sum()), float(allst["n_ic"].sum()),
+            float(allst["ransac_iters"].sum()), float(allst["ransac_scored"].sum()),
+            float((allst["status"] != 0).sum())]
+    mean = lambda i: svec[i] / tot_filters  # noqa: E731
 
     if rank == 0:
         peaks = read_peaks()
@@ -392,12 +370,12 @@ def main():
                            "note": "covariances stay resident on the device between frames (filter state, like the "
                                    "reference's persistent `filter` struct); per-frame inputs/outputs cross PCIe"}
         if not args.no_cpu_baseline:
-            cores = 1
-            nf = args.cpu_sample or 2
-            rate, wall = cpu_reference_rate(args, nf, 2, 1, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d filters x 2 steps (+1 warm-up) of the same workload, numpy oracle "
-                                              "(oracle/ekf_oracle.py), single process, %.1f s" % (nf, wall)}
+            threads = max(1, min(host_cores(), 256))
+            nf = args.cpu_sample or min(32 * threads, 2048)
+            rate, wall = cpu_reference_rate(args, nf, 3, 1, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d filters x 3 steps (+1 warm-up) of the same workload, C restatement "
+                                              "oracle/ekf_oracle.c, OpenMP %d threads, %.1f s" % (nf, threads, wall)}
         print(json.dumps(line), flush=True)
     bank.close()
     if world > 1:

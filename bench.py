@@ -316,7 +316,8 @@ def main():
         kt = {k: v for k, v in ktimes.items() if v[1] > 0}
         tot_k_ms = sum(v[0] for v in kt.values())
         top = max(kt.items(), key=lambda kv: kv[1][0])
-        dd_ms, dd_cnt = kt.get("k_downdate", (0.0, 0))
+        dd_li, dd_hi = kt.get("k_downdate", (0.0, 0)), kt.get("k_downdate_hi", (0.0, 0))
+        dd_ms, dd_cnt = dd_li[0] + dd_hi[0], dd_li[1] + dd_hi[1]
         # per launch (whole batch B): flops n^2 k (lower triangle, FMA = 2), bytes 2 n^2 * 8
         dd_flops_per_step = B * sum(n * n * k for k in (k_li, k_hi))
         dd_bytes_per_step = B * 2 * (2 * n * n * 8.0)

@@ -77,7 +77,7 @@ static void kt_collect(ekfslam_ctx* c) {
 }
 
 static const char* KT_NAMES[KT_COUNT] = {"k_begin_frame", "k_predict", "k_features", "k_hp", "k_innov", "k_ransac",
-                                         "k_upd_S", "k_chol", "k_w", "k_xupd", "k_downdate", "k_symmetrize",
+                                         "k_upd_S", "k_chol", "k_w", "k_downdate_hi", "k_downdate", "k_symmetrize",
                                          "k_add_features"};
 
 template <typename T>

@@ -50,7 +50,7 @@ struct DevView {
 
 // per-kernel timing (ekfslam_enable_timing): every launch is bracketed by an event pair
 enum {
-    KT_BEGIN_FRAME = 0, KT_PREDICT, KT_FEATURES, KT_HP, KT_INNOV, KT_RANSAC, KT_UPD_S, KT_CHOL, KT_W, KT_XUPD,
+    KT_BEGIN_FRAME = 0, KT_PREDICT, KT_FEATURES, KT_HP, KT_INNOV, KT_RANSAC, KT_UPD_S, KT_CHOL, KT_W, KT_DOWNDATE_HI,
     KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_COUNT
 };
 struct KTimer;

@@ -11,6 +11,8 @@
 // Kernels: k_upd_S (select + stack S, nu) -> k_chol (blocked Cholesky, inv(L), y) ->
 //          k_w (W = inv(L) G_sel, triangular GEMM; also x+, q normalisation, normJac) ->
 //          k_downdate (P -= W'W on 64x64 tiles of the lower triangle, mirrored).
+#include <cstdlib>
+#include <cstring>
 #include "model.cuh"
 
 #define NB 16
@@ -347,6 +349,7 @@ __global__ void __launch_bounds__(256, 3) k_w(DevView v) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int tmax_w = min(k, a0 + wr * 32 + 32);
 
 #pragma unroll
     for (int st = 0; st < NSTAGE - 1; ++st) {
@@ -366,15 +369,22 @@ __global__ void __launch_bounds__(256, 3) k_w(DevView v) {
         }
 #pragma unroll
         for (int k4 = 0; k4 < TK / 4; ++k4) {
+            const int tb = it * TK + k4 * 4;
+            if (tb >= tmax_w) break;  // X is lower triangular: rows of this warp need t <= their own index
             double af[4], bf[2];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) af[mt] = as[(wr * 32 + mt * 8 + g) * APAD + k4 * 4 + q];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) bf[nt] = bs[(k4 * 4 + q) * TPAD + wc * 16 + nt * 8 + g];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
+            for (int mt = 0; mt < 4; ++mt) {
+                // 8-row tile mt: rows r0..r0+7 exist if r0 < k and need t <= r0+7
+                const int r0 = a0 + wr * 32 + mt * 8;
+                if (r0 < k && tb <= r0 + 7) {
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+                    for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+                }
+            }
         }
     }
     cp_async_wait<0>();
@@ -422,7 +432,10 @@ __global__ void __launch_bounds__(256, 3) k_w(DevView v) {
 // columns 3-6 (tiles of tile-column 0) and rows 3-6 (tile (0,0)).  The P tile is prefetched into
 // the accumulator layout before the K loop so its HBM latency hides behind the DMMA work.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __restrict__ jn_all) {
+#ifndef DD_MINBLOCKS
+#define DD_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, DD_MINBLOCKS) k_downdate(DevView v, const double* __restrict__ jn_all) {
     extern __shared__ __align__(16) double dsm[];
     const int b = blockIdx.y;
     const int k = 2 * v.ksel[b];
@@ -463,19 +476,23 @@ __global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __
         }
     }
     const int nk = (k + TK - 1) / TK;
+    // per-thread copy slots of a [TK][64] panel: rows r and r+8, 16-byte chunk cc (hoisted out of the loop)
+    const int lr = tid >> 5, lcc = (tid & 31) * 2;
+    const bool cola = (i0 + lcc < ld), colb = (j0 + lcc < ld);
+    const double* __restrict__ wa = W + (size_t)lr * ld + i0 + lcc;
+    const double* __restrict__ wb = W + (size_t)lr * ld + j0 + lcc;
+    const int soff = lr * TPAD + lcc;
     auto load_stage = [&](int st, int t0) {
-        double* as = As + st * TK * TPAD;
-        double* bs = Bs + st * TK * TPAD;
+        double* as = As + st * TK * TPAD + soff;
+        double* bs = Bs + st * TK * TPAD + soff;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int ch = tid + 256 * j;  // 16 rows x 32 chunks of 2 doubles
-            const int r = ch >> 5, cc = (ch & 31) * 2;
-            const int tt = t0 + r;
-            const bool oka = (tt < k) && (i0 + cc < ld);
-            cp_async16(as + r * TPAD + cc, oka ? W + (size_t)tt * ld + i0 + cc : W, oka ? 16 : 0);
+            const int tt = t0 + lr + 8 * j;
+            const bool oka = (tt < k) && cola;
+            cp_async16(as + 8 * j * TPAD, oka ? wa + (size_t)(t0 + 8 * j) * ld : W, oka ? 16 : 0);
             if (!diag) {
-                const bool okb = (tt < k) && (j0 + cc < ld);
-                cp_async16(bs + r * TPAD + cc, okb ? W + (size_t)tt * ld + j0 + cc : W, okb ? 16 : 0);
+                const bool okb = (tt < k) && colb;
+                cp_async16(bs + 8 * j * TPAD, okb ? wb + (size_t)(t0 + 8 * j) * ld : W, okb ? 16 : 0);
             }
         }
     };
@@ -486,7 +503,18 @@ __global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __
         for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     // a warp whose 32x16 sub-tile lies strictly above the diagonal (diagonal tiles) or entirely
     // outside the n x n matrix has nothing to compute
-    const bool warp_active = !(diag && wc * 16 > wr * 32 + 31) && (i0 + wr * 32 < n) && (j0 + wc * 16 < n);
+    // ... and inside an active warp every 8x8 DMMA tile that is outside n x n, or strictly above the
+    // diagonal of a diagonal tile, is skipped (bit mt*2+nt of onmask)
+    unsigned onmask = 0;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int r0 = i0 + wr * 32 + mt * 8, c0 = j0 + wc * 16 + nt * 8;
+            const bool on = (r0 < n) && (c0 < n) && !(diag && c0 > r0 + 7);
+            onmask |= (on ? 1u : 0u) << (mt * 2 + nt);
+        }
+    const bool warp_active = onmask != 0;
 
 #pragma unroll
     for (int st = 0; st < NSTAGE - 1; ++st) {
@@ -513,7 +541,8 @@ __global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+                for (int nt = 0; nt < 2; ++nt)
+                    if (onmask & (1u << (mt * 2 + nt))) dmma(acc[mt][nt], af[mt], bf[nt]);
         }
     }
     cp_async_wait<0>();
@@ -618,6 +647,498 @@ __global__ void __launch_bounds__(256, 3) k_downdate(DevView v, const double* __
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Persistent form of the downdate: a CTA walks a strided list of (filter, tile) pairs and keeps
+// the cp.async ring running ACROSS tile boundaries, so the W panels of the next tile are already
+// in flight while the current tile finishes and its P tile / stores overlap the DMMA work of the
+// neighbours.  Same arithmetic, same summation order per output element as k_downdate.
+// grid = (CTAs, 1); tile t -> filter t / T, lower-triangle tile t % T (T = nt(nt+1)/2).
+// ---------------------------------------------------------------------------------------
+struct DTile {
+    int b, i0, j0, k, n, nk;
+    bool diag, col0;
+};
+
+// tile m of this CTA (global tile t = blockIdx.x + m*G): metadata comes from shared memory
+// (meta[m] = {k, n} of the tile's filter, lut[e] = ti<<16|tj), never from a dependent global load
+__device__ __forceinline__ DTile decode_tile(const int2* meta, const unsigned* lut, int m, int M, long long t, int T) {
+    DTile d;
+    d.nk = 0; d.b = 0; d.i0 = 0; d.j0 = 0; d.k = 0; d.n = 0; d.diag = false; d.col0 = false;
+    if (m >= M) return d;
+    d.b = (int)(t / T);
+    const unsigned e = lut[(int)(t - (long long)d.b * T)];
+    const int ti = (int)(e >> 16), tj = (int)(e & 0xffffu);
+    d.i0 = ti * TM; d.j0 = tj * TM;
+    d.diag = (ti == tj); d.col0 = (tj == 0);
+    const int2 kn = meta[m];
+    d.k = kn.x; d.n = kn.y;
+    d.nk = (d.i0 < d.n) ? (d.k + TK - 1) / TK : 0;
+    return d;
+}
+
+__global__ void __launch_bounds__(256, 2) k_downdate_p(DevView v, const double* __restrict__ jn_all, int T,
+                                                       long long total, int M) {
+    extern __shared__ __align__(16) double dsm[];
+    double* As = dsm;                            // [NSTAGE][TK][TPAD]
+    double* Bs = dsm + NSTAGE * TK * TPAD;       // [NSTAGE][TK][TPAD]
+    double* strip = Bs + NSTAGE * TK * TPAD;     // [64][9]: columns 0..7 of a tile-column-0 tile
+    int2* meta = reinterpret_cast<int2*>(strip + TM * 9);          // [M]
+    unsigned* lut = reinterpret_cast<unsigned*>(meta + M);          // [T]
+    const int ld = v.ld, kmax = v.kmax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
+    const long long G = gridDim.x;
+    for (int m = tid; m < M; m += blockDim.x) {
+        const long long t = blockIdx.x + (long long)m * G;
+        int2 kn = make_int2(0, 0);
+        if (t < total) { const int b = (int)(t / T); kn = make_int2(2 * v.ksel[b], v.nstate[b]); }
+        meta[m] = kn;
+    }
+    for (int e = tid; e < T; e += blockDim.x) {
+        int ti = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+        while (ti * (ti + 1) / 2 > e) --ti;
+        lut[e] = ((unsigned)ti << 16) | (unsigned)(e - ti * (ti + 1) / 2);
+    }
+    __syncthreads();
+    // number of tiles this CTA really owns
+    const int Mreal = (int)((total - blockIdx.x + G - 1) / G) < M ? (int)((total - blockIdx.x + G - 1) / G) : M;
+
+    // loader cursor
+    int lm = 0;
+    DTile L = decode_tile(meta, lut, lm, Mreal, blockIdx.x + (long long)lm * G, T);
+    while (lm < Mreal && L.nk == 0) { ++lm; L = decode_tile(meta, lut, lm, Mreal, blockIdx.x + (long long)lm * G, T); }
+    int ls = 0;          // stage within the loader tile
+    unsigned slot_l = 0; // ring slot counters (monotone)
+    auto issue = [&]() {
+        if (lm < Mreal) {
+            const double* __restrict__ W = v.W + (size_t)L.b * kmax * ld;
+            double* as = As + (slot_l % NSTAGE) * TK * TPAD;
+            double* bs = Bs + (slot_l % NSTAGE) * TK * TPAD;
+            const int t0 = ls * TK;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int ch = tid + 256 * j;
+                const int r = ch >> 5, cc = (ch & 31) * 2;
+                const int tt = t0 + r;
+                const bool oka = (tt < L.k) && (L.i0 + cc < ld);
+                cp_async16(as + r * TPAD + cc, oka ? W + (size_t)tt * ld + L.i0 + cc : W, oka ? 16 : 0);
+                if (!L.diag) {
+                    const bool okb = (tt < L.k) && (L.j0 + cc < ld);
+                    cp_async16(bs + r * TPAD + cc, okb ? W + (size_t)tt * ld + L.j0 + cc : W, okb ? 16 : 0);
+                }
+            }
+            if (++ls == L.nk) {
+                ls = 0;
+                do { ++lm; L = decode_tile(meta, lut, lm, Mreal, blockIdx.x + (long long)lm * G, T); } while (lm < Mreal && L.nk == 0);
+            }
+        }
+        ++slot_l;
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int st = 0; st < NSTAGE - 1; ++st) issue();
+
+    unsigned slot_c = 0;
+    for (int cm = 0; cm < Mreal; ++cm) {
+        const DTile C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T);
+        if (C.nk == 0) continue;
+        const int n = C.n, k = C.k, i0 = C.i0, j0 = C.j0;
+        const bool diag = C.diag;
+        double* __restrict__ P = v.P + (size_t)C.b * v.nmax * ld;
+        // P tile -> accumulator layout (consumed after the K loop)
+        double pf[4][2][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int gi = i0 + wr * 32 + mt * 8 + g;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
+                double2 val = make_double2(0.0, 0.0);
+                if (gi < n && gj < ld) val = *reinterpret_cast<const double2*>(P + (size_t)gi * ld + gj);
+                pf[mt][nt][0] = val.x; pf[mt][nt][1] = val.y;
+            }
+        }
+        unsigned onmask = 0;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int r0 = i0 + wr * 32 + mt * 8, c0 = j0 + wc * 16 + nt * 8;
+                const bool on = (r0 < n) && (c0 < n) && !(diag && c0 > r0 + 7);
+                onmask |= (on ? 1u : 0u) << (mt * 2 + nt);
+            }
+        double acc[4][2][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int it = 0; it < C.nk; ++it) {
+            cp_async_wait<NSTAGE - 2>();
+            __syncthreads();
+            issue();
+            const double* as = As + (slot_c % NSTAGE) * TK * TPAD;
+            const double* bs = diag ? as : Bs + (slot_c % NSTAGE) * TK * TPAD;
+            ++slot_c;
+            if (onmask == 0) continue;
+            const int k4n = min(TK / 4, (k - it * TK + 3) >> 2);
+#pragma unroll
+            for (int k4 = 0; k4 < TK / 4; ++k4) {
+                if (k4 >= k4n) break;
+                double af[4], bf[2];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) af[mt] = as[(k4 * 4 + q) * TPAD + wr * 32 + mt * 8 + g];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) bf[nt] = bs[(k4 * 4 + q) * TPAD + wc * 16 + nt * 8 + g];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+                        if (onmask & (1u << (mt * 2 + nt))) dmma(acc[mt][nt], af[mt], bf[nt]);
+            }
+        }
+        // ---- epilogue: C = P - W'W, stored with its mirror image straight from the fragments.
+        // In tile column 0 the 8 leading columns (they hold the quaternion, state entries 3..6) are
+        // routed through the shared strip for the normalisation Jacobian instead.
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int gi = i0 + wr * 32 + mt * 8 + g;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                if (!(onmask & (1u << (mt * 2 + nt)))) continue;
+                const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
+                const double c0 = pf[mt][nt][0] - acc[mt][nt][0];
+                const double c1 = pf[mt][nt][1] - acc[mt][nt][1];
+                if (C.col0 && wc == 0 && nt == 0) {
+                    strip[(wr * 32 + mt * 8 + g) * 9 + 2 * q] = c0;
+                    strip[(wr * 32 + mt * 8 + g) * 9 + 2 * q + 1] = c1;
+                    continue;
+                }
+                if (gi >= n) continue;
+                if (!diag) {
+                    if (gj + 1 < n) {
+                        *reinterpret_cast<double2*>(P + (size_t)gi * ld + gj) = make_double2(c0, c1);
+                        P[(size_t)gj * ld + gi] = c0;
+                        P[(size_t)(gj + 1) * ld + gi] = c1;
+                    } else if (gj < n) {
+                        P[(size_t)gi * ld + gj] = c0;
+                        P[(size_t)gj * ld + gi] = c0;
+                    }
+                } else {
+                    if (gj <= gi && gj < n) {
+                        P[(size_t)gi * ld + gj] = c0;
+                        if (gj < gi) P[(size_t)gj * ld + gi] = c0;
+                    }
+                    if (gj + 1 <= gi && gj + 1 < n) {
+                        P[(size_t)gi * ld + gj + 1] = c1;
+                        if (gj + 1 < gi) P[(size_t)(gj + 1) * ld + gi] = c1;
+                    }
+                }
+            }
+        }
+        if (C.col0) {
+            __syncthreads();
+            const double* __restrict__ Jn = jn_all + (size_t)C.b * 16;
+            if (diag) {
+                // tile (0,0): the 8x8 corner holds the 4x4 quaternion block.  Complete the corner from its
+                // lower triangle, apply Jn on both sides, and re-symmetrise (one thread; 8x8 is tiny).
+                if (tid == 0) {
+                    double Cn[8][8];
+                    for (int r = 0; r < 8; ++r)
+                        for (int c = 0; c < 8; ++c) Cn[r][c] = (c <= r) ? strip[r * 9 + c] : strip[c * 9 + r];
+                    for (int r = 0; r < 8; ++r) {  // columns 3..6 <- row * Jn'
+                        const double c3 = Cn[r][3], c4 = Cn[r][4], c5 = Cn[r][5], c6 = Cn[r][6];
+                        for (int a = 0; a < 4; ++a)
+                            Cn[r][3 + a] = c3 * Jn[a * 4 + 0] + c4 * Jn[a * 4 + 1] + c5 * Jn[a * 4 + 2] + c6 * Jn[a * 4 + 3];
+                    }
+                    for (int c = 0; c < 8; ++c) {  // rows 3..6 <- Jn * column
+                        const double r3 = Cn[3][c], r4 = Cn[4][c], r5 = Cn[5][c], r6 = Cn[6][c];
+                        for (int a = 0; a < 4; ++a)
+                            Cn[3 + a][c] = Jn[a * 4 + 0] * r3 + Jn[a * 4 + 1] * r4 + Jn[a * 4 + 2] * r5 + Jn[a * 4 + 3] * r6;
+                    }
+                    for (int r = 0; r < 8; ++r)
+                        for (int c = 0; c <= r; ++c) {
+                            if (r < n && c < n) { P[(size_t)r * ld + c] = Cn[r][c]; P[(size_t)c * ld + r] = Cn[r][c]; }
+                        }
+                }
+                // rows 8..63 of the strip: columns 3..6 <- row * Jn'
+                if (tid >= 8 && tid < TM) {
+                    const int r = tid;
+                    if (i0 + r < n) {
+                        double o[8];
+                        for (int c = 0; c < 8; ++c) o[c] = strip[r * 9 + c];
+                        const double c3 = o[3], c4 = o[4], c5 = o[5], c6 = o[6];
+                        for (int a = 0; a < 4; ++a)
+                            o[3 + a] = c3 * Jn[a * 4 + 0] + c4 * Jn[a * 4 + 1] + c5 * Jn[a * 4 + 2] + c6 * Jn[a * 4 + 3];
+                        for (int c = 0; c < 8; ++c) { P[(size_t)(i0 + r) * ld + c] = o[c]; P[(size_t)c * ld + i0 + r] = o[c]; }
+                    }
+                }
+            } else {
+                if (tid < TM) {
+                    const int r = tid;
+                    if (i0 + r < n) {
+                        double o[8];
+                        for (int c = 0; c < 8; ++c) o[c] = strip[r * 9 + c];
+                        const double c3 = o[3], c4 = o[4], c5 = o[5], c6 = o[6];
+                        for (int a = 0; a < 4; ++a)
+                            o[3 + a] = c3 * Jn[a * 4 + 0] + c4 * Jn[a * 4 + 1] + c5 * Jn[a * 4 + 2] + c6 * Jn[a * 4 + 3];
+                        for (int c = 0; c < 8; ++c) { P[(size_t)(i0 + r) * ld + c] = o[c]; P[(size_t)c * ld + i0 + r] = o[c]; }
+                    }
+                }
+            }
+            __syncthreads();  // the strip is reused by the next tile-column-0 tile of this CTA
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------
+// Warp-specialised persistent downdate (the default).  One producer warp streams the W panels with
+// bulk asynchronous copies (cp.async.bulk, SASS UBLKCP) that complete on mbarriers; eight consumer
+// warps only wait, load fragments and issue DMMAs — no per-thread address arithmetic, no block
+// barrier in the K loop, and the ring keeps running across tile boundaries.
+//   full[s]  : 32 producer-lane arrivals + the bytes of the stage (complete_tx)
+//   empty[s] : 8 consumer-warp arrivals
+// ---------------------------------------------------------------------------------------
+#define WS_STAGES 4
+#define WS_CONSUMERS 8
+#define WS_THREADS ((WS_CONSUMERS + 1) * 32)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const double* __restrict__ jn_all, int T,
+                                                               long long total, int M) {
+    extern __shared__ __align__(16) double dsm[];
+    double* As = dsm;                                   // [WS_STAGES][TK][TPAD]
+    double* Bs = dsm + WS_STAGES * TK * TPAD;           // [WS_STAGES][TK][TPAD]
+    double* strip = Bs + WS_STAGES * TK * TPAD;         // [64][9]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(strip + TM * 9);   // [WS_STAGES]
+    unsigned long long* empty = full + WS_STAGES;                                        // [WS_STAGES]
+    int2* meta = reinterpret_cast<int2*>(empty + WS_STAGES);                             // [M]
+    unsigned* lut = reinterpret_cast<unsigned*>(meta + M);                               // [T]
+    const int ld = v.ld, kmax = v.kmax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long G = gridDim.x;
+    for (int m = tid; m < M; m += blockDim.x) {
+        const long long t = blockIdx.x + (long long)m * G;
+        int2 kn = make_int2(0, 0);
+        if (t < total) { const int b = (int)(t / T); kn = make_int2(2 * v.ksel[b], v.nstate[b]); }
+        meta[m] = kn;
+    }
+    for (int e = tid; e < T; e += blockDim.x) {
+        int ti = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+        while (ti * (ti + 1) / 2 > e) --ti;
+        lut[e] = ((unsigned)ti << 16) | (unsigned)(e - ti * (ti + 1) / 2);
+    }
+    if (tid == 0) {
+        for (int s2 = 0; s2 < WS_STAGES; ++s2) { mbar_init(full + s2, 32); mbar_init(empty + s2, WS_CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int own = (int)((total - blockIdx.x + G - 1) / G);
+    const int Mreal = own < M ? own : M;
+
+    if (warp == WS_CONSUMERS) {
+        // ================= producer warp =================
+        unsigned cnt = 0;
+        const int pr = lane & 15;        // row of the [TK][64] panel this lane copies
+        const bool isB = lane >= 16;     // lanes 0-15: A panel (rows of W at i0), 16-31: B panel (at j0)
+        for (int m = 0; m < Mreal; ++m) {
+            const DTile L = decode_tile(meta, lut, m, Mreal, blockIdx.x + (long long)m * G, T);
+            if (L.nk == 0) continue;
+            const double* __restrict__ W = v.W + (size_t)L.b * kmax * ld;
+            const int c0 = isB ? L.j0 : L.i0;
+            const unsigned rowbytes = (unsigned)(min(TM, ld - c0) * 8);
+            const unsigned bytesA = (unsigned)(min(TM, ld - L.i0) * 8), bytesB = (unsigned)(min(TM, ld - L.j0) * 8);
+            for (int st = 0; st < L.nk; ++st, ++cnt) {
+                const unsigned slot = cnt % WS_STAGES, ph = (cnt / WS_STAGES) & 1u;
+                mbar_wait(empty + slot, ph ^ 1u);
+                const int t0 = st * TK;
+                const int nvalid = min(TK, L.k - t0);
+                double* dst = (isB ? Bs : As) + slot * TK * TPAD + pr * TPAD;
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(full + slot, (unsigned)nvalid * (bytesA + (L.diag ? 0u : bytesB)));
+                }
+                const bool mine = !(isB && L.diag);
+                if (mine && pr < nvalid) {
+                    bulk_g2s(dst, W + (size_t)(t0 + pr) * ld + c0, rowbytes, full + slot);
+                } else if (mine && pr < ((nvalid + 3) & ~3)) {
+                    // rows between k and the next multiple of 4 are read by the last k4 step: zero them
+                    for (int c = 0; c < TM; ++c) dst[c] = 0.0;
+                }
+                if (lane != 0) mbar_arrive(full + slot);
+            }
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
+    const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
+    unsigned cnt = 0;
+    for (int cm = 0; cm < Mreal; ++cm) {
+        const DTile C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T);
+        if (C.nk == 0) continue;
+        const int n = C.n, k = C.k, i0 = C.i0, j0 = C.j0;
+        const bool diag = C.diag;
+        double* __restrict__ P = v.P + (size_t)C.b * v.nmax * ld;
+        double pf[4][2][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int gi = i0 + wr * 32 + mt * 8 + g;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
+                double2 val = make_double2(0.0, 0.0);
+                if (gi < n && gj < ld) val = *reinterpret_cast<const double2*>(P + (size_t)gi * ld + gj);
+                pf[mt][nt][0] = val.x; pf[mt][nt][1] = val.y;
+            }
+        }
+        unsigned onmask = 0;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int r0 = i0 + wr * 32 + mt * 8, c0 = j0 + wc * 16 + nt * 8;
+                const bool on = (r0 < n) && (c0 < n) && !(diag && c0 > r0 + 7);
+                onmask |= (on ? 1u : 0u) << (mt * 2 + nt);
+            }
+        double acc[4][2][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int it = 0; it < C.nk; ++it, ++cnt) {
+            const unsigned slot = cnt % WS_STAGES, ph = (cnt / WS_STAGES) & 1u;
+            mbar_wait(full + slot, ph);
+            const double* as = As + slot * TK * TPAD;
+            const double* bs = diag ? as : Bs + slot * TK * TPAD;
+            if (onmask != 0) {
+                const int k4n = min(TK / 4, (k - it * TK + 3) >> 2);
+#pragma unroll
+                for (int k4 = 0; k4 < TK / 4; ++k4) {
+                    if (k4 >= k4n) break;
+                    double af[4], bf[2];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) af[mt] = as[(k4 * 4 + q) * TPAD + wr * 32 + mt * 8 + g];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) bf[nt] = bs[(k4 * 4 + q) * TPAD + wc * 16 + nt * 8 + g];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+                            if (onmask & (1u << (mt * 2 + nt))) dmma(acc[mt][nt], af[mt], bf[nt]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);
+        }
+        // ---- epilogue (same as k_downdate_p)
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int gi = i0 + wr * 32 + mt * 8 + g;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                if (!(onmask & (1u << (mt * 2 + nt)))) continue;
+                const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
+                const double c0 = pf[mt][nt][0] - acc[mt][nt][0];
+                const double c1 = pf[mt][nt][1] - acc[mt][nt][1];
+                if (C.col0 && wc == 0 && nt == 0) {
+                    strip[(wr * 32 + mt * 8 + g) * 9 + 2 * q] = c0;
+                    strip[(wr * 32 + mt * 8 + g) * 9 + 2 * q + 1] = c1;
+                    continue;
+                }
+                if (gi >= n) continue;
+                if (!diag) {
+                    if (gj + 1 < n) {
+                        *reinterpret_cast<double2*>(P + (size_t)gi * ld + gj) = make_double2(c0, c1);
+                        P[(size_t)gj * ld + gi] = c0;
+                        P[(size_t)(gj + 1) * ld + gi] = c1;
+                    } else if (gj < n) {
+                        P[(size_t)gi * ld + gj] = c0;
+                        P[(size_t)gj * ld + gi] = c0;
+                    }
+                } else {
+                    if (gj <= gi && gj < n) {
+                        P[(size_t)gi * ld + gj] = c0;
+                        if (gj < gi) P[(size_t)gj * ld + gi] = c0;
+                    }
+                    if (gj + 1 <= gi && gj + 1 < n) {
+                        P[(size_t)gi * ld + gj + 1] = c1;
+                        if (gj + 1 < gi) P[(size_t)(gj + 1) * ld + gi] = c1;
+                    }
+                }
+            }
+        }
+        if (C.col0) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 consumer warps only
+            const double* __restrict__ Jn = jn_all + (size_t)C.b * 16;
+            if (diag && tid < 8) {
+                // tile (0,0): the 8x8 corner (strip rows 0..7) holds the 4x4 quaternion block.  Threads 0..7
+                // of warp 0 work in place in shared memory: complete the corner from its lower triangle,
+                // apply Jn from the right (thread = row) and from the left (thread = column), store the
+                // lower triangle and its mirror.
+                const int r = tid;
+                for (int c = r + 1; c < 8; ++c) strip[r * 9 + c] = strip[c * 9 + r];
+                __syncwarp(0xffu);
+                {
+                    const double c3 = strip[r * 9 + 3], c4 = strip[r * 9 + 4], c5 = strip[r * 9 + 5], c6 = strip[r * 9 + 6];
+                    for (int a = 0; a < 4; ++a)
+                        strip[r * 9 + 3 + a] = c3 * Jn[a * 4 + 0] + c4 * Jn[a * 4 + 1] + c5 * Jn[a * 4 + 2] + c6 * Jn[a * 4 + 3];
+                }
+                __syncwarp(0xffu);
+                {
+                    const int c = tid;
+                    const double r3 = strip[3 * 9 + c], r4 = strip[4 * 9 + c], r5 = strip[5 * 9 + c], r6 = strip[6 * 9 + c];
+                    for (int a = 0; a < 4; ++a)
+                        strip[(3 + a) * 9 + c] = Jn[a * 4 + 0] * r3 + Jn[a * 4 + 1] * r4 + Jn[a * 4 + 2] * r5 + Jn[a * 4 + 3] * r6;
+                }
+                __syncwarp(0xffu);
+                for (int c = 0; c <= r; ++c)
+                    if (r < n && c < n) { const double val = strip[r * 9 + c]; P[(size_t)r * ld + c] = val; P[(size_t)c * ld + r] = val; }
+            }
+            if (tid < TM && !(diag && tid < 8)) {
+                const int r = tid;
+                if (i0 + r < n) {
+                    double o[8];
+                    for (int c = 0; c < 8; ++c) o[c] = strip[r * 9 + c];
+                    const double c3 = o[3], c4 = o[4], c5 = o[5], c6 = o[6];
+                    for (int a = 0; a < 4; ++a)
+                        o[3 + a] = c3 * Jn[a * 4 + 0] + c4 * Jn[a * 4 + 1] + c5 * Jn[a * 4 + 2] + c6 * Jn[a * 4 + 3];
+                    for (int c = 0; c < 8; ++c) { P[(size_t)(i0 + r) * ld + c] = o[c]; P[(size_t)c * ld + i0 + r] = o[c]; }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+}
+
 void launch_update(ekfslam_ctx* c, int mask, int which_prior) {
     DevView& v = c->v;
     cudaStream_t st = c->stream;
@@ -640,6 +1161,39 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior) {
     }
     { KScope ks(c, KT_W); k_w<<<gw, 256, w_sm, st>>>(v); }
     const int nt = (v.nmax + TM - 1) / TM;
-    dim3 gd(nt * (nt + 1) / 2, v.B);
-    { KScope ks(c, KT_DOWNDATE); k_downdate<<<gd, 256, dd_sm, st>>>(v, v.jn); }
+    const int T = nt * (nt + 1) / 2;
+    static int mode = -1, sms = 0;
+    if (mode < 0) {
+        const char* e = getenv("EKFSLAM_DOWNDATE");
+        mode = (e && !strcmp(e, "tile")) ? 0 : (e && !strcmp(e, "persistent")) ? 1 : 2;  // default: warp-specialised
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    }
+    KScope ks(c, (mask & EKFSLAM_F_HI) ? KT_DOWNDATE_HI : KT_DOWNDATE);
+    if (mode == 0) {
+        dim3 gd(T, v.B);
+        k_downdate<<<gd, 256, dd_sm, st>>>(v, v.jn);
+    } else if (mode == 2) {
+        const long long total = (long long)T * v.B;
+        const long long ctas = total < (long long)sms * 2 ? total : (long long)sms * 2;
+        const int M = (int)((total + ctas - 1) / ctas);
+        const size_t ws_sm = sizeof(double) * (2 * WS_STAGES * TK * TPAD + TM * 9) + sizeof(unsigned long long) * 2 * WS_STAGES +
+                             sizeof(int2) * M + sizeof(unsigned) * T;
+        static size_t ws_cfg = 0;
+        if (ws_sm > ws_cfg) {
+            cudaFuncSetAttribute(k_downdate_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_sm);
+            ws_cfg = ws_sm;
+        }
+        k_downdate_ws<<<(unsigned)ctas, WS_THREADS, ws_sm, st>>>(v, v.jn, T, total, M);
+    } else {
+        const long long total = (long long)T * v.B;
+        const long long ctas = total < (long long)sms * 2 ? total : (long long)sms * 2;
+        const int M = (int)((total + ctas - 1) / ctas);
+        const size_t ddp_sm = sizeof(double) * (2 * NSTAGE * TK * TPAD + TM * 9) + sizeof(int2) * M + sizeof(unsigned) * T;
+        static size_t ddp_cfg = 0;
+        if (ddp_sm > ddp_cfg) {
+            cudaFuncSetAttribute(k_downdate_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ddp_sm);
+            ddp_cfg = ddp_sm;
+        }
+        k_downdate_p<<<(unsigned)ctas, 256, ddp_sm, st>>>(v, v.jn, T, total, M);
+    }
 }

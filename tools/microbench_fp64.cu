@@ -82,10 +82,27 @@ int main() {
     a.in = in; a.o2 = o2; a.n = n; a.blocks = sms * 16; a.threads = 512;
     const float ms_c = best_ms(l_copy, &a, 6);
     const double copy_gbs = 2.0 * n * sizeof(double2) / (ms_c * 1e-3) / 1e9;
+    // sustained: the same DMMA / DFMA kernels back to back for ~2 s each (power / clock steady state)
+    a.threads = 256; a.blocks = sms * 8; a.iters = 4096;
+    double sus[2];
+    for (int which = 0; which < 2; ++which) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        const int reps = which == 0 ? (int)(2000.0f / ms_m) : (int)(2000.0f / ms_f);
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; ++r) { if (which == 0) l_dmma(&a); else l_dfma(&a); }
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double per = ms / reps;
+        sus[which] = which == 0 ? 2.0 * 8 * 8 * 4 * 8.0 * a.iters * (double)a.blocks * (a.threads / 32) / (per * 1e-3) / 1e12
+                                : 2.0 * 16.0 * a.iters * (double)a.blocks * a.threads / (per * 1e-3) / 1e12;
+    }
     int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_clock_khz_max\": %d, \"dfma_tflops\": %.3f, \"dmma_m8n8k4_tflops\": %.3f, "
-           "\"copy_gbs\": %.1f, \"dfma_ms\": %.4f, \"dmma_ms\": %.4f, \"copy_ms\": %.4f}\n",
-           prop.name, sms, clk, dfma_tf, dmma_tf, copy_gbs, ms_f, ms_m, ms_c);
+           "\"copy_gbs\": %.1f, \"dfma_ms\": %.4f, \"dmma_ms\": %.4f, \"copy_ms\": %.4f, "
+           "\"dmma_sustained_2s_tflops\": %.3f, \"dfma_sustained_2s_tflops\": %.3f}\n",
+           prop.name, sms, clk, dfma_tf, dmma_tf, copy_gbs, ms_f, ms_m, ms_c, sus[0], sus[1]);
     cudaError_t e = cudaDeviceSynchronize();
     return e == cudaSuccess ? 0 : 1;
 }

@@ -84,6 +84,7 @@ _SIGS = {
     "ekfslam_update_masked": (_I, [_P, _I, _I]),
     "ekfslam_step": (_I, [_P, _I, _I]),
     "ekfslam_step_host": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P]),
+    "ekfslam_reset_filters": (_I, [_P, _I, _I, _P, _P]),
     "ekfslam_add_features": (_I, [_P, _I, _I, _P, _P, C.c_double, C.c_double, C.c_double]),
     "ekfslam_device_ptr": (_P, [_P, C.c_char_p]),
     "ekfslam_enable_timing": (_I, [_P, _I]),

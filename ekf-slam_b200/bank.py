@@ -204,6 +204,28 @@ class FilterBank:
         L.check(self.lib.ekfslam_download_stats(self._h, b0, nb, _ptr(st)))
         return {k: st[:, i].copy() for i, k in enumerate(L.STATS_FIELDS)}
 
+    # -- map management ("next" rows of SURVEY §8f) ------------------------------------------
+    def reset_filters(self, xv=None, Pxv=None, b0=0, nb=None):
+        """mc/initialize_x_and_p.m for filters [b0, b0+nb): camera-only state, empty map."""
+        nb = self.B - b0 if nb is None else nb
+        if xv is None:
+            xv = np.array([0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1e-15, 1e-15, 1e-15], dtype=np.float64)
+        if Pxv is None:
+            eps = float(np.finfo(np.float64).eps)
+            Pxv = np.diag([eps] * 7 + [0.025 ** 2] * 6)
+        xv = _c(xv, np.float64, (13,))
+        Pxv = _c(Pxv, np.float64, (13, 13))
+        L.check(self.lib.ekfslam_reset_filters(self._h, b0, nb, _ptr(xv), _ptr(Pxv)))
+
+    def add_features_inverse_depth(self, uvd, add=None, std_pxl=1.0, initial_rho=1.0, std_rho=1.0, b0=0):
+        """mc/add_features_inverse_depth.m: one new inverse-depth feature per filter from uvd [nb,2]."""
+        uvd = _c(uvd, np.float64)
+        nb = uvd.shape[0]
+        uvd = _c(uvd, np.float64, (nb, 2))
+        add = None if add is None else _c(add, np.uint8, (nb,))
+        L.check(self.lib.ekfslam_add_features(self._h, b0, nb, _ptr(uvd), _ptr(add), float(std_pxl),
+                                              float(initial_rho), float(std_rho)))
+
     # -- stages (names follow the reference functions they replace) --------------------------
     def begin_frame(self):
         L.check(self.lib.ekfslam_begin_frame(self._h))

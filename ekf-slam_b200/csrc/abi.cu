@@ -245,7 +245,7 @@ int ekfslam_destroy(ekfslam_ctx* c) {
         c->timer = nullptr;
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
-    if (c->pin) cudaFreeHost(c->pin);
+    if (c->pin) cudaFree(c->pin);
     delete c;
     return EKFSLAM_OK;
 }
@@ -667,11 +667,56 @@ int ekfslam_step_host(ekfslam_ctx* c, int match_mode, const double* zc, const ui
     return EKFSLAM_OK;
 }
 
+int ekfslam_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* xv, const double* Pxv) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!xv || !Pxv) return fail(EKFSLAM_ERR_INVALID, "xv / Pxv is null");
+    DevView& v = c->v;
+    const size_t need = sizeof(double) * (13 + 169);
+    if (need > c->pin_bytes) {
+        if (c->pin) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(c->pin)); c->pin = nullptr; c->pin_bytes = 0; }
+        CK(cudaMalloc(&c->pin, need));
+        c->pin_bytes = need;
+    }
+    double* d = (double*)c->pin;
+    CK(cudaMemcpyAsync(d, xv, sizeof(double) * 13, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + 13, Pxv, sizeof(double) * 169, cudaMemcpyHostToDevice, c->stream));
+    const size_t o = (size_t)b0 * v.N;
+    CK(cudaMemsetAsync(v.x + (size_t)b0 * v.ld, 0, sizeof(double) * (size_t)nb * v.ld, c->stream));
+    CK(cudaMemsetAsync(v.xp + (size_t)b0 * v.ld, 0, sizeof(double) * (size_t)nb * v.ld, c->stream));
+    CK(cudaMemsetAsync(v.P + (size_t)b0 * v.nmax * v.ld, 0, sizeof(double) * (size_t)nb * v.nmax * v.ld, c->stream));
+    CK(cudaMemsetAsync(v.ftype + o, 0, (size_t)nb * v.N, c->stream));
+    CK(cudaMemsetAsync(v.flags + o, 0, (size_t)nb * v.N, c->stream));
+    CK(cudaMemsetAsync(v.mflags + o, 0, (size_t)nb * v.N, c->stream));
+    CK(cudaMemsetAsync(v.foff + o, 0, sizeof(int32_t) * nb * v.N, c->stream));
+    CK(cudaMemsetAsync(v.counters + 2 * o, 0, sizeof(int32_t) * 2 * nb * v.N, c->stream));
+    CK(cudaMemsetAsync(v.stats + b0, 0, sizeof(ekfslam_stats) * nb, c->stream));
+    launch_reset_filters(c, b0, nb, d, d + 13);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
 int ekfslam_add_features(ekfslam_ctx* c, int b0, int nb, const double* uvd, const uint8_t* add, double std_pxl,
                          double initial_rho, double std_rho) {
     NEED_CTX(c);
-    (void)b0; (void)nb; (void)uvd; (void)add; (void)std_pxl; (void)initial_rho; (void)std_rho;
-    return fail(EKFSLAM_ERR_STATE, "ekfslam_add_features: not built yet (SURVEY §8f rank 1)");
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!uvd) return fail(EKFSLAM_ERR_INVALID, "uvd is null");
+    // staging buffers for the pixels / mask (grown on demand, freed with the context)
+    const size_t need = sizeof(double) * 2 * (size_t)nb + (size_t)nb;
+    if (need > c->pin_bytes) {
+        if (c->pin) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(c->pin)); c->pin = nullptr; c->pin_bytes = 0; }
+        CK(cudaMalloc(&c->pin, need));
+        c->pin_bytes = need;
+    }
+    double* d_uvd = (double*)c->pin;
+    uint8_t* d_add = (uint8_t*)(d_uvd + 2 * (size_t)nb);
+    CK(cudaMemcpyAsync(d_uvd, uvd, sizeof(double) * 2 * nb, cudaMemcpyHostToDevice, c->stream));
+    if (add) CK(cudaMemcpyAsync(d_add, add, nb, cudaMemcpyHostToDevice, c->stream));
+    launch_add_features(c, b0, nb, d_uvd, add ? d_add : nullptr, std_pxl, initial_rho, std_rho);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
 }
 
 void* ekfslam_device_ptr(ekfslam_ctx* c, const char* name) {

@@ -94,5 +94,6 @@ void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gat
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
 void launch_ransac(ekfslam_ctx* c);
 void launch_update(ekfslam_ctx* c, int mask, int which_prior);
+void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv);
 void launch_add_features(ekfslam_ctx* c, int b0, int nb, const double* d_uvd, const uint8_t* d_add,
                          double std_pxl, double rho0, double std_rho);

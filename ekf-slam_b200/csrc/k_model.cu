@@ -440,3 +440,152 @@ void launch_symmetrize(ekfslam_ctx* c, int b0, int nb) {
     KScope ks(c, KT_SYMMETRIZE);
     k_symmetrize<<<grid, block, 0, c->stream>>>(c->v, b0);
 }
+
+// ---------------------------------------------------------------------------------------
+// Map management, SURVEY §8f rank 1: append one inverse-depth feature per filter from its distorted
+// pixel.  mc/add_features_inverse_depth.m:18-22 -> mc/hinv.m:3-26 (state) and
+// mc/add_a_feature_covariance_inverse_depth.m:3-64 (covariance augmentation):
+//   P <- [P, P(:,1:13) J'; J P(1:13,:), J Pxv J' + D],  J = dy_dxv (6x13), D = dy_dhd Padd dy_dhd'.
+// J is [I3 0 0; 0 dtheta_dq 0; 0 dphi_dq 0; 0 0 0], so a new row is a combination of P rows 0..6.
+// One block per filter; operates on (x_k_k, p_k_k).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_add_feature(DevView v, DevCam cam, int b0, const double* __restrict__ uvd,
+                                                     const uint8_t* __restrict__ add, double std_pxl, double rho0,
+                                                     double std_rho) {
+    const int lb = blockIdx.x;
+    const int b = b0 + lb;
+    if (add && !add[lb]) return;
+    const int n = v.nstate[b], nf = v.nfeat[b];
+    if (n + 6 > v.nmax || nf >= v.N) {
+        if (threadIdx.x == 0) atomicOr(&v.stats[b].status, 4);  // no room: reported, feature not added
+        return;
+    }
+    const int ld = v.ld;
+    double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    double* __restrict__ x = v.x + (size_t)b * ld;
+    __shared__ double dth_dq[4], dph_dq[4], D[6][6], newf[6];
+    if (threadIdx.x == 0) {
+        const double fku = cam.f / cam.dx, fkv = cam.f / cam.dy;  // cam.K(1,1), cam.K(2,2)
+        const double ud = uvd[2 * lb], vd = uvd[2 * lb + 1];
+        // mc/undistort_fm.m:18-27
+        const double xd = (ud - cam.Cx) * cam.dx, yd = (vd - cam.Cy) * cam.dy;
+        const double rd = sqrt(xd * xd + yd * yd);
+        const double Dd = 1.0 + cam.k1 * rd * rd + cam.k2 * rd * rd * rd * rd;
+        const double uu = xd * Dd / cam.dx + cam.Cx, vu = yd * Dd / cam.dy + cam.Cy;
+        const double hc[3] = {-(cam.Cx - uu) / fku, -(cam.Cy - vu) / fkv, 1.0};
+        double R[9];
+        q2r_dev(x + 3, R);
+        const double nx = R[0] * hc[0] + R[1] * hc[1] + R[2] * hc[2];
+        const double ny = R[3] * hc[0] + R[4] * hc[1] + R[5] * hc[2];
+        const double nz = R[6] * hc[0] + R[7] * hc[1] + R[8] * hc[2];
+        newf[0] = x[0]; newf[1] = x[1]; newf[2] = x[2];
+        newf[3] = atan2(nx, nz);
+        newf[4] = atan2(-ny, sqrt(nx * nx + nz * nz));
+        newf[5] = rho0;
+        // derivatives, mc/add_a_feature_covariance_inverse_depth.m:28-49
+        const double xz2 = nx * nx + nz * nz, n2 = xz2 + ny * ny, sxz = sqrt(xz2);
+        const double dth[3] = {nz / xz2, 0.0, -nx / xz2};
+        const double dph[3] = {(nx * ny) / (n2 * sxz), -sxz / n2, (nz * ny) / (n2 * sxz)};
+        const double q0 = x[3], qx = x[4], qy = x[5], qz = x[6];
+        // dgw_dqwr = dRq_times_a_by_dq(q, hc)  (3x4)
+        double T[12];
+        T[0] = 2 * q0 * hc[0] - 2 * qz * hc[1] + 2 * qy * hc[2];
+        T[4] = 2 * qz * hc[0] + 2 * q0 * hc[1] - 2 * qx * hc[2];
+        T[8] = -2 * qy * hc[0] + 2 * qx * hc[1] + 2 * q0 * hc[2];
+        T[1] = 2 * qx * hc[0] + 2 * qy * hc[1] + 2 * qz * hc[2];
+        T[5] = 2 * qy * hc[0] - 2 * qx * hc[1] - 2 * q0 * hc[2];
+        T[9] = 2 * qz * hc[0] + 2 * q0 * hc[1] - 2 * qx * hc[2];
+        T[2] = -2 * qy * hc[0] + 2 * qx * hc[1] + 2 * q0 * hc[2];
+        T[6] = 2 * qx * hc[0] + 2 * qy * hc[1] + 2 * qz * hc[2];
+        T[10] = -2 * q0 * hc[0] + 2 * qz * hc[1] - 2 * qy * hc[2];
+        T[3] = -2 * qz * hc[0] - 2 * q0 * hc[1] + 2 * qx * hc[2];
+        T[7] = 2 * q0 * hc[0] - 2 * qz * hc[1] + 2 * qy * hc[2];
+        T[11] = 2 * qx * hc[0] + 2 * qy * hc[1] + 2 * qz * hc[2];
+        for (int k = 0; k < 4; ++k) {
+            dth_dq[k] = dth[0] * T[k] + dth[1] * T[4 + k] + dth[2] * T[8 + k];
+            dph_dq[k] = dph[0] * T[k] + dph[1] * T[4 + k] + dph[2] * T[8 + k];
+        }
+        // dyprima_dhd (5x2) = dyprima_dgw * R * dgc_dhu * dhu_dhd ; rows 0..2 are zero
+        const double du = ud - cam.Cx, dv = vd - cam.Cy;
+        const double rd2 = xd * xd + yd * yd, rd4 = rd2 * rd2;
+        const double gg = 1.0 + cam.k1 * rd2 + cam.k2 * rd4, ee = cam.k1 + 2.0 * cam.k2 * rd2;
+        const double Ju[4] = {gg + du * ee * (2.0 * du * cam.dx * cam.dx), du * ee * (2.0 * dv * cam.dy * cam.dy),
+                              dv * ee * (2.0 * du * cam.dx * cam.dx), gg + dv * ee * (2.0 * dv * cam.dy * cam.dy)};
+        double RG[6];  // R * dgc_dhu = first two columns of R scaled by 1/fku, 1/fkv   (3x2)
+        for (int r = 0; r < 3; ++r) { RG[2 * r] = R[3 * r] / fku; RG[2 * r + 1] = R[3 * r + 1] / fkv; }
+        double A[4];   // rows theta, phi of dyprima_dgw * RG  (2x2)
+        A[0] = dth[0] * RG[0] + dth[1] * RG[2] + dth[2] * RG[4]; A[1] = dth[0] * RG[1] + dth[1] * RG[3] + dth[2] * RG[5];
+        A[2] = dph[0] * RG[0] + dph[1] * RG[2] + dph[2] * RG[4]; A[3] = dph[0] * RG[1] + dph[1] * RG[3] + dph[2] * RG[5];
+        double Bm[4];  // * dhu_dhd
+        Bm[0] = A[0] * Ju[0] + A[1] * Ju[2]; Bm[1] = A[0] * Ju[1] + A[1] * Ju[3];
+        Bm[2] = A[2] * Ju[0] + A[3] * Ju[2]; Bm[3] = A[2] * Ju[1] + A[3] * Ju[3];
+        // D = dy_dhd * diag(std_pxl^2, std_pxl^2, std_rho^2) * dy_dhd'
+        for (int r = 0; r < 6; ++r) for (int cc = 0; cc < 6; ++cc) D[r][cc] = 0.0;
+        const double sp = std_pxl * std_pxl;
+        D[3][3] = (Bm[0] * Bm[0] + Bm[1] * Bm[1]) * sp; D[3][4] = (Bm[0] * Bm[2] + Bm[1] * Bm[3]) * sp;
+        D[4][3] = D[3][4];                              D[4][4] = (Bm[2] * Bm[2] + Bm[3] * Bm[3]) * sp;
+        D[5][5] = std_rho * std_rho;
+    }
+    __syncthreads();
+    // new rows n..n+5 against the existing columns j < n (and their mirror images)
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double p0 = P[(size_t)0 * ld + j], p1 = P[(size_t)1 * ld + j], p2 = P[(size_t)2 * ld + j];
+        const double p3 = P[(size_t)3 * ld + j], p4 = P[(size_t)4 * ld + j], p5 = P[(size_t)5 * ld + j], p6 = P[(size_t)6 * ld + j];
+        double o[6];
+        o[0] = p0; o[1] = p1; o[2] = p2;
+        o[3] = dth_dq[0] * p3 + dth_dq[1] * p4 + dth_dq[2] * p5 + dth_dq[3] * p6;
+        o[4] = dph_dq[0] * p3 + dph_dq[1] * p4 + dph_dq[2] * p5 + dph_dq[3] * p6;
+        o[5] = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { P[(size_t)(n + r) * ld + j] = o[r]; P[(size_t)j * ld + n + r] = o[r]; }
+    }
+    __syncthreads();
+    // corner J Pxv J' + D: (J Pxv J')[r][c] = sum_j (J P)[r][j] J[c][j], with (J P)[r][j] = P[n+r][j] just written
+    if (threadIdx.x < 36) {
+        const int r = threadIdx.x / 6, cc = threadIdx.x % 6;
+        if (cc <= r) {
+            const double* row = P + (size_t)(n + r) * ld;
+            double s;
+            if (cc < 3) s = row[cc];
+            else if (cc == 3) s = row[3] * dth_dq[0] + row[4] * dth_dq[1] + row[5] * dth_dq[2] + row[6] * dth_dq[3];
+            else if (cc == 4) s = row[3] * dph_dq[0] + row[4] * dph_dq[1] + row[5] * dph_dq[2] + row[6] * dph_dq[3];
+            else s = 0.0;
+            s += D[r][cc];
+            P[(size_t)(n + r) * ld + n + cc] = s;
+            P[(size_t)(n + cc) * ld + n + r] = s;
+        }
+    }
+    if (threadIdx.x < 6) x[n + threadIdx.x] = newf[threadIdx.x];
+    if (threadIdx.x == 0) {
+        const size_t t = (size_t)b * v.N + nf;
+        v.ftype[t] = EKFSLAM_FEAT_INVERSEDEPTH;
+        v.foff[t] = n;
+        v.flags[t] = 0; v.mflags[t] = 0;
+        v.counters[2 * t] = 0; v.counters[2 * t + 1] = 0;
+        v.nstate[b] = n + 6;
+        v.nfeat[b] = nf + 1;
+    }
+}
+
+void launch_add_features(ekfslam_ctx* c, int b0, int nb, const double* d_uvd, const uint8_t* d_add, double std_pxl,
+                         double rho0, double std_rho) {
+    KScope ks(c, KT_ADD_FEATURES);
+    k_add_feature<<<nb, 128, 0, c->stream>>>(c->v, c->cam, b0, d_uvd, d_add, std_pxl, rho0, std_rho);
+}
+
+// ---------------------------------------------------------------------------------------
+// mc/initialize_x_and_p.m broadcast: every filter in [b0, b0+nb) becomes the 13-state camera-only
+// filter (xv, Pxv) with an empty map (the caller zeroed x and P beforehand).
+// ---------------------------------------------------------------------------------------
+__global__ void k_reset_filters(DevView v, int b0, const double* __restrict__ xv, const double* __restrict__ Pxv) {
+    const int b = b0 + blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < 169) v.P[(size_t)b * v.nmax * v.ld + (size_t)(t / 13) * v.ld + (t % 13)] = Pxv[t];
+    if (t < 13) v.x[(size_t)b * v.ld + t] = xv[t];
+    if (t == 0) { v.nstate[b] = 13; v.nfeat[b] = 0; }
+}
+
+void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv) {
+    KScope ks(c, KT_ADD_FEATURES);
+    k_reset_filters<<<nb, 192, 0, c->stream>>>(c->v, b0, d_xv, d_Pxv);
+}

@@ -87,7 +87,8 @@ typedef struct {
     int32_t max_support;   /* support of the winning hypothesis                        */
     int32_t n_li;          /* low-innovation inliers used in the first update          */
     int32_t n_hi;          /* high-innovation inliers used in the second update        */
-    int32_t status;        /* bit0: uniform stream exhausted; bit1: S not SPD          */
+    int32_t status;        /* bit0: uniform stream exhausted; bit1: S not SPD;
+                              bit2: add_features found no room (n_max / N_max)         */
     int32_t reserved;
 } ekfslam_stats;
 
@@ -203,10 +204,13 @@ int ekfslam_step_host(ekfslam_ctx* ctx, int match_mode, const double* zc, const 
                       ekfslam_stats* stats_out);
 
 /* ---- "next" rows: map management on the device ---------------- */
+/* mc/initialize_x_and_p.m:3-24 broadcast: filters [b0,b0+nb) become the camera-only filter with state
+ * xv [13] and covariance Pxv [13*13] and an EMPTY map (nstate = 13, nfeat = 0). */
+int ekfslam_reset_filters(ekfslam_ctx* ctx, int b0, int nb, const double* xv, const double* Pxv);
 /* mc/add_features_inverse_depth.m:18-22 -> mc/hinv.m:3-26 +
  * mc/add_a_feature_covariance_inverse_depth.m:3-64: append one inverse-depth feature per
- * filter from its distorted pixel uvd [nb][2] (add[b]==0 skips filter b). Operates on
- * (x_k_k,p_k_k). */
+ * filter from its distorted pixel uvd [nb][2] (add may be NULL = all; add[b]==0 skips filter b).
+ * Operates on (x_k_k,p_k_k); grows nstate by 6 and nfeat by 1. */
 int ekfslam_add_features(ekfslam_ctx* ctx, int b0, int nb, const double* uvd, const uint8_t* add,
                          double std_pxl, double initial_rho, double std_rho);
 

@@ -15,6 +15,9 @@
 #include <cstring>
 #include "model.cuh"
 
+int g_ekfslam_debug = 0;  // analysis knob, see k_downdate_ws
+extern "C" void ekfslam_debug_flag(int f) { g_ekfslam_debug = f; }
+
 #define NB 16
 
 // ---------------------------------------------------------------------------------------
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_pr
 // Blocked right-looking Cholesky S = L L' (lower, in place), X = inv(L), y <- X nu.
 // One block per filter, panels of NB columns.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_chol(DevView v) {
+__global__ void __launch_bounds__(128) k_chol(DevView v) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     const int k = 2 * v.ksel[b];
@@ -107,36 +110,55 @@ __global__ void __launch_bounds__(256) k_chol(DevView v) {
         const int nb = min(NB, k - j0);
         for (int e = tid; e < NB * NB; e += blockDim.x) {
             const int r = e / NB, c = e - r * NB;
-            D[r * (NB + 1) + c] = (r < nb && c <= r) ? S[(size_t)(j0 + r) * kmax + j0 + c] : 0.0;
+            // rows >= nb are padded with the identity so that the register factorisation below is benign
+            D[r * (NB + 1) + c] = (r < nb && c <= r) ? S[(size_t)(j0 + r) * kmax + j0 + c] : ((r >= nb && r == c) ? 1.0 : 0.0);
             Di[r * (NB + 1) + c] = 0.0;
         }
         __syncthreads();
         if (warp == 0) {
-            // unblocked Cholesky of the nb x nb block, lane = row
-            for (int c = 0; c < nb; ++c) {
-                if (lane == c) {
-                    const double d = D[c * (NB + 1) + c];
-                    if (!(d > 0.0)) s_bad = 1;
-                    D[c * (NB + 1) + c] = sqrt(d);
+            // Cholesky of the NB x NB diagonal block in registers: lane i holds row i (lanes 16-31 mirror
+            // lanes 0-15 so that every shuffle is full-warp); column c is broadcast by shuffles.
+            const unsigned full_mask = 0xffffffffu;
+            const int i = lane & (NB - 1);
+            double a[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) a[c] = D[i * (NB + 1) + c];
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                const double piv = __shfl_sync(full_mask, a[c], c);
+                bad = bad || !(piv > 0.0);
+                const double d = sqrt(piv);
+                const double lic = (i == c) ? d : a[c] / d;  // rows above the diagonal carry don't-care values
+                a[c] = lic;
+#pragma unroll
+                for (int j = c + 1; j < NB; ++j) {
+                    const double ljc = __shfl_sync(full_mask, lic, j);
+                    a[j] -= lic * ljc;
                 }
-                __syncwarp();
-                const double dc = D[c * (NB + 1) + c];
-                if (lane > c && lane < nb) D[lane * (NB + 1) + c] /= dc;
-                __syncwarp();
-                if (lane > c && lane < nb) {
-                    const double lic = D[lane * (NB + 1) + c];
-                    for (int j = c + 1; j <= lane; ++j) D[lane * (NB + 1) + j] -= lic * D[j * (NB + 1) + c];
-                }
-                __syncwarp();
             }
-            // inverse of the triangular block, lane = column
-            if (lane < nb) {
-                const int c = lane;
-                Di[c * (NB + 1) + c] = 1.0 / D[c * (NB + 1) + c];
-                for (int i = c + 1; i < nb; ++i) {
-                    double s = 0.0;
-                    for (int t = c; t < i; ++t) s += D[i * (NB + 1) + t] * Di[t * (NB + 1) + c];
-                    Di[i * (NB + 1) + c] = -s / D[i * (NB + 1) + i];
+            if (bad && lane == 0) s_bad = 1;
+            if (lane < NB) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) D[i * (NB + 1) + c] = (c <= i) ? a[c] : 0.0;
+            }
+            __syncwarp();
+            // inverse of the triangular block: lane c solves column c by forward substitution; every lane
+            // reads the same L entry at the same time (shared-memory broadcast)
+            {
+                const int c = i;
+                double x[NB];
+#pragma unroll
+                for (int ii = 0; ii < NB; ++ii) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < ii; ++t) sacc += D[ii * (NB + 1) + t] * x[t];
+                    const double lii = D[ii * (NB + 1) + ii];
+                    x[ii] = (ii == c) ? 1.0 / lii : ((ii > c) ? -sacc / lii : 0.0);
+                }
+                if (lane < NB) {
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii) Di[ii * (NB + 1) + c] = x[ii];
                 }
             }
         }
@@ -901,7 +923,7 @@ __global__ void __launch_bounds__(256, 2) k_downdate_p(DevView v, const double* 
 //   full[s]  : 32 producer-lane arrivals + the bytes of the stage (complete_tx)
 //   empty[s] : 8 consumer-warp arrivals
 // ---------------------------------------------------------------------------------------
-#define WS_STAGES 4
+#define WS_STAGES 3
 #define WS_CONSUMERS 8
 #define WS_THREADS ((WS_CONSUMERS + 1) * 32)
 
@@ -931,15 +953,20 @@ __device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gmem_sr
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// dbg (analysis only, set through ekfslam_debug_flag): 1 = producer arrives without copying (consumer-side
+// ceiling), 2 = consumers skip the DMMAs (producer / async-copy ceiling), 4 = consumers skip the stores
 __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const double* __restrict__ jn_all, int T,
-                                                               long long total, int M) {
+                                                               long long total, int M, int dbg) {
     extern __shared__ __align__(16) double dsm[];
     double* As = dsm;                                   // [WS_STAGES][TK][TPAD]
     double* Bs = dsm + WS_STAGES * TK * TPAD;           // [WS_STAGES][TK][TPAD]
-    double* strip = Bs + WS_STAGES * TK * TPAD;         // [64][9]
+    double* Pt = Bs + WS_STAGES * TK * TPAD;            // [64][TPAD] the P tile of the current compute tile
+    double* strip = Pt + TM * TPAD;                     // [64][9]
     unsigned long long* full = reinterpret_cast<unsigned long long*>(strip + TM * 9);   // [WS_STAGES]
     unsigned long long* empty = full + WS_STAGES;                                        // [WS_STAGES]
-    int2* meta = reinterpret_cast<int2*>(empty + WS_STAGES);                             // [M]
+    unsigned long long* pfull = empty + WS_STAGES;                                       // P tile landed
+    unsigned long long* pempty = pfull + 1;                                              // P tile consumed
+    int2* meta = reinterpret_cast<int2*>(pempty + 1);                                    // [M]
     unsigned* lut = reinterpret_cast<unsigned*>(meta + M);                               // [T]
     const int ld = v.ld, kmax = v.kmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -958,6 +985,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
     }
     if (tid == 0) {
         for (int s2 = 0; s2 < WS_STAGES; ++s2) { mbar_init(full + s2, 32); mbar_init(empty + s2, WS_CONSUMERS); }
+        mbar_init(pfull, 32);
+        mbar_init(pempty, WS_CONSUMERS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -966,13 +995,21 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
 
     if (warp == WS_CONSUMERS) {
         // ================= producer warp =================
-        unsigned cnt = 0;
+        unsigned cnt = 0, pcnt = 0;
         const int pr = lane & 15;        // row of the [TK][64] panel this lane copies
         const bool isB = lane >= 16;     // lanes 0-15: A panel (rows of W at i0), 16-31: B panel (at j0)
         for (int m = 0; m < Mreal; ++m) {
             const DTile L = decode_tile(meta, lut, m, Mreal, blockIdx.x + (long long)m * G, T);
             if (L.nk == 0) continue;
             const double* __restrict__ W = v.W + (size_t)L.b * kmax * ld;
+            const double* __restrict__ Pg = v.P + (size_t)L.b * v.nmax * ld;
+            // The P tile (64 rows x 512 B) goes through the same async engine.  The single buffer is free
+            // once the consumers finished the previous tile's epilogue; that is guaranteed by the time the
+            // ring lets the producer issue stage WS_STAGES of this tile, so issue it there (or with the last
+            // stage of a short tile) and never block the W stream on it.
+            const int p_at = min(L.nk - 1, WS_STAGES);
+            const unsigned pbytes = (unsigned)(min(TM, ld - L.j0) * 8);
+            const int prow_n = min(TM, L.n - L.i0);   // rows of the tile that exist
             const int c0 = isB ? L.j0 : L.i0;
             const unsigned rowbytes = (unsigned)(min(TM, ld - c0) * 8);
             const unsigned bytesA = (unsigned)(min(TM, ld - L.i0) * 8), bytesB = (unsigned)(min(TM, ld - L.j0) * 8);
@@ -983,9 +1020,9 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
                 const int nvalid = min(TK, L.k - t0);
                 double* dst = (isB ? Bs : As) + slot * TK * TPAD + pr * TPAD;
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(full + slot, (unsigned)nvalid * (bytesA + (L.diag ? 0u : bytesB)));
+                    mbar_arrive_expect_tx(full + slot, (dbg & 1) ? 0u : (unsigned)nvalid * (bytesA + (L.diag ? 0u : bytesB)));
                 }
-                const bool mine = !(isB && L.diag);
+                const bool mine = !(isB && L.diag) && !(dbg & 1);
                 if (mine && pr < nvalid) {
                     bulk_g2s(dst, W + (size_t)(t0 + pr) * ld + c0, rowbytes, full + slot);
                 } else if (mine && pr < ((nvalid + 3) & ~3)) {
@@ -993,6 +1030,17 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
                     for (int c = 0; c < TM; ++c) dst[c] = 0.0;
                 }
                 if (lane != 0) mbar_arrive(full + slot);
+                if (st == p_at) {
+                    mbar_wait(pempty, (pcnt & 1u) ^ 1u);
+                    if (lane == 0) mbar_arrive_expect_tx(pfull, (dbg & 1) ? 0u : (unsigned)prow_n * pbytes);
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int r = lane + 32 * h2;
+                        if (r < prow_n && !(dbg & 1)) bulk_g2s(Pt + r * TPAD, Pg + (size_t)(L.i0 + r) * ld + L.j0, pbytes, pfull);
+                    }
+                    if (lane != 0) mbar_arrive(pfull);
+                    ++pcnt;
+                }
             }
         }
         return;
@@ -1000,25 +1048,13 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
 
     // ================= consumer warps =================
     const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
-    unsigned cnt = 0;
+    unsigned cnt = 0, pcnt = 0;
     for (int cm = 0; cm < Mreal; ++cm) {
         const DTile C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T);
         if (C.nk == 0) continue;
         const int n = C.n, k = C.k, i0 = C.i0, j0 = C.j0;
         const bool diag = C.diag;
         double* __restrict__ P = v.P + (size_t)C.b * v.nmax * ld;
-        double pf[4][2][2];
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-            const int gi = i0 + wr * 32 + mt * 8 + g;
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
-                double2 val = make_double2(0.0, 0.0);
-                if (gi < n && gj < ld) val = *reinterpret_cast<const double2*>(P + (size_t)gi * ld + gj);
-                pf[mt][nt][0] = val.x; pf[mt][nt][1] = val.y;
-            }
-        }
         unsigned onmask = 0;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
@@ -1039,7 +1075,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
             mbar_wait(full + slot, ph);
             const double* as = As + slot * TK * TPAD;
             const double* bs = diag ? as : Bs + slot * TK * TPAD;
-            if (onmask != 0) {
+            if (onmask != 0 && !(dbg & 2)) {
                 const int k4n = min(TK / 4, (k - it * TK + 3) >> 2);
 #pragma unroll
                 for (int k4 = 0; k4 < TK / 4; ++k4) {
@@ -1059,16 +1095,20 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + slot);
         }
-        // ---- epilogue (same as k_downdate_p)
+        // ---- epilogue: the P tile arrives through shared memory (bulk copies issued by the producer)
+        mbar_wait(pfull, pcnt & 1u);
+        ++pcnt;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
             const int gi = i0 + wr * 32 + mt * 8 + g;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                if (!(onmask & (1u << (mt * 2 + nt)))) continue;
+                if (!(onmask & (1u << (mt * 2 + nt))) || (dbg & 4)) continue;
                 const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
-                const double c0 = pf[mt][nt][0] - acc[mt][nt][0];
-                const double c1 = pf[mt][nt][1] - acc[mt][nt][1];
+                double2 pv = make_double2(0.0, 0.0);
+                if (gi < n && gj < ld) pv = *reinterpret_cast<const double2*>(Pt + (wr * 32 + mt * 8 + g) * TPAD + wc * 16 + nt * 8 + 2 * q);
+                const double c0 = pv.x - acc[mt][nt][0];
+                const double c1 = pv.y - acc[mt][nt][1];
                 if (C.col0 && wc == 0 && nt == 0) {
                     strip[(wr * 32 + mt * 8 + g) * 9 + 2 * q] = c0;
                     strip[(wr * 32 + mt * 8 + g) * 9 + 2 * q + 1] = c1;
@@ -1096,6 +1136,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
                 }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pempty);
         if (C.col0) {
             asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 consumer warps only
             const double* __restrict__ Jn = jn_all + (size_t)C.b * 16;
@@ -1149,7 +1191,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior) {
         cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_sm);
         chol_cfg = chol_sm;
     }
-    { KScope ks(c, KT_CHOL); k_chol<<<v.B, 256, chol_sm, st>>>(v); }
+    { KScope ks(c, KT_CHOL); k_chol<<<v.B, 128, chol_sm, st>>>(v); }
     dim3 gw((v.nmax + TM - 1) / TM, (v.kmax + TM - 1) / TM, v.B);
     const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax);
     const size_t dd_sm = sizeof(double) * (size_t)max(2 * NSTAGE * TK * TPAD, TM * (TM + 1));
@@ -1176,14 +1218,14 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior) {
         const long long total = (long long)T * v.B;
         const long long ctas = total < (long long)sms * 2 ? total : (long long)sms * 2;
         const int M = (int)((total + ctas - 1) / ctas);
-        const size_t ws_sm = sizeof(double) * (2 * WS_STAGES * TK * TPAD + TM * 9) + sizeof(unsigned long long) * 2 * WS_STAGES +
+        const size_t ws_sm = sizeof(double) * (2 * WS_STAGES * TK * TPAD + TM * TPAD + TM * 9) + sizeof(unsigned long long) * (2 * WS_STAGES + 2) +
                              sizeof(int2) * M + sizeof(unsigned) * T;
         static size_t ws_cfg = 0;
         if (ws_sm > ws_cfg) {
             cudaFuncSetAttribute(k_downdate_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_sm);
             ws_cfg = ws_sm;
         }
-        k_downdate_ws<<<(unsigned)ctas, WS_THREADS, ws_sm, st>>>(v, v.jn, T, total, M);
+        k_downdate_ws<<<(unsigned)ctas, WS_THREADS, ws_sm, st>>>(v, v.jn, T, total, M, g_ekfslam_debug);
     } else {
         const long long total = (long long)T * v.B;
         const long long ctas = total < (long long)sms * 2 ? total : (long long)sms * 2;

@@ -137,3 +137,9 @@ def test_no_matches_is_passthrough(ekf):
         assert T.rel_err(xg[b], f.x_k_km1) < 1e-12
         assert T.rel_err(Pg[b], f.p_k_km1) < 1e-12
     bank.close()
+
+
+def test_large_map_n500(ekf):
+    """BASELINE config 4 shape: N=500 features (n=3013), dense covariance update on the DMMA path."""
+    worst, tot = _run_sequence(ekf, B=1, N=500, frames=2, seed=700, n_u=64)
+    assert tot["li"] > 200

@@ -66,6 +66,20 @@ def algorithmic_work(n, N, m, hyps, k_li, k_hi):
     return nbytes, flops
 
 
+def read_traffic(kernel_prefix):
+    """dram__bytes_read+write per launch of a kernel from the committed ncu capture of this shape."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        rows = [x for k, v in d["kernels"].items() if k.startswith(kernel_prefix) for x in v]
+        if rows:
+            return sum(x["dram_read"] + x["dram_write"] for x in rows) / len(rows)
+    except Exception:
+        pass
+    return None
+
+
 def read_peaks():
     peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "fp64_tflops": 37.0,
              "fp64_src": "nominal (no measurement found)"}
@@ -349,6 +363,9 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": dd_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": dd_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": "hbm " + peaks["hbm_src"]}
+        if B == 4096 and N == 100:
+            roof["traffic"] = read_traffic("k_downdate")
+            roof["traffic_source"] = "profiles/ncu_traffic_r1.json (ncu --set full at this shape, mean of the li and hi launches)"
         roof.update({"kernel": "k_downdate", "kernel_share_of_step": dd_ms / tot_k_ms if tot_k_ms else None,
                      "kernel_ms_per_launch": dd_ms / dd_cnt if dd_cnt else None, "launches_timed": dd_cnt,
                      "algorithmic_flops_per_launch": dd_flops_per_step / 2.0,

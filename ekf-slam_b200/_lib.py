@@ -82,6 +82,7 @@ _SIGS = {
     "ekfslam_rescue": (_I, [_P]),
     "ekfslam_update_hi": (_I, [_P]),
     "ekfslam_update_masked": (_I, [_P, _I, _I]),
+    "ekfslam_update_iterated": (_I, [_P, _I, _I, _I]),
     "ekfslam_step": (_I, [_P, _I, _I]),
     "ekfslam_step_host": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "ekfslam_reset_filters": (_I, [_P, _I, _I, _P, _P]),

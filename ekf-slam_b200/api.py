@@ -289,6 +289,22 @@ def ekf_update_hi_inliers(f, features_info):
     return _update(f, features_info, L.F_HI, 0)
 
 
+def ekf_update_iterated(f, features_info, cam, flag="low_innovation_inlier", n_iter=3):
+    """mc/ekf_update_iterated.m names an ``update_iterated`` that the reference never ships; this is the
+    standard iterated EKF over the features whose ``flag`` field is 1 (EXTENSION — no reference
+    semantics exist).  Prior: (x_k_km1, p_k_km1) for the li flag, (x_k_k, p_k_k) otherwise."""
+    mask = {"low_innovation_inlier": L.F_LI, "high_innovation_inlier": L.F_HI}[flag]
+    which_prior = 1 if mask == L.F_LI else 0
+    x = f.x_k_km1 if which_prior else f.x_k_k
+    P = f.p_k_km1 if which_prior else f.p_k_k
+    bank, n = _setup(features_info, x, P, which=which_prior, f=f, cam=cam)
+    _push_features(bank, features_info)
+    bank.update_iterated(mask, which_prior, n_iter)
+    xs, Ps, _ = bank.download_state(which=0)
+    f.x_k_k, f.p_k_k = xs[0], Ps[0]
+    return f
+
+
 def update_features_info(features_info):
     """mc/update_features_info.m:1-18 (host-side bookkeeping of the struct array)."""
     for fi in features_info:

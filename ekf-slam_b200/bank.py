@@ -266,6 +266,10 @@ class FilterBank:
     def update_masked(self, mask, which_prior):
         L.check(self.lib.ekfslam_update_masked(self._h, mask, which_prior))
 
+    def update_iterated(self, mask, which_prior=1, n_iter=3):
+        """Iterated EKF update (extension; see ekfslam_update_iterated)."""
+        L.check(self.lib.ekfslam_update_iterated(self._h, mask, which_prior, n_iter))
+
     def step(self, reset=True, match_mode=1):
         """One filter step on resident data (mc/mono_slam.m:56-74)."""
         L.check(self.lib.ekfslam_step(self._h, 1 if reset else 0, match_mode))

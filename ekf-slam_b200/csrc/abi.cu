@@ -616,6 +616,24 @@ int ekfslam_update_masked(ekfslam_ctx* c, int mask, int which_prior) {
 
 int ekfslam_update_li(ekfslam_ctx* c) { return ekfslam_update_masked(c, EKFSLAM_F_LI, 1); }
 
+int ekfslam_update_iterated(ekfslam_ctx* c, int mask, int which_prior, int n_iter) {
+    NEED_CTX(c);
+    if (!(mask & 0xff)) return fail(EKFSLAM_ERR_INVALID, "empty mask");
+    if (n_iter < 1 || n_iter > 64) return fail(EKFSLAM_ERR_INVALID, "n_iter must be in [1, 64]");
+    DevView& v = c->v;
+    const size_t xbytes = sizeof(double) * (size_t)v.B * v.ld;
+    // the prior lives in xp; the running iterate x_j in x (x_0 = prior)
+    if (which_prior) CK(cudaMemcpyAsync(v.x, v.xp, xbytes, cudaMemcpyDeviceToDevice, c->stream));
+    else CK(cudaMemcpyAsync(v.xp, v.x, xbytes, cudaMemcpyDeviceToDevice, c->stream));
+    for (int j = 0; j < n_iter; ++j) {
+        launch_features(c, 0, 3);         // h(x_j), H_j for every feature (stale-h rule as in the reference)
+        launch_hp(c, mask & 0xff, 0);     // G = H_j P^-  (P is untouched until the last iteration)
+        launch_update(c, mask, 1, 1 | (j + 1 < n_iter ? 2 : 0));
+    }
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
 int ekfslam_rescue(ekfslam_ctx* c) {
     NEED_CTX(c);
     launch_features(c, 0, 3);                            // h, H of ALL features at x_k_k (:6-7)

@@ -93,7 +93,8 @@ void launch_hp(ekfslam_ctx* c, int need, int forbid);  // G rows for features wi
 void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gate / explicit matches / rescue gate
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
 void launch_ransac(ekfslam_ctx* c);
-void launch_update(ekfslam_ctx* c, int mask, int which_prior);
+void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags = 0);
+bool launch_downdate128(ekfslam_ctx* c, int sms);
 void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv);
 void launch_add_features(ekfslam_ctx* c, int b0, int nb, const double* d_uvd, const uint8_t* d_add,
                          double std_pxl, double rho0, double std_rho);

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "model.cuh"
+#include "tc_common.cuh"
 
 int g_ekfslam_debug = 0;  // analysis knob, see k_downdate_ws
 extern "C" void ekfslam_debug_flag(int f) { g_ekfslam_debug = f; }
@@ -23,7 +24,7 @@ extern "C" void ekfslam_debug_flag(int f) { g_ekfslam_debug = f; }
 // ---------------------------------------------------------------------------------------
 // select + S + nu.  One block per filter.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_prior) {
+__global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_prior, int iter_nu) {
     const int b = blockIdx.x;
     const int N = v.N, ld = v.ld, kmax = v.kmax;
     const int nf = v.nfeat[b];
@@ -42,6 +43,28 @@ __global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_pr
     __syncthreads();
     const int ns = s_k;
     const int k = 2 * ns;
+    // innovation nu = z - h; for an iterated update (x holds the current iterate x_j, xp the prior x^-)
+    // nu_j = z - h(x_j) - H_j (x^- - x_j).  Computed before x is reset to the prior below.
+    {
+        double* __restrict__ yv0 = v.yv + (size_t)b * kmax;
+        const double* __restrict__ xj = v.x + (size_t)b * ld;
+        const double* __restrict__ x0 = v.xp + (size_t)b * ld;
+        for (int a = tid; a < k; a += blockDim.x) {
+            const size_t t = (size_t)b * N + sel[a >> 1];
+            double nu = v.z[2 * t + (a & 1)] - v.h[2 * t + (a & 1)];
+            if (iter_nu) {
+                const double* __restrict__ H = v.Hc + t * EKF_HSTRIDE + (a & 1) * EKF_HC;
+                const int off = v.foff[t];
+                const int w = (v.ftype[t] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+                double s = 0.0;
+                for (int c = 0; c < 7; ++c) s += H[c] * (x0[c] - xj[c]);
+                for (int c = 0; c < w; ++c) s += H[7 + c] * (x0[off + c] - xj[off + c]);
+                nu -= s;
+            }
+            yv0[a] = nu;
+        }
+    }
+    __syncthreads();
     if (which_prior == 1) {  // x_k_k starts from x_k_km1 (also the pass-through of mc/update.m:28)
         const int n = v.nstate[b];
         for (int j = tid; j < n; j += blockDim.x) v.x[(size_t)b * ld + j] = v.xp[(size_t)b * ld + j];
@@ -79,11 +102,6 @@ __global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_pr
         S[(size_t)(2 * fa) * kmax + 2 * fb + 1] = s01;      // (for fa == fb this upper entry is never read)
         S[(size_t)(2 * fa + 1) * kmax + 2 * fb] = s10;
         S[(size_t)(2 * fa + 1) * kmax + 2 * fb + 1] = s11;
-    }
-    double* __restrict__ yv = v.yv + (size_t)b * kmax;
-    for (int a = tid; a < k; a += blockDim.x) {
-        const size_t t = (size_t)b * N + sel[a >> 1];
-        yv[a] = v.z[2 * t + (a & 1)] - v.h[2 * t + (a & 1)];
     }
 }
 
@@ -289,34 +307,10 @@ __global__ void __launch_bounds__(128) k_chol(DevView v) {
 }
 
 // ---------------------------------------------------------------------------------------
-// fp64 tensor-core building blocks.  mma.sync m8n8k4 f64 (SASS DMMA.8x8x4) fragment layout, lane
-// l, g = l>>2, q = l&3:  A[g][q],  B[q][g],  C[g][2q], C[g][2q+1].
-// Both GEMMs below use 64x64 block tiles, 8 warps in a 2x4 grid, 32x16 per warp (4x2 DMMA tiles),
-// K panels of 16 staged through a 3-deep cp.async (LDGSTS) ring.
-// ---------------------------------------------------------------------------------------
-#define TM 64
-#define TK 16
-#define TPAD 68    // row stride (doubles) of a K-major panel [TK][64]: stride % 16 == 4 -> conflict-free frags
-#define APAD 20    // row stride of a row-major A panel [64][TK]: same property
-#define NSTAGE 3
-
-__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-}
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src, int src_bytes) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// ---------------------------------------------------------------------------------------
 // W = X * G_sel  (X = inv(L) lower triangular k x k with an explicitly zeroed upper triangle,
 // G_sel = the selected rows of G, k x n).  grid = (column tiles, row tiles, B).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) k_w(DevView v) {
+__global__ void __launch_bounds__(256, 3) k_w(DevView v, int finalize) {
     extern __shared__ __align__(16) double dsm[];
     const int b = blockIdx.z;
     const int k = 2 * v.ksel[b];
@@ -428,7 +422,7 @@ __global__ void __launch_bounds__(256, 3) k_w(DevView v) {
     if (xrole) {
         double* __restrict__ x = v.x + (size_t)b * ld;
         if (tid < TM && c0 + tid < n) x[c0 + tid] += xacc;
-        if (c0 == 0) {
+        if (c0 == 0 && finalize) {
             // this block owns state entries 0..63: normJac(q+) (mc/normJac.m) from the un-normalised
             // quaternion, then q+ <- q+/|q+|  (mc/update.m:18,24)
             __syncthreads();
@@ -676,28 +670,6 @@ __global__ void __launch_bounds__(256, DD_MINBLOCKS) k_downdate(DevView v, const
 // neighbours.  Same arithmetic, same summation order per output element as k_downdate.
 // grid = (CTAs, 1); tile t -> filter t / T, lower-triangle tile t % T (T = nt(nt+1)/2).
 // ---------------------------------------------------------------------------------------
-struct DTile {
-    int b, i0, j0, k, n, nk;
-    bool diag, col0;
-};
-
-// tile m of this CTA (global tile t = blockIdx.x + m*G): metadata comes from shared memory
-// (meta[m] = {k, n} of the tile's filter, lut[e] = ti<<16|tj), never from a dependent global load
-__device__ __forceinline__ DTile decode_tile(const int2* meta, const unsigned* lut, int m, int M, long long t, int T) {
-    DTile d;
-    d.nk = 0; d.b = 0; d.i0 = 0; d.j0 = 0; d.k = 0; d.n = 0; d.diag = false; d.col0 = false;
-    if (m >= M) return d;
-    d.b = (int)(t / T);
-    const unsigned e = lut[(int)(t - (long long)d.b * T)];
-    const int ti = (int)(e >> 16), tj = (int)(e & 0xffffu);
-    d.i0 = ti * TM; d.j0 = tj * TM;
-    d.diag = (ti == tj); d.col0 = (tj == 0);
-    const int2 kn = meta[m];
-    d.k = kn.x; d.n = kn.y;
-    d.nk = (d.i0 < d.n) ? (d.k + TK - 1) / TK : 0;
-    return d;
-}
-
 __global__ void __launch_bounds__(256, 2) k_downdate_p(DevView v, const double* __restrict__ jn_all, int T,
                                                        long long total, int M) {
     extern __shared__ __align__(16) double dsm[];
@@ -923,50 +895,19 @@ __global__ void __launch_bounds__(256, 2) k_downdate_p(DevView v, const double* 
 //   full[s]  : 32 producer-lane arrivals + the bytes of the stage (complete_tx)
 //   empty[s] : 8 consumer-warp arrivals
 // ---------------------------------------------------------------------------------------
-#define WS_STAGES 3
+#define WS_STAGES 4
 #define WS_CONSUMERS 8
 #define WS_THREADS ((WS_CONSUMERS + 1) * 32)
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gmem_src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// dbg (analysis only, set through ekfslam_debug_flag): 1 = producer arrives without copying (consumer-side
-// ceiling), 2 = consumers skip the DMMAs (producer / async-copy ceiling), 4 = consumers skip the stores
 __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const double* __restrict__ jn_all, int T,
-                                                               long long total, int M, int dbg) {
+                                                               long long total, int M) {
     extern __shared__ __align__(16) double dsm[];
     double* As = dsm;                                   // [WS_STAGES][TK][TPAD]
     double* Bs = dsm + WS_STAGES * TK * TPAD;           // [WS_STAGES][TK][TPAD]
-    double* Pt = Bs + WS_STAGES * TK * TPAD;            // [64][TPAD] the P tile of the current compute tile
-    double* strip = Pt + TM * TPAD;                     // [64][9]
+    double* strip = Bs + WS_STAGES * TK * TPAD;         // [64][9]
     unsigned long long* full = reinterpret_cast<unsigned long long*>(strip + TM * 9);   // [WS_STAGES]
     unsigned long long* empty = full + WS_STAGES;                                        // [WS_STAGES]
-    unsigned long long* pfull = empty + WS_STAGES;                                       // P tile landed
-    unsigned long long* pempty = pfull + 1;                                              // P tile consumed
-    int2* meta = reinterpret_cast<int2*>(pempty + 1);                                    // [M]
+    int2* meta = reinterpret_cast<int2*>(empty + WS_STAGES);                             // [M]
     unsigned* lut = reinterpret_cast<unsigned*>(meta + M);                               // [T]
     const int ld = v.ld, kmax = v.kmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -985,8 +926,6 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
     }
     if (tid == 0) {
         for (int s2 = 0; s2 < WS_STAGES; ++s2) { mbar_init(full + s2, 32); mbar_init(empty + s2, WS_CONSUMERS); }
-        mbar_init(pfull, 32);
-        mbar_init(pempty, WS_CONSUMERS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -995,21 +934,13 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
 
     if (warp == WS_CONSUMERS) {
         // ================= producer warp =================
-        unsigned cnt = 0, pcnt = 0;
+        unsigned cnt = 0;
         const int pr = lane & 15;        // row of the [TK][64] panel this lane copies
         const bool isB = lane >= 16;     // lanes 0-15: A panel (rows of W at i0), 16-31: B panel (at j0)
         for (int m = 0; m < Mreal; ++m) {
             const DTile L = decode_tile(meta, lut, m, Mreal, blockIdx.x + (long long)m * G, T);
             if (L.nk == 0) continue;
             const double* __restrict__ W = v.W + (size_t)L.b * kmax * ld;
-            const double* __restrict__ Pg = v.P + (size_t)L.b * v.nmax * ld;
-            // The P tile (64 rows x 512 B) goes through the same async engine.  The single buffer is free
-            // once the consumers finished the previous tile's epilogue; that is guaranteed by the time the
-            // ring lets the producer issue stage WS_STAGES of this tile, so issue it there (or with the last
-            // stage of a short tile) and never block the W stream on it.
-            const int p_at = min(L.nk - 1, WS_STAGES);
-            const unsigned pbytes = (unsigned)(min(TM, ld - L.j0) * 8);
-            const int prow_n = min(TM, L.n - L.i0);   // rows of the tile that exist
             const int c0 = isB ? L.j0 : L.i0;
             const unsigned rowbytes = (unsigned)(min(TM, ld - c0) * 8);
             const unsigned bytesA = (unsigned)(min(TM, ld - L.i0) * 8), bytesB = (unsigned)(min(TM, ld - L.j0) * 8);
@@ -1020,9 +951,9 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
                 const int nvalid = min(TK, L.k - t0);
                 double* dst = (isB ? Bs : As) + slot * TK * TPAD + pr * TPAD;
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(full + slot, (dbg & 1) ? 0u : (unsigned)nvalid * (bytesA + (L.diag ? 0u : bytesB)));
+                    mbar_arrive_expect_tx(full + slot, (unsigned)nvalid * (bytesA + (L.diag ? 0u : bytesB)));
                 }
-                const bool mine = !(isB && L.diag) && !(dbg & 1);
+                const bool mine = !(isB && L.diag);
                 if (mine && pr < nvalid) {
                     bulk_g2s(dst, W + (size_t)(t0 + pr) * ld + c0, rowbytes, full + slot);
                 } else if (mine && pr < ((nvalid + 3) & ~3)) {
@@ -1030,17 +961,6 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
                     for (int c = 0; c < TM; ++c) dst[c] = 0.0;
                 }
                 if (lane != 0) mbar_arrive(full + slot);
-                if (st == p_at) {
-                    mbar_wait(pempty, (pcnt & 1u) ^ 1u);
-                    if (lane == 0) mbar_arrive_expect_tx(pfull, (dbg & 1) ? 0u : (unsigned)prow_n * pbytes);
-#pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        const int r = lane + 32 * h2;
-                        if (r < prow_n && !(dbg & 1)) bulk_g2s(Pt + r * TPAD, Pg + (size_t)(L.i0 + r) * ld + L.j0, pbytes, pfull);
-                    }
-                    if (lane != 0) mbar_arrive(pfull);
-                    ++pcnt;
-                }
             }
         }
         return;
@@ -1048,13 +968,25 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
 
     // ================= consumer warps =================
     const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
-    unsigned cnt = 0, pcnt = 0;
+    unsigned cnt = 0;
     for (int cm = 0; cm < Mreal; ++cm) {
         const DTile C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T);
         if (C.nk == 0) continue;
         const int n = C.n, k = C.k, i0 = C.i0, j0 = C.j0;
         const bool diag = C.diag;
         double* __restrict__ P = v.P + (size_t)C.b * v.nmax * ld;
+        double pf[4][2][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int gi = i0 + wr * 32 + mt * 8 + g;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
+                double2 val = make_double2(0.0, 0.0);
+                if (gi < n && gj < ld) val = *reinterpret_cast<const double2*>(P + (size_t)gi * ld + gj);
+                pf[mt][nt][0] = val.x; pf[mt][nt][1] = val.y;
+            }
+        }
         unsigned onmask = 0;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
@@ -1075,7 +1007,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
             mbar_wait(full + slot, ph);
             const double* as = As + slot * TK * TPAD;
             const double* bs = diag ? as : Bs + slot * TK * TPAD;
-            if (onmask != 0 && !(dbg & 2)) {
+            if (onmask != 0) {
                 const int k4n = min(TK / 4, (k - it * TK + 3) >> 2);
 #pragma unroll
                 for (int k4 = 0; k4 < TK / 4; ++k4) {
@@ -1095,20 +1027,16 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + slot);
         }
-        // ---- epilogue: the P tile arrives through shared memory (bulk copies issued by the producer)
-        mbar_wait(pfull, pcnt & 1u);
-        ++pcnt;
+        // ---- epilogue (same as k_downdate_p)
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
             const int gi = i0 + wr * 32 + mt * 8 + g;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                if (!(onmask & (1u << (mt * 2 + nt))) || (dbg & 4)) continue;
+                if (!(onmask & (1u << (mt * 2 + nt)))) continue;
                 const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
-                double2 pv = make_double2(0.0, 0.0);
-                if (gi < n && gj < ld) pv = *reinterpret_cast<const double2*>(Pt + (wr * 32 + mt * 8 + g) * TPAD + wc * 16 + nt * 8 + 2 * q);
-                const double c0 = pv.x - acc[mt][nt][0];
-                const double c1 = pv.y - acc[mt][nt][1];
+                const double c0 = pf[mt][nt][0] - acc[mt][nt][0];
+                const double c1 = pf[mt][nt][1] - acc[mt][nt][1];
                 if (C.col0 && wc == 0 && nt == 0) {
                     strip[(wr * 32 + mt * 8 + g) * 9 + 2 * q] = c0;
                     strip[(wr * 32 + mt * 8 + g) * 9 + 2 * q + 1] = c1;
@@ -1136,8 +1064,6 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pempty);
         if (C.col0) {
             asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 consumer warps only
             const double* __restrict__ Jn = jn_all + (size_t)C.b * 16;
@@ -1181,10 +1107,12 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, const 
     }
 }
 
-void launch_update(ekfslam_ctx* c, int mask, int which_prior) {
+void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
+    // flags: 1 = iterated-update innovation (see k_upd_S), 2 = not the final iteration (no quaternion
+    // normalisation, no covariance downdate)
     DevView& v = c->v;
     cudaStream_t st = c->stream;
-    { KScope ks(c, KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior); }
+    { KScope ks(c, KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1); }
     const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
     static size_t chol_cfg = 0;
     if (chol_sm > 48 * 1024 && chol_sm > chol_cfg) {
@@ -1201,31 +1129,35 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior) {
         cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dd_sm);
         attr_done = w_sm;
     }
-    { KScope ks(c, KT_W); k_w<<<gw, 256, w_sm, st>>>(v); }
+    { KScope ks(c, KT_W); k_w<<<gw, 256, w_sm, st>>>(v, (flags & 2) ? 0 : 1); }
+    if (flags & 2) return;
     const int nt = (v.nmax + TM - 1) / TM;
     const int T = nt * (nt + 1) / 2;
     static int mode = -1, sms = 0;
     if (mode < 0) {
         const char* e = getenv("EKFSLAM_DOWNDATE");
-        mode = (e && !strcmp(e, "tile")) ? 0 : (e && !strcmp(e, "persistent")) ? 1 : 2;  // default: warp-specialised
+        // default: warp-specialised 64x64 ("ws"); "ws128" = experimental 128x128 (slower: one CTA per SM
+        // serialises K loop and epilogue); "persistent" / "tile" = cp.async 64x64
+        mode = (e && !strcmp(e, "tile")) ? 0 : (e && !strcmp(e, "persistent")) ? 1 : (e && !strcmp(e, "ws128")) ? 3 : 2;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     }
     KScope ks(c, (mask & EKFSLAM_F_HI) ? KT_DOWNDATE_HI : KT_DOWNDATE);
+    if (mode == 3 && launch_downdate128(c, sms)) return;
     if (mode == 0) {
         dim3 gd(T, v.B);
         k_downdate<<<gd, 256, dd_sm, st>>>(v, v.jn);
-    } else if (mode == 2) {
+    } else if (mode >= 2) {
         const long long total = (long long)T * v.B;
         const long long ctas = total < (long long)sms * 2 ? total : (long long)sms * 2;
         const int M = (int)((total + ctas - 1) / ctas);
-        const size_t ws_sm = sizeof(double) * (2 * WS_STAGES * TK * TPAD + TM * TPAD + TM * 9) + sizeof(unsigned long long) * (2 * WS_STAGES + 2) +
+        const size_t ws_sm = sizeof(double) * (2 * WS_STAGES * TK * TPAD + TM * 9) + sizeof(unsigned long long) * 2 * WS_STAGES +
                              sizeof(int2) * M + sizeof(unsigned) * T;
         static size_t ws_cfg = 0;
         if (ws_sm > ws_cfg) {
             cudaFuncSetAttribute(k_downdate_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_sm);
             ws_cfg = ws_sm;
         }
-        k_downdate_ws<<<(unsigned)ctas, WS_THREADS, ws_sm, st>>>(v, v.jn, T, total, M, g_ekfslam_debug);
+        k_downdate_ws<<<(unsigned)ctas, WS_THREADS, ws_sm, st>>>(v, v.jn, T, total, M);
     } else {
         const long long total = (long long)T * v.B;
         const long long ctas = total < (long long)sms * 2 ? total : (long long)sms * 2;

@@ -187,6 +187,13 @@ int ekfslam_update_hi(ekfslam_ctx* ctx);
  * byte has any bit of `mask`; which_prior 1 = from x_k_km1, 0 = from x_k_k */
 int ekfslam_update_masked(ekfslam_ctx* ctx, int mask, int which_prior);
 
+/* EXTENSION (mc/ekf_update_iterated.m:3 calls update_iterated, which does not exist in the reference):
+ * standard iterated EKF over the features whose flag byte has a bit of `mask`,
+ *   x_{j+1} = x^- + K_j (z - h(x_j) - H_j (x^- - x_j)),  j = 0..n_iter-1,  x_0 = x^-,
+ * h/H re-evaluated at every iterate, P from the last linearisation, then the quaternion fix-up of
+ * mc/update.m:18-24.  which_prior 1: prior (x_k_km1, P), 0: prior (x_k_k, P) (x_k_km1 is overwritten). */
+int ekfslam_update_iterated(ekfslam_ctx* ctx, int mask, int which_prior, int n_iter);
+
 /* one whole filter step on resident state = mc/mono_slam.m:56-74 without takeImage:
  * begin_frame (if reset!=0), predict, measure(1), matcher (match_mode 1 = gate the staged
  * candidates, 2 = apply the staged explicit matches, 0 = flags already on the device),

@@ -104,3 +104,44 @@ def test_filter_step_matches_stagewise(golden):
         assert [a.low_innovation_inlier for a in fia] == [b.low_innovation_inlier for b in fib]
         assert [a.high_innovation_inlier for a in fia] == [b.high_innovation_inlier for b in fib]
         assert rel_err(fa.x_k_k, fb.x_k_k) < 1e-12 and rel_err(fa.p_k_k, fb.p_k_k) < 1e-11
+
+
+def test_iterated_update_matches_oracle_extension():
+    """ekf_update_iterated: the reference names it but ships no implementation; both sides implement the
+    standard IEKF (oracle.update_iterated), so this is GPU-vs-oracle consistency, not reference parity."""
+    import ekf_slam_b200.api as api
+    import ekf_slam_b200.synth as synth
+    seq = synth.SynthSequence(B=1, N=18, T=3, seed=88)
+    x0, P0, types = seq.initial_state()
+    cam = api.initialize_cam()
+    cam_o = O.initialize_cam()
+    f = api.ekf_filter(x0[0], P0[0], 0.007, 0.007, 1.0)
+    fi = [api.new_feature() for _ in range(18)]
+    for t in range(1, 3):   # two ordinary frames so the covariance is dense
+        fi = api.update_features_info(fi)
+        f, fi = api.filter_step(f, fi, cam, (seq.zc[t, 0], seq.has[t, 0]), u=seq.uniforms(t)[0])
+    fi = api.update_features_info(fi)
+    f, fi = api.ekf_prediction(f, fi)
+    fi = api.search_IC_matches(f, fi, cam, (seq.zc[3, 0], seq.has[3, 0]))
+    fi = api.ransac_hypotheses(f, fi, cam, u=seq.uniforms(3)[0])
+    # oracle twin of the same state
+    fo = O.ekf_filter(f.x_k_k, f.p_k_k, 0.007, 0.007, 1.0, "constant_velocity")
+    fo.x_k_km1, fo.p_k_km1 = f.x_k_km1.copy(), f.p_k_km1.copy()
+    feats_o = []
+    for a in fi:
+        o = O.Feature(type=a.type, z=None if a.z is None else a.z.copy(), h=None if a.h is None else a.h.copy(),
+                      H=None if a.H is None else a.H.copy(), S=None, R=np.eye(2),
+                      individually_compatible=a.individually_compatible,
+                      low_innovation_inlier=a.low_innovation_inlier, high_innovation_inlier=0)
+        feats_o.append(o)
+    assert sum(a.low_innovation_inlier for a in fi) >= 4
+    for n_iter in (1, 3):
+        import copy
+        fg = copy.deepcopy(f)
+        fg = api.ekf_update_iterated(fg, copy.deepcopy(fi), cam, "low_innovation_inlier", n_iter=n_iter)
+        xo, Po = O.update_iterated(fo.x_k_km1, fo.p_k_km1, copy.deepcopy(feats_o), cam_o, "low_innovation_inlier", n_iter=n_iter)
+        assert rel_err(fg.x_k_k, xo) < 1e-10 and rel_err(fg.p_k_k, Po) < 1e-9
+    # one iteration is the plain update
+    fp = api.ekf_update_li_inliers(copy.deepcopy(f), copy.deepcopy(fi))
+    f1 = api.ekf_update_iterated(copy.deepcopy(f), copy.deepcopy(fi), cam, "low_innovation_inlier", n_iter=1)
+    assert rel_err(f1.x_k_k, fp.x_k_k) < 1e-13 and rel_err(f1.p_k_k, fp.p_k_k) < 1e-13

@@ -1,8 +1,11 @@
+# Round evidence: (1) launch list of a short default-shape bench run, (2) --set full capture of the heavy
+# kernels of one step at the FULL bench shape (B=4096, N=100).  Each ncu run is preceded by the same
+# command without ncu (exit code checked).
 mkdir -p gpurun_out
-BENCH="python bench.py --batch 512 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
-$BENCH > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1.csv $BENCH > gpurun_out/ncu_list.log 2>&1
-$BENCH > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k_downdate|k_hp|k_chol|k_w|k_ransac" -s 10 -c 10 -o gpurun_out/prof_r1a $BENCH > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/ncu_list.log gpurun_out/ncu_full.log
-ls -la gpurun_out
+R=${ROUND:-r1}
+BENCH="python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu-baseline"
+$BENCH > gpurun_out/plain_$R.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$R.csv $BENCH > gpurun_out/ncu_list_$R.log 2>&1
+$BENCH > gpurun_out/plain2_$R.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"k_downdate|k_hp|k_chol|k_w|k_ransac|k_upd_S|k_predict|k_features|k_innov" -s 36 -c 18 -o gpurun_out/prof_$R $BENCH > gpurun_out/ncu_full_$R.log 2>&1
+tail -n 2 gpurun_out/ncu_list_$R.log gpurun_out/ncu_full_$R.log

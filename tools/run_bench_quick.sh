@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for mode in ${MODES:-ws tile}; do
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for mode in ${MODES:-ws128 ws}; do
 EKFSLAM_DOWNDATE=$mode timeout 900 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_$mode.json 2> gpurun_out/bench_$mode.err
 python - <<PY
 import json

@@ -68,6 +68,7 @@ _SIGS = {
     "ekfslam_upload_uniforms": (_I, [_P, _I, _I, _P, _I]),
     "ekfslam_download_features": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "ekfslam_upload_features": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    "ekfslam_download_feature_types": (_I, [_P, _I, _I, _P, _P]),
     "ekfslam_download_stats": (_I, [_P, _I, _I, _P]),
     "ekfslam_begin_frame": (_I, [_P]),
     "ekfslam_predict": (_I, [_P]),
@@ -86,6 +87,8 @@ _SIGS = {
     "ekfslam_step": (_I, [_P, _I, _I]),
     "ekfslam_step_host": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "ekfslam_reset_filters": (_I, [_P, _I, _I, _P, _P]),
+    "ekfslam_inversedepth_2_cartesian": (_I, [_P, C.c_double, _I, _P]),
+    "ekfslam_delete_features": (_I, [_P, _I, _I, _P]),
     "ekfslam_add_features": (_I, [_P, _I, _I, _P, _P, C.c_double, C.c_double, C.c_double]),
     "ekfslam_device_ptr": (_P, [_P, C.c_char_p]),
     "ekfslam_enable_timing": (_I, [_P, _I]),

@@ -226,6 +226,27 @@ class FilterBank:
         L.check(self.lib.ekfslam_add_features(self._h, b0, nb, _ptr(uvd), _ptr(add), float(std_pxl),
                                               float(initial_rho), float(std_rho)))
 
+    def inversedepth_2_cartesian(self, threshold=0.1, force_index=-1):
+        """mc/inversedepth_2_cartesian.m for every filter; returns the converted feature index per filter (-1 = none)."""
+        conv = np.empty(self.B, dtype=np.int32)
+        L.check(self.lib.ekfslam_inversedepth_2_cartesian(self._h, float(threshold), int(force_index), _ptr(conv)))
+        return conv
+
+    def delete_features(self, delete, b0=0):
+        """mc/delete_a_feature.m for every feature with delete[b, i] != 0."""
+        delete = _c(delete, np.uint8)
+        nb = delete.shape[0]
+        delete = _c(delete, np.uint8, (nb, self.N))
+        L.check(self.lib.ekfslam_delete_features(self._h, b0, nb, _ptr(delete)))
+
+    def download_feature_types(self, b0=0, nb=None):
+        """(types [nb, N_max] u8, nfeat [nb] i32) — the map layout after conversions / deletions."""
+        nb = self.B - b0 if nb is None else nb
+        t = np.empty((nb, self.N), dtype=np.uint8)
+        nf = np.empty(nb, dtype=np.int32)
+        L.check(self.lib.ekfslam_download_feature_types(self._h, b0, nb, _ptr(t), _ptr(nf)))
+        return t, nf
+
     # -- stages (names follow the reference functions they replace) --------------------------
     def begin_frame(self):
         L.check(self.lib.ekfslam_begin_frame(self._h))

@@ -520,6 +520,16 @@ int ekfslam_upload_features(ekfslam_ctx* c, int b0, int nb, const double* h, con
     return EKFSLAM_OK;
 }
 
+int ekfslam_download_feature_types(ekfslam_ctx* c, int b0, int nb, uint8_t* type, int32_t* nfeat) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    DevView& v = c->v;
+    if (type) CK(cudaMemcpyAsync(type, v.ftype + (size_t)b0 * v.N, (size_t)nb * v.N, cudaMemcpyDeviceToHost, c->stream));
+    if (nfeat) CK(cudaMemcpyAsync(nfeat, v.nfeat + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
 int ekfslam_download_stats(ekfslam_ctx* c, int b0, int nb, ekfslam_stats* stats) {
     NEED_CTX(c);
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
@@ -732,6 +742,42 @@ int ekfslam_add_features(ekfslam_ctx* c, int b0, int nb, const double* uvd, cons
     CK(cudaMemcpyAsync(d_uvd, uvd, sizeof(double) * 2 * nb, cudaMemcpyHostToDevice, c->stream));
     if (add) CK(cudaMemcpyAsync(d_add, add, nb, cudaMemcpyHostToDevice, c->stream));
     launch_add_features(c, b0, nb, d_uvd, add ? d_add : nullptr, std_pxl, initial_rho, std_rho);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+static int ensure_scratch(ekfslam_ctx* c, size_t need) {
+    if (need > c->pin_bytes) {
+        if (c->pin) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(c->pin)); c->pin = nullptr; c->pin_bytes = 0; }
+        CK(cudaMalloc(&c->pin, need));
+        c->pin_bytes = need;
+    }
+    return EKFSLAM_OK;
+}
+
+int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* c, double threshold, int force_index, int32_t* converted) {
+    NEED_CTX(c);
+    DevView& v = c->v;
+    if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "inversedepth_2_cartesian supports n_max <= 4096");
+    if (force_index >= v.N) return fail(EKFSLAM_ERR_INVALID, "force_index out of range");
+    if (int r = ensure_scratch(c, sizeof(int32_t) * (size_t)v.B)) return r;
+    launch_id2cart(c, threshold, force_index, (int32_t*)c->pin);
+    LAUNCHED();
+    if (converted) CK(cudaMemcpyAsync(converted, c->pin, sizeof(int32_t) * v.B, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* del) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!del) return fail(EKFSLAM_ERR_INVALID, "del is null");
+    DevView& v = c->v;
+    if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "delete_features supports n_max <= 4096");
+    if (int r = ensure_scratch(c, (size_t)nb * v.N)) return r;
+    CK(cudaMemcpyAsync(c->pin, del, (size_t)nb * v.N, cudaMemcpyHostToDevice, c->stream));
+    launch_delete_features(c, b0, nb, (const uint8_t*)c->pin);
     LAUNCHED();
     CK(cudaStreamSynchronize(c->stream));
     return EKFSLAM_OK;

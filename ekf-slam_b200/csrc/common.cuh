@@ -96,5 +96,7 @@ void launch_ransac(ekfslam_ctx* c);
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags = 0);
 bool launch_downdate128(ekfslam_ctx* c, int sms);
 void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv);
+void launch_id2cart(ekfslam_ctx* c, double threshold, int force_index, int32_t* d_conv);
+void launch_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* d_del);
 void launch_add_features(ekfslam_ctx* c, int b0, int nb, const double* d_uvd, const uint8_t* d_add,
                          double std_pxl, double rho0, double std_rho);

@@ -589,3 +589,182 @@ void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, co
     KScope ks(c, KT_ADD_FEATURES);
     k_reset_filters<<<nb, 192, 0, c->stream>>>(c->v, b0, d_xv, d_Pxv);
 }
+
+// ---------------------------------------------------------------------------------------
+// Map management, SURVEY §8f rank 2: inverse-depth -> Cartesian conversion and feature deletion.
+// Both shrink the state: rows/columns [start, start+cnt) of P (and entries of x) are removed and
+// everything behind them moves up.  Block-wide, in place, row by row in increasing order; inside a row
+// every thread first reads its source element, then all write (the source can be the same row).
+// ---------------------------------------------------------------------------------------
+__device__ void compact_remove(double* __restrict__ P, double* __restrict__ x, int n, int ld, int start, int cnt) {
+    const int nn = n - cnt;
+    for (int r = 0; r < nn; ++r) {
+        const int sr = (r < start) ? r : r + cnt;
+        // each thread handles columns c = tid, tid+blockDim, ... ; read all first
+        double vals[8];
+        int q = 0;
+        for (int c = threadIdx.x; c < nn && q < 8; c += blockDim.x, ++q) vals[q] = P[(size_t)sr * ld + ((c < start) ? c : c + cnt)];
+        __syncthreads();
+        q = 0;
+        for (int c = threadIdx.x; c < nn && q < 8; c += blockDim.x, ++q) P[(size_t)r * ld + c] = vals[q];
+        __syncthreads();
+    }
+    // clear the vacated tail so that the padding invariants (zeros beyond n) keep holding
+    for (int r = 0; r < n; ++r)
+        for (int c = threadIdx.x; c < n; c += blockDim.x)
+            if (r >= nn || c >= nn) P[(size_t)r * ld + c] = 0.0;
+    __syncthreads();
+    double xv[8];
+    int q = 0;
+    for (int c = threadIdx.x; c < nn && q < 8; c += blockDim.x, ++q) xv[q] = x[(c < start) ? c : c + cnt];
+    __syncthreads();
+    q = 0;
+    for (int c = threadIdx.x; c < nn && q < 8; c += blockDim.x, ++q) x[c] = xv[q];
+    for (int c = nn + threadIdx.x; c < n; c += blockDim.x) x[c] = 0.0;
+    __syncthreads();
+}
+
+// mc/inversedepth_2_cartesian.m:3-52: per filter, the FIRST inverse-depth feature whose linearity index
+// 4*std_d*cos(alpha)/d is below the threshold is converted (at most one per call, :49).
+// force_index >= 0 converts that feature unconditionally (the transformation of :35-48 alone).
+// Requires blockDim.x * 8 >= n.  conv_out[b] = converted feature index or -1.
+__global__ void __launch_bounds__(512) k_id2cart(DevView v, double threshold, int force_index, int32_t* conv_out) {
+    const int b = blockIdx.x;
+    const int n = v.nstate[b], nf = v.nfeat[b], ld = v.ld, N = v.N;
+    double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    double* __restrict__ x = v.x + (size_t)b * ld;
+    double* __restrict__ R3 = v.G + (size_t)b * v.kmax * ld;  // scratch: 3 rows of length ld
+    __shared__ int s_sel, s_pos;
+    __shared__ double J[3][6], pnew[3];
+    if (threadIdx.x == 0) {
+        int sel = -1;
+        for (int i = 0; i < nf && sel < 0; ++i) {
+            const size_t t = (size_t)b * N + i;
+            if (v.ftype[t] != EKFSLAM_FEAT_INVERSEDEPTH) continue;
+            if (force_index >= 0) { if (i == force_index) sel = i; continue; }
+            const int pos = v.foff[t];
+            const double rho = x[pos + 5], th = x[pos + 3], ph = x[pos + 4];
+            const double std_rho = sqrt(P[(size_t)(pos + 5) * ld + pos + 5]);
+            const double std_d = std_rho / (rho * rho);
+            const double m0 = cos(ph) * sin(th), m1 = -sin(ph), m2 = cos(ph) * cos(th);
+            const double p0 = x[pos] + (1.0 / rho) * m0, p1 = x[pos + 1] + (1.0 / rho) * m1, p2 = x[pos + 2] + (1.0 / rho) * m2;
+            const double a0 = p0 - x[pos], a1 = p1 - x[pos + 1], a2 = p2 - x[pos + 2];   // p - x_c1
+            const double c0 = p0 - x[0], c1 = p1 - x[1], c2 = p2 - x[2];                 // p - x_c2
+            const double na = sqrt(a0 * a0 + a1 * a1 + a2 * a2), nc = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+            const double cos_alpha = (a0 * c0 + a1 * c1 + a2 * c2) / (na * nc);
+            if (4.0 * std_d * cos_alpha / nc < threshold) sel = i;
+        }
+        s_sel = sel;
+        if (sel >= 0) {
+            const int pos = v.foff[(size_t)b * N + sel];
+            s_pos = pos;
+            const double rho = x[pos + 5], th = x[pos + 3], ph = x[pos + 4];
+            const double mi[3] = {cos(ph) * sin(th), -sin(ph), cos(ph) * cos(th)};
+            const double dmt[3] = {cos(ph) * cos(th), 0.0, -cos(ph) * sin(th)};
+            const double dmp[3] = {-sin(ph) * sin(th), -cos(ph), -sin(ph) * cos(th)};
+            for (int r = 0; r < 3; ++r) {
+                pnew[r] = x[pos + r] + (1.0 / rho) * mi[r];
+                for (int c = 0; c < 3; ++c) J[r][c] = (r == c) ? 1.0 : 0.0;
+                J[r][3] = (1.0 / rho) * dmt[r];
+                J[r][4] = (1.0 / rho) * dmp[r];
+                J[r][5] = -mi[r] / (rho * rho);
+            }
+        }
+        if (conv_out) conv_out[b] = sel;
+    }
+    __syncthreads();
+    const int sel = s_sel;
+    if (sel < 0) return;
+    const int pos = s_pos;
+    // R3 = J * P[pos..pos+5, :]   (3 x n)
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        double pc[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) pc[m] = P[(size_t)(pos + m) * ld + c];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) sacc += J[r][m] * pc[m];
+            R3[(size_t)r * ld + c] = sacc;
+        }
+    }
+    __syncthreads();
+    // block = R3[:, pos..pos+5] * J'
+    __shared__ double blk[3][3];
+    if (threadIdx.x < 9) {
+        const int r = threadIdx.x / 3, sc = threadIdx.x % 3;
+        double sacc = 0.0;
+        for (int m = 0; m < 6; ++m) sacc += R3[(size_t)r * ld + pos + m] * J[sc][m];
+        blk[r][sc] = sacc;
+    }
+    __syncthreads();
+    // write the 3 new rows / columns at pos..pos+2 (columns pos+3..pos+5 are removed next)
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        if (c >= pos && c < pos + 6) continue;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double val = R3[(size_t)r * ld + c];
+            P[(size_t)(pos + r) * ld + c] = val;
+            P[(size_t)c * ld + pos + r] = val;
+        }
+    }
+    if (threadIdx.x < 9) {
+        const int r = threadIdx.x / 3, sc = threadIdx.x % 3;
+        P[(size_t)(pos + r) * ld + pos + sc] = (sc <= r) ? blk[r][sc] : blk[sc][r];  // lower triangle authoritative
+    }
+    if (threadIdx.x < 3) x[pos + threadIdx.x] = pnew[threadIdx.x];
+    __syncthreads();
+    compact_remove(P, x, n, ld, pos + 3, 3);
+    if (threadIdx.x == 0) {
+        v.ftype[(size_t)b * N + sel] = EKFSLAM_FEAT_CARTESIAN;
+        for (int i = sel + 1; i < nf; ++i) v.foff[(size_t)b * N + i] -= 3;
+        v.nstate[b] = n - 3;
+    }
+}
+
+// mc/delete_a_feature.m:4-25 for every feature with del[b][i] != 0 (highest index first so that the
+// offsets of the remaining candidates stay valid); the per-feature arrays are compacted as well.
+__global__ void __launch_bounds__(512) k_delete_features(DevView v, int b0, const uint8_t* __restrict__ del) {
+    const int lb = blockIdx.x, b = b0 + lb;
+    const int N = v.N, ld = v.ld;
+    double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    double* __restrict__ x = v.x + (size_t)b * ld;
+    __shared__ int s_n, s_nf;
+    if (threadIdx.x == 0) { s_n = v.nstate[b]; s_nf = v.nfeat[b]; }
+    __syncthreads();
+    for (int i = s_nf - 1; i >= 0; --i) {
+        if (!del[(size_t)lb * N + i]) continue;    // uniform over the block
+        const size_t t = (size_t)b * N + i;
+        const int pos = v.foff[t];
+        const int w = (v.ftype[t] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+        const int n = s_n, nf = s_nf;
+        __syncthreads();
+        compact_remove(P, x, n, ld, pos, w);
+        // features_info(i) = []: shift the per-feature fields of the features behind it
+        if (threadIdx.x == 0) {
+            for (int j = i; j < nf - 1; ++j) {
+                const size_t d = (size_t)b * N + j, sidx = d + 1;
+                v.ftype[d] = v.ftype[sidx]; v.foff[d] = v.foff[sidx] - w; v.flags[d] = v.flags[sidx]; v.mflags[d] = v.mflags[sidx];
+                for (int q = 0; q < 2; ++q) { v.h[2 * d + q] = v.h[2 * sidx + q]; v.z[2 * d + q] = v.z[2 * sidx + q]; v.zc[2 * d + q] = v.zc[2 * sidx + q]; v.counters[2 * d + q] = v.counters[2 * sidx + q]; }
+                for (int q = 0; q < 4; ++q) v.S[4 * d + q] = v.S[4 * sidx + q];
+                for (int q = 0; q < EKF_HSTRIDE; ++q) v.Hc[EKF_HSTRIDE * d + q] = v.Hc[EKF_HSTRIDE * sidx + q];
+            }
+            const size_t last = (size_t)b * N + nf - 1;
+            v.ftype[last] = EKFSLAM_FEAT_NONE; v.flags[last] = 0; v.mflags[last] = 0; v.foff[last] = 0;
+            s_n = n - w; s_nf = nf - 1;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { v.nstate[b] = s_n; v.nfeat[b] = s_nf; }
+}
+
+void launch_id2cart(ekfslam_ctx* c, double threshold, int force_index, int32_t* d_conv) {
+    KScope ks(c, KT_ADD_FEATURES);
+    k_id2cart<<<c->v.B, 512, 0, c->stream>>>(c->v, threshold, force_index, d_conv);
+}
+
+void launch_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* d_del) {
+    KScope ks(c, KT_ADD_FEATURES);
+    k_delete_features<<<nb, 512, 0, c->stream>>>(c->v, b0, d_del);
+}

@@ -146,6 +146,8 @@ int ekfslam_download_features(ekfslam_ctx* ctx, int b0, int nb, double* h, doubl
 /* the inverse of ekfslam_download_features for the fields a stage reads (NULL = keep) */
 int ekfslam_upload_features(ekfslam_ctx* ctx, int b0, int nb, const double* h, const double* Hc,
                             const double* S, const double* z, const uint8_t* flags);
+/* the map layout: type [nb][N_max] EKFSLAM_FEAT_*, nfeat [nb] (either may be NULL) */
+int ekfslam_download_feature_types(ekfslam_ctx* ctx, int b0, int nb, uint8_t* type, int32_t* nfeat);
 int ekfslam_download_stats(ekfslam_ctx* ctx, int b0, int nb, ekfslam_stats* stats);
 
 /* ---- the filter step, stage by stage (all B filters, stream-ordered) ------- */
@@ -220,6 +222,15 @@ int ekfslam_reset_filters(ekfslam_ctx* ctx, int b0, int nb, const double* xv, co
  * Operates on (x_k_k,p_k_k); grows nstate by 6 and nfeat by 1. */
 int ekfslam_add_features(ekfslam_ctx* ctx, int b0, int nb, const double* uvd, const uint8_t* add,
                          double std_pxl, double initial_rho, double std_rho);
+
+/* mc/inversedepth_2_cartesian.m:3-52 on (x_k_k,p_k_k) of every filter: the FIRST inverse-depth feature whose
+ * linearity index 4*std_d*cos(alpha)/d is below `threshold` (reference: 0.1) becomes Cartesian (at most one
+ * per call, :49): x block [x y z theta phi rho] -> [X Y Z], P <- J P J'.  force_index >= 0 instead converts
+ * that feature of every filter unconditionally.  converted [B] (may be NULL) receives the index or -1. */
+int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* ctx, double threshold, int force_index, int32_t* converted);
+/* mc/delete_a_feature.m:4-25 for every feature with del[b][i] != 0 (del: [nb][N_max]); the state, the
+ * covariance and the features_info arrays are compacted. */
+int ekfslam_delete_features(ekfslam_ctx* ctx, int b0, int nb, const uint8_t* del);
 
 /* ---- measurement hooks ------------------------------------------------------ */
 /* bracket every kernel launch with a CUDA event pair on the context's stream and accumulate the

@@ -78,7 +78,7 @@ static void kt_collect(ekfslam_ctx* c) {
 
 static const char* KT_NAMES[KT_COUNT] = {"k_begin_frame", "k_predict", "k_features", "k_hp", "k_innov", "k_ransac",
                                          "k_upd_S", "k_chol", "k_w", "k_downdate_hi", "k_downdate", "k_symmetrize",
-                                         "k_add_features"};
+                                         "k_add_features", "k_wfix", "k_v", "k_g2"};
 
 template <typename T>
 static cudaError_t dalloc(T** p, size_t count, int64_t* total) {
@@ -193,6 +193,11 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     DA(v.Li, Bz * v.kmax * v.kmax);
     DA(v.yv, Bz * v.kmax);
     DA(v.jn, Bz * 16);
+    DA(v.jnt, Bz * 16);
+    DA(v.jn1, Bz * 16);
+    DA(v.kpend, Bz);
+    DA(v.roff, Bz);
+    DA(v.ktot, Bz);
     DA(v.cv, Bz * v.kmax);
     DA(v.h, Bz * v.N * 2);
     DA(v.Hc, Bz * v.N * EKF_HSTRIDE);
@@ -224,6 +229,12 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
         return fail(EKFSLAM_ERR_CUDA, std::string("context init: ") + cudaGetErrorString(e));
     }
     c->stream = c->own_stream;
+    {
+        // EKFSLAM_FUSE=1: one covariance pass per frame (deferred li downdate, see ekfslam_step).  Off by
+        // default: at N=100 the rescue-row correction GEMM costs as much as the saved pass.
+        const char* e = getenv("EKFSLAM_FUSE");
+        c->fuse_downdates = (e && e[0] == '1') ? 1 : 0;
+    }
     *out = c;
     return EKFSLAM_OK;
 }
@@ -233,7 +244,7 @@ int ekfslam_destroy(ekfslam_ctx* c) {
     cudaSetDevice(c->device);
     if (c->own_zc) { c->v.zc = c->own_zc; c->v.mflags = c->own_mflags; c->v.u = c->own_u; c->own_zc = nullptr; }
     DevView& v = c->v;
-    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
+    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.jnt, v.jn1, v.kpend, v.roff, v.ktot, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
                     v.flags, v.mflags, v.foff, v.nstate, v.nfeat, v.counters, v.sel, v.ksel, v.stats, v.nhyp_tab};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -666,11 +677,23 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
     launch_innov(c, 0);
     if (match_mode) launch_innov(c, match_mode);
     launch_ransac(c);
-    launch_update(c, EKFSLAM_F_LI, 1);
-    launch_features(c, 0, 3);
-    launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);
-    launch_innov(c, 3);
-    launch_update(c, EKFSLAM_F_HI, 0);
+    if (c->fuse_downdates) {
+        // one pass over P per frame: the li update is computed (x_k_k, W_li) but its covariance downdate is
+        // deferred; the rescue stage works on the implied p_k_k = Jn (P - W_li' W_li) Jn' through
+        // G = H P - (H W_li') W_li; the hi update stacks its W below and a single downdate applies both.
+        launch_update(c, EKFSLAM_F_LI, 1, 4);
+        launch_features(c, 0, 3);
+        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI, 1);
+        launch_pending_rows(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);
+        launch_innov(c, 3);
+        launch_update(c, EKFSLAM_F_HI, 0);
+    } else {
+        launch_update(c, EKFSLAM_F_LI, 1);
+        launch_features(c, 0, 3);
+        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);
+        launch_innov(c, 3);
+        launch_update(c, EKFSLAM_F_HI, 0);
+    }
     LAUNCHED();
     return EKFSLAM_OK;
 }

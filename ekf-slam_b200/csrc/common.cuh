@@ -27,7 +27,9 @@ struct DevView {
     double* Sb;           // [B][kmax][kmax] stacked innovation covariance / its Cholesky factor
     double* Li;           // [B][kmax][kmax] inverse of the Cholesky factor
     double* yv;           // [B][kmax]     inv(L)*(z-h)
-    double* jn;           // [B][16]       normJac(q+) of the running update
+    double* jn;           // [B][16]       normalisation Jacobian the covariance downdate applies (product over the pending updates)
+    double* jnt;          // [B][16]       normJac(q+) of the update being computed
+    double* jn1;          // [B][16]       normJac of a deferred (not yet applied) update
     double* cv;           // [B][kmax]     inv(S)*(z-h) = inv(L)' * yv
     double* h;            // [B][N][2]
     double* Hc;           // [B][N][26]
@@ -44,6 +46,9 @@ struct DevView {
     int32_t* counters;    // [B][N][2]
     int32_t* sel;         // [B][N]   selected feature list of the running update
     int32_t* ksel;        // [B]      number of selected features
+    int32_t* kpend;       // [B]      rows of W left pending by a deferred update (0 = none)
+    int32_t* roff;        // [B]      row offset of the running update inside W (= pending rows before it)
+    int32_t* ktot;        // [B]      rows of W the covariance downdate has to apply
     int32_t* nhyp_tab;    // [(N+1)(N+2)/2] adaptive hypothesis count, host libm (see abi.cu)
     ekfslam_stats* stats; // [B]
 };
@@ -51,7 +56,7 @@ struct DevView {
 // per-kernel timing (ekfslam_enable_timing): every launch is bracketed by an event pair
 enum {
     KT_BEGIN_FRAME = 0, KT_PREDICT, KT_FEATURES, KT_HP, KT_INNOV, KT_RANSAC, KT_UPD_S, KT_CHOL, KT_W, KT_DOWNDATE_HI,
-    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_COUNT
+    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_WFIX, KT_V, KT_G2, KT_COUNT
 };
 struct KTimer;
 
@@ -66,6 +71,7 @@ struct ekfslam_ctx {
     int64_t bytes;
     int64_t launches;
     int stage;  // call-order tracking
+    int fuse_downdates;  // ekfslam_step: defer the li covariance downdate and apply it together with the hi one
     // pinned staging
     void* pin;
     size_t pin_bytes;
@@ -89,12 +95,13 @@ struct KScope {
 void launch_begin_frame(ekfslam_ctx* c);
 void launch_predict(ekfslam_ctx* c);
 void launch_features(ekfslam_ctx* c, int which, int parts);  // parts: 1 = h, 2 = H, 3 = both
-void launch_hp(ekfslam_ctx* c, int need, int forbid);  // G rows for features with (flags&need)==need && !(flags&forbid)
+void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending = 0);  // G rows for features with (flags&need)==need && !(flags&forbid)
 void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gate / explicit matches / rescue gate
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
 void launch_ransac(ekfslam_ctx* c);
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags = 0);
-bool launch_downdate128(ekfslam_ctx* c, int sms);
+void launch_pending_rows(ekfslam_ctx* c, int need, int forbid);  // G rows of the selected features against the pending update
+void launch_downdate(ekfslam_ctx* c, int slot);
 void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv);
 void launch_id2cart(ekfslam_ctx* c, double threshold, int force_index, int32_t* d_conv);
 void launch_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* d_del);

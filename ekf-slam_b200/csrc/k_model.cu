@@ -228,7 +228,7 @@ void launch_features(ekfslam_ctx* c, int which, int parts) {
 // K = P H_i' inv(S_i) (mc/ransac_hypotheses.m:24-25) and P H' of the update (mc/update.m:8-9).
 // ---------------------------------------------------------------------------------------
 #define HP_CHUNK 64
-__global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid) {
+__global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int use_pending) {
     const int b = blockIdx.y;
     const int n = v.nstate[b];
     const int ld = v.ld;
@@ -283,6 +283,18 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid) {
             sH[s][k] = v.Hc[((size_t)b * v.N + sIdx[s]) * EKF_HSTRIDE + k];
         }
         __syncthreads();
+        if (use_pending && v.kpend[b] > 0) {
+            // a deferred update is pending: the covariance in memory is still P, the current one is
+            // J1 (P - W'W) J1'.  This pass produces (H J1) P; k_v / k_gemm(mode 1) finish the job.
+            const double* __restrict__ J1 = v.jn1 + (size_t)b * 16;
+            for (int e = threadIdx.x; e < cnt * 2; e += blockDim.x) {
+                double* Hr = &sH[e >> 1][(e & 1) * EKF_HC + 3];
+                const double h3 = Hr[0], h4 = Hr[1], h5 = Hr[2], h6 = Hr[3];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) Hr[a] = h3 * J1[0 * 4 + a] + h4 * J1[1 * 4 + a] + h5 * J1[2 * 4 + a] + h6 * J1[3 * 4 + a];
+            }
+            __syncthreads();
+        }
         if (!active) continue;
         for (int s = 0; s < cnt; ++s) {
             const double* Hs = sH[s];
@@ -321,10 +333,10 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid) {
     }
 }
 
-void launch_hp(ekfslam_ctx* c, int need, int forbid) {
+void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending) {
     dim3 grid((c->v.nmax + 255) / 256, c->v.B);
     KScope ks(c, KT_HP);
-    k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid);
+    k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid, use_pending);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -143,3 +143,13 @@ def test_large_map_n500(ekf):
     """BASELINE config 4 shape: N=500 features (n=3013), dense covariance update on the DMMA path."""
     worst, tot = _run_sequence(ekf, B=1, N=500, frames=2, seed=700, n_u=64)
     assert tot["li"] > 200
+
+
+def test_fused_single_pass_mode(ekf, monkeypatch):
+    """EKFSLAM_FUSE=1: the li covariance downdate is deferred and applied together with the hi one (one pass
+    over P per frame); the rescue stage then works on the implied p_k_k.  Same parity bar."""
+    monkeypatch.setenv("EKFSLAM_FUSE", "1")
+    worst, tot = _run_sequence(ekf, B=3, N=40, frames=5, seed=800)
+    assert tot["li"] > 40 and tot["hi"] > 0
+    worst, tot = _run_sequence(ekf, B=2, N=20, frames=4, seed=801, cart=[0, 3, 4, 9, 15, 19])
+    assert tot["li"] > 0

@@ -24,7 +24,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -103,29 +102,38 @@ def read_peaks():
     return peaks
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+class ClockSampler:
+    """`nvidia-smi -lms 100` running for the duration of the timed regions (one long-lived process: spawning
+    nvidia-smi per sample is too slow for a sub-second region)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
         self.index = index
+        self.proc = None
         self.samples = []
-        self.stop_flag = threading.Event()
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            out = ""
+        for line in out.splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7 and parts[0].replace(".", "", 1).isdigit():
+                self.samples.append(parts)
 
     def summary(self):
         if not self.samples:
@@ -136,8 +144,8 @@ class ClockSampler(threading.Thread):
             if any(s[3 + i].lower().startswith("active") for s in self.samples):
                 reasons.append(name)
         pw = [float(s[2]) for s in self.samples if s[2].replace(".", "", 1).isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 # ------------------------------------------------------------------------------------------
@@ -322,8 +330,7 @@ def main():
         h2d = zc_h[1].nbytes + fl_h[1].nbytes + u_h[1].nbytes
         d2h = xo.nbytes + fo.nbytes + so.nbytes
         e2e = (ms_e2e, h2d, d2h)
-    sampler.stop_flag.set()
-    sampler.join(timeout=2)
+    sampler.stop()
 
     # ---- reduce over ranks (max time), gather per-filter statistics over NCCL ---------------
     import ekf_slam_b200.sharding as sharding

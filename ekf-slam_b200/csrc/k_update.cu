@@ -142,12 +142,14 @@ __global__ void __launch_bounds__(128) k_chol(DevView v) {
 #pragma unroll
             for (int c = 0; c < NB; ++c) a[c] = D[i * (NB + 1) + c];
             bool bad = false;
+            double rdiag[NB];  // 1 / L[c][c]: one rsqrt per pivot replaces the sqrt and every division
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
                 const double piv = __shfl_sync(full_mask, a[c], c);
                 bad = bad || !(piv > 0.0);
-                const double d = sqrt(piv);
-                const double lic = (i == c) ? d : a[c] / d;  // rows above the diagonal carry don't-care values
+                const double rs = rsqrt(piv);
+                rdiag[c] = rs;
+                const double lic = (i == c) ? piv * rs : a[c] * rs;  // rows above the diagonal carry don't-care values
                 a[c] = lic;
 #pragma unroll
                 for (int j = c + 1; j < NB; ++j) {
@@ -171,8 +173,7 @@ __global__ void __launch_bounds__(128) k_chol(DevView v) {
                     double sacc = 0.0;
 #pragma unroll
                     for (int t = 0; t < ii; ++t) sacc += D[ii * (NB + 1) + t] * x[t];
-                    const double lii = D[ii * (NB + 1) + ii];
-                    x[ii] = (ii == c) ? 1.0 / lii : ((ii > c) ? -sacc / lii : 0.0);
+                    x[ii] = (ii == c) ? rdiag[ii] : ((ii > c) ? -sacc * rdiag[ii] : 0.0);
                 }
                 if (lane < NB) {
 #pragma unroll
@@ -263,10 +264,17 @@ __global__ void __launch_bounds__(128) k_chol(DevView v) {
             double y[NB];
 #pragma unroll
             for (int r = 0; r < NB; ++r) y[r] = 0.0;
-            for (int t = c; t < I0; ++t) {
-                const double xv = X[(size_t)t * kmax + c];
+            // batches of 8 independent global loads keep the memory pipeline full (the FMAs only need them later)
+            for (int t = c; t < I0; t += 8) {
+                double xv[8];
 #pragma unroll
-                for (int r = 0; r < NB; ++r) y[r] += Pn[t * (NB + 1) + r] * xv;
+                for (int u8 = 0; u8 < 8; ++u8) xv[u8] = (t + u8 < I0) ? X[(size_t)(t + u8) * kmax + c] : 0.0;
+#pragma unroll
+                for (int u8 = 0; u8 < 8; ++u8) {
+                    const int tt = min(t + u8, I0 - 1);
+#pragma unroll
+                    for (int r = 0; r < NB; ++r) y[r] += Pn[tt * (NB + 1) + r] * xv[u8];
+                }
             }
 #pragma unroll
             for (int r = 0; r < NB; ++r) {
@@ -283,27 +291,303 @@ __global__ void __launch_bounds__(128) k_chol(DevView v) {
         const int r = e / k, c = e - r * k;
         if (c > r) X[(size_t)r * kmax + c] = 0.0;
     }
-    // y = X nu (in place through shared memory)
-    double* nu = Pn;
+    // y = X nu and cv = X' y = inv(S) nu (the state update is x+ = x + G_sel' cv, accumulated inside k_gemm).
+    // One warp per row of X, lanes along the row (coalesced); fixed summation orders -> deterministic.
+    double* nu = Pn;                 // [k]
+    double* part = Pn + kmax;        // [nwarps][k] partial column sums of the second product
+    const int nwarps = blockDim.x >> 5;
     double* __restrict__ yv = v.yv + (size_t)b * kmax;
+    __syncthreads();
     for (int a = tid; a < k; a += blockDim.x) nu[a] = yv[a];
     __syncthreads();
-    for (int a = tid; a < k; a += blockDim.x) {
+    for (int a = warp; a < k; a += nwarps) {
         double s = 0.0;
-        for (int t = 0; t <= a; ++t) s += X[(size_t)a * kmax + t] * nu[t];
-        yv[a] = s;
+        for (int t = lane; t <= a; t += 32) s += X[(size_t)a * kmax + t] * nu[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) yv[a] = s;
     }
     __syncthreads();
-    // cv = X' y = inv(S) nu  (the state update is x+ = x + G_sel' cv, accumulated inside k_w)
     for (int a = tid; a < k; a += blockDim.x) nu[a] = yv[a];
+    for (int e = tid; e < nwarps * k; e += blockDim.x) part[e] = 0.0;
+    __syncthreads();
+    for (int a = warp; a < k; a += nwarps) {
+        const double ya = nu[a];
+        for (int t = lane; t <= a; t += 32) part[warp * k + t] += X[(size_t)a * kmax + t] * ya;
+    }
     __syncthreads();
     double* __restrict__ cv = v.cv + (size_t)b * kmax;
     for (int t = tid; t < k; t += blockDim.x) {
         double s = 0.0;
-        for (int a = t; a < k; ++a) s += X[(size_t)a * kmax + t] * nu[a];
+        for (int w2 = 0; w2 < nwarps; ++w2) s += part[w2 * k + t];
         cv[t] = s;
     }
     if (tid == 0 && s_bad) atomicOr(&v.stats[b].status, 2);
+}
+
+// ---------------------------------------------------------------------------------------
+// Batched lock-step factorisation (large batches).  The single-block kernel above leaves most threads
+// waiting at block barriers while one warp factors a 16x16 diagonal block (clock64 profile: ~570 k cycles
+// per filter at k = 98, dominated by serial phases).  Here every phase is its own kernel over ALL filters,
+// with the thread count that phase can use: diagonal block = one warp per filter, panel = one thread per
+// row, trailing update = 32x32 tiles, inverse = one thread per column.  Filters whose k is smaller than the
+// current panel offset simply exit.  Same arithmetic as k_chol (right-looking, NB = 16, rsqrt pivots).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mk_diag(DevView v, int j0) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= v.B) return;
+    const int k = 2 * v.ksel[b];
+    if (j0 >= k) return;
+    const int kmax = v.kmax, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nb = min(NB, k - j0);
+    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
+    __shared__ double Dsh[4][NB][NB + 1];
+    const unsigned full_mask = 0xffffffffu;
+    const int i = lane & (NB - 1);
+    double a[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) a[c] = (i < nb && c <= i) ? S[(size_t)(j0 + i) * kmax + j0 + c] : ((i >= nb && c == i) ? 1.0 : 0.0);
+    bool bad = false;
+    double rdiag[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        const double piv = __shfl_sync(full_mask, a[c], c);
+        bad = bad || !(piv > 0.0);
+        const double rs = rsqrt(piv);
+        rdiag[c] = rs;
+        const double lic = (i == c) ? piv * rs : a[c] * rs;
+        a[c] = lic;
+#pragma unroll
+        for (int j = c + 1; j < NB; ++j) {
+            const double ljc = __shfl_sync(full_mask, lic, j);
+            a[j] -= lic * ljc;
+        }
+    }
+    if (bad && lane == 0) atomicOr(&v.stats[b].status, 2);
+    if (lane < NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) Dsh[w][i][c] = (c <= i) ? a[c] : 0.0;
+    }
+    __syncwarp();
+    const int c = i;
+    double x[NB];
+#pragma unroll
+    for (int ii = 0; ii < NB; ++ii) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int t = 0; t < ii; ++t) sacc += Dsh[w][ii][t] * x[t];
+        x[ii] = (ii == c) ? rdiag[ii] : ((ii > c) ? -sacc * rdiag[ii] : 0.0);
+    }
+    if (lane < nb) {
+#pragma unroll
+        for (int cc = 0; cc < NB; ++cc)
+            if (cc <= i) S[(size_t)(j0 + i) * kmax + j0 + cc] = a[cc];          // L_jj (row i)
+#pragma unroll
+        for (int ii = 0; ii < NB; ++ii)
+            if (ii < nb && ii >= c) X[(size_t)(j0 + ii) * kmax + j0 + c] = x[ii];  // inv(L_jj) (column c)
+    }
+}
+
+// panel rows i in [j0+nb, k): L[i][j0+c] = sum_{t<=c} S[i][j0+t] * Dinv[c][t].  grid = (row chunks of 128, B)
+__global__ void __launch_bounds__(128) k_mk_panel(DevView v, int j0) {
+    const int b = blockIdx.y;
+    const int k = 2 * v.ksel[b];
+    if (j0 >= k) return;
+    const int nb = min(NB, k - j0);
+    const int i1 = j0 + nb;
+    if (i1 + (int)(blockIdx.x * blockDim.x) >= k) return;
+    const int i = i1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int kmax = v.kmax;
+    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    const double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
+    __shared__ double Di[NB][NB + 1];
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+        const int r = e / NB, cc = e - r * NB;
+        Di[r][cc] = (r < nb && cc <= r) ? X[(size_t)(j0 + r) * kmax + j0 + cc] : 0.0;
+    }
+    __syncthreads();
+    if (i >= k) return;
+    double row[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) row[t] = (t < nb) ? S[(size_t)i * kmax + j0 + t] : 0.0;
+#pragma unroll
+    for (int cc = 0; cc < NB; ++cc) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int t = 0; t <= cc; ++t) sacc += row[t] * Di[cc][t];
+        if (cc < nb) S[(size_t)i * kmax + j0 + cc] = sacc;
+    }
+}
+
+// trailing update S[i][c] -= sum_t L[i][j0+t] L[c][j0+t] on 32x32 tiles of the lower triangle behind the panel.
+// grid = (tile index, B), 64 threads, 4x4 per thread.
+__global__ void __launch_bounds__(64) k_mk_trail(DevView v, int j0) {
+    const int b = blockIdx.y;
+    const int k = 2 * v.ksel[b];
+    if (j0 >= k) return;
+    const int nb = min(NB, k - j0);
+    const int i1 = j0 + nb;
+    const int m = k - i1;
+    if (m <= 0) return;
+    const int e = blockIdx.x;
+    int ti = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+    while (ti * (ti + 1) / 2 > e) --ti;
+    const int tj = e - ti * (ti + 1) / 2;
+    if (ti * 32 >= m) return;
+    const int kmax = v.kmax;
+    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    __shared__ double Pa[32][NB + 1], Pb[32][NB + 1];
+    for (int q = threadIdx.x; q < 32 * NB; q += blockDim.x) {
+        const int r = q / NB, t = q - r * NB;
+        const int ia = ti * 32 + r, ib = tj * 32 + r;
+        Pa[r][t] = (ia < m && t < nb) ? S[(size_t)(i1 + ia) * kmax + j0 + t] : 0.0;
+        Pb[r][t] = (ib < m && t < nb) ? S[(size_t)(i1 + ib) * kmax + j0 + t] : 0.0;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) acc[a][cc] = 0.0;
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+        double ra[4], rc[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { ra[a] = Pa[ty * 4 + a][t]; rc[a] = Pb[tx * 4 + a][t]; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) acc[a][cc] += ra[a] * rc[cc];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int ia = ti * 32 + ty * 4 + a, ic = tj * 32 + tx * 4 + cc;
+            if (ia < m && ic <= ia) S[(size_t)(i1 + ia) * kmax + i1 + ic] -= acc[a][cc];
+        }
+}
+
+// block row I0 of X = inv(L):  X[I0+r][c] = -sum_j Dinv_I[r][j] * sum_{t=c}^{I0-1} L[I0+j][t] X[t][c].
+// grid = (column chunks of 128, B); the 16 x I0 row panel of L is staged in shared memory.
+__global__ void __launch_bounds__(128) k_mk_linv(DevView v, int I0) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.y;
+    const int k = 2 * v.ksel[b];
+    if (I0 >= k || (int)(blockIdx.x * blockDim.x) >= I0) return;
+    const int nb = min(NB, k - I0);
+    const int kmax = v.kmax;
+    const double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
+    double* Pn = sm;                          // [I0][NB+1]  Pn[t][r] = L[I0+r][t]
+    double* Di = sm + (size_t)I0 * (NB + 1);  // [NB][NB+1]
+    for (int e = threadIdx.x; e < NB * I0; e += blockDim.x) {
+        const int r = e / I0, t = e - r * I0;
+        Pn[t * (NB + 1) + r] = (r < nb) ? S[(size_t)(I0 + r) * kmax + t] : 0.0;
+    }
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+        const int r = e / NB, cc = e - r * NB;
+        Di[r * (NB + 1) + cc] = (r < nb && cc <= r) ? X[(size_t)(I0 + r) * kmax + I0 + cc] : 0.0;
+    }
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= I0) return;
+    double y[NB];
+#pragma unroll
+    for (int r = 0; r < NB; ++r) y[r] = 0.0;
+    for (int t = c; t < I0; ++t) {
+        const double xv = X[(size_t)t * kmax + c];
+#pragma unroll
+        for (int r = 0; r < NB; ++r) y[r] += Pn[t * (NB + 1) + r] * xv;
+    }
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= r; ++j) sacc += Di[r * (NB + 1) + j] * y[j];
+        if (r < nb) X[(size_t)(I0 + r) * kmax + c] = -sacc;
+    }
+}
+
+// zeros above the diagonal of X, y = X nu, cv = X' y.  One block per filter.
+__global__ void __launch_bounds__(128) k_mk_tail(DevView v) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    const int k = 2 * v.ksel[b];
+    if (k == 0) return;
+    const int kmax = v.kmax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
+    double* nu = sm;             // [kmax]
+    double* part = sm + kmax;    // [nwarps][k]
+    double* __restrict__ yv = v.yv + (size_t)b * kmax;
+    for (int r = warp; r < k; r += nwarps)
+        for (int c = r + 1 + lane; c < k; c += 32) X[(size_t)r * kmax + c] = 0.0;
+    for (int a = tid; a < k; a += blockDim.x) nu[a] = yv[a];
+    __syncthreads();
+    for (int a = warp; a < k; a += nwarps) {
+        double s = 0.0;
+        for (int t = lane; t <= a; t += 32) s += X[(size_t)a * kmax + t] * nu[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) yv[a] = s;
+    }
+    __syncthreads();
+    for (int a = tid; a < k; a += blockDim.x) nu[a] = yv[a];
+    for (int e = tid; e < nwarps * k; e += blockDim.x) part[e] = 0.0;
+    __syncthreads();
+    for (int a = warp; a < k; a += nwarps) {
+        const double ya = nu[a];
+        for (int t = lane; t <= a; t += 32) part[warp * k + t] += X[(size_t)a * kmax + t] * ya;
+    }
+    __syncthreads();
+    double* __restrict__ cv = v.cv + (size_t)b * kmax;
+    for (int t = tid; t < k; t += blockDim.x) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < nwarps; ++w2) s += part[w2 * k + t];
+        cv[t] = s;
+    }
+}
+
+static void launch_chol_lockstep(ekfslam_ctx* c) {
+    DevView& v = c->v;
+    cudaStream_t st = c->stream;
+    const int kmax = v.kmax;
+    KScope ks(c, KT_CHOL);  // timed as one stage; every launch is counted
+    for (int j0 = 0; j0 < kmax; j0 += NB) {
+        k_mk_diag<<<(v.B + 3) / 4, 128, 0, st>>>(v, j0);
+        c->launches += 1;
+        const int rows = kmax - j0 - 1;
+        if (rows > 0) {
+            c->launches += 2;
+            dim3 gp((rows + 127) / 128, v.B);
+            k_mk_panel<<<gp, 128, 0, st>>>(v, j0);
+            const int mt = (rows + 31) / 32;
+            dim3 gt(mt * (mt + 1) / 2, v.B);
+            k_mk_trail<<<gt, 64, 0, st>>>(v, j0);
+        }
+    }
+    static size_t linv_cfg = 0;
+    const size_t linv_max = sizeof(double) * ((size_t)kmax * (NB + 1) + NB * (NB + 1));
+    if (linv_max > 48 * 1024 && linv_max > linv_cfg) {
+        cudaFuncSetAttribute(k_mk_linv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linv_max);
+        linv_cfg = linv_max;
+    }
+    for (int I0 = NB; I0 < kmax; I0 += NB) {
+        dim3 gl((I0 + 127) / 128, v.B);
+        k_mk_linv<<<gl, 128, sizeof(double) * ((size_t)I0 * (NB + 1) + NB * (NB + 1)), st>>>(v, I0);
+        c->launches += 1;
+    }
+    static size_t tail_cfg = 0;
+    const size_t tail_sm = sizeof(double) * (size_t)kmax * 5;
+    if (tail_sm > 48 * 1024 && tail_sm > tail_cfg) {
+        cudaFuncSetAttribute(k_mk_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_sm);
+        tail_cfg = tail_sm;
+    }
+    k_mk_tail<<<v.B, 128, tail_sm, st>>>(v);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -578,7 +862,21 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_sm);
         chol_cfg = chol_sm;
     }
-    { KScope ks(c, KT_CHOL); k_chol<<<v.B, 128, chol_sm, st>>>(v); }
+    // One block per filter fills the GPU once there are a few hundred filters (measured B=4096, k~98: block
+    // 2.2 ms, lock-step 3.8 ms).  Few filters with a large stacked innovation (large maps): the single block is a
+    // serial bottleneck (N=500, B=8: 7.1 of 11.5 ms per step), so every phase becomes its own launch over all
+    // filters with the parallelism that phase has.
+    static int chol_mode = -1;
+    if (chol_mode < 0) {
+        const char* e = getenv("EKFSLAM_CHOL");
+        chol_mode = (e && !strcmp(e, "block")) ? 0 : (e && !strcmp(e, "lockstep")) ? 1 : 2;  // 2 = by shape
+    }
+    if (chol_mode == 1 || (chol_mode == 2 && v.B < 128 && v.kmax >= 256)) {
+        launch_chol_lockstep(c);
+    } else {
+        KScope ks(c, KT_CHOL);
+        k_chol<<<v.B, 128, chol_sm, st>>>(v);
+    }
     dim3 gw((v.nmax + TM - 1) / TM, (v.kmax + TM - 1) / TM, v.B);
     const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax);
     gemm_attr(c, w_sm);

@@ -135,6 +135,50 @@ __device__ __forceinline__ void store_tile(double* __restrict__ P, int ld, int n
     }
 }
 
+
+// ---- K chunk: acc += A' B over n4 steps of 4 rows of the staged panels ------------------------------------
+// `a` / `b` point at this lane's first fragment element of the stage (q*TPAD + warp offset + g).  A warp whose
+// eight 8x8 DMMA tiles all have work (the common case) runs branch-free, fully unrolled code; the compiler
+// otherwise brackets every predicated mma.sync with WARPSYNC/NOP and re-derives the predicate per tile, which
+// made the DMMA one instruction in ten (ncu, round 1).
+__device__ __forceinline__ void mma_step_full(const double* __restrict__ a, const double* __restrict__ b, double (&acc)[4][2][2]) {
+    double af[4], bf[2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) af[mt] = a[mt * 8];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) bf[nt] = b[nt * 8];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+}
+__device__ __forceinline__ void mma_chunk(const double* __restrict__ a, const double* __restrict__ b, int n4, unsigned onmask,
+                                          double (&acc)[4][2][2]) {
+    if (onmask == 0xffu) {
+        if (n4 == TK / 4) {
+#pragma unroll
+            for (int k4 = 0; k4 < TK / 4; ++k4) mma_step_full(a + k4 * 4 * TPAD, b + k4 * 4 * TPAD, acc);
+        } else {
+#pragma unroll 1
+            for (int k4 = 0; k4 < n4; ++k4) mma_step_full(a + k4 * 4 * TPAD, b + k4 * 4 * TPAD, acc);
+        }
+    } else if (onmask != 0u) {
+#pragma unroll 1
+        for (int k4 = 0; k4 < n4; ++k4) {
+            double af[4], bf[2];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) af[mt] = a[k4 * 4 * TPAD + mt * 8];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) bf[nt] = b[k4 * 4 * TPAD + nt * 8];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+                    if (onmask & (1u << (mt * 2 + nt))) dmma(acc[mt][nt], af[mt], bf[nt]);
+        }
+    }
+}
+
 // ---- one CTA per tile, cp.async ring ------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
     extern __shared__ __align__(16) double dsm[];
@@ -187,6 +231,7 @@ __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const unsigned onmask = tile_mask(i0, j0, wr, wc, n, diag);
+    const int aoff = q * TPAD + wr * 32 + g, boff = q * TPAD + wc * 16 + g;
 
 #pragma unroll
     for (int st = 0; st < NSTAGE - 1; ++st) {
@@ -198,24 +243,9 @@ __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
         __syncthreads();
         if (it + NSTAGE - 1 < nk) load_stage((it + NSTAGE - 1) % NSTAGE, (it + NSTAGE - 1) * TK);
         cp_async_commit();
-        if (onmask == 0) continue;
         const double* as = As + (it % NSTAGE) * TK * TPAD;
         const double* bs = diag ? as : Bs + (it % NSTAGE) * TK * TPAD;
-        const int k4n = min(TK / 4, (k - it * TK + 3) >> 2);  // the tail panel stops at k (rounded to 4)
-#pragma unroll
-        for (int k4 = 0; k4 < TK / 4; ++k4) {
-            if (k4 >= k4n) break;
-            double af[4], bf[2];
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) af[mt] = as[(k4 * 4 + q) * TPAD + wr * 32 + mt * 8 + g];
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) bf[nt] = bs[(k4 * 4 + q) * TPAD + wc * 16 + nt * 8 + g];
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-                    if (onmask & (1u << (mt * 2 + nt))) dmma(acc[mt][nt], af[mt], bf[nt]);
-        }
+        mma_chunk(as + aoff, bs + boff, min(TK / 4, (k - it * TK + 3) >> 2), onmask, acc);  // the tail panel stops at k (rounded to 4)
     }
     cp_async_wait<0>();
     if (tj == 0)
@@ -289,6 +319,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, int T,
 
     // ================= consumer warps: 2 (rows) x 4 (cols), 32 x 16 each =================
     const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
+    const int aoff = q * TPAD + wr * 32 + g, boff = q * TPAD + wc * 16 + g;
     unsigned cnt = 0;
     for (int cm = 0; cm < Mreal; ++cm) {
         const DTile C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T);
@@ -310,23 +341,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, int T,
             mbar_wait(full + slot, ph);
             const double* as = As + slot * TK * TPAD;
             const double* bs = diag ? as : Bs + slot * TK * TPAD;
-            if (onmask != 0) {
-                const int k4n = min(TK / 4, (k - it * TK + 3) >> 2);
-#pragma unroll
-                for (int k4 = 0; k4 < TK / 4; ++k4) {
-                    if (k4 >= k4n) break;
-                    double af[4], bf[2];
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) af[mt] = as[(k4 * 4 + q) * TPAD + wr * 32 + mt * 8 + g];
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) bf[nt] = bs[(k4 * 4 + q) * TPAD + wc * 16 + nt * 8 + g];
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < 2; ++nt)
-                            if (onmask & (1u << (mt * 2 + nt))) dmma(acc[mt][nt], af[mt], bf[nt]);
-                }
-            }
+            mma_chunk(as + aoff, bs + boff, min(TK / 4, (k - it * TK + 3) >> 2), onmask, acc);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + slot);
         }
@@ -337,18 +352,260 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, int T,
     }
 }
 
+
+// ---- persistent, warp-specialised, with epilogue warps (default) ----------------------------------------
+// Roles per CTA (13 warps, 2 CTAs per SM); X = one shared [64][XP] tile buffer:
+//   warp  8     producer: streams the W panels with bulk copies through the mbarrier ring (as in k_downdate_ws).
+//   warps 0-7   consumers: K loop; then J on tile column 0 of X (the prefetched P tile), X <- X - acc, and straight on
+//               to the next tile.
+//   warps 9-12  epilogue: row-coalesced stores of the tile and of its mirror image (read
+//               transposed from X), then the bulk-copy prefetch of the NEXT tile's P into X, which completes
+//               (mbarrier pfull) while the consumers run that tile's K loop.
+// k_downdate_ws keeps the P loads and the stores in the consumer warps, so each CTA alternates between a DMMA phase
+// and a load/store phase and the two CTAs of an SM drift into the same phase (ablation in DESIGN.md §3.1: consumers
+// without copies 3.42 ms = DMMA 2.03 + stores 1.39); here both phases run concurrently inside every CTA and no
+// P value is ever held in registers across the K loop.
+#define WS2_EPI 4
+#define WS2_THREADS ((WS_CONSUMERS + 1 + WS2_EPI) * 32)
+#define XP 66   // row pitch of X in doubles: rows stay 16-byte aligned for bulk copies and double2 access
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// bulk-copy prefetch of the P tile of `t` into X (one epilogue warp; two rows per lane)
+__device__ __forceinline__ void epi_prefetch_p(double* X, const double* __restrict__ P, int ld, const DTile& t, int lane,
+                                               unsigned long long* pfull) {
+    const int nrows = min(TM, t.n - t.i0);
+    const unsigned rowbytes = (unsigned)(min(TM, ld - t.j0) * 8);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // X was last read through the generic proxy
+    if (lane == 0) mbar_arrive_expect_tx(pfull, (unsigned)nrows * rowbytes);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r = lane + 32 * h;
+        if (r < nrows) bulk_g2s(X + r * XP, P + (size_t)(t.i0 + r) * ld + t.j0, rowbytes, pfull);
+    }
+}
+
+__global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int T, int b0, long long total, int M) {
+    extern __shared__ __align__(16) double dsm[];
+    double* As = dsm;                                   // [WS_STAGES][TK][TPAD]
+    double* Bs = dsm + WS_STAGES * TK * TPAD;           // [WS_STAGES][TK][TPAD]
+    double* X = Bs + WS_STAGES * TK * TPAD;             // [64][XP]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(X + TM * XP);   // [WS_STAGES]
+    unsigned long long* empty = full + WS_STAGES;                                     // [WS_STAGES]
+    unsigned long long* pfull = empty + WS_STAGES;   // P tile landed in X
+    unsigned long long* cfull = pfull + 1;           // X holds P - acc
+    int2* meta = reinterpret_cast<int2*>(cfull + 1);                                  // [M]  {ktot, n}
+    unsigned* lut = reinterpret_cast<unsigned*>(meta + M);                            // [T]  ti<<16|tj
+    const int ld = v.ld, kmax = v.kmax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long G = gridDim.x;
+    for (int m = tid; m < M; m += blockDim.x) {
+        const long long t = blockIdx.x + (long long)m * G;
+        int2 kn = make_int2(0, 0);
+        if (t < total) { const int b = b0 + (int)(t / T); kn = make_int2(v.ktot[b], v.nstate[b]); }
+        meta[m] = kn;
+    }
+    for (int e = tid; e < T; e += blockDim.x) {
+        int ti = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+        while (ti * (ti + 1) / 2 > e) --ti;
+        lut[e] = ((unsigned)ti << 16) | (unsigned)(e - ti * (ti + 1) / 2);
+    }
+    if (tid == 0) {
+        for (int s2 = 0; s2 < WS_STAGES; ++s2) { mbar_init(full + s2, 32); mbar_init(empty + s2, WS_CONSUMERS); }
+        mbar_init(pfull, 1);
+        mbar_init(cfull, WS_CONSUMERS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int own = (int)((total - blockIdx.x + G - 1) / G);
+    const int Mreal = own < M ? own : M;
+
+    if (warp == WS_CONSUMERS) {
+        // ================= producer warp =================
+        unsigned cnt = 0;
+        const int pr = lane & 15;        // row of the [TK][64] panel this lane copies
+        const bool isB = lane >= 16;     // lanes 0-15: A panel (rows of W at i0), 16-31: B panel (at j0)
+        for (int m = 0; m < Mreal; ++m) {
+            const DTile L = decode_tile(meta, lut, m, Mreal, blockIdx.x + (long long)m * G, T);
+            if (L.nk == 0) continue;
+            const double* __restrict__ W = v.W + (size_t)(b0 + L.b) * kmax * ld;
+            const int c0 = isB ? L.j0 : L.i0;
+            const unsigned rowbytes = (unsigned)(min(TM, ld - c0) * 8);
+            const unsigned bytesA = (unsigned)(min(TM, ld - L.i0) * 8), bytesB = (unsigned)(min(TM, ld - L.j0) * 8);
+            for (int st = 0; st < L.nk; ++st, ++cnt) {
+                const unsigned slot = cnt % WS_STAGES, ph = (cnt / WS_STAGES) & 1u;
+                mbar_wait(empty + slot, ph ^ 1u);
+                const int t0 = st * TK;
+                const int nvalid = min(TK, L.k - t0);
+                double* dst = (isB ? Bs : As) + slot * TK * TPAD + pr * TPAD;
+                if (lane == 0) mbar_arrive_expect_tx(full + slot, (unsigned)nvalid * (bytesA + (L.diag ? 0u : bytesB)));
+                const bool mine = !(isB && L.diag);
+                if (mine && pr < nvalid) {
+                    bulk_g2s(dst, W + (size_t)(t0 + pr) * ld + c0, rowbytes, full + slot);
+                } else if (mine && pr < ((nvalid + 3) & ~3)) {
+                    for (int c = 0; c < TM; ++c) dst[c] = 0.0;  // rows between k and the next multiple of 4
+                }
+                if (lane != 0) mbar_arrive(full + slot);
+            }
+        }
+        return;
+    }
+
+    if (warp < WS_CONSUMERS) {
+        // ================= consumer warps: 2 (rows) x 4 (cols), 32 x 16 each =================
+        const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
+        const int aoff = q * TPAD + wr * 32 + g, boff = q * TPAD + wc * 16 + g;
+        double* xdst = X + (wr * 32 + g) * XP + wc * 16 + 2 * q;
+        unsigned cnt = 0, tiles = 0;
+        for (int cm = 0; cm < Mreal; ++cm) {
+            const DTile C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T);
+            if (C.nk == 0) continue;
+            const unsigned onmask = tile_mask(C.i0, C.j0, wr, wc, C.n, C.diag);
+            double acc[4][2][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int it = 0; it < C.nk; ++it, ++cnt) {
+                const unsigned slot = cnt % WS_STAGES, ph = (cnt / WS_STAGES) & 1u;
+                mbar_wait(full + slot, ph);
+                const double* as = As + slot * TK * TPAD;
+                const double* bs = C.diag ? as : Bs + slot * TK * TPAD;
+                mma_chunk(as + aoff, bs + boff, min(TK / 4, (C.k - it * TK + 3) >> 2), onmask, acc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + slot);
+            }
+            mbar_wait(pfull, tiles & 1u);   // this tile's P has landed (and the previous tile has left X)
+            if (C.col0) {
+                // J P J' on the P tile itself (W already carries J, see k_wfix): columns 3..6 of tile column 0, rows 3..6
+                // of tile (0,0)
+                const double* __restrict__ Jn = v.jn + (size_t)(b0 + C.b) * 16;
+                if (tid < TM) {
+                    double* xr = X + tid * XP;
+                    const double c3 = xr[3], c4 = xr[4], c5 = xr[5], c6 = xr[6];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) xr[3 + a] = c3 * Jn[a * 4 + 0] + c4 * Jn[a * 4 + 1] + c5 * Jn[a * 4 + 2] + c6 * Jn[a * 4 + 3];
+                }
+                cons_bar();
+                if (C.diag) {
+                    if (tid < 8) {
+                        const double r3 = X[3 * XP + tid], r4 = X[4 * XP + tid], r5 = X[5 * XP + tid], r6 = X[6 * XP + tid];
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+                            X[(3 + a) * XP + tid] = Jn[a * 4 + 0] * r3 + Jn[a * 4 + 1] * r4 + Jn[a * 4 + 2] * r5 + Jn[a * 4 + 3] * r6;
+                    }
+                    cons_bar();
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    double2* xp = reinterpret_cast<double2*>(xdst + (mt * 8) * XP + nt * 8);
+                    double2 pv = *xp;
+                    pv.x -= acc[mt][nt][0];
+                    pv.y -= acc[mt][nt][1];
+                    *xp = pv;
+                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cfull);
+            ++tiles;
+        }
+        return;
+    }
+
+    // ================= epilogue warps =================
+    const int et = tid - (WS_CONSUMERS + 1) * 32, ew = et >> 5;
+    unsigned tiles = 0;
+    int cm = 0;
+    DTile C = decode_tile(meta, lut, 0, Mreal, blockIdx.x, T);
+    while (cm < Mreal && C.nk == 0) { ++cm; C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T); }
+    if (cm < Mreal && ew == 0) epi_prefetch_p(X, v.P + (size_t)(b0 + C.b) * v.nmax * ld, ld, C, lane, pfull);
+    while (cm < Mreal) {
+        double* __restrict__ P = v.P + (size_t)(b0 + C.b) * v.nmax * ld;
+        const int n = C.n, i0 = C.i0, j0 = C.j0;
+        mbar_wait(cfull, tiles & 1u);
+        // stores: one 512-byte row segment (tile) / two 256-byte segments (mirror image) per warp instruction
+        const int c = 2 * lane;
+        if (!C.diag) {
+#pragma unroll 4
+            for (int p = 0; p < 16; ++p) {
+                const int r = ew + 4 * p;
+                if (i0 + r < n) {
+                    const double2 val = *reinterpret_cast<const double2*>(X + r * XP + c);
+                    double* o = P + (size_t)(i0 + r) * ld + j0 + c;
+                    if (j0 + c + 1 < n) *reinterpret_cast<double2*>(o) = val;
+                    else if (j0 + c < n) o[0] = val.x;
+                }
+                if (j0 + r < n) {   // mirror image: row j0 + r of P, columns i0 ..
+                    double* mrow = P + (size_t)(j0 + r) * ld + i0;
+                    if (i0 + lane < n) mrow[lane] = X[lane * XP + r];
+                    if (i0 + lane + 32 < n) mrow[lane + 32] = X[(lane + 32) * XP + r];
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int p = 0; p < 16; ++p) {
+                const int r = ew + 4 * p;
+                if (i0 + r < n) {
+                    const double a = (c <= r) ? X[r * XP + c] : X[c * XP + r];
+                    const double bq = (c + 1 <= r) ? X[r * XP + c + 1] : X[(c + 1) * XP + r];
+                    double* o = P + (size_t)(i0 + r) * ld + i0 + c;
+                    if (i0 + c + 1 < n) *reinterpret_cast<double2*>(o) = make_double2(a, bq);
+                    else if (i0 + c < n) o[0] = a;
+                }
+            }
+        }
+        epi_bar();   // every epilogue thread is done reading X
+        ++tiles;
+        do { ++cm; C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T); } while (cm < Mreal && C.nk == 0);
+        if (cm < Mreal && ew == 0) epi_prefetch_p(X, v.P + (size_t)(b0 + C.b) * v.nmax * ld, ld, C, lane, pfull);
+    }
+}
+
 void launch_downdate(ekfslam_ctx* c, int slot) {
     DevView& v = c->v;
     static int mode = -1, sms = 0;
     if (mode < 0) {
         const char* e = getenv("EKFSLAM_DOWNDATE");
-        mode = (e && !strcmp(e, "tile")) ? 0 : 1;  // default: warp-specialised persistent kernel
+        mode = (e && !strcmp(e, "tile")) ? 0 : (e && !strcmp(e, "ws")) ? 1 : 2;  // default: epilogue-warp kernel
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     }
     const int nt = (v.nmax + TM - 1) / TM;
     const int T = nt * (nt + 1) / 2;
     KScope ks(c, slot);
-    if (mode == 1) {
+    if (mode == 2) {
+        // filters are processed in groups small enough for the per-CTA tile metadata (8 B per tile) to stay
+        // within the shared-memory budget of two CTAs per SM
+        const long long ctas_full = (long long)sms * 2;
+        const size_t fixed = sizeof(double) * (2 * WS_STAGES * TK * TPAD + TM * XP) + sizeof(unsigned long long) * (2 * WS_STAGES + 2) +
+                             sizeof(unsigned) * T;
+        const size_t budget = 111 * 1024;
+        if (fixed + 64 * sizeof(int2) <= budget) {
+            const long long Mcap = (long long)((budget - fixed) / sizeof(int2));
+            long long bgroup = (Mcap * ctas_full) / T;
+            if (bgroup < 1) bgroup = 1;
+            static size_t cfg2 = 0;
+            for (long long b0 = 0; b0 < v.B; b0 += bgroup) {
+                const long long nb = (v.B - b0 < bgroup) ? (v.B - b0) : bgroup;
+                const long long total = (long long)T * nb;
+                const long long ctas = total < ctas_full ? total : ctas_full;
+                const int M = (int)((total + ctas - 1) / ctas);
+                const size_t sm2 = fixed + sizeof(int2) * M;
+                if (sm2 > cfg2) {
+                    cudaFuncSetAttribute(k_downdate_ws2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+                    cfg2 = sm2;
+                }
+                k_downdate_ws2<<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M);
+                if (b0 > 0) c->launches++;
+            }
+            return;
+        }
+    }
+    if (mode >= 1) {
         const long long total = (long long)T * v.B;
         const long long ctas = total < (long long)sms * 2 ? total : (long long)sms * 2;
         const int M = (int)((total + ctas - 1) / ctas);

@@ -656,6 +656,8 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const int tmax_w = (mode == 0) ? min(k, a0 + wr * 32 + 32) : kk;
+    const int rbase = a0 + wr * 32;
+    const int mt_hi = max(0, min(4, (k - rbase + 7) >> 3));
 
 #pragma unroll
     for (int st = 0; st < NSTAGE - 1; ++st) {
@@ -673,22 +675,42 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
             const int tmax = min(TK, k - it * TK);
             for (int t = 0; t < tmax; ++t) xacc += bs[t * TPAD + tid] * cs[it * TK + t];
         }
+        // 8-row tile mt of this warp (rows rbase + 8 mt ..) takes part in step tb when it exists (mt < mt_hi) and,
+        // for the triangular A of mode 0, when tb <= its last row (mt >= mt_lo): a contiguous range.  Steps where all
+        // four take part run branch-free (a predicated mma.sync costs a WARPSYNC/NOP pair and a predicate each).
+        const double* ap = as + (wr * 32 + g) * APAD + q;
+        const double* bp = bs + q * TPAD + wc * 16 + g;
+        const int tb0 = it * TK;
+        if (mt_hi == 4 && tb0 + TK <= tmax_w && (mode != 0 || tb0 + TK - 4 < rbase + 8)) {
 #pragma unroll
-        for (int k4 = 0; k4 < TK / 4; ++k4) {
-            const int tb = it * TK + k4 * 4;
-            if (tb >= tmax_w) break;
-            double af[4], bf[2];
+            for (int k4 = 0; k4 < TK / 4; ++k4) {
+                double af[4], bf[2];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) af[mt] = as[(wr * 32 + mt * 8 + g) * APAD + k4 * 4 + q];
+                for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * APAD + k4 * 4];
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) bf[nt] = bs[(k4 * 4 + q) * TPAD + wc * 16 + nt * 8 + g];
+                for (int nt = 0; nt < 2; ++nt) bf[nt] = bp[k4 * 4 * TPAD + nt * 8];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
-                // 8-row tile mt: rows r0..r0+7 exist if r0 < k; a triangular A needs t <= r0+7 only
-                const int r0 = a0 + wr * 32 + mt * 8;
-                if (r0 < k && (mode != 0 || tb <= r0 + 7)) {
+                for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+            }
+        } else {
+#pragma unroll 1
+            for (int k4 = 0; k4 < TK / 4; ++k4) {
+                const int tb = tb0 + k4 * 4;
+                if (tb >= tmax_w) break;
+                const int mt_lo = (mode == 0) ? max(0, (tb - rbase) >> 3) : 0;
+                double af[4], bf[2];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * APAD + k4 * 4];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) bf[nt] = bp[k4 * 4 * TPAD + nt * 8];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    if (mt >= mt_lo && mt < mt_hi) {
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+                    }
                 }
             }
         }

@@ -188,7 +188,8 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     DA(v.xp, Bz * v.ld);
     DA(v.P, Bz * v.nmax * v.ld);
     DA(v.G, Bz * v.kmax * v.ld);
-    DA(v.W, Bz * v.kmax * v.ld);
+    v.wstride = (long long)((v.ld + 63) / 64) * v.kmax * EKF_WPAD;
+    DA(v.W, Bz * (size_t)v.wstride);
     DA(v.Sb, Bz * v.kmax * v.kmax);
     DA(v.Li, Bz * v.kmax * v.kmax);
     DA(v.yv, Bz * v.kmax);

@@ -23,7 +23,8 @@ struct DevView {
     double* xp;           // [B][ld]      x_k_km1
     double* P;            // [B][nmax][ld] covariance (single buffer, updated in place)
     double* G;            // [B][kmax][ld] rows 2i,2i+1 = H_i * P
-    double* W;            // [B][kmax][ld] W = inv(L) * G_sel
+    double* W;            // [B][ncb][kmax][EKF_WPAD] W = inv(L) * G_sel, stored by 64-column panels (see w_at)
+    long long wstride;    // doubles per filter in W = ncb * kmax * EKF_WPAD, ncb = ceil(ld / 64)
     double* Sb;           // [B][kmax][kmax] stacked innovation covariance / its Cholesky factor
     double* Li;           // [B][kmax][kmax] inverse of the Cholesky factor
     double* yv;           // [B][kmax]     inv(L)*(z-h)
@@ -79,6 +80,14 @@ struct ekfslam_ctx {
     // the context's own frame buffers while caller-owned ones are bound (ekfslam_bind_frame)
     double* own_zc; uint8_t* own_mflags; double* own_u; int own_n_u;
 };
+
+// W is stored panel-major: element (row t, column c) of a filter lives at ((c / 64) * kmax + t) * EKF_WPAD + c % 64.
+// A K-chunk of a 64-column panel ([rows][68] doubles, the padded shared-memory layout of the tensor-core
+// kernels) is then ONE contiguous range, i.e. one bulk copy per panel and stage instead of one per row.
+#define EKF_WPAD 68
+__host__ __device__ __forceinline__ size_t w_at(int kmax, int t, int c) {
+    return ((size_t)(c >> 6) * kmax + t) * EKF_WPAD + (c & 63);
+}
 
 #define EKF_TRI(nic, s) (((nic) * ((nic) + 1)) / 2 + (s))
 

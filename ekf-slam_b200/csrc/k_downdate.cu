@@ -7,13 +7,13 @@
 // because the lower triangle is authoritative and every tile is stored together with its mirror image.
 //
 // Two kernels, same arithmetic and summation order (k ascending, DMMA m8n8k4):
-//   k_downdate_ws   (default) persistent, warp-specialised: a producer warp streams the W panels with bulk
-//                   asynchronous copies (cp.async.bulk -> SASS UBLKCP) completing on a 4-stage mbarrier ring
-//                   that keeps running across tile boundaries; 8 consumer warps issue the DMMAs.
+//   k_downdate_ws2  (default) persistent, warp-specialised, 2 CTAs per SM: a producer warp streams the W panels with
+//                   bulk asynchronous copies (cp.async.bulk -> SASS UBLKCP, one per panel and stage thanks to the
+//                   panel-major W layout) on a 4-stage mbarrier ring that keeps running across tile boundaries; 8
+//                   consumer warps issue the DMMAs; 4 epilogue warps prefetch the next P tile into shared memory and
+//                   store the finished tile and its mirror image while the consumers are already in the next K loop.
 //   k_downdate_tile (EKFSLAM_DOWNDATE=tile, and the fallback for shapes whose tile list does not fit the
 //                   persistent kernel's shared memory) one CTA per tile, cp.async (LDGSTS) ring.
-// Measured (tools/dbg_downdate.py ablation): the kernel is bound by the bytes moved between
-// L2 and the SMs (W panel re-reads + P tile + mirrored stores), not by the fp64 tensor pipe.
 #include <cstdlib>
 #include <cstring>
 #include "model.cuh"
@@ -21,7 +21,6 @@
 
 #define WS_STAGES 4
 #define WS_CONSUMERS 8
-#define WS_THREADS ((WS_CONSUMERS + 1) * 32)
 
 // ---- shared epilogue pieces ---------------------------------------------------------------------------
 // bit mt*2+nt of the mask: the warp's 8x8 DMMA tile (mt, nt) has work (inside n x n, not strictly above the
@@ -194,7 +193,7 @@ __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
     const int i0 = ti * TM, j0 = tj * TM;
     if (i0 >= n) return;
     const int ld = v.ld, kmax = v.kmax;
-    const double* __restrict__ W = v.W + (size_t)b * kmax * ld;
+    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
     double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
     const bool diag = (ti == tj);
     double* As = dsm;                            // [NSTAGE][TK][TPAD]
@@ -208,8 +207,8 @@ __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
     const int nk = (k + TK - 1) / TK;
     const int lr = tid >> 5, lcc = (tid & 31) * 2;
     const bool cola = (i0 + lcc < ld), colb = (j0 + lcc < ld);
-    const double* __restrict__ wa = W + (size_t)lr * ld + i0 + lcc;
-    const double* __restrict__ wb = W + (size_t)lr * ld + j0 + lcc;
+    const double* __restrict__ wa = W + w_at(kmax, lr, i0 + lcc);   // panel-major W: row stride EKF_WPAD inside a panel
+    const double* __restrict__ wb = W + w_at(kmax, lr, j0 + lcc);
     const int soff = lr * TPAD + lcc;
     auto load_stage = [&](int st, int t0) {
         double* as = As + st * TK * TPAD + soff;
@@ -218,10 +217,10 @@ __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
         for (int j = 0; j < 2; ++j) {
             const int tt = t0 + lr + 8 * j;
             const bool oka = (tt < k) && cola;
-            cp_async16(as + 8 * j * TPAD, oka ? wa + (size_t)(t0 + 8 * j) * ld : W, oka ? 16 : 0);
+            cp_async16(as + 8 * j * TPAD, oka ? wa + (size_t)(t0 + 8 * j) * EKF_WPAD : W, oka ? 16 : 0);
             if (!diag) {
                 const bool okb = (tt < k) && colb;
-                cp_async16(bs + 8 * j * TPAD, okb ? wb + (size_t)(t0 + 8 * j) * ld : W, okb ? 16 : 0);
+                cp_async16(bs + 8 * j * TPAD, okb ? wb + (size_t)(t0 + 8 * j) * EKF_WPAD : W, okb ? 16 : 0);
             }
         }
     };
@@ -253,118 +252,18 @@ __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
     store_tile(P, ld, n, i0, j0, wr, wc, g, q, diag, onmask, pf, acc);
 }
 
-// ---- persistent, warp-specialised ---------------------------------------------------------------------
-__global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, int T, long long total, int M) {
-    extern __shared__ __align__(16) double dsm[];
-    double* As = dsm;                                   // [WS_STAGES][TK][TPAD]
-    double* Bs = dsm + WS_STAGES * TK * TPAD;           // [WS_STAGES][TK][TPAD]
-    double* strip = Bs + WS_STAGES * TK * TPAD;         // [64][9]
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(strip + TM * 9);   // [WS_STAGES]
-    unsigned long long* empty = full + WS_STAGES;                                        // [WS_STAGES]
-    int2* meta = reinterpret_cast<int2*>(empty + WS_STAGES);                             // [M]  {ktot, n}
-    unsigned* lut = reinterpret_cast<unsigned*>(meta + M);                               // [T]  ti<<16|tj
-    const int ld = v.ld, kmax = v.kmax;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long G = gridDim.x;
-    for (int m = tid; m < M; m += blockDim.x) {
-        const long long t = blockIdx.x + (long long)m * G;
-        int2 kn = make_int2(0, 0);
-        if (t < total) { const int b = (int)(t / T); kn = make_int2(v.ktot[b], v.nstate[b]); }
-        meta[m] = kn;
-    }
-    for (int e = tid; e < T; e += blockDim.x) {
-        int ti = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
-        while (ti * (ti + 1) / 2 > e) --ti;
-        lut[e] = ((unsigned)ti << 16) | (unsigned)(e - ti * (ti + 1) / 2);
-    }
-    if (tid == 0) {
-        for (int s2 = 0; s2 < WS_STAGES; ++s2) { mbar_init(full + s2, 32); mbar_init(empty + s2, WS_CONSUMERS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int own = (int)((total - blockIdx.x + G - 1) / G);
-    const int Mreal = own < M ? own : M;
-
-    if (warp == WS_CONSUMERS) {
-        // ================= producer warp =================
-        unsigned cnt = 0;
-        const int pr = lane & 15;        // row of the [TK][64] panel this lane copies
-        const bool isB = lane >= 16;     // lanes 0-15: A panel (rows of W at i0), 16-31: B panel (at j0)
-        for (int m = 0; m < Mreal; ++m) {
-            const DTile L = decode_tile(meta, lut, m, Mreal, blockIdx.x + (long long)m * G, T);
-            if (L.nk == 0) continue;
-            const double* __restrict__ W = v.W + (size_t)L.b * kmax * ld;
-            const int c0 = isB ? L.j0 : L.i0;
-            const unsigned rowbytes = (unsigned)(min(TM, ld - c0) * 8);
-            const unsigned bytesA = (unsigned)(min(TM, ld - L.i0) * 8), bytesB = (unsigned)(min(TM, ld - L.j0) * 8);
-            for (int st = 0; st < L.nk; ++st, ++cnt) {
-                const unsigned slot = cnt % WS_STAGES, ph = (cnt / WS_STAGES) & 1u;
-                mbar_wait(empty + slot, ph ^ 1u);
-                const int t0 = st * TK;
-                const int nvalid = min(TK, L.k - t0);
-                double* dst = (isB ? Bs : As) + slot * TK * TPAD + pr * TPAD;
-                if (lane == 0) mbar_arrive_expect_tx(full + slot, (unsigned)nvalid * (bytesA + (L.diag ? 0u : bytesB)));
-                const bool mine = !(isB && L.diag);
-                if (mine && pr < nvalid) {
-                    bulk_g2s(dst, W + (size_t)(t0 + pr) * ld + c0, rowbytes, full + slot);
-                } else if (mine && pr < ((nvalid + 3) & ~3)) {
-                    for (int c = 0; c < TM; ++c) dst[c] = 0.0;  // rows between k and the next multiple of 4
-                }
-                if (lane != 0) mbar_arrive(full + slot);
-            }
-        }
-        return;
-    }
-
-    // ================= consumer warps: 2 (rows) x 4 (cols), 32 x 16 each =================
-    const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
-    const int aoff = q * TPAD + wr * 32 + g, boff = q * TPAD + wc * 16 + g;
-    unsigned cnt = 0;
-    for (int cm = 0; cm < Mreal; ++cm) {
-        const DTile C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T);
-        if (C.nk == 0) continue;
-        const int n = C.n, k = C.k, i0 = C.i0, j0 = C.j0;
-        const bool diag = C.diag;
-        double* __restrict__ P = v.P + (size_t)C.b * v.nmax * ld;
-        double pf[4][2][2];
-        load_p_frags(P, ld, n, i0, j0, wr, wc, g, q, pf);
-        const unsigned onmask = tile_mask(i0, j0, wr, wc, n, diag);
-        double acc[4][2][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-        for (int it = 0; it < C.nk; ++it, ++cnt) {
-            const unsigned slot = cnt % WS_STAGES, ph = (cnt / WS_STAGES) & 1u;
-            mbar_wait(full + slot, ph);
-            const double* as = As + slot * TK * TPAD;
-            const double* bs = diag ? as : Bs + slot * TK * TPAD;
-            mma_chunk(as + aoff, bs + boff, min(TK / 4, (k - it * TK + 3) >> 2), onmask, acc);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);
-        }
-        if (C.col0)
-            apply_j_col0(strip, v.jn + (size_t)C.b * 16, diag, wr, wc, g, q, tid, pf,
-                         [] { asm volatile("bar.sync 1, 256;" ::: "memory"); });  // the 8 consumer warps only
-        store_tile(P, ld, n, i0, j0, wr, wc, g, q, diag, onmask, pf, acc);
-    }
-}
-
-
 // ---- persistent, warp-specialised, with epilogue warps (default) ----------------------------------------
 // Roles per CTA (13 warps, 2 CTAs per SM); X = one shared [64][XP] tile buffer:
-//   warp  8     producer: streams the W panels with bulk copies through the mbarrier ring (as in k_downdate_ws).
+//   warp  8     producer: streams the W panels with bulk copies through the mbarrier ring (one per panel and stage).
 //   warps 0-7   consumers: K loop; then J on tile column 0 of X (the prefetched P tile), X <- X - acc, and straight on
 //               to the next tile.
 //   warps 9-12  epilogue: row-coalesced stores of the tile and of its mirror image (read
 //               transposed from X), then the bulk-copy prefetch of the NEXT tile's P into X, which completes
 //               (mbarrier pfull) while the consumers run that tile's K loop.
-// k_downdate_ws keeps the P loads and the stores in the consumer warps, so each CTA alternates between a DMMA phase
-// and a load/store phase and the two CTAs of an SM drift into the same phase (ablation in DESIGN.md §3.1: consumers
-// without copies 3.42 ms = DMMA 2.03 + stores 1.39); here both phases run concurrently inside every CTA and no
-// P value is ever held in registers across the K loop.
+// The round-1 kernel kept the P loads and the stores in the consumer warps, so each CTA alternated between a DMMA
+// phase and a load/store phase and the two CTAs of an SM drifted into the same phase (ablation in DESIGN.md §3.1:
+// consumers without copies 3.42 ms = DMMA 2.03 + stores 1.39); here both phases run concurrently inside every CTA
+// and no P value is held in registers across the K loop.
 #define WS2_EPI 4
 #define WS2_THREADS ((WS_CONSUMERS + 1 + WS2_EPI) * 32)
 #define XP 66   // row pitch of X in doubles: rows stay 16-byte aligned for bulk copies and double2 access
@@ -372,19 +271,16 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_downdate_ws(DevView v, int T,
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// bulk-copy prefetch of the P tile of `t` into X (one epilogue warp; two rows per lane)
-__device__ __forceinline__ void epi_prefetch_p(double* X, const double* __restrict__ P, int ld, const DTile& t, int lane,
+// bulk-copy prefetch of the P tile of `t` into X: 16 rows per epilogue warp, one row per lane (a bulk copy is a
+// uniform-datapath instruction, so the copies of one warp issue one after the other; four warps issue in parallel)
+__device__ __forceinline__ void epi_prefetch_p(double* X, const double* __restrict__ P, int ld, const DTile& t, int ew, int lane,
                                                unsigned long long* pfull) {
     const int nrows = min(TM, t.n - t.i0);
     const unsigned rowbytes = (unsigned)(min(TM, ld - t.j0) * 8);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // X was last read through the generic proxy
-    if (lane == 0) mbar_arrive_expect_tx(pfull, (unsigned)nrows * rowbytes);
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int r = lane + 32 * h;
-        if (r < nrows) bulk_g2s(X + r * XP, P + (size_t)(t.i0 + r) * ld + t.j0, rowbytes, pfull);
-    }
+    if (ew == 0 && lane == 0) mbar_arrive_expect_tx(pfull, (unsigned)nrows * rowbytes);
+    const int r = ew * 16 + lane;
+    if (lane < 16 && r < nrows) bulk_g2s(X + r * XP, P + (size_t)(t.i0 + r) * ld + t.j0, rowbytes, pfull);
 }
 
 __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int T, int b0, long long total, int M) {
@@ -425,30 +321,37 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
 
     if (warp == WS_CONSUMERS) {
         // ================= producer warp =================
+        // W is panel-major (common.cuh, w_at): the K chunk of a 64-column panel is one contiguous range that already
+        // has the padded [TK][TPAD] shared-memory layout -> one bulk copy per panel and stage, issued by lane 0.
         unsigned cnt = 0;
-        const int pr = lane & 15;        // row of the [TK][64] panel this lane copies
-        const bool isB = lane >= 16;     // lanes 0-15: A panel (rows of W at i0), 16-31: B panel (at j0)
         for (int m = 0; m < Mreal; ++m) {
             const DTile L = decode_tile(meta, lut, m, Mreal, blockIdx.x + (long long)m * G, T);
             if (L.nk == 0) continue;
-            const double* __restrict__ W = v.W + (size_t)(b0 + L.b) * kmax * ld;
-            const int c0 = isB ? L.j0 : L.i0;
-            const unsigned rowbytes = (unsigned)(min(TM, ld - c0) * 8);
-            const unsigned bytesA = (unsigned)(min(TM, ld - L.i0) * 8), bytesB = (unsigned)(min(TM, ld - L.j0) * 8);
+            const double* __restrict__ W = v.W + (size_t)(b0 + L.b) * v.wstride;
+            const double* __restrict__ wa = W + w_at(kmax, 0, L.i0);
+            const double* __restrict__ wb = W + w_at(kmax, 0, L.j0);
             for (int st = 0; st < L.nk; ++st, ++cnt) {
                 const unsigned slot = cnt % WS_STAGES, ph = (cnt / WS_STAGES) & 1u;
                 mbar_wait(empty + slot, ph ^ 1u);
                 const int t0 = st * TK;
                 const int nvalid = min(TK, L.k - t0);
-                double* dst = (isB ? Bs : As) + slot * TK * TPAD + pr * TPAD;
-                if (lane == 0) mbar_arrive_expect_tx(full + slot, (unsigned)nvalid * (bytesA + (L.diag ? 0u : bytesB)));
-                const bool mine = !(isB && L.diag);
-                if (mine && pr < nvalid) {
-                    bulk_g2s(dst, W + (size_t)(t0 + pr) * ld + c0, rowbytes, full + slot);
-                } else if (mine && pr < ((nvalid + 3) & ~3)) {
-                    for (int c = 0; c < TM; ++c) dst[c] = 0.0;  // rows between k and the next multiple of 4
+                double* da = As + slot * TK * TPAD;
+                double* db = Bs + slot * TK * TPAD;
+                if (lane == 0) {
+                    const unsigned bytes = (unsigned)(nvalid * TPAD * 8);
+                    mbar_arrive_expect_tx(full + slot, L.diag ? bytes : 2u * bytes);
+                    bulk_g2s(da, wa + (size_t)t0 * TPAD, bytes, full + slot);
+                    if (!L.diag) bulk_g2s(db, wb + (size_t)t0 * TPAD, bytes, full + slot);
+                } else {
+                    if (nvalid & 3) {   // rows between k and the next multiple of 4 are zero
+                        const int nz = (((nvalid + 3) & ~3) - nvalid) * TPAD;
+                        for (int e = lane - 1; e < nz; e += 31) {
+                            da[nvalid * TPAD + e] = 0.0;
+                            if (!L.diag) db[nvalid * TPAD + e] = 0.0;
+                        }
+                    }
+                    mbar_arrive(full + slot);
                 }
-                if (lane != 0) mbar_arrive(full + slot);
             }
         }
         return;
@@ -523,7 +426,7 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
     int cm = 0;
     DTile C = decode_tile(meta, lut, 0, Mreal, blockIdx.x, T);
     while (cm < Mreal && C.nk == 0) { ++cm; C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T); }
-    if (cm < Mreal && ew == 0) epi_prefetch_p(X, v.P + (size_t)(b0 + C.b) * v.nmax * ld, ld, C, lane, pfull);
+    if (cm < Mreal) epi_prefetch_p(X, v.P + (size_t)(b0 + C.b) * v.nmax * ld, ld, C, ew, lane, pfull);
     while (cm < Mreal) {
         double* __restrict__ P = v.P + (size_t)(b0 + C.b) * v.nmax * ld;
         const int n = C.n, i0 = C.i0, j0 = C.j0;
@@ -562,7 +465,7 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
         epi_bar();   // every epilogue thread is done reading X
         ++tiles;
         do { ++cm; C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T); } while (cm < Mreal && C.nk == 0);
-        if (cm < Mreal && ew == 0) epi_prefetch_p(X, v.P + (size_t)(b0 + C.b) * v.nmax * ld, ld, C, lane, pfull);
+        if (cm < Mreal) epi_prefetch_p(X, v.P + (size_t)(b0 + C.b) * v.nmax * ld, ld, C, ew, lane, pfull);
     }
 }
 
@@ -571,7 +474,7 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
     static int mode = -1, sms = 0;
     if (mode < 0) {
         const char* e = getenv("EKFSLAM_DOWNDATE");
-        mode = (e && !strcmp(e, "tile")) ? 0 : (e && !strcmp(e, "ws")) ? 1 : 2;  // default: epilogue-warp kernel
+        mode = (e && !strcmp(e, "tile")) ? 0 : 2;  // default: persistent warp-specialised kernel
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     }
     const int nt = (v.nmax + TM - 1) / TM;
@@ -602,22 +505,6 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
                 k_downdate_ws2<<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M);
                 if (b0 > 0) c->launches++;
             }
-            return;
-        }
-    }
-    if (mode >= 1) {
-        const long long total = (long long)T * v.B;
-        const long long ctas = total < (long long)sms * 2 ? total : (long long)sms * 2;
-        const int M = (int)((total + ctas - 1) / ctas);
-        const size_t ws_sm = sizeof(double) * (2 * WS_STAGES * TK * TPAD + TM * 9) + sizeof(unsigned long long) * 2 * WS_STAGES +
-                             sizeof(int2) * M + sizeof(unsigned) * T;
-        if (ws_sm <= 110 * 1024) {  // two CTAs per SM
-            static size_t ws_cfg = 0;
-            if (ws_sm > ws_cfg) {
-                cudaFuncSetAttribute(k_downdate_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_sm);
-                ws_cfg = ws_sm;
-            }
-            k_downdate_ws<<<(unsigned)ctas, WS_THREADS, ws_sm, c->stream>>>(v, T, total, M);
             return;
         }
     }

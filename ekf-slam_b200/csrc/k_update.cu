@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
     const int ld = v.ld, kmax = v.kmax;
     const double* __restrict__ A = (mode == 0 ? v.Li : v.Sb) + (size_t)b * kmax * kmax;
     double* __restrict__ G = v.G + (size_t)b * kmax * ld;
-    double* __restrict__ W = v.W + (size_t)b * kmax * ld;
+    double* __restrict__ W = v.W + (size_t)b * v.wstride;
     const int* __restrict__ sel = v.sel + (size_t)b * v.N;
     const int roff = (mode == 0) ? v.roff[b] : 0;
 
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
                 const bool ok = (tt < kk) && (c0 + cc < ld);
                 const double* src = G;
                 if (ok) src = (mode == 0) ? G + (size_t)(2 * sel[tt >> 1] + (tt & 1)) * ld + c0 + cc
-                                          : W + (size_t)tt * ld + c0 + cc;
+                                          : W + w_at(kmax, tt, c0 + cc);
                 cp_async16(bs + r * TPAD + cc, src, ok ? 16 : 0);
             }
         }
@@ -720,7 +720,8 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
     for (int mt = 0; mt < 4; ++mt) {
         const int a = a0 + wr * 32 + mt * 8 + g;
         if (a >= k) continue;
-        double* __restrict__ orow = (mode == 0) ? W + (size_t)(roff + a) * ld : G + (size_t)(2 * sel[a >> 1] + (a & 1)) * ld;
+        // c0 is a multiple of 64: the block's 64 output columns are one panel of W
+        double* __restrict__ orow = (mode == 0) ? W + w_at(kmax, roff + a, c0) - c0 : G + (size_t)(2 * sel[a >> 1] + (a & 1)) * ld;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
             const int c = c0 + wc * 16 + nt * 8 + 2 * q;
@@ -773,13 +774,13 @@ __global__ void __launch_bounds__(128) k_wfix(DevView v, int defer) {
     const int k = 2 * v.ksel[b], roff = v.roff[b];
     const int rows = roff + k;
     const int ld = v.ld;
-    double* __restrict__ W = v.W + (size_t)b * v.kmax * ld;
+    double* __restrict__ W = v.W + (size_t)b * v.wstride;
     __shared__ double Jt[16];
     if (threadIdx.x < 16) Jt[threadIdx.x] = v.jnt[(size_t)b * 16 + threadIdx.x];
     __syncthreads();
     if (k > 0) {
         for (int a = threadIdx.x; a < rows; a += blockDim.x) {
-            double* w = W + (size_t)a * ld + 3;
+            double* w = W + w_at(v.kmax, a, 3);
             const double w3 = w[0], w4 = w[1], w5 = w[2], w6 = w[3];
 #pragma unroll
             for (int i = 0; i < 4; ++i) w[i] = w3 * Jt[i * 4 + 0] + w4 * Jt[i * 4 + 1] + w5 * Jt[i * 4 + 2] + w6 * Jt[i * 4 + 3];
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid) {
     const int rows = 2 * s_cnt;
     if (rows == 0) return;
     double* __restrict__ G = v.G + (size_t)b * kmax * ld;
-    const double* __restrict__ W = v.W + (size_t)b * kmax * ld;
+    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
     double* __restrict__ V = v.Sb + (size_t)b * kmax * kmax;
     const double* __restrict__ J1 = v.jn1 + (size_t)b * 16;
     for (int r = threadIdx.x; r < rows; r += blockDim.x) {
@@ -846,11 +847,10 @@ __global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid) {
         const double* __restrict__ H = v.Hc + t * EKF_HSTRIDE + (r & 1) * EKF_HC;
         const int off = v.foff[t];
         const int w = (v.ftype[t] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
-        const double* __restrict__ wa = W + (size_t)a * ld;
         double s = 0.0;
 #pragma unroll
-        for (int c = 0; c < 7; ++c) s += H[c] * wa[c];
-        for (int c = 0; c < w; ++c) s += H[7 + c] * wa[off + c];
+        for (int c = 0; c < 7; ++c) s += H[c] * W[w_at(kmax, a, c)];
+        for (int c = 0; c < w; ++c) s += H[7 + c] * W[w_at(kmax, a, off + c)];
         V[(size_t)r * kmax + a] = s;
     }
 }

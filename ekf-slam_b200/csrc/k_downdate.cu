@@ -19,7 +19,6 @@
 #include "model.cuh"
 #include "tc_common.cuh"
 
-#define WS_STAGES 4
 #define WS_CONSUMERS 8
 
 // ---- shared epilogue pieces ---------------------------------------------------------------------------
@@ -283,16 +282,19 @@ __device__ __forceinline__ void epi_prefetch_p(double* X, const double* __restri
     if (lane < 16 && r < nrows) bulk_g2s(X + r * XP, P + (size_t)(t.i0 + r) * ld + t.j0, rowbytes, pfull);
 }
 
+// S = stages of the W ring, NX = P tile buffers.  <4,1>: deep ring for long K loops (li update); <2,2>: short K loops
+// (small k, the kernel streams P): the next-but-one P tile is prefetched while the current one is being stored.
+template <int S, int NX>
 __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int T, int b0, long long total, int M) {
     extern __shared__ __align__(16) double dsm[];
-    double* As = dsm;                                   // [WS_STAGES][TK][TPAD]
-    double* Bs = dsm + WS_STAGES * TK * TPAD;           // [WS_STAGES][TK][TPAD]
-    double* X = Bs + WS_STAGES * TK * TPAD;             // [64][XP]
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(X + TM * XP);   // [WS_STAGES]
-    unsigned long long* empty = full + WS_STAGES;                                     // [WS_STAGES]
-    unsigned long long* pfull = empty + WS_STAGES;   // P tile landed in X
-    unsigned long long* cfull = pfull + 1;           // X holds P - acc
-    int2* meta = reinterpret_cast<int2*>(cfull + 1);                                  // [M]  {ktot, n}
+    double* As = dsm;                                   // [S][TK][TPAD]
+    double* Bs = dsm + S * TK * TPAD;           // [S][TK][TPAD]
+    double* X0 = Bs + S * TK * TPAD;            // [NX][64][XP]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(X0 + NX * TM * XP);   // [S]
+    unsigned long long* empty = full + S;                                     // [S]
+    unsigned long long* pfull = empty + S;   // [NX] P tile landed in X[j]
+    unsigned long long* cfull = pfull + NX;  // [NX] X[j] holds P - acc
+    int2* meta = reinterpret_cast<int2*>(cfull + NX);                                  // [M]  {ktot, n}
     unsigned* lut = reinterpret_cast<unsigned*>(meta + M);                            // [T]  ti<<16|tj
     const int ld = v.ld, kmax = v.kmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -310,9 +312,9 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
         lut[e] = ((unsigned)ti << 16) | (unsigned)(e - ti * (ti + 1) / 2);
     }
     if (tid == 0) {
-        for (int s2 = 0; s2 < WS_STAGES; ++s2) { mbar_init(full + s2, 32); mbar_init(empty + s2, WS_CONSUMERS); }
-        mbar_init(pfull, 1);
-        mbar_init(cfull, WS_CONSUMERS);
+        for (int s2 = 0; s2 < S; ++s2) { mbar_init(full + s2, 32); mbar_init(empty + s2, WS_CONSUMERS); }
+        for (int j = 0; j < NX; ++j) mbar_init(pfull + j, 1);
+        for (int j = 0; j < NX; ++j) mbar_init(cfull + j, WS_CONSUMERS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
             const double* __restrict__ wa = W + w_at(kmax, 0, L.i0);
             const double* __restrict__ wb = W + w_at(kmax, 0, L.j0);
             for (int st = 0; st < L.nk; ++st, ++cnt) {
-                const unsigned slot = cnt % WS_STAGES, ph = (cnt / WS_STAGES) & 1u;
+                const unsigned slot = cnt % S, ph = (cnt / S) & 1u;
                 mbar_wait(empty + slot, ph ^ 1u);
                 const int t0 = st * TK;
                 const int nvalid = min(TK, L.k - t0);
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
         // ================= consumer warps: 2 (rows) x 4 (cols), 32 x 16 each =================
         const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
         const int aoff = q * TPAD + wr * 32 + g, boff = q * TPAD + wc * 16 + g;
-        double* xdst = X + (wr * 32 + g) * XP + wc * 16 + 2 * q;
+        const int xoff = (wr * 32 + g) * XP + wc * 16 + 2 * q;
         unsigned cnt = 0, tiles = 0;
         for (int cm = 0; cm < Mreal; ++cm) {
             const DTile C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T);
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
 #pragma unroll
                 for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
             for (int it = 0; it < C.nk; ++it, ++cnt) {
-                const unsigned slot = cnt % WS_STAGES, ph = (cnt / WS_STAGES) & 1u;
+                const unsigned slot = cnt % S, ph = (cnt / S) & 1u;
                 mbar_wait(full + slot, ph);
                 const double* as = As + slot * TK * TPAD;
                 const double* bs = C.diag ? as : Bs + slot * TK * TPAD;
@@ -381,7 +383,8 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + slot);
             }
-            mbar_wait(pfull, tiles & 1u);   // this tile's P has landed (and the previous tile has left X)
+            double* X = X0 + (tiles % NX) * TM * XP;
+            mbar_wait(pfull + tiles % NX, (tiles / NX) & 1u);   // this tile's P has landed (and an earlier tile has left X)
             if (C.col0) {
                 // J P J' on the P tile itself (W already carries J, see k_wfix): columns 3..6 of tile column 0, rows 3..6
                 // of tile (0,0)
@@ -407,14 +410,14 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
-                    double2* xp = reinterpret_cast<double2*>(xdst + (mt * 8) * XP + nt * 8);
+                    double2* xp = reinterpret_cast<double2*>(X + xoff + (mt * 8) * XP + nt * 8);
                     double2 pv = *xp;
                     pv.x -= acc[mt][nt][0];
                     pv.y -= acc[mt][nt][1];
                     *xp = pv;
                 }
             __syncwarp();
-            if (lane == 0) mbar_arrive(cfull);
+            if (lane == 0) mbar_arrive(cfull + tiles % NX);
             ++tiles;
         }
         return;
@@ -423,14 +426,25 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
     // ================= epilogue warps =================
     const int et = tid - (WS_CONSUMERS + 1) * 32, ew = et >> 5;
     unsigned tiles = 0;
-    int cm = 0;
-    DTile C = decode_tile(meta, lut, 0, Mreal, blockIdx.x, T);
-    while (cm < Mreal && C.nk == 0) { ++cm; C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T); }
-    if (cm < Mreal) epi_prefetch_p(X, v.P + (size_t)(b0 + C.b) * v.nmax * ld, ld, C, ew, lane, pfull);
+    // two cursors over this CTA's tile list: pm = next tile whose P has to be prefetched, cm = tile being stored
+    int pm = -1;
+    DTile Pn;
+    auto next_valid = [&](int m, DTile& t) {
+        do { ++m; t = decode_tile(meta, lut, m, Mreal, blockIdx.x + (long long)m * G, T); } while (m < Mreal && t.nk == 0);
+        return m;
+    };
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        pm = next_valid(pm, Pn);
+        if (pm < Mreal) epi_prefetch_p(X0 + j * TM * XP, v.P + (size_t)(b0 + Pn.b) * v.nmax * ld, ld, Pn, ew, lane, pfull + j);
+    }
+    DTile C;
+    int cm = next_valid(-1, C);
     while (cm < Mreal) {
         double* __restrict__ P = v.P + (size_t)(b0 + C.b) * v.nmax * ld;
+        double* X = X0 + (tiles % NX) * TM * XP;
         const int n = C.n, i0 = C.i0, j0 = C.j0;
-        mbar_wait(cfull, tiles & 1u);
+        mbar_wait(cfull + tiles % NX, (tiles / NX) & 1u);
         // stores: one 512-byte row segment (tile) / two 256-byte segments (mirror image) per warp instruction
         const int c = 2 * lane;
         if (!C.diag) {
@@ -463,9 +477,12 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
             }
         }
         epi_bar();   // every epilogue thread is done reading X
+        if (pm < Mreal) {
+            pm = next_valid(pm, Pn);
+            if (pm < Mreal) epi_prefetch_p(X, v.P + (size_t)(b0 + Pn.b) * v.nmax * ld, ld, Pn, ew, lane, pfull + tiles % NX);
+        }
         ++tiles;
-        do { ++cm; C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T); } while (cm < Mreal && C.nk == 0);
-        if (cm < Mreal) epi_prefetch_p(X, v.P + (size_t)(b0 + C.b) * v.nmax * ld, ld, C, ew, lane, pfull);
+        cm = next_valid(cm, C);
     }
 }
 
@@ -481,28 +498,39 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
     const int T = nt * (nt + 1) / 2;
     KScope ks(c, slot);
     if (mode == 2) {
+        // ring depth / P buffers by update kind: the hi update usually stacks few rows (short K loops, the kernel
+        // streams P), the li update many.  EKFSLAM_DD_CFG=A|B forces one configuration for both.
+        static int cfgsel = -1;
+        if (cfgsel < 0) {
+            const char* e = getenv("EKFSLAM_DD_CFG");
+            cfgsel = (e && e[0] == 'A') ? 1 : (e && e[0] == 'B') ? 2 : 0;
+        }
+        const bool cfgB = cfgsel ? (cfgsel == 2) : (slot == KT_DOWNDATE_HI);
+        const int S = cfgB ? 2 : 4, NX = cfgB ? 2 : 1;
         // filters are processed in groups small enough for the per-CTA tile metadata (8 B per tile) to stay
         // within the shared-memory budget of two CTAs per SM
         const long long ctas_full = (long long)sms * 2;
-        const size_t fixed = sizeof(double) * (2 * WS_STAGES * TK * TPAD + TM * XP) + sizeof(unsigned long long) * (2 * WS_STAGES + 2) +
+        const size_t fixed = sizeof(double) * (2 * S * TK * TPAD + NX * TM * XP) + sizeof(unsigned long long) * (2 * S + 2 * NX) +
                              sizeof(unsigned) * T;
         const size_t budget = 111 * 1024;
         if (fixed + 64 * sizeof(int2) <= budget) {
             const long long Mcap = (long long)((budget - fixed) / sizeof(int2));
             long long bgroup = (Mcap * ctas_full) / T;
             if (bgroup < 1) bgroup = 1;
-            static size_t cfg2 = 0;
+            static size_t cfg2[2] = {0, 0};
             for (long long b0 = 0; b0 < v.B; b0 += bgroup) {
                 const long long nb = (v.B - b0 < bgroup) ? (v.B - b0) : bgroup;
                 const long long total = (long long)T * nb;
                 const long long ctas = total < ctas_full ? total : ctas_full;
                 const int M = (int)((total + ctas - 1) / ctas);
                 const size_t sm2 = fixed + sizeof(int2) * M;
-                if (sm2 > cfg2) {
-                    cudaFuncSetAttribute(k_downdate_ws2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-                    cfg2 = sm2;
+                if (sm2 > cfg2[cfgB]) {
+                    if (cfgB) cudaFuncSetAttribute(k_downdate_ws2<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+                    else cudaFuncSetAttribute(k_downdate_ws2<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+                    cfg2[cfgB] = sm2;
                 }
-                k_downdate_ws2<<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M);
+                if (cfgB) k_downdate_ws2<2, 2><<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M);
+                else k_downdate_ws2<4, 1><<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M);
                 if (b0 > 0) c->launches++;
             }
             return;

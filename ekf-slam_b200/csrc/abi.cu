@@ -225,6 +225,10 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     build_nhyp_table(tab, v.N, c->prm.p_spurious_free);
     cudaError_t e = cudaMemcpy(v.nhyp_tab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         ekfslam_destroy(c);
         return fail(EKFSLAM_ERR_CUDA, std::string("context init: ") + cudaGetErrorString(e));
@@ -257,6 +261,10 @@ int ekfslam_destroy(ekfslam_ctx* c) {
         c->timer = nullptr;
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_out) cudaEventDestroy(c->ev_out);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->pin) cudaFree(c->pin);
     delete c;
     return EKFSLAM_OK;
@@ -676,6 +684,7 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
     launch_features(c, 1, 3);
     launch_hp(c, EKFSLAM_F_HAS_H, 0);
     launch_innov(c, 0);
+    if (c->wait_inputs) { cudaStreamWaitEvent(c->stream, c->ev_in, 0); c->wait_inputs = 0; }
     if (match_mode) launch_innov(c, match_mode);
     launch_ransac(c);
     if (c->fuse_downdates) {
@@ -707,14 +716,29 @@ int ekfslam_step_host(ekfslam_ctx* c, int match_mode, const double* zc, const ui
     DevView& v = c->v;
     if (int r = ensure_u(c, n_u)) return r;
     v.n_u = n_u;
-    if (int r = upload_zc(c, 0, v.B, zc, fl, false)) return r;
-    CK(cudaMemcpyAsync(v.u, u, sizeof(double) * (size_t)v.B * n_u, cudaMemcpyHostToDevice, c->stream));
-    if (int r = ekfslam_step(c, 1, match_mode)) return r;
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
+    // inputs: copy stream, ordered after whatever the compute stream still has queued
+    const size_t bn = (size_t)v.B * v.N;
+    CK(cudaEventRecord(c->ev_main, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+    CK(cudaMemcpyAsync(v.zc, zc, sizeof(double) * 2 * bn, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(v.mflags, fl, bn, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(v.u, u, sizeof(double) * (size_t)v.B * n_u, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(c->ev_in, c->copy_stream));
+    c->wait_inputs = 1;
+    c->arm_out = 1;
+    const int rs = ekfslam_step(c, 1, match_mode);
+    c->wait_inputs = 0;
+    if (rs) { c->arm_out = 0; return rs; }
+    if (c->arm_out) { CK(cudaEventRecord(c->ev_out, c->stream)); c->arm_out = 0; }   // not recorded inside the step
+    // outputs: x_k_k, flags and stats are final before the last covariance downdate (it only writes P)
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_out, 0));
     if (x_out)
         CK(cudaMemcpy2DAsync(x_out, sizeof(double) * v.nmax, v.x, sizeof(double) * v.ld, sizeof(double) * v.nmax, v.B,
-                             cudaMemcpyDeviceToHost, c->stream));
-    if (flags_out) CK(cudaMemcpyAsync(flags_out, v.flags, (size_t)v.B * v.N, cudaMemcpyDeviceToHost, c->stream));
-    if (stats_out) CK(cudaMemcpyAsync(stats_out, v.stats, sizeof(ekfslam_stats) * v.B, cudaMemcpyDeviceToHost, c->stream));
+                             cudaMemcpyDeviceToHost, c->copy_stream));
+    if (flags_out) CK(cudaMemcpyAsync(flags_out, v.flags, bn, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (stats_out) CK(cudaMemcpyAsync(stats_out, v.stats, sizeof(ekfslam_stats) * v.B, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
     CK(cudaStreamSynchronize(c->stream));
     return EKFSLAM_OK;
 }

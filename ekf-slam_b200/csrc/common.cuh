@@ -73,6 +73,13 @@ struct ekfslam_ctx {
     int64_t launches;
     int stage;  // call-order tracking
     int fuse_downdates;  // ekfslam_step: defer the li covariance downdate and apply it together with the hi one
+    // ekfslam_step_host overlaps its PCIe copies with the step: inputs go up on copy_stream while prediction and the
+    // measurement model run (first needed by the matcher gate), x / flags / stats come down while the last covariance
+    // downdate (which only touches P) is still running.
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_in, ev_out, ev_main;
+    int wait_inputs;     // ekfslam_step: make the stream wait for ev_in before the first kernel that reads zc / mflags / u
+    int arm_out;         // launch_update(HI): record ev_out before the covariance downdate; cleared when recorded
     // pinned staging
     void* pin;
     size_t pin_bytes;

@@ -906,5 +906,6 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     if (flags & 2) return;   // not the last iterate of an iterated update: W is recomputed, nothing pending
     { KScope ks(c, KT_WFIX); k_wfix<<<v.B, 128, 0, st>>>(v, (flags & 4) ? 1 : 0); }
     if (flags & 4) return;   // deferred: the covariance downdate happens with the next (non-deferred) update
+    if (c->arm_out && (mask & EKFSLAM_F_HI)) { cudaEventRecord(c->ev_out, st); c->arm_out = 0; }  // x, flags, stats are final
     launch_downdate(c, (mask & EKFSLAM_F_HI) ? KT_DOWNDATE_HI : KT_DOWNDATE);
 }

@@ -109,11 +109,11 @@ __global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_pr
 // Blocked right-looking Cholesky S = L L' (lower, in place), X = inv(L), y <- X nu.
 // One block per filter, panels of NB columns.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_chol(DevView v) {
+__global__ void __launch_bounds__(128) k_chol(DevView v, int kskip) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     const int k = 2 * v.ksel[b];
-    if (k == 0) return;
+    if (k == 0 || k <= kskip) return;   // k <= kskip: handled by k_chol_sm
     const int kmax = v.kmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
@@ -320,6 +320,227 @@ __global__ void __launch_bounds__(128) k_chol(DevView v) {
     for (int t = tid; t < k; t += blockDim.x) {
         double s = 0.0;
         for (int w2 = 0; w2 < nwarps; ++w2) s += part[w2 * k + t];
+        cv[t] = s;
+    }
+    if (tid == 0 && s_bad) atomicOr(&v.stats[b].status, 2);
+}
+
+// ---------------------------------------------------------------------------------------
+// Shared-memory resident variant for k <= CHS_K (the common case at N = 100: k ~ 100): the lower triangle of S
+// lives packed in shared memory for the whole factorisation and inv(L) is formed IN PLACE (block row I of X only
+// needs block row I of L and the rows of X above it), so global memory is touched twice: S in, inv(L) out.
+// k_chol above works on S in global memory (every panel / trailing update is an L2 round trip: long-scoreboard
+// stalls were half of its issue stalls) and stays as the path for larger k.  Same blocked algorithm and pivots.
+// ---------------------------------------------------------------------------------------
+#define CHS_K 128
+#define CHS_T 256
+__device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
+
+__global__ void __launch_bounds__(CHS_T, 2) k_chol_sm(DevView v) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    const int k = 2 * v.ksel[b];
+    if (k == 0 || k > CHS_K) return;
+    const int kmax = v.kmax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = CHS_T / 32;
+    const double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    double* __restrict__ Xg = v.Li + (size_t)b * kmax * kmax;
+    double* Ls = sm;                                   // packed lower triangle: L, then inv(L) in place
+    double* D = Ls + (CHS_K * (CHS_K + 1)) / 2;        // [NB][NB+1] diagonal block factor
+    double* Di = D + NB * (NB + 1);                    // [NB][NB+1] its inverse
+    double* Pn = Di + NB * (NB + 1);                   // [CHS_K][NB+1] transposed row panel (inverse phase) / vectors
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = 0;
+    for (int r = warp; r < k; r += nwarps)
+        for (int c = lane; c <= r; c += 32) Ls[tri(r, c)] = S[(size_t)r * kmax + c];
+    __syncthreads();
+
+    for (int j0 = 0; j0 < k; j0 += NB) {
+        const int nb = min(NB, k - j0);
+        for (int e = tid; e < NB * NB; e += CHS_T) {
+            const int r = e / NB, c = e - r * NB;
+            D[r * (NB + 1) + c] = (r < nb && c <= r) ? Ls[tri(j0 + r, j0 + c)] : ((r >= nb && r == c) ? 1.0 : 0.0);
+            Di[r * (NB + 1) + c] = 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // as in k_chol: lane i holds row i of the block, pivots by rsqrt, then the triangular inverse
+            const unsigned full_mask = 0xffffffffu;
+            const int i = lane & (NB - 1);
+            double a[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) a[c] = D[i * (NB + 1) + c];
+            bool bad = false;
+            double rdiag[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                const double piv = __shfl_sync(full_mask, a[c], c);
+                bad = bad || !(piv > 0.0);
+                const double rs = rsqrt(piv);
+                rdiag[c] = rs;
+                const double lic = (i == c) ? piv * rs : a[c] * rs;
+                a[c] = lic;
+#pragma unroll
+                for (int j = c + 1; j < NB; ++j) {
+                    const double ljc = __shfl_sync(full_mask, lic, j);
+                    a[j] -= lic * ljc;
+                }
+            }
+            if (bad && lane == 0) s_bad = 1;
+            if (lane < NB) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) D[i * (NB + 1) + c] = (c <= i) ? a[c] : 0.0;
+            }
+            __syncwarp();
+            {
+                const int c = i;
+                double x[NB];
+#pragma unroll
+                for (int ii = 0; ii < NB; ++ii) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < ii; ++t) sacc += D[ii * (NB + 1) + t] * x[t];
+                    x[ii] = (ii == c) ? rdiag[ii] : ((ii > c) ? -sacc * rdiag[ii] : 0.0);
+                }
+                if (lane < NB) {
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii) Di[ii * (NB + 1) + c] = x[ii];
+                }
+            }
+        }
+        __syncthreads();
+        // the diagonal block of X replaces the one of L (the panel solve and the inverse phase only use Di)
+        for (int e = tid; e < nb * nb; e += CHS_T) {
+            const int r = e / nb, c = e - r * nb;
+            if (c <= r) Ls[tri(j0 + r, j0 + c)] = Di[r * (NB + 1) + c];
+        }
+        // panel: L[i][j0+c] = sum_{t<=c} S[i][j0+t] * Di[c][t]
+        const int i1 = j0 + nb;
+        for (int i = i1 + tid; i < k; i += CHS_T) {
+            double* lrow = Ls + tri(i, j0);
+            double row[NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) row[t] = (t < nb) ? lrow[t] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int t = 0; t <= c; ++t) s += row[t] * Di[c * (NB + 1) + t];
+                if (c < nb) lrow[c] = s;
+            }
+        }
+        __syncthreads();
+        // trailing update of the lower triangle: S[i][c] -= sum_t L[i][j0+t] L[c][j0+t]   (4x4 micro tiles)
+        const int m = k - i1;
+        if (m > 0) {
+            const int mt = (m + 3) / 4;
+            const int ntile = mt * (mt + 1) / 2;
+            for (int e = tid; e < ntile; e += CHS_T) {
+                int ti = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+                while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+                while (ti * (ti + 1) / 2 > e) --ti;
+                const int tj = e - ti * (ti + 1) / 2;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+                const double* pa[4];
+                const double* pc[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    pa[a] = Ls + tri(min(i1 + ti * 4 + a, k - 1), j0);   // clamped rows are masked at the store
+                    pc[a] = Ls + tri(min(i1 + tj * 4 + a, k - 1), j0);
+                }
+                for (int t = 0; t < nb; ++t) {
+                    double ra[4], rc[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { ra[a] = pa[a][t]; rc[a] = pc[a][t]; }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[a][c] += ra[a] * rc[c];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int ia = ti * 4 + a, ic = tj * 4 + c;
+                        if (ia < m && ic <= ia) Ls[tri(i1 + ia, i1 + ic)] -= acc[a][c];
+                    }
+            }
+        }
+        __syncthreads();
+    }
+
+    // X = inv(L) in place, block row by block row:  X[I][0:I0] = -Di_I * ( L[I][0:I0] * X[0:I0][0:I0] ).
+    // Two threads per column c (even / odd t), combined by a shuffle.
+    for (int I0 = NB; I0 < k; I0 += NB) {
+        const int nb = min(NB, k - I0);
+        for (int e = tid; e < nb * I0; e += CHS_T) {
+            const int r = e / I0, t = e - r * I0;
+            Pn[t * (NB + 1) + r] = Ls[tri(I0 + r, t)];
+        }
+        if (nb < NB)
+            for (int e = tid; e < (NB - nb) * I0; e += CHS_T) {
+                const int r = nb + e / I0, t = e % I0;
+                Pn[t * (NB + 1) + r] = 0.0;
+            }
+        for (int e = tid; e < NB * NB; e += CHS_T) {
+            const int r = e / NB, c = e - r * NB;
+            Di[r * (NB + 1) + c] = (r < nb && c <= r) ? Ls[tri(I0 + r, I0 + c)] : 0.0;
+        }
+        __syncthreads();
+        {
+            const int c = tid >> 1, hh = tid & 1;
+            double y[NB];
+#pragma unroll
+            for (int r = 0; r < NB; ++r) y[r] = 0.0;
+            if (c < I0) {
+                for (int t = c + hh; t < I0; t += 2) {
+                    const double xv = Ls[tri(t, c)];
+#pragma unroll
+                    for (int r = 0; r < NB; ++r) y[r] += Pn[t * (NB + 1) + r] * xv;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NB; ++r) y[r] += __shfl_xor_sync(0xffffffffu, y[r], 1);
+            if (c < I0) {
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    if ((r & 1) == hh && r < nb) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int j = 0; j <= r; ++j) s += Di[r * (NB + 1) + j] * y[j];
+                        Ls[tri(I0 + r, c)] = -s;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // inv(L) to global memory with explicit zeros above the diagonal (k_gemm streams it unmasked)
+    for (int r = warp; r < k; r += nwarps)
+        for (int c = lane; c < k; c += 32) Xg[(size_t)r * kmax + c] = (c <= r) ? Ls[tri(r, c)] : 0.0;
+    // y = X nu and cv = X' y = inv(S) nu
+    double* nu = Pn;            // [k]
+    double* ys = Pn + CHS_K;    // [k]
+    double* __restrict__ yv = v.yv + (size_t)b * kmax;
+    for (int a = tid; a < k; a += CHS_T) nu[a] = yv[a];
+    __syncthreads();
+    for (int a = warp; a < k; a += nwarps) {
+        double s = 0.0;
+        for (int t = lane; t <= a; t += 32) s += Ls[tri(a, t)] * nu[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) { yv[a] = s; ys[a] = s; }
+    }
+    __syncthreads();
+    double* __restrict__ cv = v.cv + (size_t)b * kmax;
+    for (int t = tid; t < k; t += CHS_T) {
+        double s = 0.0;
+        for (int a = t; a < k; ++a) s += Ls[tri(a, t)] * ys[a];
         cv[t] = s;
     }
     if (tid == 0 && s_bad) atomicOr(&v.stats[b].status, 2);
@@ -879,6 +1100,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     cudaStream_t st = c->stream;
     { KScope ks(c, KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, (flags & 4) ? 1 : 0); }
     const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
+    const size_t chs_sm = sizeof(double) * ((CHS_K * (CHS_K + 1)) / 2 + 2 * NB * (NB + 1) + CHS_K * (NB + 1));
     static size_t chol_cfg = 0;
     if (chol_sm > 48 * 1024 && chol_sm > chol_cfg) {
         cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_sm);
@@ -897,7 +1119,18 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         launch_chol_lockstep(c);
     } else {
         KScope ks(c, KT_CHOL);
-        k_chol<<<v.B, 128, chol_sm, st>>>(v);
+        static int resident = -1;
+        if (resident < 0) {
+            const char* e = getenv("EKFSLAM_CHOL_SM");
+            resident = (e && e[0] == '0') ? 0 : 1;
+            cudaFuncSetAttribute(k_chol_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chs_sm);
+        }
+        if (resident) {
+            k_chol_sm<<<v.B, CHS_T, chs_sm, st>>>(v);
+            if (v.kmax > CHS_K) { k_chol<<<v.B, 128, chol_sm, st>>>(v, CHS_K); c->launches++; }
+        } else {
+            k_chol<<<v.B, 128, chol_sm, st>>>(v, 0);
+        }
     }
     dim3 gw((v.nmax + TM - 1) / TM, (v.kmax + TM - 1) / TM, v.B);
     const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax);

@@ -238,7 +238,7 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
         // EKFSLAM_FUSE=1: one covariance pass per frame (deferred li downdate, see ekfslam_step).  Off by
         // default: at N=100 the rescue-row correction GEMM costs as much as the saved pass.
         const char* e = getenv("EKFSLAM_FUSE");
-        c->fuse_downdates = (e && e[0] == '1') ? 1 : 0;
+        c->fuse_downdates = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
     }
     *out = c;
     return EKFSLAM_OK;
@@ -687,7 +687,16 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
     if (c->wait_inputs) { cudaStreamWaitEvent(c->stream, c->ev_in, 0); c->wait_inputs = 0; }
     if (match_mode) launch_innov(c, match_mode);
     launch_ransac(c);
-    if (c->fuse_downdates) {
+    if (c->fuse_downdates == 2) {
+        // as below, but the rescue gate works from 13x13 gathers of P and of the pending rows (k_rescue_gate), so
+        // full rows H p_k_k are only produced for the candidates that passed (the hi inliers)
+        launch_update(c, EKFSLAM_F_LI, 1, 4);
+        launch_features(c, 0, 3);
+        launch_rescue_gate(c);
+        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, 1);
+        launch_pending_rows(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0);
+        launch_update(c, EKFSLAM_F_HI, 0);
+    } else if (c->fuse_downdates) {
         // one pass over P per frame: the li update is computed (x_k_k, W_li) but its covariance downdate is
         // deferred; the rescue stage works on the implied p_k_k = Jn (P - W_li' W_li) Jn' through
         // G = H P - (H W_li') W_li; the hi update stacks its W below and a single downdate applies both.

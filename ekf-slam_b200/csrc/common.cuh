@@ -116,7 +116,8 @@ void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gat
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
 void launch_ransac(ekfslam_ctx* c);
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags = 0);
-void launch_pending_rows(ekfslam_ctx* c, int need, int forbid);  // G rows of the selected features against the pending update
+void launch_pending_rows(ekfslam_ctx* c, int need, int forbid);
+void launch_rescue_gate(ekfslam_ctx* c);  // rescue gate against a pending update, from 13x13 gathers (no candidate G rows)  // G rows of the selected features against the pending update
 void launch_downdate(ekfslam_ctx* c, int slot);
 void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv);
 void launch_id2cart(ekfslam_ctx* c, double threshold, int force_index, int32_t* d_conv);

@@ -1076,6 +1076,107 @@ __global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Rescue gate against a pending (deferred) li update, mc/rescue_hi_inliers.m:11-20, WITHOUT the G rows of the
+// candidates: the 2x2  S_c = H_c p_k_k H_c'  with  p_k_k = J1 (P - W'W) J1' = J1 P J1' - Wt'Wt  (Wt = W J1', what
+// k_wfix leaves in memory) is   (H_c J1) P[c,c] (H_c J1)' - (H_c Wt')(H_c Wt')'   where c are the 13 (10) columns
+// H_c touches: a 13x13 gather of the stored covariance and 13 columns of the k1 pending rows.  Only the
+// candidates that pass (HI) then need full rows H p_k_k (k_hp + k_v + k_gemm mode 1 on those rows).
+// One block per filter, one warp per candidate (round robin), fixed-order warp reductions.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rescue_gate(DevView v, ekfslam_params prm) {
+    extern __shared__ double wcam[];   // [k1][7] camera columns of the pending rows
+    const int b = blockIdx.x;
+    const int N = v.N, ld = v.ld, kmax = v.kmax;
+    const int k1 = v.kpend[b];
+    const int nf = v.nfeat[b];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
+    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    __shared__ double J1[16];
+    if (tid < 16) J1[tid] = (k1 > 0) ? v.jn1[(size_t)b * 16 + tid] : ((tid >> 2) == (tid & 3) ? 1.0 : 0.0);
+    for (int e = tid; e < k1 * 7; e += blockDim.x) {
+        const int a = e / 7, m = e - a * 7;
+        wcam[e] = W[w_at(kmax, a, m)];
+    }
+    __syncthreads();
+    for (int i = warp; i < nf; i += (blockDim.x >> 5)) {
+        const size_t t = (size_t)b * N + i;
+        const int type = v.ftype[t];
+        uint8_t f = v.flags[t];
+        if (type == EKFSLAM_FEAT_NONE || !(f & EKFSLAM_F_HAS_H) || !(f & EKFSLAM_F_IC) || (f & EKFSLAM_F_LI)) continue;
+        const double* __restrict__ H = v.Hc + t * EKF_HSTRIDE;
+        const int off = v.foff[t];
+        const int w = (type == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+        const int nc = 7 + w;
+        double h0[EKF_HC], h1[EKF_HC];     // H_c (for the W part) ...
+#pragma unroll
+        for (int m = 0; m < EKF_HC; ++m) { h0[m] = (m < nc) ? H[m] : 0.0; h1[m] = (m < nc) ? H[EKF_HC + m] : 0.0; }
+        double j0[EKF_HC], j1[EKF_HC];     // ... and H_c J1 (for the P part): columns 3..6 mix
+#pragma unroll
+        for (int m = 0; m < EKF_HC; ++m) { j0[m] = h0[m]; j1[m] = h1[m]; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            j0[3 + a] = h0[3] * J1[0 * 4 + a] + h0[4] * J1[1 * 4 + a] + h0[5] * J1[2 * 4 + a] + h0[6] * J1[3 * 4 + a];
+            j1[3 + a] = h1[3] * J1[0 * 4 + a] + h1[4] * J1[1 * 4 + a] + h1[5] * J1[2 * 4 + a] + h1[6] * J1[3 * 4 + a];
+        }
+        // (H J1) P[c,c] (H J1)': entries e = r * nc + cc of the gather spread over the lanes
+        double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+        for (int e = lane; e < nc * nc; e += 32) {
+            const int r = e / nc, cc = e - r * nc;
+            const int gr = (r < 7) ? r : off + r - 7, gc = (cc < 7) ? cc : off + cc - 7;
+            const double pv = P[(size_t)gr * ld + gc];
+            // register arrays are indexed with compile-time constants only: select by unrolled compare
+            double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < EKF_HC; ++m) {
+                if (m == r) { a0 = j0[m]; a1 = j1[m]; }
+                if (m == cc) { c0 = j0[m]; c1 = j1[m]; }
+            }
+            s00 += a0 * pv * c0; s01 += a0 * pv * c1; s10 += a1 * pv * c0; s11 += a1 * pv * c1;
+        }
+        // (H Wt') over the pending rows, lanes along the rows
+        double q00 = 0.0, q01 = 0.0, q11 = 0.0;
+        for (int a = lane; a < k1; a += 32) {
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < 7; ++m) { const double wv = wcam[a * 7 + m]; v0 += h0[m] * wv; v1 += h1[m] * wv; }
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                if (m < w) { const double wv = W[w_at(kmax, a, off + m)]; v0 += h0[7 + m] * wv; v1 += h1[7 + m] * wv; }
+            }
+            q00 += v0 * v0; q01 += v0 * v1; q11 += v1 * v1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s00 += __shfl_xor_sync(0xffffffffu, s00, o); s01 += __shfl_xor_sync(0xffffffffu, s01, o);
+            s10 += __shfl_xor_sync(0xffffffffu, s10, o); s11 += __shfl_xor_sync(0xffffffffu, s11, o);
+            q00 += __shfl_xor_sync(0xffffffffu, q00, o); q01 += __shfl_xor_sync(0xffffffffu, q01, o);
+            q11 += __shfl_xor_sync(0xffffffffu, q11, o);
+        }
+        if (lane == 0) {
+            s00 -= q00; s01 -= q01; s10 -= q01; s11 -= q11;
+            const double n0 = v.z[2 * t] - v.h[2 * t], n1 = v.z[2 * t + 1] - v.h[2 * t + 1];
+            const double det = s00 * s11 - s01 * s10;
+            const double d2 = (n0 * (s11 * n0 - s01 * n1) + n1 * (-s10 * n0 + s00 * n1)) / det;
+            if (d2 < prm.chi2_gate) f |= EKFSLAM_F_HI; else f &= ~EKFSLAM_F_HI;
+            v.flags[t] = f;
+        }
+    }
+}
+
+void launch_rescue_gate(ekfslam_ctx* c) {
+    DevView& v = c->v;
+    const size_t sm = sizeof(double) * (size_t)v.kmax * 7;
+    static size_t cfg = 0;
+    if (sm > 48 * 1024 && sm > cfg) {
+        cudaFuncSetAttribute(k_rescue_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cfg = sm;
+    }
+    KScope ks(c, KT_INNOV);
+    k_rescue_gate<<<v.B, 256, sm, c->stream>>>(v, c->prm);
+}
+
 static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
     static size_t attr_done = 0;
     if (attr_done < w_sm) {

@@ -145,10 +145,12 @@ def test_large_map_n500(ekf):
     assert tot["li"] > 200
 
 
-def test_fused_single_pass_mode(ekf, monkeypatch):
-    """EKFSLAM_FUSE=1: the li covariance downdate is deferred and applied together with the hi one (one pass
-    over P per frame); the rescue stage then works on the implied p_k_k.  Same parity bar."""
-    monkeypatch.setenv("EKFSLAM_FUSE", "1")
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_fused_single_pass_mode(ekf, monkeypatch, mode):
+    """EKFSLAM_FUSE=1/2: the li covariance downdate is deferred and applied together with the hi one (one pass
+    over P per frame); the rescue stage then works on the implied p_k_k (2: gate from 13x13 gathers, full rows
+    only for the hi inliers).  Same parity bar."""
+    monkeypatch.setenv("EKFSLAM_FUSE", mode)
     worst, tot = _run_sequence(ekf, B=3, N=40, frames=5, seed=800)
     assert tot["li"] > 40 and tot["hi"] > 0
     worst, tot = _run_sequence(ekf, B=2, N=20, frames=4, seed=801, cart=[0, 3, 4, 9, 15, 19])

@@ -812,7 +812,7 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Tensor-core GEMM of the update, 64x64 tiles, grid = (column tiles, row tiles, B), two uses:
+// Tensor-core GEMM of the update, 64x64 tiles, grid = (row tiles, B), each CTA walking all column tiles; two uses:
 //   mode 0:  W[roff + a] = sum_t X[a][t] * G[selrow(t)]       (X = inv(L), lower triangular, explicit zeros
 //            above the diagonal; G_sel = the selected rows of G).  The last row tile also accumulates the
 //            state update x+ = x + G_sel' inv(S) nu (mc/update.m:12) for its 64 columns, and column tile 0
@@ -822,14 +822,12 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finalize) {
     extern __shared__ __align__(16) double dsm[];
-    const int b = blockIdx.z;
+    const int b = blockIdx.y;
     const int k = 2 * v.ksel[b];                        // rows of the output
     const int kk = (mode == 0) ? k : v.kpend[b];        // contraction length
-    const int a0 = blockIdx.y * TM;
+    const int a0 = blockIdx.x * TM;
     if (a0 >= k || kk == 0) return;
     const int n = v.nstate[b];
-    const int c0 = blockIdx.x * TM;
-    if (c0 >= n) return;
     const int ld = v.ld, kmax = v.kmax;
     const double* __restrict__ A = (mode == 0 ? v.Li : v.Sb) + (size_t)b * kmax * kmax;
     double* __restrict__ G = v.G + (size_t)b * kmax * ld;
@@ -840,34 +838,42 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
     double* As = dsm;                           // [NSTAGE][64][APAD]   As[i][t] = A[a0+i][t0+t]
     double* Bs = dsm + NSTAGE * TM * APAD;      // [NSTAGE][TK][TPAD]   Bs[t][j] = B[t0+t][c0+j]
     double* cs = Bs + NSTAGE * TK * TPAD;       // [kmax]               inv(S) nu
+    int* grow = reinterpret_cast<int*>(cs + kmax);   // [kmax]  G row of stacked row t: 2 sel[t/2] + (t&1)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
     const bool xrole = (mode == 0) && (a0 + TM >= k);
     if (xrole)
         for (int t = tid; t < k; t += blockDim.x) cs[t] = v.cv[(size_t)b * kmax + t];
-    double xacc = 0.0;
+    for (int t = tid; t < k; t += blockDim.x) grow[t] = 2 * sel[t >> 1] + (t & 1);
+    __syncthreads();
 
+    // One CTA owns a 64-row tile of the output for ALL column tiles: the cp.async ring runs over the flattened
+    // (column tile, K chunk) sequence, so the pipeline fills once per CTA instead of once per 64x64 tile (short K
+    // loops - few stacked rows - were all pipeline fill).
     const int tend = (mode == 0) ? min(k, a0 + TM) : kk;  // mode 0: X[a][t] = 0 for t > a
     const int nk = (tend + TK - 1) / TK;
-    auto load_stage = [&](int st, int t0) {
+    const int ncb = (n + TM - 1) / TM;
+    const int total = ncb * nk;
+    // this thread's two 16-byte pieces of an A stage (64 rows x 8 chunks) and of a B stage (16 rows x 32 chunks)
+    const int ar = tid >> 3, acc2 = (tid & 7) * 2;
+    const int br = tid >> 5, bcc = (tid & 31) * 2;
+    auto load_stage = [&](int st, int cb, int it) {
+        const int t0 = it * TK, c0 = cb * TM;
         double* as = As + st * TM * APAD;
         double* bs = Bs + st * TK * TPAD;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int ch = tid + 256 * j;          // 512 chunks of 2 doubles
-            {   // A: 64 rows x 8 chunks
-                const int r = ch >> 3, cc = (ch & 7) * 2;
-                const bool ok = (a0 + r < k) && (t0 + cc < kk);
-                cp_async16(as + r * APAD + cc, ok ? A + (size_t)(a0 + r) * kmax + t0 + cc : A, ok ? 16 : 0);
+            {   // A: rows ar, ar + 32
+                const int r = ar + 32 * j;
+                const bool ok = (a0 + r < k) && (t0 + acc2 < kk);
+                cp_async16(as + r * APAD + acc2, ok ? A + (size_t)(a0 + r) * kmax + t0 + acc2 : A, ok ? 16 : 0);
             }
-            {   // B: 16 rows x 32 chunks
-                const int r = ch >> 5, cc = (ch & 31) * 2;
-                const int tt = t0 + r;
-                const bool ok = (tt < kk) && (c0 + cc < ld);
+            {   // B: rows br, br + 8
+                const int tt = t0 + br + 8 * j;
+                const bool ok = (tt < kk) && (c0 + bcc < ld);
                 const double* src = G;
-                if (ok) src = (mode == 0) ? G + (size_t)(2 * sel[tt >> 1] + (tt & 1)) * ld + c0 + cc
-                                          : W + w_at(kmax, tt, c0 + cc);
-                cp_async16(bs + r * TPAD + cc, src, ok ? 16 : 0);
+                if (ok) src = (mode == 0) ? G + (size_t)grow[tt] * ld + c0 + bcc : W + w_at(kmax, tt, c0 + bcc);
+                cp_async16(bs + (br + 8 * j) * TPAD + bcc, src, ok ? 16 : 0);
             }
         }
     };
@@ -876,22 +882,25 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double xacc = 0.0;
     const int tmax_w = (mode == 0) ? min(k, a0 + wr * 32 + 32) : kk;
     const int rbase = a0 + wr * 32;
     const int mt_hi = max(0, min(4, (k - rbase + 7) >> 3));
 
+    int lcb = 0, lit = 0;   // (column tile, chunk) of the next stage to load
 #pragma unroll
     for (int st = 0; st < NSTAGE - 1; ++st) {
-        if (st < nk) load_stage(st, st * TK);
+        if (lcb < ncb) { load_stage(st, lcb, lit); if (++lit == nk) { lit = 0; ++lcb; } }
         cp_async_commit();
     }
-    for (int it = 0; it < nk; ++it) {
+    int cb = 0, it = 0;
+    for (int j = 0; j < total; ++j) {
         cp_async_wait<NSTAGE - 2>();
         __syncthreads();
-        if (it + NSTAGE - 1 < nk) load_stage((it + NSTAGE - 1) % NSTAGE, (it + NSTAGE - 1) * TK);
+        if (lcb < ncb) { load_stage((j + NSTAGE - 1) % NSTAGE, lcb, lit); if (++lit == nk) { lit = 0; ++lcb; } }
         cp_async_commit();
-        const double* as = As + (it % NSTAGE) * TM * APAD;
-        const double* bs = Bs + (it % NSTAGE) * TK * TPAD;
+        const double* as = As + (j % NSTAGE) * TM * APAD;
+        const double* bs = Bs + (j % NSTAGE) * TK * TPAD;
         if (xrole && tid < TM) {
             const int tmax = min(TK, k - it * TK);
             for (int t = 0; t < tmax; ++t) xacc += bs[t * TPAD + tid] * cs[it * TK + t];
@@ -935,52 +944,60 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
                 }
             }
         }
+        if (++it < nk) continue;
+        // ---- last chunk of column tile cb: store the 64x64 tile, fold the state update, restart the accumulators
+        const int c0 = cb * TM;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int a = a0 + wr * 32 + mt * 8 + g;
+            if (a < k) {
+                // the 64 output columns of a column tile are one panel of W
+                double* __restrict__ orow = (mode == 0) ? W + w_at(kmax, roff + a, c0) - c0 : G + (size_t)grow[a] * ld;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int c = c0 + wc * 16 + nt * 8 + 2 * q;
+                    if (c < ld) {  // ld is even: c+1 < ld as well; the padding columns [n, ld) are kept zero
+                        double2 o;
+                        if (mode == 0) {
+                            o.x = (c < n) ? acc[mt][nt][0] : 0.0;
+                            o.y = (c + 1 < n) ? acc[mt][nt][1] : 0.0;
+                        } else {
+                            o = *reinterpret_cast<const double2*>(orow + c);
+                            o.x = (c < n) ? o.x - acc[mt][nt][0] : 0.0;
+                            o.y = (c + 1 < n) ? o.y - acc[mt][nt][1] : 0.0;
+                        }
+                        *reinterpret_cast<double2*>(orow + c) = o;
+                    }
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        }
+        if (xrole) {
+            double* __restrict__ x = v.x + (size_t)b * ld;
+            if (tid < TM && c0 + tid < n) x[c0 + tid] += xacc;
+            xacc = 0.0;
+            if (c0 == 0 && finalize) {
+                // this block owns state entries 0..63: normJac(q+) (mc/normJac.m) from the un-normalised
+                // quaternion, then q+ <- q+/|q+|  (mc/update.m:18,24)
+                __syncthreads();
+                if (tid == 0) {
+                    const double r = x[3], qx = x[4], qy = x[5], qz = x[6];
+                    const double nn = r * r + qx * qx + qy * qy + qz * qz;
+                    const double sc = 1.0 / (nn * sqrt(nn));  // (.)^(-3/2)
+                    double* J = v.jnt + (size_t)b * 16;
+                    J[0] = sc * (qx * qx + qy * qy + qz * qz); J[1] = sc * (-r * qx); J[2] = sc * (-r * qy); J[3] = sc * (-r * qz);
+                    J[4] = sc * (-qx * r); J[5] = sc * (r * r + qy * qy + qz * qz); J[6] = sc * (-qx * qy); J[7] = sc * (-qx * qz);
+                    J[8] = sc * (-qy * r); J[9] = sc * (-qy * qx); J[10] = sc * (r * r + qx * qx + qz * qz); J[11] = sc * (-qy * qz);
+                    J[12] = sc * (-qz * r); J[13] = sc * (-qz * qx); J[14] = sc * (-qz * qy); J[15] = sc * (r * r + qx * qx + qy * qy);
+                    const double nrm = sqrt(nn);
+                    x[3] = r / nrm; x[4] = qx / nrm; x[5] = qy / nrm; x[6] = qz / nrm;
+                }
+            }
+        }
+        it = 0; ++cb;
     }
     cp_async_wait<0>();
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-        const int a = a0 + wr * 32 + mt * 8 + g;
-        if (a >= k) continue;
-        // c0 is a multiple of 64: the block's 64 output columns are one panel of W
-        double* __restrict__ orow = (mode == 0) ? W + w_at(kmax, roff + a, c0) - c0 : G + (size_t)(2 * sel[a >> 1] + (a & 1)) * ld;
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            const int c = c0 + wc * 16 + nt * 8 + 2 * q;
-            if (c < ld) {  // ld is even: c+1 < ld as well; the padding columns [n, ld) are kept zero
-                double2 o;
-                if (mode == 0) {
-                    o.x = (c < n) ? acc[mt][nt][0] : 0.0;
-                    o.y = (c + 1 < n) ? acc[mt][nt][1] : 0.0;
-                } else {
-                    o = *reinterpret_cast<const double2*>(orow + c);
-                    o.x = (c < n) ? o.x - acc[mt][nt][0] : 0.0;
-                    o.y = (c + 1 < n) ? o.y - acc[mt][nt][1] : 0.0;
-                }
-                *reinterpret_cast<double2*>(orow + c) = o;
-            }
-        }
-    }
-    if (xrole) {
-        double* __restrict__ x = v.x + (size_t)b * ld;
-        if (tid < TM && c0 + tid < n) x[c0 + tid] += xacc;
-        if (c0 == 0 && finalize) {
-            // this block owns state entries 0..63: normJac(q+) (mc/normJac.m) from the un-normalised
-            // quaternion, then q+ <- q+/|q+|  (mc/update.m:18,24)
-            __syncthreads();
-            if (tid == 0) {
-                const double r = x[3], qx = x[4], qy = x[5], qz = x[6];
-                const double nn = r * r + qx * qx + qy * qy + qz * qz;
-                const double sc = 1.0 / (nn * sqrt(nn));  // (.)^(-3/2)
-                double* J = v.jnt + (size_t)b * 16;
-                J[0] = sc * (qx * qx + qy * qy + qz * qz); J[1] = sc * (-r * qx); J[2] = sc * (-r * qy); J[3] = sc * (-r * qz);
-                J[4] = sc * (-qx * r); J[5] = sc * (r * r + qy * qy + qz * qz); J[6] = sc * (-qx * qy); J[7] = sc * (-qx * qz);
-                J[8] = sc * (-qy * r); J[9] = sc * (-qy * qx); J[10] = sc * (r * r + qx * qx + qz * qz); J[11] = sc * (-qy * qz);
-                J[12] = sc * (-qz * r); J[13] = sc * (-qz * qx); J[14] = sc * (-qz * qy); J[15] = sc * (r * r + qx * qx + qy * qy);
-                const double nrm = sqrt(nn);
-                x[3] = r / nrm; x[4] = qx / nrm; x[5] = qy / nrm; x[6] = qz / nrm;
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1188,8 +1205,8 @@ static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
 void launch_pending_rows(ekfslam_ctx* c, int need, int forbid) {
     DevView& v = c->v;
     { KScope ks(c, KT_V); k_v<<<v.B, 256, 0, c->stream>>>(v, need, forbid); }
-    dim3 gw((v.nmax + TM - 1) / TM, (v.kmax + TM - 1) / TM, v.B);
-    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax);
+    dim3 gw((v.kmax + TM - 1) / TM, v.B);   // (64-row tiles, filters); each CTA walks all column tiles
+    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax) + sizeof(int) * v.kmax;
     gemm_attr(c, w_sm);
     { KScope ks(c, KT_G2); k_gemm<<<gw, 256, w_sm, c->stream>>>(v, 1, 0); }
 }
@@ -1233,8 +1250,8 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
             k_chol<<<v.B, 128, chol_sm, st>>>(v, 0);
         }
     }
-    dim3 gw((v.nmax + TM - 1) / TM, (v.kmax + TM - 1) / TM, v.B);
-    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax);
+    dim3 gw((v.kmax + TM - 1) / TM, v.B);   // (64-row tiles, filters); each CTA walks all column tiles
+    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax) + sizeof(int) * v.kmax;
     gemm_attr(c, w_sm);
     { KScope ks(c, KT_W); k_gemm<<<gw, 256, w_sm, st>>>(v, 0, (flags & 2) ? 0 : 1); }
     if (flags & 2) return;   // not the last iterate of an iterated update: W is recomputed, nothing pending

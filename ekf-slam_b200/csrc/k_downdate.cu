@@ -517,6 +517,9 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
             const long long Mcap = (long long)((budget - fixed) / sizeof(int2));
             long long bgroup = (Mcap * ctas_full) / T;
             if (bgroup < 1) bgroup = 1;
+            const char* eg = getenv("EKFSLAM_DD_GROUP");   // =g: at most g filters per launch (exercises the grouping in tests)
+            const long long force_group = eg ? atoll(eg) : 0;
+            if (force_group > 0 && force_group < bgroup) bgroup = force_group;
             static size_t cfg2[2] = {0, 0};
             for (long long b0 = 0; b0 < v.B; b0 += bgroup) {
                 const long long nb = (v.B - b0 < bgroup) ? (v.B - b0) : bgroup;

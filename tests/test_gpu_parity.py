@@ -155,3 +155,12 @@ def test_fused_single_pass_mode(ekf, monkeypatch, mode):
     assert tot["li"] > 40 and tot["hi"] > 0
     worst, tot = _run_sequence(ekf, B=2, N=20, frames=4, seed=801, cart=[0, 3, 4, 9, 15, 19])
     assert tot["li"] > 0
+
+
+def test_downdate_filter_groups(ekf, monkeypatch):
+    """The persistent downdate keeps its per-CTA tile metadata in shared memory and therefore processes very large
+    batches in groups of filters (one launch per group); EKFSLAM_DD_GROUP forces tiny groups so that the
+    group offset path is exercised at test sizes.  Same parity bar."""
+    monkeypatch.setenv("EKFSLAM_DD_GROUP", "2")
+    worst, tot = _run_sequence(ekf, B=5, N=24, frames=3, seed=810)
+    assert tot["li"] > 20

@@ -78,7 +78,8 @@ static void kt_collect(ekfslam_ctx* c) {
 
 static const char* KT_NAMES[KT_COUNT] = {"k_begin_frame", "k_predict", "k_features", "k_hp", "k_innov", "k_ransac",
                                          "k_upd_S", "k_chol", "k_w", "k_downdate_hi", "k_downdate", "k_symmetrize",
-                                         "k_add_features", "k_wfix", "k_v", "k_g2"};
+                                         "k_add_features", "k_wfix", "k_v", "k_g2", "k_w_hi", "k_chol_hi", "k_upd_S_hi",
+                                         "k_hp_rescue"};
 
 template <typename T>
 static cudaError_t dalloc(T** p, size_t count, int64_t* total) {
@@ -709,7 +710,7 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
     } else {
         launch_update(c, EKFSLAM_F_LI, 1);
         launch_features(c, 0, 3);
-        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);
+        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI, 0, KT_HP_RESCUE);
         launch_innov(c, 3);
         launch_update(c, EKFSLAM_F_HI, 0);
     }

@@ -57,7 +57,7 @@ struct DevView {
 // per-kernel timing (ekfslam_enable_timing): every launch is bracketed by an event pair
 enum {
     KT_BEGIN_FRAME = 0, KT_PREDICT, KT_FEATURES, KT_HP, KT_INNOV, KT_RANSAC, KT_UPD_S, KT_CHOL, KT_W, KT_DOWNDATE_HI,
-    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_WFIX, KT_V, KT_G2, KT_COUNT
+    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_WFIX, KT_V, KT_G2, KT_W_HI, KT_CHOL_HI, KT_UPD_S_HI, KT_HP_RESCUE, KT_COUNT
 };
 struct KTimer;
 
@@ -111,7 +111,7 @@ struct KScope {
 void launch_begin_frame(ekfslam_ctx* c);
 void launch_predict(ekfslam_ctx* c);
 void launch_features(ekfslam_ctx* c, int which, int parts);  // parts: 1 = h, 2 = H, 3 = both
-void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending = 0);  // G rows for features with (flags&need)==need && !(flags&forbid)
+void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending = 0, int slot = KT_HP);  // G rows for features with (flags&need)==need && !(flags&forbid)
 void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gate / explicit matches / rescue gate
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
 void launch_ransac(ekfslam_ctx* c);

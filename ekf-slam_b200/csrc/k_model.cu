@@ -333,9 +333,9 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int
     }
 }
 
-void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending) {
+void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending, int slot) {
     dim3 grid((c->v.nmax + 255) / 256, c->v.B);
-    KScope ks(c, KT_HP);
+    KScope ks(c, slot);
     k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid, use_pending);
 }
 

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128) k_chol(DevView v, int kskip) {
 // k_chol above works on S in global memory (every panel / trailing update is an L2 round trip: long-scoreboard
 // stalls were half of its issue stalls) and stays as the path for larger k.  Same blocked algorithm and pivots.
 // ---------------------------------------------------------------------------------------
-#define CHS_K 128
+#define CHS_K 144
 #define CHS_T 256
 __device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
 
@@ -820,13 +820,13 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
 //   mode 1:  G[candrow(a)] -= sum_t V[a][t] * W[t]            (pending-update correction of the rescue rows:
 //            H_c P_kk = H_c P - (H_c W') W for a deferred W; V = H_c W' lives in the Sb scratch).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finalize) {
+__global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finalize, int kskip) {
     extern __shared__ __align__(16) double dsm[];
-    const int b = blockIdx.y;
+    const int b = blockIdx.z;
     const int k = 2 * v.ksel[b];                        // rows of the output
     const int kk = (mode == 0) ? k : v.kpend[b];        // contraction length
     const int a0 = blockIdx.x * TM;
-    if (a0 >= k || kk == 0) return;
+    if (a0 >= k || kk == 0 || k <= kskip) return;       // k <= kskip: handled by k_w_small
     const int n = v.nstate[b];
     const int ld = v.ld, kmax = v.kmax;
     const double* __restrict__ A = (mode == 0 ? v.Li : v.Sb) + (size_t)b * kmax * kmax;
@@ -852,8 +852,12 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
     // loops - few stacked rows - were all pipeline fill).
     const int tend = (mode == 0) ? min(k, a0 + TM) : kk;  // mode 0: X[a][t] = 0 for t > a
     const int nk = (tend + TK - 1) / TK;
-    const int ncb = (n + TM - 1) / TM;
-    const int total = ncb * nk;
+    // column tiles [cb0, cb1) of this CTA: gridDim.y CTAs share the column tiles of one row tile (1 = the CTA walks them
+    // all; more = shorter CTAs, for launches where few filters have work)
+    const int ncb_all = (n + TM - 1) / TM;
+    const int cb0 = (int)(((long long)ncb_all * blockIdx.y) / gridDim.y), ncb = (int)(((long long)ncb_all * (blockIdx.y + 1)) / gridDim.y);
+    if (cb0 >= ncb) return;
+    const int total = (ncb - cb0) * nk;
     // this thread's two 16-byte pieces of an A stage (64 rows x 8 chunks) and of a B stage (16 rows x 32 chunks)
     const int ar = tid >> 3, acc2 = (tid & 7) * 2;
     const int br = tid >> 5, bcc = (tid & 31) * 2;
@@ -887,13 +891,13 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
     const int rbase = a0 + wr * 32;
     const int mt_hi = max(0, min(4, (k - rbase + 7) >> 3));
 
-    int lcb = 0, lit = 0;   // (column tile, chunk) of the next stage to load
+    int lcb = cb0, lit = 0;   // (column tile, chunk) of the next stage to load
 #pragma unroll
     for (int st = 0; st < NSTAGE - 1; ++st) {
         if (lcb < ncb) { load_stage(st, lcb, lit); if (++lit == nk) { lit = 0; ++lcb; } }
         cp_async_commit();
     }
-    int cb = 0, it = 0;
+    int cb = cb0, it = 0;
     for (int j = 0; j < total; ++j) {
         cp_async_wait<NSTAGE - 2>();
         __syncthreads();
@@ -998,6 +1002,76 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
         it = 0; ++cb;
     }
     cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------
+// k_gemm(mode 0) for few stacked rows (k <= WS_K, the usual size of the hi update): W = inv(L) G_sel is a
+// (k x k) x (k x n) product per filter - 64-row DMMA tiles would be mostly padding and every CTA mostly pipeline
+// latency.  One block per filter, one state column per thread: the k entries of the column of G_sel stay in
+// registers, inv(L) is broadcast from shared memory.  Same epilogue duties as k_gemm: x+ = x + G_sel' inv(S) nu,
+// normJac(q+) and the quaternion normalisation.
+// ---------------------------------------------------------------------------------------
+#define WS_K 32
+__global__ void __launch_bounds__(128, 4) k_w_small(DevView v, int finalize) {
+    const int b = blockIdx.x;
+    const int k = 2 * v.ksel[b];
+    if (k == 0 || k > WS_K) return;
+    const int n = v.nstate[b], ld = v.ld, kmax = v.kmax;
+    const double* __restrict__ Xg = v.Li + (size_t)b * kmax * kmax;
+    const double* __restrict__ G = v.G + (size_t)b * kmax * ld;
+    double* __restrict__ W = v.W + (size_t)b * v.wstride;
+    const int* __restrict__ sel = v.sel + (size_t)b * v.N;
+    const int roff = v.roff[b];
+    __shared__ double Xs[WS_K][WS_K + 1];
+    __shared__ double cs[WS_K];
+    __shared__ int grow[WS_K];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < WS_K * WS_K; e += blockDim.x) {
+        const int a = e / WS_K, t = e - a * WS_K;
+        Xs[a][t] = (a < k && t <= a) ? Xg[(size_t)a * kmax + t] : 0.0;
+    }
+    if (tid < WS_K) {
+        cs[tid] = (tid < k) ? v.cv[(size_t)b * kmax + tid] : 0.0;
+        grow[tid] = (tid < k) ? 2 * sel[tid >> 1] + (tid & 1) : 0;
+    }
+    __syncthreads();
+    double* __restrict__ x = v.x + (size_t)b * ld;
+    for (int c = tid; c < ld; c += blockDim.x) {
+        double g[WS_K];
+#pragma unroll
+        for (int t = 0; t < WS_K; ++t) g[t] = (t < k) ? G[(size_t)grow[t] * ld + c] : 0.0;
+        const bool incol = c < n;
+        double xs = 0.0;
+#pragma unroll
+        for (int t = 0; t < WS_K; ++t) xs += g[t] * cs[t];
+        double* __restrict__ wcol = W + w_at(kmax, roff, c);
+#pragma unroll
+        for (int a = 0; a < WS_K; ++a) {
+            if (a < k) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int t = 0; t <= a; ++t) sacc += Xs[a][t] * g[t];
+                wcol[(size_t)a * EKF_WPAD] = incol ? sacc : 0.0;   // the padding columns [n, ld) are kept zero
+            }
+        }
+        if (incol) x[c] += xs;
+    }
+    if (finalize) {
+        __syncthreads();
+        if (tid == 0) {
+            // normJac(q+) (mc/normJac.m) from the un-normalised quaternion, then q+ <- q+/|q+|  (mc/update.m:18,24)
+            const double r = x[3], qx = x[4], qy = x[5], qz = x[6];
+            const double nn = r * r + qx * qx + qy * qy + qz * qz;
+            const double sc = 1.0 / (nn * sqrt(nn));  // (.)^(-3/2)
+            double* J = v.jnt + (size_t)b * 16;
+            J[0] = sc * (qx * qx + qy * qy + qz * qz); J[1] = sc * (-r * qx); J[2] = sc * (-r * qy); J[3] = sc * (-r * qz);
+            J[4] = sc * (-qx * r); J[5] = sc * (r * r + qy * qy + qz * qz); J[6] = sc * (-qx * qy); J[7] = sc * (-qx * qz);
+            J[8] = sc * (-qy * r); J[9] = sc * (-qy * qx); J[10] = sc * (r * r + qx * qx + qz * qz); J[11] = sc * (-qy * qz);
+            J[12] = sc * (-qz * r); J[13] = sc * (-qz * qx); J[14] = sc * (-qz * qy); J[15] = sc * (r * r + qx * qx + qy * qy);
+            const double nrm = sqrt(nn);
+            x[3] = r / nrm; x[4] = qx / nrm; x[5] = qy / nrm; x[6] = qz / nrm;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1205,10 +1279,10 @@ static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
 void launch_pending_rows(ekfslam_ctx* c, int need, int forbid) {
     DevView& v = c->v;
     { KScope ks(c, KT_V); k_v<<<v.B, 256, 0, c->stream>>>(v, need, forbid); }
-    dim3 gw((v.kmax + TM - 1) / TM, v.B);   // (64-row tiles, filters); each CTA walks all column tiles
+    dim3 gw((v.kmax + TM - 1) / TM, 2, v.B);   // (64-row tiles, column groups, filters)
     const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax) + sizeof(int) * v.kmax;
     gemm_attr(c, w_sm);
-    { KScope ks(c, KT_G2); k_gemm<<<gw, 256, w_sm, c->stream>>>(v, 1, 0); }
+    { KScope ks(c, KT_G2); k_gemm<<<gw, 256, w_sm, c->stream>>>(v, 1, 0, 0); }
 }
 
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
@@ -1216,7 +1290,8 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     // normalisation, no covariance downdate), 4 = deferred (x and W now, covariance with the next update)
     DevView& v = c->v;
     cudaStream_t st = c->stream;
-    { KScope ks(c, KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, (flags & 4) ? 1 : 0); }
+    const bool hi = (mask & EKFSLAM_F_HI) != 0;
+    { KScope ks(c, hi ? KT_UPD_S_HI : KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, (flags & 4) ? 1 : 0); }
     const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
     const size_t chs_sm = sizeof(double) * ((CHS_K * (CHS_K + 1)) / 2 + 2 * NB * (NB + 1) + CHS_K * (NB + 1));
     static size_t chol_cfg = 0;
@@ -1236,7 +1311,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     if (chol_mode == 1 || (chol_mode == 2 && v.B < 128 && v.kmax >= 256)) {
         launch_chol_lockstep(c);
     } else {
-        KScope ks(c, KT_CHOL);
+        KScope ks(c, hi ? KT_CHOL_HI : KT_CHOL);
         static int resident = -1;
         if (resident < 0) {
             const char* e = getenv("EKFSLAM_CHOL_SM");
@@ -1250,10 +1325,25 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
             k_chol<<<v.B, 128, chol_sm, st>>>(v, 0);
         }
     }
-    dim3 gw((v.kmax + TM - 1) / TM, v.B);   // (64-row tiles, filters); each CTA walks all column tiles
+    // (64-row tiles, column groups, filters): the li update has work in every filter -> long CTAs that walk all column
+    // tiles; the hi update leaves few filters for this kernel (k_w_small takes k <= WS_K) -> five shorter CTAs per row tile
+    static int cg_li = -1, cg_hi = -1;
+    if (cg_li < 0) {
+        const char* e1 = getenv("EKFSLAM_W_CG_LI"); const char* e2 = getenv("EKFSLAM_W_CG_HI");
+        cg_li = e1 ? atoi(e1) : 1; cg_hi = e2 ? atoi(e2) : 5;
+        if (cg_li < 1) cg_li = 1; if (cg_hi < 1) cg_hi = 1;
+    }
+    dim3 gw((v.kmax + TM - 1) / TM, (mask & EKFSLAM_F_HI) ? cg_hi : cg_li, v.B);
     const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax) + sizeof(int) * v.kmax;
     gemm_attr(c, w_sm);
-    { KScope ks(c, KT_W); k_gemm<<<gw, 256, w_sm, st>>>(v, 0, (flags & 2) ? 0 : 1); }
+    {
+        KScope ks(c, hi ? KT_W_HI : KT_W);
+        static int small = -1;
+        if (small < 0) { const char* e = getenv("EKFSLAM_W_SMALL"); small = (e && e[0] == '0') ? 0 : 1; }
+        const int fin = (flags & 2) ? 0 : 1;
+        if (small) { k_w_small<<<v.B, 128, 0, st>>>(v, fin); c->launches++; }
+        k_gemm<<<gw, 256, w_sm, st>>>(v, 0, fin, small ? WS_K : 0);
+    }
     if (flags & 2) return;   // not the last iterate of an iterated update: W is recomputed, nothing pending
     { KScope ks(c, KT_WFIX); k_wfix<<<v.B, 128, 0, st>>>(v, (flags & 4) ? 1 : 0); }
     if (flags & 4) return;   // deferred: the covariance downdate happens with the next (non-deferred) update

@@ -733,6 +733,66 @@ __global__ void __launch_bounds__(128) k_mk_linv(DevView v, int I0) {
     }
 }
 
+// X = inv(L) by block COLUMNS: column J of X solves L X_J = E_J by forward substitution, independently of every
+// other column:  X_JJ = Dinv_J,  X_IJ = -Dinv_I * sum_{J<=K<I} L_IK X_KJ.  One launch, grid = (block columns, B),
+// instead of one launch per block row (k_mk_linv: 62 dependent launches per update at N = 500, each a long serial
+// loop per thread - 10 of the 12.6 ms of a large-map step).  The CTA keeps its block column (k x 16) in shared
+// memory and streams the rows of L in chunks of INVC_CH columns; thread (r, c) owns entry (r, c) of the 16 x 16 block.
+#define INVC_CH 128
+__global__ void __launch_bounds__(256) k_mk_invcols(DevView v) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.y;
+    const int k = 2 * v.ksel[b];
+    const int j0 = blockIdx.x * NB;
+    if (j0 >= k) return;
+    const int kmax = v.kmax;
+    const double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
+    double* Xc = sm;                                        // [kmax][NB+1]  rows j0.. of block column J
+    double* Lc = Xc + (size_t)kmax * (NB + 1);              // [NB][INVC_CH+1]
+    double* Di = Lc + NB * (INVC_CH + 1);                   // [NB][NB+1]
+    double* Ys = Di + NB * (NB + 1);                        // [NB][NB+1]
+    const int tid = threadIdx.x, r = tid >> 4, c = tid & 15;
+    {
+        const int nbj = min(NB, k - j0);
+        Xc[r * (NB + 1) + c] = (r < nbj && c <= r && c < nbj) ? X[(size_t)(j0 + r) * kmax + j0 + c] : 0.0;
+    }
+    __syncthreads();
+    for (int i0 = j0 + NB; i0 < k; i0 += NB) {
+        const int nb = min(NB, k - i0);
+        Di[r * (NB + 1) + c] = (r < nb && c <= r) ? X[(size_t)(i0 + r) * kmax + i0 + c] : 0.0;
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+        for (int t0 = j0; t0 < i0; t0 += INVC_CH) {
+            const int len = min(INVC_CH, i0 - t0);
+            for (int e = tid; e < NB * INVC_CH; e += blockDim.x) {
+                const int rr = e / INVC_CH, tt = e - rr * INVC_CH;
+                Lc[rr * (INVC_CH + 1) + tt] = (rr < nb && tt < len) ? S[(size_t)(i0 + rr) * kmax + t0 + tt] : 0.0;
+            }
+            __syncthreads();
+            const double* lr = Lc + r * (INVC_CH + 1);
+            const double* xc = Xc + (size_t)(t0 - j0) * (NB + 1) + c;
+            const int len4 = (len + 3) & ~3;   // len is a multiple of 16 except possibly... rows of Xc beyond are zero-initialised below
+            for (int tt = 0; tt < len4; tt += 4) {
+                y0 += lr[tt] * xc[(size_t)tt * (NB + 1)];
+                y1 += lr[tt + 1] * xc[(size_t)(tt + 1) * (NB + 1)];
+                y2 += lr[tt + 2] * xc[(size_t)(tt + 2) * (NB + 1)];
+                y3 += lr[tt + 3] * xc[(size_t)(tt + 3) * (NB + 1)];
+            }
+            __syncthreads();
+        }
+        Ys[r * (NB + 1) + c] = (y0 + y1) + (y2 + y3);
+        __syncthreads();
+        double sacc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+            if (j <= r) sacc += Di[r * (NB + 1) + j] * Ys[j * (NB + 1) + c];
+        const double xv = (r < nb) ? -sacc : 0.0;
+        Xc[(size_t)(i0 - j0 + r) * (NB + 1) + c] = xv;
+        if (r < nb && j0 + c < k) X[(size_t)(i0 + r) * kmax + j0 + c] = xv;
+        __syncthreads();
+    }
+}
+
 // zeros above the diagonal of X, y = X nu, cv = X' y.  One block per filter.
 __global__ void __launch_bounds__(128) k_mk_tail(DevView v) {
     extern __shared__ double sm[];
@@ -797,10 +857,23 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
         cudaFuncSetAttribute(k_mk_linv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linv_max);
         linv_cfg = linv_max;
     }
-    for (int I0 = NB; I0 < kmax; I0 += NB) {
-        dim3 gl((I0 + 127) / 128, v.B);
-        k_mk_linv<<<gl, 128, sizeof(double) * ((size_t)I0 * (NB + 1) + NB * (NB + 1)), st>>>(v, I0);
+    // inverse: one launch over block columns when the column fits shared memory, else block row by block row
+    const size_t invc_sm = sizeof(double) * ((size_t)kmax * (NB + 1) + NB * (INVC_CH + 1) + 2 * NB * (NB + 1));
+    if (invc_sm <= 200 * 1024) {
+        static size_t invc_cfg = 0;
+        if (invc_sm > 48 * 1024 && invc_sm > invc_cfg) {
+            cudaFuncSetAttribute(k_mk_invcols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)invc_sm);
+            invc_cfg = invc_sm;
+        }
+        dim3 gi((kmax + NB - 1) / NB, v.B);
+        k_mk_invcols<<<gi, 256, invc_sm, st>>>(v);
         c->launches += 1;
+    } else {
+        for (int I0 = NB; I0 < kmax; I0 += NB) {
+            dim3 gl((I0 + 127) / 128, v.B);
+            k_mk_linv<<<gl, 128, sizeof(double) * ((size_t)I0 * (NB + 1) + NB * (NB + 1)), st>>>(v, I0);
+            c->launches += 1;
+        }
     }
     static size_t tail_cfg = 0;
     const size_t tail_sm = sizeof(double) * (size_t)kmax * 5;
@@ -1333,7 +1406,15 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         cg_li = e1 ? atoi(e1) : 1; cg_hi = e2 ? atoi(e2) : 5;
         if (cg_li < 1) cg_li = 1; if (cg_hi < 1) cg_hi = 1;
     }
-    dim3 gw((v.kmax + TM - 1) / TM, (mask & EKFSLAM_F_HI) ? cg_hi : cg_li, v.B);
+    // few filters (large maps): split the column tiles so that the grid still fills the GPU
+    int cg = (mask & EKFSLAM_F_HI) ? cg_hi : cg_li;
+    {
+        const long long ctas = (long long)((v.kmax + TM - 1) / TM) * v.B;
+        const int want = (int)((8LL * 148 + ctas - 1) / ctas);
+        const int ncb_max = (v.nmax + TM - 1) / TM;
+        if (want > cg) cg = want < ncb_max ? want : ncb_max;
+    }
+    dim3 gw((v.kmax + TM - 1) / TM, cg, v.B);
     const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax) + sizeof(int) * v.kmax;
     gemm_attr(c, w_sm);
     {

@@ -103,8 +103,10 @@ def read_peaks():
 
 
 class ClockSampler:
-    """`nvidia-smi -lms 100` running for the duration of the timed regions (one long-lived process: spawning
-    nvidia-smi per sample is too slow for a sub-second region)."""
+    """SM clock, power and throttle reasons sampled every 50 ms for the duration of the timed regions.  NVML is
+    queried in-process from a thread (nvidia_ml_py): a polling `nvidia-smi -lms` process stalls the driver for
+    milliseconds per sample, which the synchronous host-buffer (e2e) steps pay in full (measured: +5 ms per step).
+    Falls back to one long-lived `nvidia-smi -lms 250` when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -113,16 +115,58 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.samples = []
+        self.thread = None
+        self.stop_flag = False
+
+    def _nvml_loop(self, nv, h):
+        smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        R = nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                flag = lambda bit: "Active" if (rs & bit) else "Not Active"  # noqa: E731
+                self.samples.append([str(sm), str(smax), "%.2f" % pw,
+                                     flag(getattr(R, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                                     flag(getattr(R, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                                     flag(getattr(R, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                                     flag(getattr(R, "nvmlClocksThrottleReasonSwPowerCap", 0x4))])
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may remap the CUDA ordinal
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    idx = int(ids[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            import threading
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return
         if self.proc is None:
             return
         try:

@@ -22,9 +22,9 @@ def ekf():
     return pkg, synth
 
 
-def _run_sequence(ekf, B, N, frames, seed, fixed=0, n_u=64, p_outlier=0.2, teacher_forced=False, cart=None):
+def _run_sequence(ekf, B, N, frames, seed, fixed=0, n_u=64, p_outlier=0.2, teacher_forced=False, cart=None, noise_px=0.5):
     pkg, synth = ekf
-    seq = synth.SynthSequence(B=B, N=N, T=frames, seed=seed, p_outlier=p_outlier, n_u=n_u)
+    seq = synth.SynthSequence(B=B, N=N, T=frames, seed=seed, p_outlier=p_outlier, n_u=n_u, noise_px=noise_px)
     x0, P0, types = seq.initial_state()
     n_max = 13 + 6 * N
     if cart:
@@ -164,3 +164,10 @@ def test_downdate_filter_groups(ekf, monkeypatch):
     monkeypatch.setenv("EKFSLAM_DD_GROUP", "2")
     worst, tot = _run_sequence(ekf, B=5, N=24, frames=3, seed=810)
     assert tot["li"] > 20
+
+
+def test_n100_many_inliers_large_k(ekf):
+    """No gross outliers and little pixel noise at N=100: the li update stacks more than 144 rows, i.e. the Cholesky runs in the
+    global-memory kernel (k_chol) instead of the shared-memory resident one, and the W GEMM spans three row tiles."""
+    worst, tot = _run_sequence(ekf, B=2, N=100, frames=3, seed=820, p_outlier=0.0, noise_px=0.15)
+    assert tot["li"] > 2 * 3 * 72, tot

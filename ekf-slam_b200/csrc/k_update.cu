@@ -911,7 +911,8 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
     double* As = dsm;                           // [NSTAGE][64][APAD]   As[i][t] = A[a0+i][t0+t]
     double* Bs = dsm + NSTAGE * TM * APAD;      // [NSTAGE][TK][TPAD]   Bs[t][j] = B[t0+t][c0+j]
     double* cs = Bs + NSTAGE * TK * TPAD;       // [kmax]               inv(S) nu
-    int* grow = reinterpret_cast<int*>(cs + kmax);   // [kmax]  G row of stacked row t: 2 sel[t/2] + (t&1)
+    double* xred = cs + kmax;                   // [256]                partial state-update sums
+    int* grow = reinterpret_cast<int*>(xred + 256);  // [kmax]  G row of stacked row t: 2 sel[t/2] + (t&1)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
     const bool xrole = (mode == 0) && (a0 + TM >= k);
@@ -978,9 +979,15 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
         cp_async_commit();
         const double* as = As + (j % NSTAGE) * TM * APAD;
         const double* bs = Bs + (j % NSTAGE) * TK * TPAD;
-        if (xrole && tid < TM) {
-            const int tmax = min(TK, k - it * TK);
-            for (int t = 0; t < tmax; ++t) xacc += bs[t * TPAD + tid] * cs[it * TK + t];
+        if (xrole) {
+            // state update G_sel' inv(S) nu for this column tile: thread (column tid & 63, quarter tid >> 6) takes four
+            // of the chunk's 16 rows; the four partial sums meet in shared memory at the end of the column tile
+            const int xc = tid & (TM - 1), t4 = (tid >> 6) * 4;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int tt = it * TK + t4 + t;
+                if (tt < k) xacc += bs[(t4 + t) * TPAD + xc] * cs[tt];
+            }
         }
         // 8-row tile mt of this warp (rows rbase + 8 mt ..) takes part in step tb when it exists (mt < mt_hi) and,
         // for the triangular A of mode 0, when tb <= its last row (mt >= mt_lo): a contiguous range.  Steps where all
@@ -1052,8 +1059,10 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
         }
         if (xrole) {
             double* __restrict__ x = v.x + (size_t)b * ld;
-            if (tid < TM && c0 + tid < n) x[c0 + tid] += xacc;
+            xred[tid] = xacc;
             xacc = 0.0;
+            __syncthreads();
+            if (tid < TM && c0 + tid < n) x[c0 + tid] += (xred[tid] + xred[tid + 64]) + (xred[tid + 128] + xred[tid + 192]);
             if (c0 == 0 && finalize) {
                 // this block owns state entries 0..63: normJac(q+) (mc/normJac.m) from the un-normalised
                 // quaternion, then q+ <- q+/|q+|  (mc/update.m:18,24)
@@ -1353,7 +1362,7 @@ void launch_pending_rows(ekfslam_ctx* c, int need, int forbid) {
     DevView& v = c->v;
     { KScope ks(c, KT_V); k_v<<<v.B, 256, 0, c->stream>>>(v, need, forbid); }
     dim3 gw((v.kmax + TM - 1) / TM, 2, v.B);   // (64-row tiles, column groups, filters)
-    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax) + sizeof(int) * v.kmax;
+    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax + 256) + sizeof(int) * v.kmax;
     gemm_attr(c, w_sm);
     { KScope ks(c, KT_G2); k_gemm<<<gw, 256, w_sm, c->stream>>>(v, 1, 0, 0); }
 }
@@ -1415,7 +1424,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         if (want > cg) cg = want < ncb_max ? want : ncb_max;
     }
     dim3 gw((v.kmax + TM - 1) / TM, cg, v.B);
-    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax) + sizeof(int) * v.kmax;
+    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax + 256) + sizeof(int) * v.kmax;
     gemm_attr(c, w_sm);
     {
         KScope ks(c, hi ? KT_W_HI : KT_W);

@@ -45,19 +45,27 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(DevView v, DevCam cam
     for (int j = tid; j < n; j += blockDim.x) xs[j] = xp[j];
     for (int j = tid; j < N; j += blockDim.x) memo[j] = -1;
     for (int j = tid; j < nwords; j += blockDim.x) bestmask[j] = 0u;
-    if (tid == 0) {
+    if (warp == 0) {
+        // matched (HAS_Z) and individually compatible (IC) lists in feature order: ballot + prefix popcount
         int nm = 0, nic = 0;
-        for (int i = 0; i < nf; ++i) {
-            const uint8_t f = fl[i];
-            if (f & EKFSLAM_F_HAS_Z) {
-                mlist[nm] = i; moff[nm] = v.foff[b * N + i]; mtype[nm] = v.ftype[b * N + i];
-                zs[2 * nm] = v.z[2 * (b * N + i)]; zs[2 * nm + 1] = v.z[2 * (b * N + i) + 1];
-                ++nm;
+        for (int i0 = 0; i0 < nf; i0 += 32) {
+            const int i = i0 + lane;
+            const uint8_t f = (i < nf) ? fl[i] : 0;
+            const bool hz = (f & EKFSLAM_F_HAS_Z) != 0, ic = (f & EKFSLAM_F_IC) != 0;
+            const unsigned mz = __ballot_sync(0xffffffffu, hz), mi = __ballot_sync(0xffffffffu, ic);
+            const unsigned below = (1u << lane) - 1u;
+            if (hz) {
+                const int s = nm + __popc(mz & below);
+                mlist[s] = i; moff[s] = v.foff[b * N + i]; mtype[s] = v.ftype[b * N + i];
+                zs[2 * s] = v.z[2 * (b * N + i)]; zs[2 * s + 1] = v.z[2 * (b * N + i) + 1];
             }
-            if (f & EKFSLAM_F_IC) iclist[nic++] = i;
+            if (ic) iclist[nic + __popc(mi & below)] = i;
+            nm += __popc(mz); nic += __popc(mi);
         }
-        s_nm = nm; s_nic = nic; s_done = (nic == 0); s_best = 0; s_roundbest = -1; s_nhyp = prm.max_hyp; s_iters = 0; s_scored = 0;
-        s_status = 0;
+        if (lane == 0) {
+            s_nm = nm; s_nic = nic; s_done = (nic == 0); s_best = 0; s_roundbest = -1; s_nhyp = prm.max_hyp; s_iters = 0; s_scored = 0;
+            s_status = 0;
+        }
     }
     __syncthreads();
     const int nm = s_nm, nic = s_nic;

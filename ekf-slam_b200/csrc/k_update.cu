@@ -28,17 +28,26 @@ __global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_pr
     const int tid = threadIdx.x;
     __shared__ int s_k;
     int* __restrict__ sel = v.sel + (size_t)b * N;
-    if (tid == 0) {
+    if (tid < 32) {
+        // selected features in feature order: ballot + prefix popcount (a serial thread-0 loop over the features was
+        // a third of this kernel's time)
         int cnt = 0;
-        for (int i = 0; i < nf; ++i)
-            if (v.ftype[b * N + i] != EKFSLAM_FEAT_NONE && (v.flags[(size_t)b * N + i] & mask)) sel[cnt++] = i;
-        v.ksel[b] = cnt;
-        s_k = cnt;
-        // rows a deferred update left in W come first; this update appends behind them
-        v.roff[b] = v.kpend[b];
-        v.kpend[b] = defer ? 2 * cnt : 0;
-        if (mask & EKFSLAM_F_LI) v.stats[b].n_li = cnt;
-        if (mask & EKFSLAM_F_HI) v.stats[b].n_hi = cnt;
+        for (int i0 = 0; i0 < nf; i0 += 32) {
+            const int i = i0 + tid;
+            const bool on = (i < nf) && v.ftype[b * N + i] != EKFSLAM_FEAT_NONE && (v.flags[(size_t)b * N + i] & mask);
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) sel[cnt + __popc(m & ((1u << tid) - 1u))] = i;
+            cnt += __popc(m);
+        }
+        if (tid == 0) {
+            v.ksel[b] = cnt;
+            s_k = cnt;
+            // rows a deferred update left in W come first; this update appends behind them
+            v.roff[b] = v.kpend[b];
+            v.kpend[b] = defer ? 2 * cnt : 0;
+            if (mask & EKFSLAM_F_LI) v.stats[b].n_li = cnt;
+            if (mask & EKFSLAM_F_HI) v.stats[b].n_hi = cnt;
+        }
     }
     __syncthreads();
     const int ns = s_k;
@@ -1210,17 +1219,23 @@ __global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid) {
     const int k1 = v.kpend[b];
     __shared__ int s_cnt;
     int* __restrict__ sel = v.sel + (size_t)b * N;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         int cnt = 0;
         if (k1 > 0) {
             const int nf = v.nfeat[b];
-            for (int i = 0; i < nf; ++i) {
-                const uint8_t fl = v.flags[(size_t)b * N + i];
-                if (v.ftype[(size_t)b * N + i] != EKFSLAM_FEAT_NONE && (fl & need) == need && (fl & forbid) == 0) sel[cnt++] = i;
+            for (int i0 = 0; i0 < nf; i0 += 32) {
+                const int i = i0 + threadIdx.x;
+                bool on = false;
+                if (i < nf) {
+                    const uint8_t fl = v.flags[(size_t)b * N + i];
+                    on = v.ftype[(size_t)b * N + i] != EKFSLAM_FEAT_NONE && (fl & need) == need && (fl & forbid) == 0;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) sel[cnt + __popc(m & ((1u << threadIdx.x) - 1u))] = i;
+                cnt += __popc(m);
             }
         }
-        v.ksel[b] = cnt;
-        s_cnt = cnt;
+        if (threadIdx.x == 0) { v.ksel[b] = cnt; s_cnt = cnt; }
     }
     __syncthreads();
     const int rows = 2 * s_cnt;

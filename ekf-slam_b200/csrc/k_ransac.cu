@@ -15,6 +15,47 @@
 #define RANSAC_WARPS 8
 #define RANSAC_THREADS (RANSAC_WARPS * 32)
 
+// Support of the hypothesis drawn at feature `pos` (mc/ransac_hypotheses.m:22-33), one warp: lanes re-project the
+// matched features at xi; the inlier mask goes to mask[nwords].  Returns the support (same value in every lane).
+__device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& cam, int b, int pos, const double* xs,
+                                                const double* __restrict__ G, const int* moff, const int* mtype,
+                                                const double* zs, int nm, double thr, unsigned* mask, int lane) {
+    const int N = v.N, ld = v.ld;
+    const size_t t = (size_t)b * N + pos;
+    const double s00 = v.S[4 * t], s01 = v.S[4 * t + 1], s10 = v.S[4 * t + 2], s11 = v.S[4 * t + 3];
+    const double n0 = v.z[2 * t] - v.h[2 * t], n1 = v.z[2 * t + 1] - v.h[2 * t + 1];
+    const double det = s00 * s11 - s01 * s10;
+    const double g0 = (s11 * n0 - s01 * n1) / det;
+    const double g1 = (-s10 * n0 + s00 * n1) / det;
+    const double* __restrict__ Ga = G + (size_t)(2 * pos) * ld;
+    const double* __restrict__ Gb = Ga + ld;
+    double c7[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c7[k] = xs[k] + (Ga[k] * g0 + Gb[k] * g1);
+    double R[9];
+    q2r_dev(c7 + 3, R);
+    int support = 0;
+    for (int j0 = 0; j0 < nm; j0 += 32) {
+        const int j = j0 + lane;
+        bool inl = false;
+        if (j < nm) {
+            const int off = moff[j];
+            const int ty = mtype[j];
+            const int w = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+            double y[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                y[k] = (k < w) ? xs[off + k] + (Ga[off + k] * g0 + Gb[off + k] * g1) : 0.0;
+            const double res = support_residual_dev(cam, c7, R, y, ty, zs[2 * j], zs[2 * j + 1]);
+            inl = res < thr;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, inl);
+        support += __popc(m);
+        if (lane == 0) mask[j0 >> 5] = m;
+    }
+    return support;
+}
+
 __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(DevView v, DevCam cam, ekfslam_params prm) {
     extern __shared__ unsigned char smem_raw[];
     const int b = blockIdx.x;
@@ -34,7 +75,8 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(DevView v, DevCam cam
     int* iclist = mtype + N;                                       // [N] IC feature indices
     int* memo = iclist + N;                                        // [N] support per feature, -1 = unscored
     unsigned* rmask = reinterpret_cast<unsigned*>(memo + N);       // [RW][nwords]
-    unsigned* bestmask = rmask + RANSAC_WARPS * nwords;            // [nwords]
+    unsigned* bestmask = rmask + RANSAC_WARPS * nwords;            // [nwords]  (+ [N][nwords] masks of the fixed-budget path)
+    int* dl = reinterpret_cast<int*>(bestmask + nwords + N * nwords);  // [N] distinct drawn features (fixed-budget path)
     __shared__ int s_nm, s_nic, s_done, s_best, s_roundbest, s_nhyp, s_iters, s_scored, s_status;
     __shared__ int rpos[RANSAC_WARPS], rsup[RANSAC_WARPS];
 
@@ -73,6 +115,72 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(DevView v, DevCam cam
     const double thr = prm.std_z;
     const double* __restrict__ ub = v.u + (size_t)b * v.n_u;
 
+    if (prm.fixed_hyp > 0 && nic > 0) {
+        // ---- fixed hypothesis budget (BASELINE configs 2 and 5: 256 / 512 draws per frame): no adaptive break, so the
+        // outcome is "the earliest draw that reaches the maximum support".  All draws are known up front: every DISTINCT
+        // drawn feature is scored once, warp-parallel, without the per-round sequential replay of the adaptive path.
+        int* need = memo;                                   // reuse: 0/1 drawn flag, then support
+        unsigned* masks = reinterpret_cast<unsigned*>(bestmask + nwords);   // [N][nwords] inlier mask per feature
+        __shared__ int s_nd;
+        __shared__ unsigned long long s_key;
+        const int ndraw = min(n_loop, v.n_u);
+        for (int j = tid; j < N; j += blockDim.x) need[j] = 0;
+        if (tid == 0) { s_nd = 0; s_key = 0ull; }
+        __syncthreads();
+        for (int it = tid; it < ndraw; it += blockDim.x) {
+            int r = (int)floor(ub[it] * (double)nic);
+            r = min(r, nic - 1);
+            need[iclist[r]] = 1;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int nd = 0;
+            for (int i0 = 0; i0 < nf; i0 += 32) {
+                const int i = i0 + lane;
+                const bool on = (i < nf) && need[i] != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) dl[nd + __popc(m & ((1u << lane) - 1u))] = i;
+                nd += __popc(m);
+            }
+            if (lane == 0) s_nd = nd;
+        }
+        __syncthreads();
+        const int nd = s_nd;
+        for (int d = warp; d < nd; d += RANSAC_WARPS) {
+            const int pos = dl[d];
+            const int support = score_hypothesis(v, cam, b, pos, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane);
+            if (lane == 0) need[pos] = support;             // need[] now holds the support of every drawn feature
+        }
+        __syncthreads();
+        // earliest draw with the maximum support: key = support << 32 | (0xffffffff - draw index), block-wide max
+        unsigned long long key = 0ull;
+        for (int it = tid; it < ndraw; it += blockDim.x) {
+            int r = (int)floor(ub[it] * (double)nic);
+            r = min(r, nic - 1);
+            const unsigned long long kq = ((unsigned long long)(unsigned)need[iclist[r]] << 32) | (unsigned long long)(0xffffffffu - (unsigned)it);
+            key = kq > key ? kq : key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if (lane == 0) atomicMax(&s_key, key);
+        __syncthreads();
+        const int best = (int)(s_key >> 32);
+        const int bestit = (int)(0xffffffffu - (unsigned)(s_key & 0xffffffffull));
+        if (best > 0) {
+            int r = (int)floor(ub[bestit] * (double)nic);
+            r = min(r, nic - 1);
+            const int bp = iclist[r];
+            for (int j = tid; j < nwords; j += blockDim.x) bestmask[j] = masks[bp * nwords + j];
+        }
+        if (tid == 0) {
+            s_best = best; s_iters = ndraw; s_scored = nd; s_done = 1;
+            s_status = (n_loop > v.n_u) ? 1 : 0;            // uniform stream exhausted
+        }
+        __syncthreads();
+    }
     for (int i0 = 0; !s_done; i0 += RANSAC_WARPS) {
         // ---- which feature does draw i0+warp select?  (mc/select_random_match.m:12-16)
         const int it = i0 + warp;  // 0-based draw index
@@ -88,39 +196,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(DevView v, DevCam cam
         for (int w2 = 0; w2 < warp && score; ++w2)
             if (rpos[w2] == pos) score = false;
         if (score) {
-            // ---- 1-match state update (mc/ransac_hypotheses.m:22-26), only the entries needed
-            const size_t t = (size_t)b * N + pos;
-            const double s00 = v.S[4 * t], s01 = v.S[4 * t + 1], s10 = v.S[4 * t + 2], s11 = v.S[4 * t + 3];
-            const double n0 = v.z[2 * t] - v.h[2 * t], n1 = v.z[2 * t + 1] - v.h[2 * t + 1];
-            const double det = s00 * s11 - s01 * s10;
-            const double g0 = (s11 * n0 - s01 * n1) / det;
-            const double g1 = (-s10 * n0 + s00 * n1) / det;
-            const double* __restrict__ Ga = G + (size_t)(2 * pos) * ld;
-            const double* __restrict__ Gb = Ga + ld;
-            double c7[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) c7[k] = xs[k] + (Ga[k] * g0 + Gb[k] * g1);
-            double R[9];
-            q2r_dev(c7 + 3, R);
-            int support = 0;
-            for (int j0 = 0; j0 < nm; j0 += 32) {
-                const int j = j0 + lane;
-                bool inl = false;
-                if (j < nm) {
-                    const int off = moff[j];
-                    const int ty = mtype[j];
-                    const int w = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
-                    double y[6];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k)
-                        y[k] = (k < w) ? xs[off + k] + (Ga[off + k] * g0 + Gb[off + k] * g1) : 0.0;
-                    const double res = support_residual_dev(cam, c7, R, y, ty, zs[2 * j], zs[2 * j + 1]);
-                    inl = res < thr;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, inl);
-                support += __popc(m);
-                if (lane == 0) rmask[warp * nwords + (j0 >> 5)] = m;
-            }
+            const int support = score_hypothesis(v, cam, b, pos, xs, G, moff, mtype, zs, nm, thr, rmask + warp * nwords, lane);
             if (lane == 0) rsup[warp] = support;
         }
         __syncthreads();
@@ -176,8 +252,8 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(DevView v, DevCam cam
 
 static size_t ransac_smem_bytes(const DevView& v) {
     const int nwords = (v.N + 31) / 32;
-    return sizeof(double) * (v.ld + 2 * v.N) + sizeof(int) * (5 * v.N) +
-           sizeof(unsigned) * ((RANSAC_WARPS + 1) * nwords) + 16;
+    return sizeof(double) * (v.ld + 2 * v.N) + sizeof(int) * (6 * v.N) +
+           sizeof(unsigned) * ((RANSAC_WARPS + 1) * nwords + v.N * nwords) + 16;
 }
 
 void launch_ransac(ekfslam_ctx* c) {

@@ -20,6 +20,7 @@
 #include "tc_common.cuh"
 
 #define WS_CONSUMERS 8
+#define XP_ 66   // row pitch (doubles) of the shared P tile buffer X of k_downdate_ws2 (= XP below)
 
 // ---- shared epilogue pieces ---------------------------------------------------------------------------
 // bit mt*2+nt of the mask: the warp's 8x8 DMMA tile (mt, nt) has work (inside n x n, not strictly above the
@@ -99,7 +100,7 @@ __device__ __forceinline__ void apply_j_col0(double* strip, const double* __rest
 // 64-byte runs).  Diagonal tiles: the lower triangle is authoritative, the upper one its mirror.
 __device__ __forceinline__ void store_tile(double* __restrict__ P, int ld, int n, int i0, int j0, int wr, int wc, int g, int q,
                                            bool diag, unsigned onmask, const double (&pf)[4][2][2],
-                                           const double (&acc)[4][2][2]) {
+                                           const double (&acc)[8][2]) {
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
         const int gi = i0 + wr * 32 + mt * 8 + g;
@@ -108,8 +109,8 @@ __device__ __forceinline__ void store_tile(double* __restrict__ P, int ld, int n
         for (int nt = 0; nt < 2; ++nt) {
             if (!(onmask & (1u << (mt * 2 + nt)))) continue;
             const int gj = j0 + wc * 16 + nt * 8 + 2 * q;
-            const double c0 = pf[mt][nt][0] - acc[mt][nt][0];
-            const double c1 = pf[mt][nt][1] - acc[mt][nt][1];
+            const double c0 = pf[mt][nt][0] - acc[mt * 2 + nt][0];
+            const double c1 = pf[mt][nt][1] - acc[mt * 2 + nt][1];
             if (!diag) {
                 if (gj + 1 < n) {
                     *reinterpret_cast<double2*>(P + (size_t)gi * ld + gj) = make_double2(c0, c1);
@@ -139,7 +140,7 @@ __device__ __forceinline__ void store_tile(double* __restrict__ P, int ld, int n
 // eight 8x8 DMMA tiles all have work (the common case) runs branch-free, fully unrolled code; the compiler
 // otherwise brackets every predicated mma.sync with WARPSYNC/NOP and re-derives the predicate per tile, which
 // made the DMMA one instruction in ten (ncu, round 1).
-__device__ __forceinline__ void mma_step_full(const double* __restrict__ a, const double* __restrict__ b, double (&acc)[4][2][2]) {
+__device__ __forceinline__ void mma_step_full(const double* __restrict__ a, const double* __restrict__ b, double (&acc)[8][2]) {
     double af[4], bf[2];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) af[mt] = a[mt * 8];
@@ -148,10 +149,10 @@ __device__ __forceinline__ void mma_step_full(const double* __restrict__ a, cons
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+        for (int nt = 0; nt < 2; ++nt) dmma(acc[mt * 2 + nt], af[mt], bf[nt]);
 }
 __device__ __forceinline__ void mma_chunk(const double* __restrict__ a, const double* __restrict__ b, int n4, unsigned onmask,
-                                          double (&acc)[4][2][2]) {
+                                          double (&acc)[8][2]) {
     if (onmask == 0xffu) {
         if (n4 == TK / 4) {
 #pragma unroll
@@ -172,10 +173,120 @@ __device__ __forceinline__ void mma_chunk(const double* __restrict__ a, const do
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt)
-                    if (onmask & (1u << (mt * 2 + nt))) dmma(acc[mt][nt], af[mt], bf[nt]);
+                    if (onmask & (1u << (mt * 2 + nt))) dmma(acc[mt * 2 + nt], af[mt], bf[nt]);
         }
     }
 }
+
+// ---- balanced warp layouts for the tiles a 2x4 grid of 32x16 warp tiles serves badly (k_downdate_ws2) -------
+// A full diagonal tile needs 36 of its 64 8x8 blocks; in the 2x4 grid two warps have all 8 of theirs and two have none, so
+// the tile takes as long as a full one.  An off-diagonal tile of the last tile row has n - i0 < 64 rows: the upper-row warps
+// have 8 blocks, the lower-row warps 2.  At n = 613 these are 18 of the 55 tiles of a filter.
+//   TRI:   8x8 block (r, c), c <= r, of the diagonal tile -> fixed per-warp lists of <= 5 blocks in at most two block rows
+//          (one A fragment per block row); A and B fragments both come from the tile's single W panel.
+//   STRIP: warp w owns block column w and all NRB existing block rows (one B fragment, NRB A fragments).
+template <int RA, int CA, int NA, int RB, int CB, int NBK>
+struct TriW {
+    static __device__ __forceinline__ void step(const double* __restrict__ p, double (&acc)[8][2]) {
+        const double af0 = p[RA * 8];
+        double af1 = 0.0;
+        if (NBK > 0) af1 = p[RB * 8];
+        double bf[NA + NBK];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) bf[i] = p[(CA + i) * 8];
+#pragma unroll
+        for (int i = 0; i < NBK; ++i) bf[NA + i] = p[(CB + i) * 8];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) dmma(acc[i], af0, bf[i]);
+#pragma unroll
+        for (int i = 0; i < NBK; ++i) dmma(acc[NA + i], af1, bf[NA + i]);
+    }
+    static __device__ __forceinline__ void chunk(const double* __restrict__ p, int n4, double (&acc)[8][2]) {
+        if (n4 == TK / 4) {
+#pragma unroll
+            for (int k4 = 0; k4 < TK / 4; ++k4) step(p + k4 * 4 * TPAD, acc);
+        } else {
+#pragma unroll 1
+            for (int k4 = 0; k4 < n4; ++k4) step(p + k4 * 4 * TPAD, acc);
+        }
+    }
+    // X <- X - acc for this warp's blocks (x = X + g * XP + 2 q)
+    static __device__ __forceinline__ void update(double* __restrict__ x, const double (&acc)[8][2]) {
+#pragma unroll
+        for (int i = 0; i < NA + NBK; ++i) {
+            const int r = (i < NA) ? RA : RB, c = (i < NA) ? CA + i : CB + i - NA;
+            double2* xp = reinterpret_cast<double2*>(x + r * 8 * XP_ + c * 8);
+            double2 pv = *xp;
+            pv.x -= acc[i][0];
+            pv.y -= acc[i][1];
+            *xp = pv;
+        }
+    }
+};
+// warp -> block list of the lower triangle of an 8x8 block grid: row 7: w0 (cols 0-4), w1 (5-7); row 6: w2 (0-4), w3 (5-6);
+// row 5: w4 (0-4), w5 (5); row 4: w6 (0-4); row 3: w5 (0-3); row 2: w3 (0-2); row 1: w1 (0-1); row 0: w7.  36 blocks, <= 5 each.
+typedef TriW<7, 0, 5, 0, 0, 0> TriW0;
+typedef TriW<7, 5, 3, 1, 0, 2> TriW1;
+typedef TriW<6, 0, 5, 0, 0, 0> TriW2;
+typedef TriW<6, 5, 2, 2, 0, 3> TriW3;
+typedef TriW<5, 0, 5, 0, 0, 0> TriW4;
+typedef TriW<5, 5, 1, 3, 0, 4> TriW5;
+typedef TriW<4, 0, 5, 0, 0, 0> TriW6;
+typedef TriW<0, 0, 1, 0, 0, 0> TriW7;
+#define TRI_DISPATCH(warp, CALL)           \
+    switch (warp) {                        \
+        case 0: CALL(TriW0); break;        \
+        case 1: CALL(TriW1); break;        \
+        case 2: CALL(TriW2); break;        \
+        case 3: CALL(TriW3); break;        \
+        case 4: CALL(TriW4); break;        \
+        case 5: CALL(TriW5); break;        \
+        case 6: CALL(TriW6); break;        \
+        default: CALL(TriW7); break;       \
+    }
+
+template <int NRB>
+struct StripW {
+    static __device__ __forceinline__ void step(const double* __restrict__ a, const double* __restrict__ b, double (&acc)[8][2]) {
+        const double bf = b[0];
+        double af[NRB];
+#pragma unroll
+        for (int rb = 0; rb < NRB; ++rb) af[rb] = a[rb * 8];
+#pragma unroll
+        for (int rb = 0; rb < NRB; ++rb) dmma(acc[rb], af[rb], bf);
+    }
+    static __device__ __forceinline__ void chunk(const double* __restrict__ a, const double* __restrict__ b, int n4, double (&acc)[8][2]) {
+        if (n4 == TK / 4) {
+#pragma unroll
+            for (int k4 = 0; k4 < TK / 4; ++k4) step(a + k4 * 4 * TPAD, b + k4 * 4 * TPAD, acc);
+        } else {
+#pragma unroll 1
+            for (int k4 = 0; k4 < n4; ++k4) step(a + k4 * 4 * TPAD, b + k4 * 4 * TPAD, acc);
+        }
+    }
+    // x = X + g * XP + warp * 8 + 2 q
+    static __device__ __forceinline__ void update(double* __restrict__ x, const double (&acc)[8][2]) {
+#pragma unroll
+        for (int rb = 0; rb < NRB; ++rb) {
+            double2* xp = reinterpret_cast<double2*>(x + rb * 8 * XP_);
+            double2 pv = *xp;
+            pv.x -= acc[rb][0];
+            pv.y -= acc[rb][1];
+            *xp = pv;
+        }
+    }
+};
+#define STRIP_DISPATCH(nrb, CALL)                 \
+    switch (nrb) {                                \
+        case 1: CALL(StripW<1>); break;           \
+        case 2: CALL(StripW<2>); break;           \
+        case 3: CALL(StripW<3>); break;           \
+        case 4: CALL(StripW<4>); break;           \
+        case 5: CALL(StripW<5>); break;           \
+        case 6: CALL(StripW<6>); break;           \
+        case 7: CALL(StripW<7>); break;           \
+        default: CALL(StripW<8>); break;          \
+    }
 
 // ---- one CTA per tile, cp.async ring ------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
@@ -223,11 +334,9 @@ __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
             }
         }
     };
-    double acc[4][2][2];
+    double acc[8][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
     const unsigned onmask = tile_mask(i0, j0, wr, wc, n, diag);
     const int aoff = q * TPAD + wr * 32 + g, boff = q * TPAD + wc * 16 + g;
 
@@ -265,7 +374,7 @@ __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
 // and no P value is held in registers across the K loop.
 #define WS2_EPI 4
 #define WS2_THREADS ((WS_CONSUMERS + 1 + WS2_EPI) * 32)
-#define XP 66   // row pitch of X in doubles: rows stay 16-byte aligned for bulk copies and double2 access
+#define XP XP_  // row pitch of X in doubles (66): rows stay 16-byte aligned for bulk copies and double2 access
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -368,18 +477,32 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
         for (int cm = 0; cm < Mreal; ++cm) {
             const DTile C = decode_tile(meta, lut, cm, Mreal, blockIdx.x + (long long)cm * G, T);
             if (C.nk == 0) continue;
+            // warp layout of this tile: 0 = 2x4 grid of 32x16 (full tiles; masked path for the partial last diagonal tile),
+            // 1 = STRIP (off-diagonal tile with fewer than 64 rows), 2 = TRI (full diagonal tile)
+            const bool full_rows = C.i0 + TM <= C.n;
+            const int layout = C.diag ? (full_rows ? 2 : 0) : (full_rows ? 0 : 1);
+            const int nrb = (min(TM, C.n - C.i0) + 7) >> 3;
             const unsigned onmask = tile_mask(C.i0, C.j0, wr, wc, C.n, C.diag);
-            double acc[4][2][2];
+            double acc[8][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
             for (int it = 0; it < C.nk; ++it, ++cnt) {
                 const unsigned slot = cnt % S, ph = (cnt / S) & 1u;
                 mbar_wait(full + slot, ph);
                 const double* as = As + slot * TK * TPAD;
                 const double* bs = C.diag ? as : Bs + slot * TK * TPAD;
-                mma_chunk(as + aoff, bs + boff, min(TK / 4, (C.k - it * TK + 3) >> 2), onmask, acc);
+                const int n4 = min(TK / 4, (C.k - it * TK + 3) >> 2);
+                if (layout == 0) {
+                    mma_chunk(as + aoff, bs + boff, n4, onmask, acc);
+                } else if (layout == 1) {
+#define CALL_(W) W::chunk(as + q * TPAD + g, bs + q * TPAD + warp * 8 + g, n4, acc)
+                    STRIP_DISPATCH(nrb, CALL_)
+#undef CALL_
+                } else {
+#define CALL_(W) W::chunk(as + q * TPAD + g, n4, acc)
+                    TRI_DISPATCH(warp, CALL_)
+#undef CALL_
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + slot);
             }
@@ -406,16 +529,26 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
                     cons_bar();
                 }
             }
+            if (layout == 0) {
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
+                for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    double2* xp = reinterpret_cast<double2*>(X + xoff + (mt * 8) * XP + nt * 8);
-                    double2 pv = *xp;
-                    pv.x -= acc[mt][nt][0];
-                    pv.y -= acc[mt][nt][1];
-                    *xp = pv;
-                }
+                    for (int nt = 0; nt < 2; ++nt) {
+                        double2* xp = reinterpret_cast<double2*>(X + xoff + (mt * 8) * XP + nt * 8);
+                        double2 pv = *xp;
+                        pv.x -= acc[mt * 2 + nt][0];
+                        pv.y -= acc[mt * 2 + nt][1];
+                        *xp = pv;
+                    }
+            } else if (layout == 1) {
+#define CALL_(W) W::update(X + g * XP + warp * 8 + 2 * q, acc)
+                STRIP_DISPATCH(nrb, CALL_)
+#undef CALL_
+            } else {
+#define CALL_(W) W::update(X + g * XP + 2 * q, acc)
+                TRI_DISPATCH(warp, CALL_)
+#undef CALL_
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(cfull + tiles % NX);
             ++tiles;

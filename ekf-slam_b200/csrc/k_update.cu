@@ -902,6 +902,22 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
 //   mode 1:  G[candrow(a)] -= sum_t V[a][t] * W[t]            (pending-update correction of the rescue rows:
 //            H_c P_kk = H_c P - (H_c W') W for a deferred W; V = H_c W' lives in the Sb scratch).
 // ---------------------------------------------------------------------------------------
+// one K step (4 rows of the staged panels) of k_gemm for the 8-row tiles LO..HI-1 of this warp
+template <int LO, int HI>
+__device__ __forceinline__ void gemm_step(const double* __restrict__ ap, const double* __restrict__ bp, double (&acc)[4][2][2]) {
+    double bf[2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) bf[nt] = bp[nt * 8];
+#pragma unroll
+    for (int mt = LO; mt < HI; ++mt) {
+        const double af = ap[mt * 8 * APAD];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            dmma(acc[mt][nt], af, bf[nt]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finalize, int kskip) {
     extern __shared__ __align__(16) double dsm[];
     const int b = blockIdx.z;
@@ -1023,17 +1039,22 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
                 const int tb = tb0 + k4 * 4;
                 if (tb >= tmax_w) break;
                 const int mt_lo = (mode == 0) ? max(0, (tb - rbase) >> 3) : 0;
-                double af[4], bf[2];
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * APAD + k4 * 4];
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) bf[nt] = bp[k4 * 4 * TPAD + nt * 8];
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    if (mt >= mt_lo && mt < mt_hi) {
-#pragma unroll
-                        for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
-                    }
+                // real (warp-uniform) branches, one code block per range: a predicated-off mma.sync still occupies the
+                // tensor pipe (ncu: pipe-active time was twice the ideal DMMA time while this was a predicated loop)
+                const double* a4 = ap + k4 * 4;
+                const double* b4 = bp + k4 * 4 * TPAD;
+                switch (mt_lo * 5 + mt_hi) {
+                    case 0 * 5 + 1: gemm_step<0, 1>(a4, b4, acc); break;
+                    case 0 * 5 + 2: gemm_step<0, 2>(a4, b4, acc); break;
+                    case 0 * 5 + 3: gemm_step<0, 3>(a4, b4, acc); break;
+                    case 0 * 5 + 4: gemm_step<0, 4>(a4, b4, acc); break;
+                    case 1 * 5 + 2: gemm_step<1, 2>(a4, b4, acc); break;
+                    case 1 * 5 + 3: gemm_step<1, 3>(a4, b4, acc); break;
+                    case 1 * 5 + 4: gemm_step<1, 4>(a4, b4, acc); break;
+                    case 2 * 5 + 3: gemm_step<2, 3>(a4, b4, acc); break;
+                    case 2 * 5 + 4: gemm_step<2, 4>(a4, b4, acc); break;
+                    case 3 * 5 + 4: gemm_step<3, 4>(a4, b4, acc); break;
+                    default: break;
                 }
             }
         }

@@ -107,6 +107,20 @@ struct KScope {
     ~KScope() { if (c->timer) kt_end(c, slot); c->launches++; }
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: a process that drives several GPUs (one
+// context per GPU) must raise it on each of them.  The high-water mark is kept per call site and device; NEED_CTX has
+// made `dev` the current device.
+#define ENSURE_DYN_SMEM(func, bytes, dev)                                                                    \
+    do {                                                                                                     \
+        static size_t _hw[64];                                                                               \
+        const size_t _b = (size_t)(bytes);                                                                   \
+        const int _d = (dev) & 63;                                                                           \
+        if (_b > 48 * 1024 && _b > _hw[_d]) {                                                                \
+            cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)_b);                \
+            _hw[_d] = _b;                                                                                    \
+        }                                                                                                    \
+    } while (0)
+
 // launchers (defined in the kernel .cu files)
 void launch_begin_frame(ekfslam_ctx* c);
 void launch_predict(ekfslam_ctx* c);

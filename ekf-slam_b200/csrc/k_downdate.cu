@@ -653,18 +653,14 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
             const char* eg = getenv("EKFSLAM_DD_GROUP");   // =g: at most g filters per launch (exercises the grouping in tests)
             const long long force_group = eg ? atoll(eg) : 0;
             if (force_group > 0 && force_group < bgroup) bgroup = force_group;
-            static size_t cfg2[2] = {0, 0};
             for (long long b0 = 0; b0 < v.B; b0 += bgroup) {
                 const long long nb = (v.B - b0 < bgroup) ? (v.B - b0) : bgroup;
                 const long long total = (long long)T * nb;
                 const long long ctas = total < ctas_full ? total : ctas_full;
                 const int M = (int)((total + ctas - 1) / ctas);
                 const size_t sm2 = fixed + sizeof(int2) * M;
-                if (sm2 > cfg2[cfgB]) {
-                    if (cfgB) cudaFuncSetAttribute(k_downdate_ws2<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-                    else cudaFuncSetAttribute(k_downdate_ws2<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-                    cfg2[cfgB] = sm2;
-                }
+                if (cfgB) ENSURE_DYN_SMEM((k_downdate_ws2<2, 2>), sm2, c->device);
+                else ENSURE_DYN_SMEM((k_downdate_ws2<4, 1>), sm2, c->device);
                 if (cfgB) k_downdate_ws2<2, 2><<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M);
                 else k_downdate_ws2<4, 1><<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M);
                 if (b0 > 0) c->launches++;
@@ -673,11 +669,7 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
         }
     }
     const size_t sm = sizeof(double) * (2 * NSTAGE * TK * TPAD + TM * 9);
-    static bool cfg = false;
-    if (!cfg) {
-        cudaFuncSetAttribute(k_downdate_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        cfg = true;
-    }
+    ENSURE_DYN_SMEM(k_downdate_tile, sm, c->device);
     dim3 gd(T, v.B);
     k_downdate_tile<<<gd, 256, sm, c->stream>>>(v);
 }

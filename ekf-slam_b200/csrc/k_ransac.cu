@@ -258,11 +258,7 @@ static size_t ransac_smem_bytes(const DevView& v) {
 
 void launch_ransac(ekfslam_ctx* c) {
     const size_t sm = ransac_smem_bytes(c->v);
-    static size_t configured = 0;
-    if (sm > 48 * 1024 && sm > configured) {
-        cudaFuncSetAttribute(k_ransac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        configured = sm;
-    }
+    ENSURE_DYN_SMEM(k_ransac, sm, c->device);
     KScope ks(c, KT_RANSAC);
     k_ransac<<<c->v.B, RANSAC_THREADS, sm, c->stream>>>(c->v, c->cam, c->prm);
 }

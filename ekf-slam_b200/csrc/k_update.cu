@@ -860,36 +860,24 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
             k_mk_trail<<<gt, 64, 0, st>>>(v, j0);
         }
     }
-    static size_t linv_cfg = 0;
     const size_t linv_max = sizeof(double) * ((size_t)kmax * (NB + 1) + NB * (NB + 1));
-    if (linv_max > 48 * 1024 && linv_max > linv_cfg) {
-        cudaFuncSetAttribute(k_mk_linv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linv_max);
-        linv_cfg = linv_max;
-    }
     // inverse: one launch over block columns when the column fits shared memory, else block row by block row
     const size_t invc_sm = sizeof(double) * ((size_t)kmax * (NB + 1) + NB * (INVC_CH + 1) + 2 * NB * (NB + 1));
     if (invc_sm <= 200 * 1024) {
-        static size_t invc_cfg = 0;
-        if (invc_sm > 48 * 1024 && invc_sm > invc_cfg) {
-            cudaFuncSetAttribute(k_mk_invcols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)invc_sm);
-            invc_cfg = invc_sm;
-        }
+        ENSURE_DYN_SMEM(k_mk_invcols, invc_sm, c->device);
         dim3 gi((kmax + NB - 1) / NB, v.B);
         k_mk_invcols<<<gi, 256, invc_sm, st>>>(v);
         c->launches += 1;
     } else {
+        ENSURE_DYN_SMEM(k_mk_linv, linv_max, c->device);
         for (int I0 = NB; I0 < kmax; I0 += NB) {
             dim3 gl((I0 + 127) / 128, v.B);
             k_mk_linv<<<gl, 128, sizeof(double) * ((size_t)I0 * (NB + 1) + NB * (NB + 1)), st>>>(v, I0);
             c->launches += 1;
         }
     }
-    static size_t tail_cfg = 0;
     const size_t tail_sm = sizeof(double) * (size_t)kmax * 5;
-    if (tail_sm > 48 * 1024 && tail_sm > tail_cfg) {
-        cudaFuncSetAttribute(k_mk_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_sm);
-        tail_cfg = tail_sm;
-    }
+    ENSURE_DYN_SMEM(k_mk_tail, tail_sm, c->device);
     k_mk_tail<<<v.B, 128, tail_sm, st>>>(v);
 }
 
@@ -1197,7 +1185,6 @@ __global__ void __launch_bounds__(128) k_wfix(DevView v, int defer) {
     const int b = blockIdx.x;
     const int k = 2 * v.ksel[b], roff = v.roff[b];
     const int rows = roff + k;
-    const int ld = v.ld;
     double* __restrict__ W = v.W + (size_t)b * v.wstride;
     __shared__ double Jt[16];
     if (threadIdx.x < 16) Jt[threadIdx.x] = v.jnt[(size_t)b * 16 + threadIdx.x];
@@ -1377,21 +1364,13 @@ __global__ void __launch_bounds__(256) k_rescue_gate(DevView v, ekfslam_params p
 void launch_rescue_gate(ekfslam_ctx* c) {
     DevView& v = c->v;
     const size_t sm = sizeof(double) * (size_t)v.kmax * 7;
-    static size_t cfg = 0;
-    if (sm > 48 * 1024 && sm > cfg) {
-        cudaFuncSetAttribute(k_rescue_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        cfg = sm;
-    }
+    ENSURE_DYN_SMEM(k_rescue_gate, sm, c->device);
     KScope ks(c, KT_INNOV);
     k_rescue_gate<<<v.B, 256, sm, c->stream>>>(v, c->prm);
 }
 
 static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
-    static size_t attr_done = 0;
-    if (attr_done < w_sm) {
-        cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w_sm);
-        attr_done = w_sm;
-    }
+    ENSURE_DYN_SMEM(k_gemm, w_sm, c->device);
 }
 
 void launch_pending_rows(ekfslam_ctx* c, int need, int forbid) {
@@ -1412,11 +1391,8 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     { KScope ks(c, hi ? KT_UPD_S_HI : KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, (flags & 4) ? 1 : 0); }
     const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
     const size_t chs_sm = sizeof(double) * ((CHS_K * (CHS_K + 1)) / 2 + 2 * NB * (NB + 1) + CHS_K * (NB + 1));
-    static size_t chol_cfg = 0;
-    if (chol_sm > 48 * 1024 && chol_sm > chol_cfg) {
-        cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_sm);
-        chol_cfg = chol_sm;
-    }
+    ENSURE_DYN_SMEM(k_chol, chol_sm, c->device);
+    ENSURE_DYN_SMEM(k_chol_sm, chs_sm, c->device);
     // One block per filter fills the GPU once there are a few hundred filters (measured B=4096, k~98: block
     // 2.2 ms, lock-step 3.8 ms).  Few filters with a large stacked innovation (large maps): the single block is a
     // serial bottleneck (N=500, B=8: 7.1 of 11.5 ms per step), so every phase becomes its own launch over all
@@ -1434,7 +1410,6 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         if (resident < 0) {
             const char* e = getenv("EKFSLAM_CHOL_SM");
             resident = (e && e[0] == '0') ? 0 : 1;
-            cudaFuncSetAttribute(k_chol_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chs_sm);
         }
         if (resident) {
             k_chol_sm<<<v.B, CHS_T, chs_sm, st>>>(v);

@@ -73,6 +73,7 @@ struct ekfslam_ctx {
     int64_t launches;
     int stage;  // call-order tracking
     int fuse_downdates;  // ekfslam_step: defer the li covariance downdate and apply it together with the hi one
+    int rescue_gather;   // ekfslam_step: rescue gate from 13x13 gathers of P, G rows only for the hi inliers
     // ekfslam_step_host overlaps its PCIe copies with the step: inputs go up on copy_stream while prediction and the
     // measurement model run (first needed by the matcher gate), x / flags / stats come down while the last covariance
     // downdate (which only touches P) is still running.

@@ -1273,14 +1273,15 @@ __global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Rescue gate against a pending (deferred) li update, mc/rescue_hi_inliers.m:11-20, WITHOUT the G rows of the
-// candidates: the 2x2  S_c = H_c p_k_k H_c'  with  p_k_k = J1 (P - W'W) J1' = J1 P J1' - Wt'Wt  (Wt = W J1', what
+// Rescue gate, mc/rescue_hi_inliers.m:11-20, WITHOUT the G rows of the candidates (default rescue path; with a
+// pending / deferred li update under EKFSLAM_FUSE=2, without one otherwise: k1 = 0, J1 = I): the 2x2  S_c = H_c p_k_k H_c'  with  p_k_k = J1 (P - W'W) J1' = J1 P J1' - Wt'Wt  (Wt = W J1', what
 // k_wfix leaves in memory) is   (H_c J1) P[c,c] (H_c J1)' - (H_c Wt')(H_c Wt')'   where c are the 13 (10) columns
 // H_c touches: a 13x13 gather of the stored covariance and 13 columns of the k1 pending rows.  Only the
 // candidates that pass (HI) then need full rows H p_k_k (k_hp + k_v + k_gemm mode 1 on those rows).
 // One block per filter, one warp per candidate (round robin), fixed-order warp reductions.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rescue_gate(DevView v, ekfslam_params prm) {
+#define RG_THREADS 256
+__global__ void __launch_bounds__(RG_THREADS, 3) k_rescue_gate(DevView v, ekfslam_params prm) {
     extern __shared__ double wcam[];   // [k1][7] camera columns of the pending rows
     const int b = blockIdx.x;
     const int N = v.N, ld = v.ld, kmax = v.kmax;
@@ -1290,6 +1291,7 @@ __global__ void __launch_bounds__(256) k_rescue_gate(DevView v, ekfslam_params p
     const double* __restrict__ W = v.W + (size_t)b * v.wstride;
     const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
     __shared__ double J1[16];
+    __shared__ double hsm[(RG_THREADS / 32) * 4 * EKF_HC];
     if (tid < 16) J1[tid] = (k1 > 0) ? v.jn1[(size_t)b * 16 + tid] : ((tid >> 2) == (tid & 3) ? 1.0 : 0.0);
     for (int e = tid; e < k1 * 7; e += blockDim.x) {
         const int a = e / 7, m = e - a * 7;
@@ -1305,41 +1307,56 @@ __global__ void __launch_bounds__(256) k_rescue_gate(DevView v, ekfslam_params p
         const int off = v.foff[t];
         const int w = (type == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
         const int nc = 7 + w;
-        double h0[EKF_HC], h1[EKF_HC];     // H_c (for the W part) ...
-#pragma unroll
-        for (int m = 0; m < EKF_HC; ++m) { h0[m] = (m < nc) ? H[m] : 0.0; h1[m] = (m < nc) ? H[EKF_HC + m] : 0.0; }
-        double j0[EKF_HC], j1[EKF_HC];     // ... and H_c J1 (for the P part): columns 3..6 mix
-#pragma unroll
-        for (int m = 0; m < EKF_HC; ++m) { j0[m] = h0[m]; j1[m] = h1[m]; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            j0[3 + a] = h0[3] * J1[0 * 4 + a] + h0[4] * J1[1 * 4 + a] + h0[5] * J1[2 * 4 + a] + h0[6] * J1[3 * 4 + a];
-            j1[3 + a] = h1[3] * J1[0 * 4 + a] + h1[4] * J1[1 * 4 + a] + h1[5] * J1[2 * 4 + a] + h1[6] * J1[3 * 4 + a];
+        // H_c (for the W part) and H_c J1 (for the P part: columns 3..6 mix) in this warp's shared scratch
+        double* hs = hsm + warp * 4 * EKF_HC;          // [2][13] H_c, [2][13] H_c J1
+        __syncwarp();
+        if (lane < 2 * EKF_HC) {
+            const int rr = lane / EKF_HC, m = lane - rr * EKF_HC;
+            const double hv = (m < nc) ? H[rr * EKF_HC + m] : 0.0;
+            hs[rr * EKF_HC + m] = hv;
+            hs[(2 + rr) * EKF_HC + m] = hv;
         }
-        // (H J1) P[c,c] (H J1)': entries e = r * nc + cc of the gather spread over the lanes
-        double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-        for (int e = lane; e < nc * nc; e += 32) {
-            const int r = e / nc, cc = e - r * nc;
-            const int gr = (r < 7) ? r : off + r - 7, gc = (cc < 7) ? cc : off + cc - 7;
-            const double pv = P[(size_t)gr * ld + gc];
-            // register arrays are indexed with compile-time constants only: select by unrolled compare
-            double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+        __syncwarp();
+        if (lane < 8) {
+            const int rr = lane >> 2, a = lane & 3;
+            const double* hr = hs + rr * EKF_HC;
+            hs[(2 + rr) * EKF_HC + 3 + a] = hr[3] * J1[0 * 4 + a] + hr[4] * J1[1 * 4 + a] + hr[5] * J1[2 * 4 + a] + hr[6] * J1[3 * 4 + a];
+        }
+        __syncwarp();
+        const double* j0 = hs + 2 * EKF_HC;
+        const double* j1 = hs + 3 * EKF_HC;
+        // (H J1) P[c,c] (H J1)': the <= 169 entries of the gather spread over the lanes, all loads issued before use
+        double pvs[6];
 #pragma unroll
-            for (int m = 0; m < EKF_HC; ++m) {
-                if (m == r) { a0 = j0[m]; a1 = j1[m]; }
-                if (m == cc) { c0 = j0[m]; c1 = j1[m]; }
+        for (int u = 0; u < 6; ++u) {
+            const int e = lane + 32 * u;
+            double pv = 0.0;
+            if (e < nc * nc) {
+                const int r = e / nc, cc = e - r * nc;
+                const int gr = (r < 7) ? r : off + r - 7, gc = (cc < 7) ? cc : off + cc - 7;
+                pv = P[(size_t)gr * ld + gc];
             }
-            s00 += a0 * pv * c0; s01 += a0 * pv * c1; s10 += a1 * pv * c0; s11 += a1 * pv * c1;
+            pvs[u] = pv;
+        }
+        double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const int e = lane + 32 * u;
+            if (e < nc * nc) {
+                const int r = e / nc, cc = e - r * nc;
+                const double a0 = j0[r], a1 = j1[r], c0 = j0[cc], c1 = j1[cc], pv = pvs[u];
+                s00 += a0 * pv * c0; s01 += a0 * pv * c1; s10 += a1 * pv * c0; s11 += a1 * pv * c1;
+            }
         }
         // (H Wt') over the pending rows, lanes along the rows
         double q00 = 0.0, q01 = 0.0, q11 = 0.0;
         for (int a = lane; a < k1; a += 32) {
             double v0 = 0.0, v1 = 0.0;
 #pragma unroll
-            for (int m = 0; m < 7; ++m) { const double wv = wcam[a * 7 + m]; v0 += h0[m] * wv; v1 += h1[m] * wv; }
+            for (int m = 0; m < 7; ++m) { const double wv = wcam[a * 7 + m]; v0 += hs[m] * wv; v1 += hs[EKF_HC + m] * wv; }
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
-                if (m < w) { const double wv = W[w_at(kmax, a, off + m)]; v0 += h0[7 + m] * wv; v1 += h1[7 + m] * wv; }
+                if (m < w) { const double wv = W[w_at(kmax, a, off + m)]; v0 += hs[7 + m] * wv; v1 += hs[EKF_HC + 7 + m] * wv; }
             }
             q00 += v0 * v0; q01 += v0 * v1; q11 += v1 * v1;
         }
@@ -1366,7 +1383,7 @@ void launch_rescue_gate(ekfslam_ctx* c) {
     const size_t sm = sizeof(double) * (size_t)v.kmax * 7;
     ENSURE_DYN_SMEM(k_rescue_gate, sm, c->device);
     KScope ks(c, KT_INNOV);
-    k_rescue_gate<<<v.B, 256, sm, c->stream>>>(v, c->prm);
+    k_rescue_gate<<<v.B, RG_THREADS, sm, c->stream>>>(v, c->prm);
 }
 
 static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {

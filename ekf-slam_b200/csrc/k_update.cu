@@ -341,24 +341,25 @@ __global__ void __launch_bounds__(128) k_chol(DevView v, int kskip) {
 // k_chol above works on S in global memory (every panel / trailing update is an L2 round trip: long-scoreboard
 // stalls were half of its issue stalls) and stays as the path for larger k.  Same blocked algorithm and pivots.
 // ---------------------------------------------------------------------------------------
-#define CHS_K 144
-#define CHS_T 256
+#define CHS_K 144   // large variant: KMIN < k <= 144, 256 threads, 2 CTAs/SM
+#define CHS_KS 48   // small variant (hi update: k ~ 24): k <= 48, 128 threads, 20 KB of shared memory -> many CTAs/SM
 __device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
 
-__global__ void __launch_bounds__(CHS_T, 2) k_chol_sm(DevView v) {
+template <int KM, int CHS_T, int KMIN>
+__global__ void __launch_bounds__(CHS_T) k_chol_sm(DevView v) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     const int k = 2 * v.ksel[b];
-    if (k == 0 || k > CHS_K) return;
+    if (k == 0 || k > KM || k <= KMIN) return;
     const int kmax = v.kmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = CHS_T / 32;
     const double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
     double* __restrict__ Xg = v.Li + (size_t)b * kmax * kmax;
     double* Ls = sm;                                   // packed lower triangle: L, then inv(L) in place
-    double* D = Ls + (CHS_K * (CHS_K + 1)) / 2;        // [NB][NB+1] diagonal block factor
+    double* D = Ls + (KM * (KM + 1)) / 2;              // [NB][NB+1] diagonal block factor
     double* Di = D + NB * (NB + 1);                    // [NB][NB+1] its inverse
-    double* Pn = Di + NB * (NB + 1);                   // [CHS_K][NB+1] transposed row panel (inverse phase) / vectors
+    double* Pn = Di + NB * (NB + 1);                   // [KM][NB+1] transposed row panel (inverse phase) / vectors
     __shared__ int s_bad;
     if (tid == 0) s_bad = 0;
     for (int r = warp; r < k; r += nwarps)
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(CHS_T, 2) k_chol_sm(DevView v) {
         for (int c = lane; c < k; c += 32) Xg[(size_t)r * kmax + c] = (c <= r) ? Ls[tri(r, c)] : 0.0;
     // y = X nu and cv = X' y = inv(S) nu
     double* nu = Pn;            // [k]
-    double* ys = Pn + CHS_K;    // [k]
+    double* ys = Pn + KM;       // [k]
     double* __restrict__ yv = v.yv + (size_t)b * kmax;
     for (int a = tid; a < k; a += CHS_T) nu[a] = yv[a];
     __syncthreads();
@@ -1408,8 +1409,10 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     { KScope ks(c, hi ? KT_UPD_S_HI : KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, (flags & 4) ? 1 : 0); }
     const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
     const size_t chs_sm = sizeof(double) * ((CHS_K * (CHS_K + 1)) / 2 + 2 * NB * (NB + 1) + CHS_K * (NB + 1));
+    const size_t chss_sm = sizeof(double) * ((CHS_KS * (CHS_KS + 1)) / 2 + 2 * NB * (NB + 1) + CHS_KS * (NB + 1));
     ENSURE_DYN_SMEM(k_chol, chol_sm, c->device);
-    ENSURE_DYN_SMEM(k_chol_sm, chs_sm, c->device);
+    ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, 0>), chs_sm, c->device);
+    ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, CHS_KS>), chs_sm, c->device);
     // One block per filter fills the GPU once there are a few hundred filters (measured B=4096, k~98: block
     // 2.2 ms, lock-step 3.8 ms).  Few filters with a large stacked innovation (large maps): the single block is a
     // serial bottleneck (N=500, B=8: 7.1 of 11.5 ms per step), so every phase becomes its own launch over all
@@ -1429,7 +1432,13 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
             resident = (e && e[0] == '0') ? 0 : 1;
         }
         if (resident) {
-            k_chol_sm<<<v.B, CHS_T, chs_sm, st>>>(v);
+            if (hi) {   // few stacked rows are the rule: small variant first, the large one takes CHS_KS < k <= CHS_K
+                k_chol_sm<CHS_KS, 128, 0><<<v.B, 128, chss_sm, st>>>(v);
+                k_chol_sm<CHS_K, 256, CHS_KS><<<v.B, 256, chs_sm, st>>>(v);
+                c->launches++;
+            } else {
+                k_chol_sm<CHS_K, 256, 0><<<v.B, 256, chs_sm, st>>>(v);
+            }
             if (v.kmax > CHS_K) { k_chol<<<v.B, 128, chol_sm, st>>>(v, CHS_K); c->launches++; }
         } else {
             k_chol<<<v.B, 128, chol_sm, st>>>(v, 0);

@@ -200,6 +200,7 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     DA(v.kpend, Bz);
     DA(v.roff, Bz);
     DA(v.ktot, Bz);
+    DA(v.kmaxdev, 1);
     DA(v.cv, Bz * v.kmax);
     DA(v.h, Bz * v.N * 2);
     DA(v.Hc, Bz * v.N * EKF_HSTRIDE);
@@ -227,6 +228,7 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     cudaError_t e = cudaMemcpy(v.nhyp_tab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->kmax_host, sizeof(int32_t));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
@@ -252,7 +254,7 @@ int ekfslam_destroy(ekfslam_ctx* c) {
     cudaSetDevice(c->device);
     if (c->own_zc) { c->v.zc = c->own_zc; c->v.mflags = c->own_mflags; c->v.u = c->own_u; c->own_zc = nullptr; }
     DevView& v = c->v;
-    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.jnt, v.jn1, v.kpend, v.roff, v.ktot, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
+    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.jnt, v.jn1, v.kpend, v.roff, v.ktot, v.kmaxdev, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
                     v.flags, v.mflags, v.foff, v.nstate, v.nfeat, v.counters, v.sel, v.ksel, v.stats, v.nhyp_tab};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -269,6 +271,7 @@ int ekfslam_destroy(ekfslam_ctx* c) {
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->pin) cudaFree(c->pin);
+    if (c->kmax_host) cudaFreeHost(c->kmax_host);
     delete c;
     return EKFSLAM_OK;
 }

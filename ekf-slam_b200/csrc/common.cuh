@@ -50,6 +50,7 @@ struct DevView {
     int32_t* kpend;       // [B]      rows of W left pending by a deferred update (0 = none)
     int32_t* roff;        // [B]      row offset of the running update inside W (= pending rows before it)
     int32_t* ktot;        // [B]      rows of W the covariance downdate has to apply
+    int32_t* kmaxdev;     // [1]      max over the filters of the stacked rows of the running update (k_upd_S)
     int32_t* nhyp_tab;    // [(N+1)(N+2)/2] adaptive hypothesis count, host libm (see abi.cu)
     ekfslam_stats* stats; // [B]
 };
@@ -85,6 +86,7 @@ struct ekfslam_ctx {
     void* pin;
     size_t pin_bytes;
     int u_cap;
+    int32_t* kmax_host;  // pinned: host copy of *v.kmaxdev (lock-step Cholesky bounds its launch loops with it)
     // the context's own frame buffers while caller-owned ones are bound (ekfslam_bind_frame)
     double* own_zc; uint8_t* own_mflags; double* own_u; int own_n_u;
 };

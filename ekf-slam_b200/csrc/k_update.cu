@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_pr
             v.kpend[b] = defer ? 2 * cnt : 0;
             if (mask & EKFSLAM_F_LI) v.stats[b].n_li = cnt;
             if (mask & EKFSLAM_F_HI) v.stats[b].n_hi = cnt;
+            if (cnt > 0) atomicMax(v.kmaxdev, 2 * cnt);
         }
     }
     __syncthreads();
@@ -847,11 +848,16 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
     DevView& v = c->v;
     cudaStream_t st = c->stream;
     const int kmax = v.kmax;
+    // the launch loops only need to cover the largest stacked update of the batch: read it back (one small
+    // synchronous copy; this path is for few filters with large maps, where ~100 empty launches cost more)
+    cudaMemcpyAsync(c->kmax_host, v.kmaxdev, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    const int kact = min(v.kmax, max(0, (int)*c->kmax_host));
     KScope ks(c, KT_CHOL);  // timed as one stage; every launch is counted
-    for (int j0 = 0; j0 < kmax; j0 += NB) {
+    for (int j0 = 0; j0 < kact; j0 += NB) {
         k_mk_diag<<<(v.B + 3) / 4, 128, 0, st>>>(v, j0);
         c->launches += 1;
-        const int rows = kmax - j0 - 1;
+        const int rows = kact - j0 - 1;
         if (rows > 0) {
             c->launches += 2;
             dim3 gp((rows + 127) / 128, v.B);
@@ -866,7 +872,8 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
     const size_t invc_sm = sizeof(double) * ((size_t)kmax * (NB + 1) + NB * (INVC_CH + 1) + 2 * NB * (NB + 1));
     if (invc_sm <= 200 * 1024) {
         ENSURE_DYN_SMEM(k_mk_invcols, invc_sm, c->device);
-        dim3 gi((kmax + NB - 1) / NB, v.B);
+        dim3 gi((kact + NB - 1) / NB, v.B);
+        if (gi.x == 0) gi.x = 1;
         k_mk_invcols<<<gi, 256, invc_sm, st>>>(v);
         c->launches += 1;
     } else {
@@ -1406,6 +1413,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     DevView& v = c->v;
     cudaStream_t st = c->stream;
     const bool hi = (mask & EKFSLAM_F_HI) != 0;
+    cudaMemsetAsync(v.kmaxdev, 0, sizeof(int32_t), st);
     { KScope ks(c, hi ? KT_UPD_S_HI : KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, (flags & 4) ? 1 : 0); }
     const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
     const size_t chs_sm = sizeof(double) * ((CHS_K * (CHS_K + 1)) / 2 + 2 * NB * (NB + 1) + CHS_K * (NB + 1));

@@ -18,10 +18,48 @@
 
 #define NB 16
 
+// S = G_sel H_sel' + I, lower triangle at feature-pair granularity: pair e -> (fa >= fb) -> one 2x2 block
+__device__ __forceinline__ void upd_S_pairs(const DevView& v, int b, int ns, int first, int stride) {
+    const int N = v.N, ld = v.ld, kmax = v.kmax;
+    const int* __restrict__ sel = v.sel + (size_t)b * N;
+    const double* __restrict__ G = v.G + (size_t)b * kmax * ld;
+    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    const int npair = ns * (ns + 1) / 2;
+    for (int e = first; e < npair; e += stride) {
+        // unrank e -> (fa, fb), fa >= fb
+        int fa = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while ((fa + 1) * (fa + 2) / 2 <= e) ++fa;
+        while (fa * (fa + 1) / 2 > e) --fa;
+        const int fb = e - fa * (fa + 1) / 2;
+        const int ia = sel[fa], ib = sel[fb];
+        const size_t tb = (size_t)b * N + ib;
+        const double* __restrict__ H = v.Hc + tb * EKF_HSTRIDE;
+        const int off = v.foff[tb];
+        const int w = (v.ftype[tb] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+        const double* __restrict__ g0 = G + (size_t)(2 * ia) * ld;
+        const double* __restrict__ g1 = g0 + ld;
+        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const double a0 = g0[c], a1 = g1[c], h0 = H[c], h1 = H[EKF_HC + c];
+            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
+        }
+        for (int c = 0; c < w; ++c) {
+            const double a0 = g0[off + c], a1 = g1[off + c], h0 = H[7 + c], h1 = H[EKF_HC + 7 + c];
+            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
+        }
+        if (fa == fb) { s00 += 1.0; s11 += 1.0; }  // R = eye(length(z)), mc/ekf_update_li_inliers.m:18
+        S[(size_t)(2 * fa) * kmax + 2 * fb] = s00;
+        S[(size_t)(2 * fa) * kmax + 2 * fb + 1] = s01;      // (for fa == fb this upper entry is never read)
+        S[(size_t)(2 * fa + 1) * kmax + 2 * fb] = s10;
+        S[(size_t)(2 * fa + 1) * kmax + 2 * fb + 1] = s11;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // select + S + nu.  One block per filter.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_prior, int iter_nu, int defer) {
+__global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_prior, int iter_nu, int defer, int do_pairs) {
     const int b = blockIdx.x;
     const int N = v.N, ld = v.ld, kmax = v.kmax;
     const int nf = v.nfeat[b];
@@ -80,39 +118,17 @@ __global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_pr
         for (int j = tid; j < n; j += blockDim.x) v.x[(size_t)b * ld + j] = v.xp[(size_t)b * ld + j];
     }
     if (k == 0) return;
-    const double* __restrict__ G = v.G + (size_t)b * kmax * ld;
-    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
-    // lower triangle, feature-pair granularity: (fa >= fb) -> 2x2 block
-    const int npair = ns * (ns + 1) / 2;
-    for (int e = tid; e < npair; e += blockDim.x) {
-        // unrank e -> (fa, fb), fa >= fb
-        int fa = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while ((fa + 1) * (fa + 2) / 2 <= e) ++fa;
-        while (fa * (fa + 1) / 2 > e) --fa;
-        const int fb = e - fa * (fa + 1) / 2;
-        const int ia = sel[fa], ib = sel[fb];
-        const size_t tb = (size_t)b * N + ib;
-        const double* __restrict__ H = v.Hc + tb * EKF_HSTRIDE;
-        const int off = v.foff[tb];
-        const int w = (v.ftype[tb] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
-        const double* __restrict__ g0 = G + (size_t)(2 * ia) * ld;
-        const double* __restrict__ g1 = g0 + ld;
-        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const double a0 = g0[c], a1 = g1[c], h0 = H[c], h1 = H[EKF_HC + c];
-            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
-        }
-        for (int c = 0; c < w; ++c) {
-            const double a0 = g0[off + c], a1 = g1[off + c], h0 = H[7 + c], h1 = H[EKF_HC + 7 + c];
-            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
-        }
-        if (fa == fb) { s00 += 1.0; s11 += 1.0; }  // R = eye(length(z)), mc/ekf_update_li_inliers.m:18
-        S[(size_t)(2 * fa) * kmax + 2 * fb] = s00;
-        S[(size_t)(2 * fa) * kmax + 2 * fb + 1] = s01;      // (for fa == fb this upper entry is never read)
-        S[(size_t)(2 * fa + 1) * kmax + 2 * fb] = s10;
-        S[(size_t)(2 * fa + 1) * kmax + 2 * fb + 1] = s11;
-    }
+    if (!do_pairs) return;   // few filters: the pair loop runs as its own, wider launch (k_upd_pairs)
+    upd_S_pairs(v, b, ns, tid, blockDim.x);
+}
+
+// S = G_sel H_sel' + I for few filters with large maps: grid = (slices, B), the pairs of a filter spread over the slices
+// (one block per filter leaves a 148-SM GPU with 8 busy blocks at cfg4).  Runs after k_upd_S(do_pairs = 0).
+__global__ void __launch_bounds__(256) k_upd_pairs(DevView v) {
+    const int b = blockIdx.y;
+    const int ns = v.ksel[b];
+    if (ns == 0) return;
+    upd_S_pairs(v, b, ns, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1414,7 +1430,12 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     cudaStream_t st = c->stream;
     const bool hi = (mask & EKFSLAM_F_HI) != 0;
     cudaMemsetAsync(v.kmaxdev, 0, sizeof(int32_t), st);
-    { KScope ks(c, hi ? KT_UPD_S_HI : KT_UPD_S); k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, (flags & 4) ? 1 : 0); }
+    {
+        KScope ks(c, hi ? KT_UPD_S_HI : KT_UPD_S);
+        const int slices = (v.B < 296) ? (int)((8 * 148 + v.B - 1) / v.B) : 1;   // few filters: spread the pair loop
+        k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, (flags & 4) ? 1 : 0, slices == 1);
+        if (slices > 1) { dim3 gp(slices, v.B); k_upd_pairs<<<gp, 256, 0, st>>>(v); c->launches++; }
+    }
     const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
     const size_t chs_sm = sizeof(double) * ((CHS_K * (CHS_K + 1)) / 2 + 2 * NB * (NB + 1) + CHS_K * (NB + 1));
     const size_t chss_sm = sizeof(double) * ((CHS_KS * (CHS_KS + 1)) / 2 + 2 * NB * (NB + 1) + CHS_KS * (NB + 1));

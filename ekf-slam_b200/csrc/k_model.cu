@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int
 #pragma unroll
         for (int r = 0; r < 7; ++r) pc[r] = *reinterpret_cast<const double2*>(P + (size_t)r * ld + c0);
     }
-    for (int f0 = 0; f0 < nf; f0 += HP_CHUNK) {
+    // blockIdx.z splits the feature chunks among CTAs (few filters with large maps would otherwise leave most SMs idle)
+    for (int f0 = blockIdx.z * HP_CHUNK; f0 < nf; f0 += gridDim.z * HP_CHUNK) {
         __syncthreads();
         if (threadIdx.x < 32) {
             // warp 0 compacts the selected features of this chunk (ballot + prefix popcount)
@@ -334,7 +335,12 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int
 }
 
 void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending, int slot) {
-    dim3 grid((c->v.nmax + 255) / 256, c->v.B);
+    const int colchunks = (c->v.nmax + 255) / 256;
+    const int fchunks = (c->v.N + HP_CHUNK - 1) / HP_CHUNK;
+    int fz = 1;   // feature-chunk groups: only when the (column chunk, filter) grid cannot fill the GPU
+    if ((long long)colchunks * c->v.B < 4 * 148) fz = (int)((4LL * 148 + (long long)colchunks * c->v.B - 1) / ((long long)colchunks * c->v.B));
+    if (fz > fchunks) fz = fchunks;
+    dim3 grid(colchunks, c->v.B, fz);
     KScope ks(c, slot);
     k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid, use_pending);
 }

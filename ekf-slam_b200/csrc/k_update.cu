@@ -820,44 +820,60 @@ __global__ void __launch_bounds__(256) k_mk_invcols(DevView v) {
     }
 }
 
-// zeros above the diagonal of X, y = X nu, cv = X' y.  One block per filter.
-__global__ void __launch_bounds__(128) k_mk_tail(DevView v) {
-    extern __shared__ double sm[];
-    const int b = blockIdx.x;
+// y = X nu (one warp per row) and the explicit zeros k_gemm needs above the diagonal of X: k_gemm streams the rows of
+// a 64-row tile up to the tile's last column, so only columns r < c < 64 (r / 64 + 1) are ever read.
+// grid = (row chunks of 8, B); the result goes to cv as scratch (yv still holds nu for the other blocks).
+__global__ void __launch_bounds__(256) k_mk_y(DevView v) {
+    const int b = blockIdx.y;
     const int k = 2 * v.ksel[b];
-    if (k == 0) return;
     const int kmax = v.kmax;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a = blockIdx.x * 8 + warp;
+    if (a >= k) return;
     double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
-    double* nu = sm;             // [kmax]
-    double* part = sm + kmax;    // [nwarps][k]
-    double* __restrict__ yv = v.yv + (size_t)b * kmax;
-    for (int r = warp; r < k; r += nwarps)
-        for (int c = r + 1 + lane; c < k; c += 32) X[(size_t)r * kmax + c] = 0.0;
-    for (int a = tid; a < k; a += blockDim.x) nu[a] = yv[a];
-    __syncthreads();
-    for (int a = warp; a < k; a += nwarps) {
-        double s = 0.0;
-        for (int t = lane; t <= a; t += 32) s += X[(size_t)a * kmax + t] * nu[t];
+    const double* __restrict__ nu = v.yv + (size_t)b * kmax;
+    const int cend = min(k, ((a >> 6) + 1) << 6);
+    for (int c = a + 1 + lane; c < cend; c += 32) X[(size_t)a * kmax + c] = 0.0;
+    double s = 0.0;
+    for (int t = lane; t <= a; t += 32) s += X[(size_t)a * kmax + t] * nu[t];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) yv[a] = s;
-    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) v.cv[(size_t)b * kmax + a] = s;
+}
+// cv = X' y = inv(S) nu, one thread per column (rows a >= t, coalesced across the threads); y is read from the cv
+// scratch of k_mk_y into shared memory first and also stored to yv.  grid = (column chunks of 128, B).
+__global__ void __launch_bounds__(128) k_mk_cv(DevView v, double* __restrict__ out) {
+    extern __shared__ double ysh[];   // [k]
+    const int b = blockIdx.y;
+    const int k = 2 * v.ksel[b];
+    if (k == 0 || (int)(blockIdx.x * blockDim.x) >= k) return;
+    const int kmax = v.kmax;
+    const double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
+    const double* __restrict__ y = v.cv + (size_t)b * kmax;
+    for (int a = threadIdx.x; a < k; a += blockDim.x) ysh[a] = y[a];
     __syncthreads();
-    for (int a = tid; a < k; a += blockDim.x) nu[a] = yv[a];
-    for (int e = tid; e < nwarps * k; e += blockDim.x) part[e] = 0.0;
-    __syncthreads();
-    for (int a = warp; a < k; a += nwarps) {
-        const double ya = nu[a];
-        for (int t = lane; t <= a; t += 32) part[warp * k + t] += X[(size_t)a * kmax + t] * ya;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int a = t;
+    for (; a + 3 < k; a += 4) {
+        s0 += X[(size_t)a * kmax + t] * ysh[a];
+        s1 += X[(size_t)(a + 1) * kmax + t] * ysh[a + 1];
+        s2 += X[(size_t)(a + 2) * kmax + t] * ysh[a + 2];
+        s3 += X[(size_t)(a + 3) * kmax + t] * ysh[a + 3];
     }
-    __syncthreads();
-    double* __restrict__ cv = v.cv + (size_t)b * kmax;
-    for (int t = tid; t < k; t += blockDim.x) {
-        double s = 0.0;
-        for (int w2 = 0; w2 < nwarps; ++w2) s += part[w2 * k + t];
-        cv[t] = s;
-    }
+    for (; a < k; ++a) s0 += X[(size_t)a * kmax + t] * ysh[a];
+    out[(size_t)b * kmax + t] = (s0 + s1) + (s2 + s3);
+}
+// yv <- y, cv <- inv(S) nu (both were staged: y in cv, inv(S) nu in the tail of the Sb row scratch)
+__global__ void k_mk_fin(DevView v, const double* __restrict__ tmp) {
+    const int b = blockIdx.y;
+    const int k = 2 * v.ksel[b];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const size_t o = (size_t)b * v.kmax + t;
+    v.yv[o] = v.cv[o];
+    v.cv[o] = tmp[o];
 }
 
 static void launch_chol_lockstep(ekfslam_ctx* c) {
@@ -900,9 +916,17 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
             c->launches += 1;
         }
     }
-    const size_t tail_sm = sizeof(double) * (size_t)kmax * 5;
-    ENSURE_DYN_SMEM(k_mk_tail, tail_sm, c->device);
-    k_mk_tail<<<v.B, 128, tail_sm, st>>>(v);
+    // y = X nu, cv = X' y: rows / columns spread over the whole GPU (was one block per filter: 0.3 ms per update at cfg4)
+    if (kact > 0) {
+        double* tmp = v.Sb;  // [B][kmax] scratch: the factor L in Sb is dead once inv(L) exists (W may hold pending rows)
+        dim3 gy((kact + 7) / 8, v.B), gc((kact + 127) / 128, v.B);
+        k_mk_y<<<gy, 256, 0, st>>>(v);
+        const size_t cv_sm = sizeof(double) * (size_t)kact;
+        ENSURE_DYN_SMEM(k_mk_cv, cv_sm, c->device);
+        k_mk_cv<<<gc, 128, cv_sm, st>>>(v, tmp);
+        k_mk_fin<<<gc, 128, 0, st>>>(v, tmp);
+        c->launches += 2;
+    }
 }
 
 // ---------------------------------------------------------------------------------------

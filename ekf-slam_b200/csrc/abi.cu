@@ -244,6 +244,9 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
         c->fuse_downdates = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
         const char* e2 = getenv("EKFSLAM_RESCUE_GATHER");
         c->rescue_gather = (e2 && e2[0] == '0') ? 0 : 1;   // default on: gate 0.36 + rows of the hi inliers 0.61 ms vs 1.15 ms
+        const char* e3 = getenv("EKFSLAM_TRI");
+        c->tri = (e3 && e3[0] == '1') ? 1 : 0;   // opt-in: k_hp_tri is still slower than the full-row k_hp
+        c->upper_valid = 1;
     }
     *out = c;
     return EKFSLAM_OK;
@@ -420,6 +423,7 @@ int ekfslam_download_state(ekfslam_ctx* c, int b0, int nb, int which, double* x,
                              cudaMemcpyDeviceToHost, c->stream));
     }
     if (P) {
+        ensure_upper(c);
         const double* src = v.P + (size_t)b0 * v.nmax * v.ld;
         CK(cudaMemcpy2DAsync(P, sizeof(double) * v.nmax, src, sizeof(double) * v.ld, sizeof(double) * v.nmax,
                              (size_t)nb * v.nmax, cudaMemcpyDeviceToHost, c->stream));
@@ -810,6 +814,7 @@ int ekfslam_add_features(ekfslam_ctx* c, int b0, int nb, const double* uvd, cons
     uint8_t* d_add = (uint8_t*)(d_uvd + 2 * (size_t)nb);
     CK(cudaMemcpyAsync(d_uvd, uvd, sizeof(double) * 2 * nb, cudaMemcpyHostToDevice, c->stream));
     if (add) CK(cudaMemcpyAsync(d_add, add, nb, cudaMemcpyHostToDevice, c->stream));
+    ensure_upper(c);
     launch_add_features(c, b0, nb, d_uvd, add ? d_add : nullptr, std_pxl, initial_rho, std_rho);
     LAUNCHED();
     CK(cudaStreamSynchronize(c->stream));
@@ -831,6 +836,7 @@ int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* c, double threshold, int force
     if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "inversedepth_2_cartesian supports n_max <= 4096");
     if (force_index >= v.N) return fail(EKFSLAM_ERR_INVALID, "force_index out of range");
     if (int r = ensure_scratch(c, sizeof(int32_t) * (size_t)v.B)) return r;
+    ensure_upper(c);
     launch_id2cart(c, threshold, force_index, (int32_t*)c->pin);
     LAUNCHED();
     if (converted) CK(cudaMemcpyAsync(converted, c->pin, sizeof(int32_t) * v.B, cudaMemcpyDeviceToHost, c->stream));
@@ -846,6 +852,7 @@ int ekfslam_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* del) 
     if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "delete_features supports n_max <= 4096");
     if (int r = ensure_scratch(c, (size_t)nb * v.N)) return r;
     CK(cudaMemcpyAsync(c->pin, del, (size_t)nb * v.N, cudaMemcpyHostToDevice, c->stream));
+    ensure_upper(c);
     launch_delete_features(c, b0, nb, (const uint8_t*)c->pin);
     LAUNCHED();
     CK(cudaStreamSynchronize(c->stream));
@@ -855,6 +862,7 @@ int ekfslam_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* del) 
 void* ekfslam_device_ptr(ekfslam_ctx* c, const char* name) {
     if (!c || !name) return nullptr;
     DevView& v = c->v;
+    if (!strcmp(name, "P")) { cudaSetDevice(c->device); ensure_upper(c); }
     struct { const char* n; void* p; } tab[] = {
         {"x", v.x}, {"xp", v.xp}, {"P", v.P}, {"G", v.G}, {"W", v.W}, {"h", v.h}, {"Hc", v.Hc}, {"S", v.S},
         {"z", v.z}, {"zc", v.zc}, {"flags", v.flags}, {"mflags", v.mflags}, {"u", v.u}, {"stats", v.stats},

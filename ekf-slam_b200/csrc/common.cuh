@@ -75,6 +75,12 @@ struct ekfslam_ctx {
     int stage;  // call-order tracking
     int fuse_downdates;  // ekfslam_step: defer the li covariance downdate and apply it together with the hi one
     int rescue_gather;   // ekfslam_step: rescue gate from 13x13 gathers of P, G rows only for the hi inliers
+    // Lower-triangle-authoritative covariance (EKFSLAM_TRI=1, opt-in): the persistent downdate stores only the lower
+    // 64x64 tiles (diagonal tiles in full), every per-frame reader (k_predict, k_hp_tri, k_rescue_gate) takes
+    // P[max(r,c)][min(r,c)].  upper_valid = 0 once a downdate has skipped the mirror images; the rare full-matrix users
+    // (map management, P download) call ensure_upper() first.
+    int tri;
+    int upper_valid;
     // ekfslam_step_host overlaps its PCIe copies with the step: inputs go up on copy_stream while prediction and the
     // measurement model run (first needed by the matcher gate), x / flags / stats come down while the last covariance
     // downdate (which only touches P) is still running.
@@ -131,6 +137,7 @@ void launch_features(ekfslam_ctx* c, int which, int parts);  // parts: 1 = h, 2 
 void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending = 0, int slot = KT_HP);  // G rows for features with (flags&need)==need && !(flags&forbid)
 void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gate / explicit matches / rescue gate
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
+void ensure_upper(ekfslam_ctx* c);   // mirror the lower triangle of every filter's P into the upper one if a downdate left it stale
 void launch_ransac(ekfslam_ctx* c);
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags = 0);
 void launch_pending_rows(ekfslam_ctx* c, int need, int forbid);

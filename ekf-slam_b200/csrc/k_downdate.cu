@@ -394,7 +394,7 @@ __device__ __forceinline__ void epi_prefetch_p(double* X, const double* __restri
 // S = stages of the W ring, NX = P tile buffers.  <4,1>: deep ring for long K loops (li update); <2,2>: short K loops
 // (small k, the kernel streams P): the next-but-one P tile is prefetched while the current one is being stored.
 template <int S, int NX>
-__global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int T, int b0, long long total, int M) {
+__global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int T, int b0, long long total, int M, int mirror) {
     extern __shared__ __align__(16) double dsm[];
     double* As = dsm;                                   // [S][TK][TPAD]
     double* Bs = dsm + S * TK * TPAD;           // [S][TK][TPAD]
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
                     if (j0 + c + 1 < n) *reinterpret_cast<double2*>(o) = val;
                     else if (j0 + c < n) o[0] = val.x;
                 }
-                if (j0 + r < n) {   // mirror image: row j0 + r of P, columns i0 ..
+                if (mirror && j0 + r < n) {   // mirror image: row j0 + r of P, columns i0 .. (skipped when only the lower triangle is kept)
                     double* mrow = P + (size_t)(j0 + r) * ld + i0;
                     if (i0 + lane < n) mrow[lane] = X[lane * XP + r];
                     if (i0 + lane + 32 < n) mrow[lane + 32] = X[(lane + 32) * XP + r];
@@ -643,6 +643,8 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
         // filters are processed in groups small enough for the per-CTA tile metadata (8 B per tile) to stay
         // within the shared-memory budget of two CTAs per SM
         const long long ctas_full = (long long)sms * 2;
+        const int mirror = c->tri ? 0 : 1;
+        if (!mirror) c->upper_valid = 0;
         const size_t fixed = sizeof(double) * (2 * S * TK * TPAD + NX * TM * XP) + sizeof(unsigned long long) * (2 * S + 2 * NX) +
                              sizeof(unsigned) * T;
         const size_t budget = 111 * 1024;
@@ -661,8 +663,8 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
                 const size_t sm2 = fixed + sizeof(int2) * M;
                 if (cfgB) ENSURE_DYN_SMEM((k_downdate_ws2<2, 2>), sm2, c->device);
                 else ENSURE_DYN_SMEM((k_downdate_ws2<4, 1>), sm2, c->device);
-                if (cfgB) k_downdate_ws2<2, 2><<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M);
-                else k_downdate_ws2<4, 1><<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M);
+                if (cfgB) k_downdate_ws2<2, 2><<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M, mirror);
+                else k_downdate_ws2<4, 1><<<(unsigned)ctas, WS2_THREADS, sm2, c->stream>>>(v, T, (int)b0, total, M, mirror);
                 if (b0 > 0) c->launches++;
             }
             return;

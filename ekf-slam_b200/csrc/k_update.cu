@@ -1382,7 +1382,7 @@ __global__ void __launch_bounds__(RG_THREADS, 3) k_rescue_gate(DevView v, ekfsla
             if (e < nc * nc) {
                 const int r = e / nc, cc = e - r * nc;
                 const int gr = (r < 7) ? r : off + r - 7, gc = (cc < 7) ? cc : off + cc - 7;
-                pv = P[(size_t)gr * ld + gc];
+                pv = (gr >= gc) ? P[(size_t)gr * ld + gc] : P[(size_t)gc * ld + gr];   // lower triangle is authoritative
             }
             pvs[u] = pv;
         }

@@ -220,9 +220,39 @@ def cpu_reference_rate(args, n_filters, steps, warm, threads):
     return n_filters * steps / wall, wall
 
 
+def octave_probe():
+    """the number north_star asks for is the reference under GNU Octave.  Probe for it; when absent say so
+    (never a made-up number).  When present, baseline/octave/run_ref_step.m runs the unmodified reference functions."""
+    import shutil
+    exe = shutil.which("octave")
+    if exe is None:
+        sys.stderr.write("OCTAVE ABSENT - reference CPU path (GNU Octave) not measured; timing the C port instead\n")
+        return {"octave": None, "note": "OCTAVE ABSENT - reference CPU path not measured"}
+    ref = "/root/reference/matlab_code"
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "octave")
+    if not os.path.isdir(ref):
+        return {"octave": exe, "note": "octave present but the reference sources are not on this box"}
+    import subprocess, tempfile, importlib.util
+    spec = importlib.util.spec_from_file_location("export_inputs", os.path.join(here, "export_inputs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with tempfile.TemporaryDirectory() as td:
+        inp, outp = os.path.join(td, "in.mat"), os.path.join(td, "out.mat")
+        mod.export(inp, 2, 100, 3)
+        r = subprocess.run([exe, "--no-gui", "--quiet", "--eval",
+                            "addpath('%s'); run_ref_step('%s','%s','%s')" % (here, inp, outp, ref)],
+                           capture_output=True, text=True, timeout=1200)
+        rate = None
+        for ln in r.stdout.splitlines():
+            if ln.startswith("REFERENCE"):
+                rate = float(ln.split("=")[1].split()[0])
+        return {"octave": exe, "filter_steps_per_s": rate, "sample": "2 filters x 3 steps, N=100, single Octave process"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
+    octave = octave_probe()
     threads = max(1, min(host_cores(), 256))
     nf = args.cpu_sample or min(16 * threads, 2048)
     steps, warm = max(1, args.steps), max(1, min(args.warmup, 3))
@@ -242,6 +272,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "octave": octave,
     }
     emit(line)
 

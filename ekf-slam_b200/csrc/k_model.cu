@@ -336,68 +336,32 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int
 
 // ---------------------------------------------------------------------------------------
 // G = H * P reading ONLY the lower triangle of P (EKFSLAM_TRI=1): half the covariance traffic of k_hp.
+// Invariant of that mode: the lower triangle and the 64x64 DIAGONAL tiles (both halves) are valid, nothing else.
+//
+// k_hp_tri (every predicted feature selected: the pass that feeds S_i, RANSAC and the li update)
 // grid = (64-column chunks, B), 8 warps; lane l of every warp owns columns j0+l and j0+l+32 of the chunk, the warps
-// take the selected features round robin.  The rows of P the selected features touch (6 or 3 per feature) form one
-// compacted, ascending list rho_0 < rho_1 < ...  The CTA streams that list 64 rows at a time through shared memory
-// with 8-byte cp.async (NBUF = 2: the next stage is in flight while this one is consumed); T[q][jj] = P(rho_q, j0+jj):
-//   rho <  j0+64 : P[j][rho] (j >= rho) or P[rho][j] (j < rho, diagonal tile only): the chunk's OWN 64 rows, read along
-//                  rho (lanes along q: coalesced for adjacent features), landing transposed in shared memory;
-//   rho >= j0+64 : P[rho][j], lanes along j.
-// The compact Jacobians of the stage's features travel with it.  Offsets are cumulative in feature index, so a warp
-// walks its features once while the CTA walks the stages; a feature cut by a stage boundary keeps its partial sums in
-// registers.  With every feature selected each lower-triangle element is read once per filter; with few selected
-// (rescue rows: NBUF = 1, more CTAs per SM) only their strips are.
+// take the selected features round robin.  Row rho of P restricted to the chunk's columns j comes from
+//   rho >= j0      : P[rho][j]   direct, coalesced along j (rows inside the diagonal tile included: it is stored in full)
+//   rho <  j0      : P[j][rho]   the chunk's OWN 64 rows, staged 64 columns at a time: 16-byte loads along rho,
+//                                stored transposed in shared memory, T[cc][jj] = P[j0+jj][c0+cc].
+// Offsets are cumulative in feature index, so a warp walks its features once while the CTA walks the column blocks
+// 0..J-1; a feature cut by a block boundary keeps its partial sums in registers.  Every lower-triangle element is read
+// once per filter.
+//
+// k_hp_tri_sparse (few selected features: rescue rows, iterated-update rows): one thread per column, no staging;
+// element (rho, j) is read where it is valid, P[max][min].
 // ---------------------------------------------------------------------------------------
 #define HT_C 64
 #define HT_P 65
 #define HT_NW 8
-#define HT_HF 24   // features a 64-row stage can touch: ceil(64 / 3) + 1 Cartesian ones, rounded up
-__device__ __forceinline__ void cp_async8(double* smem, const double* g, bool valid) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g), "r"(sz) : "memory");
-}
-static size_t hp_tri_smem(int N, int nbuf) {
-    return sizeof(double) * nbuf * (HT_C * HT_P + HT_HF * EKF_HSTRIDE) + (sizeof(int) * 2 + sizeof(unsigned short) * 6) * (size_t)N;
-}
 
-template <int NBUF>
-__global__ void __launch_bounds__(HT_NW * 32, NBUF == 2 ? 2 : 3) k_hp_tri(DevView v, int need, int forbid, int use_pending) {
-    extern __shared__ __align__(16) unsigned char hp_sm[];
-    const int b = blockIdx.y;
-    const int n = v.nstate[b];
-    const int J = blockIdx.x, j0 = J * HT_C;
-    if (j0 >= n) return;
-    const int ld = v.ld, N = v.N;
-    const int nf = v.nfeat[b];
-    double* T = reinterpret_cast<double*>(hp_sm);                    // [NBUF][64][65]: T[q][jj] = P(rho_q, j0 + jj)
-    double* Hs = T + NBUF * HT_C * HT_P;                             // [NBUF][HT_HF][26]
-    int* sIdx = reinterpret_cast<int*>(Hs + NBUF * HT_HF * EKF_HSTRIDE);   // [N] feature index | (inverse depth ? 1 << 30 : 0)
-    int* sOQ = sIdx + N;                                             // [N] state offset | first compacted row << 16
-    unsigned short* sSlot = reinterpret_cast<unsigned short*>(sOQ + N);   // [6N] compacted row -> selected-feature slot
-    __shared__ int sWc[HT_NW][3];
-    __shared__ double sJ1[16];
-    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
-    double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
-    const double* __restrict__ Hb = v.Hc + (size_t)b * N * EKF_HSTRIDE;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lim = j0 + HT_C;   // rows below lim come from the chunk's own rows
-
-    // camera rows 0..6 of P at this lane's two columns, from the lower triangle
-    const int jA = j0 + lane, jB = jA + 32;
-    const bool okA = jA < n, okB = jB < n;
-    double pcA[7], pcB[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        pcA[k] = okA ? ((jA >= k) ? P[(size_t)jA * ld + k] : P[(size_t)k * ld + jA]) : 0.0;
-        pcB[k] = okB ? P[(size_t)jB * ld + k] : 0.0;
-    }
-    const bool pend = use_pending && v.kpend[b] > 0;   // see k_hp: this pass then produces (H J1) P
-    if (tid < 16) sJ1[tid] = pend ? v.jn1[(size_t)b * 16 + tid] : 0.0;
-
-    // selected features, compacted in index (= offset) order: every warp takes 32 features, prefix over the warps
-    int cnt = 0, Rtot = 0, Rlow = 0;
-    for (int fb = 0; fb < nf; fb += HT_NW * 32) {
+// selected features of filter b, compacted in index (= offset) order by all NW warps of the CTA (32 features per warp
+// and round, prefix over the warps).  sIdx[slot] = feature index | (inverse depth ? 1 << 30 : 0), sOff[slot] = state offset.
+template <int NW>
+__device__ __forceinline__ int hp_select(const DevView& v, int b, int nf, int need, int forbid, int* sIdx, int* sOff, int (*sWc)[2]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, N = v.N;
+    int cnt = 0;
+    for (int fb = 0; fb < nf; fb += NW * 32) {
         const int i = fb + warp * 32 + lane;
         bool selq = false;
         int ty = 0, of = 0;
@@ -408,160 +372,233 @@ __global__ void __launch_bounds__(HT_NW * 32, NBUF == 2 ? 2 : 3) k_hp_tri(DevVie
             of = v.foff[t];
             selq = (ty != EKFSLAM_FEAT_NONE) && ((fl & need) == need) && ((fl & forbid) == 0);
         }
-        const bool id = selq && ty == EKFSLAM_FEAT_INVERSEDEPTH;
-        const int w = id ? 6 : 3;
         const unsigned m = __ballot_sync(0xffffffffu, selq);
-        const unsigned m6 = __ballot_sync(0xffffffffu, id);
-        const int low = selq ? min(max(lim - of, 0), w) : 0;
-        const int lowsum = __reduce_add_sync(0xffffffffu, low);
-        if (lane == 0) { sWc[warp][0] = __popc(m); sWc[warp][1] = 3 * __popc(m) + 3 * __popc(m6); sWc[warp][2] = lowsum; }
+        if (lane == 0) sWc[warp][0] = __popc(m);
         __syncthreads();
-        int pcn = cnt, pq = Rtot;
+        int pcn = cnt;
 #pragma unroll
-        for (int w2 = 0; w2 < HT_NW; ++w2) {
-            const int c_ = sWc[w2][0], q_ = sWc[w2][1], l_ = sWc[w2][2];
-            if (w2 < warp) { pcn += c_; pq += q_; }
-            cnt += c_; Rtot += q_; Rlow += l_;
+        for (int w2 = 0; w2 < NW; ++w2) {
+            const int c_ = sWc[w2][0];
+            if (w2 < warp) pcn += c_;
+            cnt += c_;
         }
         if (selq) {
-            const unsigned below = (1u << lane) - 1u;
-            const int slot = pcn + __popc(m & below);
-            const int q0 = pq + 3 * __popc(m & below) + 3 * __popc(m6 & below);
-            sIdx[slot] = i | (id ? (1 << 30) : 0);
-            sOQ[slot] = of | (q0 << 16);
-            for (int r = 0; r < w; ++r) sSlot[q0 + r] = (unsigned short)slot;
+            const int slot = pcn + __popc(m & ((1u << lane) - 1u));
+            sIdx[slot] = i | (ty == EKFSLAM_FEAT_INVERSEDEPTH ? (1 << 30) : 0);
+            sOff[slot] = of;
         }
         __syncthreads();
     }
+    return cnt;
+}
 
-    auto stage = [&](int g, int buf) {
-        double* Tb = T + buf * HT_C * HT_P;
-        double* Hsb = Hs + buf * HT_HF * EKF_HSTRIDE;
-        const int qbase = g * HT_C;
-        if (qbase < Rlow) {   // rows above / inside the diagonal tile: lanes along the compacted rows
-            const int q = tid & 63, qg = qbase + q;
-            if (qg < Rlow) {
-                const int oq = sOQ[sSlot[qg]];
-                const int rho = (oq & 0xffff) + qg - (oq >> 16);
-                double* dst = Tb + q * HT_P;
-#pragma unroll 4
-                for (int u = 0; u < HT_C / 4; ++u) {
-                    const int jj = (tid >> 6) + 4 * u, row = j0 + jj;
-                    const double* src = (row >= rho) ? P + (size_t)row * ld + rho : P + (size_t)rho * ld + row;
-                    cp_async8(dst + jj, row < n ? src : P, row < n);
-                }
-            }
+// camera columns of the two Jacobian rows of a feature, times J1 when a deferred update is pending (see k_hp)
+__device__ __forceinline__ void hp_cam_rows(const double* __restrict__ H, bool pend, const double* sJ1, double* h0, double* h1) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { h0[k] = H[k]; h1[k] = H[EKF_HC + k]; }
+    if (pend) {
+        double t0[4], t1[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            t0[a] = h0[3] * sJ1[0 * 4 + a] + h0[4] * sJ1[1 * 4 + a] + h0[5] * sJ1[2 * 4 + a] + h0[6] * sJ1[3 * 4 + a];
+            t1[a] = h1[3] * sJ1[0 * 4 + a] + h1[4] * sJ1[1 * 4 + a] + h1[5] * sJ1[2 * 4 + a] + h1[6] * sJ1[3 * 4 + a];
         }
-        if (qbase + HT_C > Rlow) {   // rows below the chunk: lanes along the chunk's columns
-            const int jj = tid & 63, col = j0 + jj;
-#pragma unroll 4
-            for (int u = 0; u < HT_C / 4; ++u) {
-                const int q = (tid >> 6) + 4 * u, qg = qbase + q;
-                if (qg >= Rlow && qg < Rtot) {
-                    const int oq = sOQ[sSlot[qg]];
-                    const int rho = (oq & 0xffff) + qg - (oq >> 16);
-                    cp_async8(Tb + q * HT_P + jj, col < n ? P + (size_t)rho * ld + col : P, col < n);
-                }
-            }
-        }
-        const int first = sSlot[qbase], last = sSlot[min(qbase + HT_C, Rtot) - 1];
-        for (int e = tid; e < (last - first + 1) * EKF_HSTRIDE; e += HT_NW * 32) {
-            const int f = e / EKF_HSTRIDE, k = e - f * EKF_HSTRIDE;
-            cp_async8(Hsb + e, Hb + (size_t)(sIdx[first + f] & 0x3fffffff) * EKF_HSTRIDE + k, true);
-        }
-    };
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { h0[3 + a] = t0[a]; h1[3 + a] = t1[a]; }
+    }
+}
+
+__global__ void __launch_bounds__(HT_NW * 32, 3) k_hp_tri(DevView v, int need, int forbid, int use_pending) {
+    extern __shared__ __align__(16) unsigned char hp_sm[];
+    const int b = blockIdx.y;
+    const int n = v.nstate[b];
+    const int J = blockIdx.x, j0 = J * HT_C;
+    if (j0 >= n) return;
+    const int ld = v.ld, N = v.N;
+    const int nf = v.nfeat[b];
+    double* T = reinterpret_cast<double*>(hp_sm);          // [64][65]: T[cc][jj] = P[j0 + jj][c0 + cc]
+    int* sIdx = reinterpret_cast<int*>(T + HT_C * HT_P);   // [N]
+    int* sOff = sIdx + N;                                  // [N]
+    __shared__ double sPc[7][HT_C];                        // camera rows 0..6 of P at the chunk's columns
+    __shared__ int sWc[HT_NW][2];
+    __shared__ double sJ1[16];
+    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
+    const double* __restrict__ Hb = v.Hc + (size_t)b * N * EKF_HSTRIDE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // camera rows 0..6 of P at this lane's two columns, from the lower triangle / the full diagonal tile
+    const int jA = j0 + lane, jB = jA + 32;
+    const bool okA = jA < n, okB = jB < n;
+    for (int e = tid; e < 7 * HT_C; e += HT_NW * 32) {
+        const int jj = e / 7, k = e - jj * 7;
+        sPc[k][jj] = (j0 + jj < n) ? P[(size_t)(j0 + jj) * ld + k] : 0.0;
+    }
+    const bool pend = use_pending && v.kpend[b] > 0;
+    if (tid < 16) sJ1[tid] = pend ? v.jn1[(size_t)b * 16 + tid] : 0.0;
+    const int cnt = hp_select<HT_NW>(v, b, nf, need, forbid, sIdx, sOff, sWc);
 
     int s = warp, r = 0;
     double g0A = 0.0, g0B = 0.0, g1A = 0.0, g1B = 0.0;
-    const int ngroups = (Rtot + HT_C - 1) / HT_C;
-    if (NBUF == 2) {
-        if (ngroups > 0) stage(0, 0);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (ngroups > 1) stage(1, 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    for (int g = 0; g < ngroups; ++g) {
-        const int buf = (NBUF == 2) ? (g & 1) : 0;
-        if (NBUF == 2) {
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            if (g > 0) __syncthreads();   // the previous stage has been consumed
-            stage(g, 0);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    for (int c = 0; c < J; ++c) {
+        if (c > 0) __syncthreads();   // the previous block has been consumed
+        {
+            // 64 rows x 32 column pairs, 8 per thread: lanes along the columns (512 B per warp instruction)
+            const int c0 = c * HT_C;
+            double2 tmp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = tid + 256 * u;
+                const int jj = e >> 5, row = j0 + jj;
+                tmp[u] = (row < n) ? *reinterpret_cast<const double2*>(P + (size_t)row * ld + c0 + 2 * (e & 31)) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = tid + 256 * u;
+                double* d = T + (2 * (e & 31)) * HT_P + (e >> 5);
+                d[0] = tmp[u].x; d[HT_P] = tmp[u].y;
+            }
         }
         __syncthreads();
-        const double* Tb = T + buf * HT_C * HT_P + lane;
-        const double* Hsb = Hs + buf * HT_HF * EKF_HSTRIDE;
-        const int first = sSlot[g * HT_C];
-        const int qhi = min((g + 1) * HT_C, Rtot);
+        const int hi = (c + 1) * HT_C;
+        const int c0 = c * HT_C;
         while (s < cnt) {
-            const int q0 = sOQ[s] >> 16;
-            if (q0 + r >= qhi) break;
-            const int idx = sIdx[s], w = (idx >> 30) ? 6 : 3;
-            const double* H = Hsb + (s - first) * EKF_HSTRIDE;
+            const int off = sOff[s];
+            if (off + r >= hi) break;
+            const int idx = sIdx[s], w = (idx >> 30) ? 6 : 3, i = idx & 0x3fffffff;
+            const double* __restrict__ H = Hb + (size_t)i * EKF_HSTRIDE;
             if (r == 0) {
-                // camera part (columns 0..6 of H, rows 0..6 of P): the start of the feature's accumulation
                 double h0[7], h1[7];
-#pragma unroll
-                for (int k = 0; k < 7; ++k) { h0[k] = H[k]; h1[k] = H[EKF_HC + k]; }
-                if (pend) {
-                    double t0[4], t1[4];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        t0[a] = h0[3] * sJ1[0 * 4 + a] + h0[4] * sJ1[1 * 4 + a] + h0[5] * sJ1[2 * 4 + a] + h0[6] * sJ1[3 * 4 + a];
-                        t1[a] = h1[3] * sJ1[0 * 4 + a] + h1[4] * sJ1[1 * 4 + a] + h1[5] * sJ1[2 * 4 + a] + h1[6] * sJ1[3 * 4 + a];
-                    }
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) { h0[3 + a] = t0[a]; h1[3 + a] = t1[a]; }
-                }
+                hp_cam_rows(H, pend, sJ1, h0, h1);
                 g0A = g0B = g1A = g1B = 0.0;
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
-                    g0A += h0[k] * pcA[k]; g0B += h0[k] * pcB[k];
-                    g1A += h1[k] * pcA[k]; g1B += h1[k] * pcB[k];
+                    const double pa = sPc[k][lane], pb = sPc[k][lane + 32];
+                    g0A += h0[k] * pa; g0B += h0[k] * pb;
+                    g1A += h1[k] * pa; g1B += h1[k] * pb;
                 }
             }
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
-                if (q >= r && q < w && q0 + q < qhi) {
-                    const double* tr = Tb + ((q0 + q) & 63) * HT_P;
+                if (q >= r && q < w && off + q < hi) {
+                    const double* tr = T + (off + q - c0) * HT_P + lane;
                     const double pA = tr[0], pB = tr[32];
                     const double h0 = H[7 + q], h1 = H[EKF_HC + 7 + q];
                     g0A += h0 * pA; g0B += h0 * pB; g1A += h1 * pA; g1B += h1 * pB;
                 }
             }
-            r = min(w, qhi - q0);
-            if (r < w) break;   // continues in the next stage
-            const int i = idx & 0x3fffffff;
+            r = min(w, hi - off);
+            if (r < w) break;   // continues in the next block / in the direct region
             double* go0 = G + (size_t)(2 * i) * ld;
             double* go1 = go0 + ld;
             if (okA) { go0[jA] = g0A; go1[jA] = g1A; }
             if (okB) { go0[jB] = g0B; go1[jB] = g1B; }
             s += HT_NW; r = 0;
         }
-        if (NBUF == 2) {
-            __syncthreads();
-            if (g + 2 < ngroups) stage(g + 2, buf);
-            asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // rows from the diagonal tile downwards: direct, coalesced
+    while (s < cnt) {
+        const int off = sOff[s];
+        const int idx = sIdx[s], w = (idx >> 30) ? 6 : 3, i = idx & 0x3fffffff;
+        const double* __restrict__ H = Hb + (size_t)i * EKF_HSTRIDE;
+        const double* __restrict__ Pr = P + (size_t)off * ld;
+        double pA[6], pB[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const bool use = q >= r && q < w;
+            pA[q] = (use && okA) ? Pr[(size_t)q * ld + jA] : 0.0;
+            pB[q] = (use && okB) ? Pr[(size_t)q * ld + jB] : 0.0;
+        }
+        if (r == 0) {
+            double h0[7], h1[7];
+            hp_cam_rows(H, pend, sJ1, h0, h1);
+            g0A = g0B = g1A = g1B = 0.0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const double pa = sPc[k][lane], pb = sPc[k][lane + 32];
+                g0A += h0[k] * pa; g0B += h0[k] * pb;
+                g1A += h1[k] * pa; g1B += h1[k] * pb;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const bool use = q >= r && q < w;
+            const double hr0 = use ? H[7 + q] : 0.0, hr1 = use ? H[EKF_HC + 7 + q] : 0.0;
+            g0A += hr0 * pA[q]; g0B += hr0 * pB[q]; g1A += hr1 * pA[q]; g1B += hr1 * pB[q];
+        }
+        double* go0 = G + (size_t)(2 * i) * ld;
+        double* go1 = go0 + ld;
+        if (okA) { go0[jA] = g0A; go1[jA] = g1A; }
+        if (okB) { go0[jB] = g0B; go1[jB] = g1B; }
+        s += HT_NW; r = 0;
+    }
+}
+
+#define HTS_NW 4
+__global__ void __launch_bounds__(HTS_NW * 32, 6) k_hp_tri_sparse(DevView v, int need, int forbid, int use_pending) {
+    extern __shared__ __align__(16) unsigned char hp_sm[];
+    const int b = blockIdx.y;
+    const int n = v.nstate[b];
+    if (blockIdx.x * (HTS_NW * 32) >= n) return;
+    const int ld = v.ld, N = v.N;
+    const int nf = v.nfeat[b];
+    int* sIdx = reinterpret_cast<int*>(hp_sm);   // [N]
+    int* sOff = sIdx + N;                        // [N]
+    __shared__ int sWc[HTS_NW][2];
+    __shared__ double sJ1[16];
+    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
+    const double* __restrict__ Hb = v.Hc + (size_t)b * N * EKF_HSTRIDE;
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x * (HTS_NW * 32) + tid;
+    const bool ok = j < n;
+    const int jc = ok ? j : 0;
+    const double* __restrict__ Pj = P + (size_t)jc * ld;   // this column's own row
+    double pc[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pc[k] = (jc >= k) ? Pj[k] : P[(size_t)k * ld + jc];
+    const bool pend = use_pending && v.kpend[b] > 0;
+    if (tid < 16) sJ1[tid] = pend ? v.jn1[(size_t)b * 16 + tid] : 0.0;
+    const int cnt = hp_select<HTS_NW>(v, b, nf, need, forbid, sIdx, sOff, sWc);
+    for (int s = 0; s < cnt; ++s) {
+        const int off = sOff[s];
+        const int idx = sIdx[s], w = (idx >> 30) ? 6 : 3, i = idx & 0x3fffffff;
+        const double* __restrict__ H = Hb + (size_t)i * EKF_HSTRIDE;
+        double p[6], hr0[6], hr1[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int rho = off + q;
+            p[q] = (q < w) ? ((rho >= jc) ? P[(size_t)rho * ld + jc] : Pj[rho]) : 0.0;
+            hr0[q] = (q < w) ? H[7 + q] : 0.0;
+            hr1[q] = (q < w) ? H[EKF_HC + 7 + q] : 0.0;
+        }
+        double h0[7], h1[7];
+        hp_cam_rows(H, pend, sJ1, h0, h1);
+        double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { g0 += h0[k] * pc[k]; g1 += h1[k] * pc[k]; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { g0 += hr0[q] * p[q]; g1 += hr1[q] * p[q]; }
+        if (ok) {
+            G[(size_t)(2 * i) * ld + j] = g0;
+            G[(size_t)(2 * i + 1) * ld + j] = g1;
         }
     }
 }
 
 void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending, int slot) {
     if (c->tri) {
-        // the full pass (every predicted feature) streams half of P: double-buffered stages; passes over a few features
-        // (rescue rows, iterated-update rows) are latency-bound: single buffer, more CTAs per SM
-        dim3 grid((c->v.nmax + HT_C - 1) / HT_C, c->v.B);
-        const bool full = (slot == KT_HP);
-        const size_t sm = hp_tri_smem(c->v.N, full ? 2 : 1);
         KScope ks(c, slot);
-        if (full) {
-            ENSURE_DYN_SMEM(k_hp_tri<2>, sm, c->device);
-            k_hp_tri<2><<<grid, HT_NW * 32, sm, c->stream>>>(c->v, need, forbid, use_pending);
-        } else {
-            ENSURE_DYN_SMEM(k_hp_tri<1>, sm, c->device);
-            k_hp_tri<1><<<grid, HT_NW * 32, sm, c->stream>>>(c->v, need, forbid, use_pending);
+        if (slot == KT_HP) {   // every predicted feature: stream the lower triangle once
+            dim3 grid((c->v.nmax + HT_C - 1) / HT_C, c->v.B);
+            const size_t sm = sizeof(double) * HT_C * HT_P + sizeof(int) * 2 * (size_t)c->v.N;
+            ENSURE_DYN_SMEM(k_hp_tri, sm, c->device);
+            k_hp_tri<<<grid, HT_NW * 32, sm, c->stream>>>(c->v, need, forbid, use_pending);
+        } else {               // a few features (rescue rows)
+            dim3 grid((c->v.nmax + HTS_NW * 32 - 1) / (HTS_NW * 32), c->v.B);
+            const size_t sm = sizeof(int) * 2 * (size_t)c->v.N;
+            k_hp_tri_sparse<<<grid, HTS_NW * 32, sm, c->stream>>>(c->v, need, forbid, use_pending);
         }
         return;
     }

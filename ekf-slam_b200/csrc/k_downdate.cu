@@ -638,7 +638,7 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
             const char* e = getenv("EKFSLAM_DD_CFG");
             cfgsel = (e && e[0] == 'A') ? 1 : (e && e[0] == 'B') ? 2 : 0;
         }
-        const bool cfgB = cfgsel ? (cfgsel == 2) : (slot == KT_DOWNDATE_HI);
+        const bool cfgB = cfgsel ? (cfgsel == 2) : (slot == KT_DOWNDATE_HI && !c->fuse_downdates);   // fused: the one downdate carries the li rows too
         const int S = cfgB ? 2 : 4, NX = cfgB ? 2 : 1;
         // filters are processed in groups small enough for the per-CTA tile metadata (8 B per tile) to stay
         // within the shared-memory budget of two CTAs per SM

@@ -1434,6 +1434,107 @@ void launch_rescue_gate(ekfslam_ctx* c) {
     k_rescue_gate<<<v.B, RG_THREADS, sm, c->stream>>>(v, c->prm);
 }
 
+// ---------------------------------------------------------------------------------------
+// G[rows of the selection] -= V W  for filters with FEW selected rows (<= G2S_ROWS, in groups of G2S_M; the hi inliers of a frame are
+// typically ~12 features).  The DMMA tile kernel (k_gemm mode 1, which keeps the filters with more rows) spends a 64-row
+// tile, a cp.async ring and a pipeline fill on these.  Here: grid = (128-column chunks, B), 8 warps x 16 columns; a
+// warp holds MT (1..4) 8-row tiles x 2 column tiles of accumulators on DMMA m8n8k4, the A fragments (V, staged 128
+// pending rows at a time, pitch 132: conflict-free) come from shared memory, the B fragments (W, panel-major: a
+// fragment is four 64-byte runs) straight from global memory, four K steps in flight.
+// (A DFMA version with V broadcast from shared memory was shared-memory-bound: 1.7 ms vs 1.57 ms for k_gemm.)
+// ---------------------------------------------------------------------------------------
+#define G2S_M 32      // rows per group
+#define G2S_ROWS 128  // filters with more selected rows go to k_gemm
+#define G2S_VC 128
+#define G2S_VP 132
+#define G2S_U 8       // K steps (of 4 pending rows) whose B fragments are in flight per warp
+template <int MT>
+__device__ __forceinline__ void g2_small_body(const DevView& v, int b, int r0, int rows, int kk, double* Vs, const int* grow) {
+    const int n = v.nstate[b], ld = v.ld, kmax = v.kmax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int c0 = blockIdx.x * 128 + warp * 16;
+    const double* __restrict__ V = v.Sb + (size_t)b * kmax * kmax;
+    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
+    double* __restrict__ G = v.G + (size_t)b * kmax * ld;
+    const bool ok0 = c0 + g < n, ok1 = c0 + 8 + g < n;
+    const double* __restrict__ w0 = W + w_at(kmax, 0, ok0 ? c0 + g : 0);       // row a at + a * EKF_WPAD
+    const double* __restrict__ w1 = W + w_at(kmax, 0, ok1 ? c0 + 8 + g : 0);
+    double acc[MT][2][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int a0 = 0; a0 < kk; a0 += G2S_VC) {
+        __syncthreads();
+        for (int e = tid; e < MT * 8 * G2S_VC; e += 256) {
+            const int r = e / G2S_VC, a = e - r * G2S_VC;
+            Vs[r * G2S_VP + a] = (r0 + r < rows && a0 + a < kk) ? V[(size_t)(r0 + r) * kmax + a0 + a] : 0.0;
+        }
+        __syncthreads();
+        if (c0 >= n) continue;   // warp-uniform; the warp still takes part in the barriers
+        const int nk4 = (min(G2S_VC, kk - a0) + 3) >> 2;
+        const double* ap = Vs + g * G2S_VP + q;
+        for (int k4 = 0; k4 < nk4; k4 += G2S_U) {
+            double b0[G2S_U], b1[G2S_U];
+#pragma unroll
+            for (int u = 0; u < G2S_U; ++u) {
+                const int a = a0 + 4 * (k4 + u) + q;
+                const bool va = (k4 + u < nk4) && a < kk;
+                b0[u] = (va && ok0) ? w0[(size_t)a * EKF_WPAD] : 0.0;
+                b1[u] = (va && ok1) ? w1[(size_t)a * EKF_WPAD] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < G2S_U; ++u) {
+                if (k4 + u < nk4) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const double af = ap[mt * 8 * G2S_VP + 4 * (k4 + u)];
+                        dmma(acc[mt][0], af, b0[u]);
+                        dmma(acc[mt][1], af, b1[u]);
+                    }
+                }
+            }
+        }
+    }
+    if (c0 >= n) return;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int r = r0 + mt * 8 + g;
+        if (r < rows) {
+            double* gr = G + (size_t)grow[r] * ld;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int c = c0 + nt * 8 + 2 * q;
+                if (c + 1 < n) {
+                    double2* p2 = reinterpret_cast<double2*>(gr + c);
+                    double2 t = *p2;
+                    t.x -= acc[mt][nt][0]; t.y -= acc[mt][nt][1];
+                    *p2 = t;
+                } else if (c < n) {
+                    gr[c] -= acc[mt][nt][0];
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 3) k_g2_small(DevView v) {
+    __shared__ __align__(16) double Vs[G2S_M * G2S_VP];
+    __shared__ int grow[G2S_ROWS];
+    const int b = blockIdx.y;
+    const int rows = 2 * v.ksel[b], kk = v.kpend[b];
+    if (rows == 0 || rows > G2S_ROWS || kk == 0 || blockIdx.x * 128 >= v.nstate[b]) return;
+    if (threadIdx.x < rows) grow[threadIdx.x] = 2 * v.sel[(size_t)b * v.N + (threadIdx.x >> 1)] + (threadIdx.x & 1);
+    // (the first __syncthreads of the body orders grow before its use)
+    for (int r0 = 0; r0 < rows; r0 += G2S_M) {   // 32-row groups; W is re-read from L2 for every group
+        const int left = rows - r0;
+        if (left <= 8) g2_small_body<1>(v, b, r0, rows, kk, Vs, grow);
+        else if (left <= 16) g2_small_body<2>(v, b, r0, rows, kk, Vs, grow);
+        else if (left <= 24) g2_small_body<3>(v, b, r0, rows, kk, Vs, grow);
+        else g2_small_body<4>(v, b, r0, rows, kk, Vs, grow);
+    }
+}
+
 static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
     ENSURE_DYN_SMEM(k_gemm, w_sm, c->device);
 }
@@ -1444,7 +1545,13 @@ void launch_pending_rows(ekfslam_ctx* c, int need, int forbid) {
     dim3 gw((v.kmax + TM - 1) / TM, 2, v.B);   // (64-row tiles, column groups, filters)
     const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax + 256) + sizeof(int) * v.kmax;
     gemm_attr(c, w_sm);
-    { KScope ks(c, KT_G2); k_gemm<<<gw, 256, w_sm, c->stream>>>(v, 1, 0, 0); }
+    {
+        KScope ks(c, KT_G2);
+        static int small = -1;
+        if (small < 0) { const char* e = getenv("EKFSLAM_G2_SMALL"); small = (e && e[0] == '0') ? 0 : 1; }
+        if (small) { dim3 gs((v.nmax + 127) / 128, v.B); k_g2_small<<<gs, 256, 0, c->stream>>>(v); c->launches++; }
+        k_gemm<<<gw, 256, w_sm, c->stream>>>(v, 1, 0, small ? G2S_ROWS : 0);
+    }
 }
 
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {

@@ -157,6 +157,17 @@ def test_fused_single_pass_mode(ekf, monkeypatch, mode):
     assert tot["li"] > 0
 
 
+def test_lower_triangle_mode(ekf, monkeypatch):
+    """EKFSLAM_TRI=1: only the lower triangle (and the diagonal 64x64 tiles) of P is kept current between frames - the
+    downdate stores no mirror images, k_hp_tri / k_hp_tri_sparse / k_predict / k_rescue_gate read P[max][min]; the
+    upper triangle is rebuilt on demand for the download.  Same parity bar, and N=100 spans several 64-column chunks."""
+    monkeypatch.setenv("EKFSLAM_TRI", "1")
+    worst, tot = _run_sequence(ekf, B=2, N=100, frames=3, seed=830)
+    assert tot["li"] > 100 and tot["hi"] > 0
+    worst, tot = _run_sequence(ekf, B=2, N=20, frames=4, seed=831, cart=[0, 3, 4, 9, 15, 19])
+    assert tot["li"] > 0
+
+
 def test_downdate_filter_groups(ekf, monkeypatch):
     """The persistent downdate keeps its per-CTA tile metadata in shared memory and therefore processes very large
     batches in groups of filters (one launch per group); EKFSLAM_DD_GROUP forces tiny groups so that the

@@ -1,6 +1,7 @@
 // Per-frame bookkeeping, state/covariance prediction, measurement prediction + analytic
 // Jacobians, G = H*P row products and per-feature innovation covariances.
 #include "model.cuh"
+#include "tc_common.cuh"
 
 // ---------------------------------------------------------------------------------------
 // mc/update_features_info.m:4-18 — one thread per (filter, feature)
@@ -342,8 +343,8 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int
 // grid = (64-column chunks, B), 8 warps; lane l of every warp owns columns j0+l and j0+l+32 of the chunk, the warps
 // take the selected features round robin.  Row rho of P restricted to the chunk's columns j comes from
 //   rho >= j0      : P[rho][j]   direct, coalesced along j (rows inside the diagonal tile included: it is stored in full)
-//   rho <  j0      : P[j][rho]   the chunk's OWN 64 rows, staged 64 columns at a time: 16-byte loads along rho,
-//                                stored transposed in shared memory, T[cc][jj] = P[j0+jj][c0+cc].
+//   rho <  j0      : P[j][rho]   the chunk's OWN 64 rows, staged 64 columns at a time by 16-byte cp.async (row-major
+//                                copy, double buffered), read transposed from shared memory (pitch 66: 2-way conflicts).
 // Offsets are cumulative in feature index, so a warp walks its features once while the CTA walks the column blocks
 // 0..J-1; a feature cut by a block boundary keeps its partial sums in registers.  Every lower-triangle element is read
 // once per filter.
@@ -408,6 +409,7 @@ __device__ __forceinline__ void hp_cam_rows(const double* __restrict__ H, bool p
     }
 }
 
+#define HT_P2 66   // pitch of the staged block (row-major copy of P rows, 16-byte cp.async): transposed reads are 2-way conflicted
 __global__ void __launch_bounds__(HT_NW * 32, 3) k_hp_tri(DevView v, int need, int forbid, int use_pending) {
     extern __shared__ __align__(16) unsigned char hp_sm[];
     const int b = blockIdx.y;
@@ -416,10 +418,10 @@ __global__ void __launch_bounds__(HT_NW * 32, 3) k_hp_tri(DevView v, int need, i
     if (j0 >= n) return;
     const int ld = v.ld, N = v.N;
     const int nf = v.nfeat[b];
-    double* T = reinterpret_cast<double*>(hp_sm);          // [64][65]: T[cc][jj] = P[j0 + jj][c0 + cc]
-    int* sIdx = reinterpret_cast<int*>(T + HT_C * HT_P);   // [N]
-    int* sOff = sIdx + N;                                  // [N]
-    __shared__ double sPc[7][HT_C];                        // camera rows 0..6 of P at the chunk's columns
+    double* T = reinterpret_cast<double*>(hp_sm);              // [2][64][66]: T[buf][jj][cc] = P[j0 + jj][c0 + cc]
+    int* sIdx = reinterpret_cast<int*>(T + 2 * HT_C * HT_P2);  // [N]
+    int* sOff = sIdx + N;                                      // [N]
+    __shared__ double sPc[7][HT_C];                            // camera rows 0..6 of P at the chunk's columns
     __shared__ int sWc[HT_NW][2];
     __shared__ double sJ1[16];
     const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
@@ -427,7 +429,22 @@ __global__ void __launch_bounds__(HT_NW * 32, 3) k_hp_tri(DevView v, int need, i
     const double* __restrict__ Hb = v.Hc + (size_t)b * N * EKF_HSTRIDE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // camera rows 0..6 of P at this lane's two columns, from the lower triangle / the full diagonal tile
+    // block c of the chunk's own rows: 64 rows x 32 sixteen-byte pieces, 8 per thread, lanes along the row
+    auto stage = [&](int c, int buf) {
+        double* Tb = T + buf * HT_C * HT_P2;
+        const double* src0 = P + (size_t)j0 * ld + c * HT_C + 2 * lane;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int jj = warp + HT_NW * u;
+            const bool ok = j0 + jj < n;
+            cp_async16(Tb + jj * HT_P2 + 2 * lane, ok ? src0 + (size_t)jj * ld : P, ok ? 16 : 0);
+        }
+    };
+    if (J > 0) stage(0, 0);
+    cp_async_commit();
+    if (J > 1) stage(1, 1);
+    cp_async_commit();
+
     const int jA = j0 + lane, jB = jA + 32;
     const bool okA = jA < n, okB = jB < n;
     for (int e = tid; e < 7 * HT_C; e += HT_NW * 32) {
@@ -442,27 +459,11 @@ __global__ void __launch_bounds__(HT_NW * 32, 3) k_hp_tri(DevView v, int need, i
     double g0A = 0.0, g0B = 0.0, g1A = 0.0, g1B = 0.0;
 
     for (int c = 0; c < J; ++c) {
-        if (c > 0) __syncthreads();   // the previous block has been consumed
-        {
-            // 64 rows x 32 column pairs, 8 per thread: lanes along the columns (512 B per warp instruction)
-            const int c0 = c * HT_C;
-            double2 tmp[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = tid + 256 * u;
-                const int jj = e >> 5, row = j0 + jj;
-                tmp[u] = (row < n) ? *reinterpret_cast<const double2*>(P + (size_t)row * ld + c0 + 2 * (e & 31)) : make_double2(0.0, 0.0);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = tid + 256 * u;
-                double* d = T + (2 * (e & 31)) * HT_P + (e >> 5);
-                d[0] = tmp[u].x; d[HT_P] = tmp[u].y;
-            }
-        }
+        cp_async_wait<1>();
         __syncthreads();
-        const int hi = (c + 1) * HT_C;
-        const int c0 = c * HT_C;
+        const int c0 = c * HT_C, hi = c0 + HT_C;
+        const double* Ta = T + (c & 1) * HT_C * HT_P2 + lane * HT_P2 - c0;   // element (own row lane, column rho) at Ta[rho]
+        const double* Tb2 = Ta + 32 * HT_P2;
         while (s < cnt) {
             const int off = sOff[s];
             if (off + r >= hi) break;
@@ -482,8 +483,7 @@ __global__ void __launch_bounds__(HT_NW * 32, 3) k_hp_tri(DevView v, int need, i
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
                 if (q >= r && q < w && off + q < hi) {
-                    const double* tr = T + (off + q - c0) * HT_P + lane;
-                    const double pA = tr[0], pB = tr[32];
+                    const double pA = Ta[off + q], pB = Tb2[off + q];
                     const double h0 = H[7 + q], h1 = H[EKF_HC + 7 + q];
                     g0A += h0 * pA; g0B += h0 * pB; g1A += h1 * pA; g1B += h1 * pB;
                 }
@@ -496,6 +496,9 @@ __global__ void __launch_bounds__(HT_NW * 32, 3) k_hp_tri(DevView v, int need, i
             if (okB) { go0[jB] = g0B; go1[jB] = g1B; }
             s += HT_NW; r = 0;
         }
+        __syncthreads();   // every warp is done with this buffer
+        if (c + 2 < J) stage(c + 2, c & 1);
+        cp_async_commit();
     }
     // rows from the diagonal tile downwards: direct, coalesced
     while (s < cnt) {
@@ -592,7 +595,7 @@ void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending, int slot) 
         KScope ks(c, slot);
         if (slot == KT_HP) {   // every predicted feature: stream the lower triangle once
             dim3 grid((c->v.nmax + HT_C - 1) / HT_C, c->v.B);
-            const size_t sm = sizeof(double) * HT_C * HT_P + sizeof(int) * 2 * (size_t)c->v.N;
+            const size_t sm = sizeof(double) * 2 * HT_C * HT_P2 + sizeof(int) * 2 * (size_t)c->v.N;
             ENSURE_DYN_SMEM(k_hp_tri, sm, c->device);
             k_hp_tri<<<grid, HT_NW * 32, sm, c->stream>>>(c->v, need, forbid, use_pending);
         } else {               // a few features (rescue rows)

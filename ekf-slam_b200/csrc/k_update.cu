@@ -359,11 +359,12 @@ __global__ void __launch_bounds__(128) k_chol(DevView v, int kskip) {
 // stalls were half of its issue stalls) and stays as the path for larger k.  Same blocked algorithm and pivots.
 // ---------------------------------------------------------------------------------------
 #define CHS_K 144   // large variant: KMIN < k <= 144, 256 threads, 2 CTAs/SM
+#define CHS_KM 112  // middle variant (li update at N = 100: k ~ 100): 256 threads, <= 85 registers, 70 KB -> 3 CTAs/SM (EKFSLAM_CHOL_MID=0 disables)
 #define CHS_KS 48   // small variant (hi update: k ~ 24): k <= 48, 128 threads, 20 KB of shared memory -> many CTAs/SM
 __device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
 
-template <int KM, int CHS_T, int KMIN>
-__global__ void __launch_bounds__(CHS_T) k_chol_sm(DevView v) {
+template <int KM, int CHS_T, int KMIN, int MINB = 1>
+__global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     const int k = 2 * v.ksel[b];
@@ -1571,8 +1572,11 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     const size_t chs_sm = sizeof(double) * ((CHS_K * (CHS_K + 1)) / 2 + 2 * NB * (NB + 1) + CHS_K * (NB + 1));
     const size_t chss_sm = sizeof(double) * ((CHS_KS * (CHS_KS + 1)) / 2 + 2 * NB * (NB + 1) + CHS_KS * (NB + 1));
     ENSURE_DYN_SMEM(k_chol, chol_sm, c->device);
-    ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, 0>), chs_sm, c->device);
-    ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, CHS_KS>), chs_sm, c->device);
+    const size_t chsm_sm = sizeof(double) * ((CHS_KM * (CHS_KM + 1)) / 2 + 2 * NB * (NB + 1) + CHS_KM * (NB + 1));
+    ENSURE_DYN_SMEM((k_chol_sm<CHS_KM, 256, 0, 3>), chsm_sm, c->device);
+    ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, CHS_KM, 2>), chs_sm, c->device);
+    ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, 0, 2>), chs_sm, c->device);
+    ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, CHS_KS, 2>), chs_sm, c->device);
     // One block per filter fills the GPU once there are a few hundred filters (measured B=4096, k~98: block
     // 2.2 ms, lock-step 3.8 ms).  Few filters with a large stacked innovation (large maps): the single block is a
     // serial bottleneck (N=500, B=8: 7.1 of 11.5 ms per step), so every phase becomes its own launch over all
@@ -1594,10 +1598,18 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         if (resident) {
             if (hi) {   // few stacked rows are the rule: small variant first, the large one takes CHS_KS < k <= CHS_K
                 k_chol_sm<CHS_KS, 128, 0><<<v.B, 128, chss_sm, st>>>(v);
-                k_chol_sm<CHS_K, 256, CHS_KS><<<v.B, 256, chs_sm, st>>>(v);
+                k_chol_sm<CHS_K, 256, CHS_KS, 2><<<v.B, 256, chs_sm, st>>>(v);
                 c->launches++;
             } else {
-                k_chol_sm<CHS_K, 256, 0><<<v.B, 256, chs_sm, st>>>(v);
+                static int mid = -1;
+                if (mid < 0) { const char* e = getenv("EKFSLAM_CHOL_MID"); mid = (e && e[0] == '0') ? 0 : 1; }
+                if (mid && v.kmax > CHS_KM) {   // the common stacked sizes at 3 CTAs/SM, the rest in the large variant
+                    k_chol_sm<CHS_KM, 256, 0, 3><<<v.B, 256, chsm_sm, st>>>(v);
+                    k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, st>>>(v);
+                    c->launches++;
+                } else {
+                    k_chol_sm<CHS_K, 256, 0, 2><<<v.B, 256, chs_sm, st>>>(v);
+                }
             }
             if (v.kmax > CHS_K) { k_chol<<<v.B, 128, chol_sm, st>>>(v, CHS_K); c->launches++; }
         } else {

@@ -28,7 +28,7 @@ void launch_begin_frame(ekfslam_ctx* c) {
 // place: F differs from the identity only in rows 0-6 (r and q), so only rows/columns 0-6 of P
 // change:  P[0:13,j] <- F P[0:13,j]  and  Pxx <- F Pxx F' + Q.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_predict(DevView v, ekfslam_params prm) {
+__global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params prm) {
     const int b = blockIdx.x;
     const int n = v.nstate[b];
     const int ld = v.ld;
@@ -177,7 +177,7 @@ void launch_predict(ekfslam_ctx* c) {
 // state (a stale h from earlier in the frame survives, and H is then linearised at that stale
 // pixel — mc/predict_camera_measurements.m:14-16, mc/calculate_Hi_inverse_depth.m:3).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_features(DevView v, DevCam cam, int which, int parts) {
+__global__ void __launch_bounds__(128, 6) k_features(DevView v, DevCam cam, int which, int parts) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= v.B * v.N) return;
     const int b = t / v.N, i = t - b * v.N;

@@ -14,6 +14,9 @@
 
 #define RANSAC_WARPS 8
 #define RANSAC_THREADS (RANSAC_WARPS * 32)
+#ifndef RANSAC_MINB
+#define RANSAC_MINB 4   // 64 registers: the kernel is latency-bound, 4 CTAs/SM instead of 2
+#endif
 
 // Support of the hypothesis drawn at feature `pos` (mc/ransac_hypotheses.m:22-33), one warp: lanes re-project the
 // matched features at xi; the inlier mask goes to mask[nwords].  Returns the support (same value in every lane).
@@ -56,7 +59,7 @@ __device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& 
     return support;
 }
 
-__global__ void __launch_bounds__(RANSAC_THREADS) k_ransac(DevView v, DevCam cam, ekfslam_params prm) {
+__global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView v, DevCam cam, ekfslam_params prm) {
     extern __shared__ unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int n = v.nstate[b];

@@ -1330,7 +1330,7 @@ __global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid) {
 // One block per filter, one warp per candidate (round robin), fixed-order warp reductions.
 // ---------------------------------------------------------------------------------------
 #define RG_THREADS 256
-__global__ void __launch_bounds__(RG_THREADS, 3) k_rescue_gate(DevView v, ekfslam_params prm) {
+__global__ void __launch_bounds__(RG_THREADS, 4) k_rescue_gate(DevView v, ekfslam_params prm) {
     extern __shared__ double wcam[];   // [k1][7] camera columns of the pending rows
     const int b = blockIdx.x;
     const int N = v.N, ld = v.ld, kmax = v.kmax;
@@ -1577,6 +1577,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, CHS_KM, 2>), chs_sm, c->device);
     ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, 0, 2>), chs_sm, c->device);
     ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, CHS_KS, 2>), chs_sm, c->device);
+    ENSURE_DYN_SMEM((k_chol_sm<CHS_KM, 256, CHS_KS, 3>), chsm_sm, c->device);
     // One block per filter fills the GPU once there are a few hundred filters (measured B=4096, k~98: block
     // 2.2 ms, lock-step 3.8 ms).  Few filters with a large stacked innovation (large maps): the single block is a
     // serial bottleneck (N=500, B=8: 7.1 of 11.5 ms per step), so every phase becomes its own launch over all
@@ -1596,14 +1597,21 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
             resident = (e && e[0] == '0') ? 0 : 1;
         }
         if (resident) {
-            if (hi) {   // few stacked rows are the rule: small variant first, the large one takes CHS_KS < k <= CHS_K
+            static int mid = -1;
+            if (mid < 0) { const char* e = getenv("EKFSLAM_CHOL_MID"); mid = (e && e[0] == '0') ? 0 : 1; }
+            const bool use_mid = mid && v.kmax > CHS_KM;
+            if (hi) {   // few stacked rows are the rule: small variant first, then CHS_KS < k <= CHS_KM, then the rest
                 k_chol_sm<CHS_KS, 128, 0><<<v.B, 128, chss_sm, st>>>(v);
-                k_chol_sm<CHS_K, 256, CHS_KS, 2><<<v.B, 256, chs_sm, st>>>(v);
+                if (use_mid) {
+                    k_chol_sm<CHS_KM, 256, CHS_KS, 3><<<v.B, 256, chsm_sm, st>>>(v);
+                    k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, st>>>(v);
+                    c->launches++;
+                } else {
+                    k_chol_sm<CHS_K, 256, CHS_KS, 2><<<v.B, 256, chs_sm, st>>>(v);
+                }
                 c->launches++;
             } else {
-                static int mid = -1;
-                if (mid < 0) { const char* e = getenv("EKFSLAM_CHOL_MID"); mid = (e && e[0] == '0') ? 0 : 1; }
-                if (mid && v.kmax > CHS_KM) {   // the common stacked sizes at 3 CTAs/SM, the rest in the large variant
+                if (use_mid) {   // the common stacked sizes at 3 CTAs/SM, the rest in the large variant
                     k_chol_sm<CHS_KM, 256, 0, 3><<<v.B, 256, chsm_sm, st>>>(v);
                     k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, st>>>(v);
                     c->launches++;

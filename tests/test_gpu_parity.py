@@ -22,11 +22,26 @@ def ekf():
     return pkg, synth
 
 
-def _run_sequence(ekf, B, N, frames, seed, fixed=0, n_u=64, p_outlier=0.2, teacher_forced=False, cart=None, noise_px=0.5):
+def _run_sequence(ekf, B, N, frames, seed, fixed=0, n_u=64, p_outlier=0.2, teacher_forced=False, cart=None, noise_px=0.5,
+                  nfeat=None, behind=None):
     pkg, synth = ekf
     seq = synth.SynthSequence(B=B, N=N, T=frames, seed=seed, p_outlier=p_outlier, n_u=n_u, noise_px=noise_px)
     x0, P0, types = seq.initial_state()
     n_max = 13 + 6 * N
+    if behind:
+        # features whose ray points away from the camera: never predicted (h stays empty), never matched
+        for (b, i) in behind:
+            x0[b, 13 + 6 * i + 3] += np.pi
+    if nfeat is not None:
+        # ragged batch: filter b keeps its first nfeat[b] features (0 = a camera-only filter)
+        types = types.copy()
+        for b in range(B):
+            nb_ = 13 + 6 * nfeat[b]
+            types[b, nfeat[b]:] = 0
+            x0[b, nb_:] = 0.0
+            P0[b, nb_:, :] = 0.0
+            P0[b, :, nb_:] = 0.0
+            seq.has[:, b, nfeat[b]:] = 0
     if cart:
         xs, Ps, ts = [], [], []
         for b in range(B):
@@ -166,6 +181,22 @@ def test_lower_triangle_mode(ekf, monkeypatch):
     assert tot["li"] > 100 and tot["hi"] > 0
     worst, tot = _run_sequence(ekf, B=2, N=20, frames=4, seed=831, cart=[0, 3, 4, 9, 15, 19])
     assert tot["li"] > 0
+
+
+def test_ragged_batch_and_unpredicted_features(ekf):
+    """Filters of one batch with different map sizes (24, 17, 5 and 0 features: n = 157, 115, 43, 13) and features that
+    are never predicted (ray pointing away from the camera: h / H / S stay empty, mc/predict_camera_measurements.m:14-16),
+    in the default and in the lower-triangle mode."""
+    nf = [24, 17, 5, 0]
+    worst, tot = _run_sequence(ekf, B=4, N=24, frames=4, seed=840, nfeat=nf, behind=[(0, 3), (0, 11), (1, 0), (2, 4)])
+    assert tot["li"] > 20 and tot["ic"] > 40
+
+
+def test_ragged_batch_lower_triangle_mode(ekf, monkeypatch):
+    monkeypatch.setenv("EKFSLAM_TRI", "1")
+    nf = [24, 17, 5, 0]
+    worst, tot = _run_sequence(ekf, B=4, N=24, frames=4, seed=841, nfeat=nf, behind=[(0, 3), (1, 16)])
+    assert tot["li"] > 20
 
 
 def test_downdate_filter_groups(ekf, monkeypatch):

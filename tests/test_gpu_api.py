@@ -145,3 +145,44 @@ def test_iterated_update_matches_oracle_extension():
     fp = api.ekf_update_li_inliers(copy.deepcopy(f), copy.deepcopy(fi))
     f1 = api.ekf_update_iterated(copy.deepcopy(f), copy.deepcopy(fi), cam, "low_innovation_inlier", n_iter=1)
     assert rel_err(f1.x_k_k, fp.x_k_k) < 1e-13 and rel_err(f1.p_k_k, fp.p_k_k) < 1e-13
+
+
+def test_c_abi_error_behaviour_on_device():
+    """Every entry returns a status, never throws across the boundary: bad shapes / ranges / call order give the
+    documented negative codes and a message in ekfslam_last_error(); the context stays usable afterwards."""
+    import ctypes as C
+    import ekf_slam_b200 as pkg
+    from ekf_slam_b200 import _lib
+    lib = _lib.load()
+    bank = pkg.FilterBank(2, 4)
+    h = bank._h
+    types = np.ones((2, 4), dtype=np.uint8)
+    nfeat = np.array([4, 4], dtype=np.int32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    # filter range out of bounds
+    assert lib.ekfslam_upload_feature_types(h, 1, 2, P(types), P(nfeat)) == -1
+    assert b"out of bounds" in lib.ekfslam_last_error()
+    # unknown feature type, nfeat beyond N_max
+    bad = types.copy(); bad[0, 1] = 7
+    assert lib.ekfslam_upload_feature_types(h, 0, 2, P(bad), P(nfeat)) == -1
+    assert lib.ekfslam_upload_feature_types(h, 0, 2, P(types), P(np.array([4, 5], dtype=np.int32))) == -1
+    # null pointers
+    assert lib.ekfslam_upload_candidates(h, 0, 2, None, None) == -1
+    assert lib.ekfslam_upload_uniforms(h, 0, 2, None, 8) == -1
+    # step before any uniform stream exists: call-order error, not a crash
+    assert lib.ekfslam_upload_feature_types(h, 0, 2, P(types), P(nfeat)) == 0
+    assert lib.ekfslam_step(h, 1, 1) == -4
+    assert b"uniform" in lib.ekfslam_last_error()
+    assert lib.ekfslam_step(h, 1, 5) == -1
+    # the Python layer raises from the status code
+    with pytest.raises(pkg.EkfSlamError) as e:
+        bank.upload_feature_types(bad)
+    assert e.value.code == -1
+    # still usable
+    u = np.random.RandomState(0).rand(2, 8)
+    bank.upload_uniforms(u)
+    bank.upload_candidates(np.zeros((2, 4, 2)), np.zeros((2, 4), dtype=np.uint8))
+    bank.step(reset=True, match_mode=1)
+    st = bank.download_stats()
+    assert (st["status"] == 0).all() and (st["n_li"] == 0).all()
+    bank.close()

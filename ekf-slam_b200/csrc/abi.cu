@@ -702,9 +702,9 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
         // full rows H p_k_k are only produced for the candidates that passed (the hi inliers)
         launch_update(c, EKFSLAM_F_LI, 1, 4);
         launch_features(c, 0, 3);
-        launch_rescue_gate(c);
+        launch_rescue_gate(c, 1);
         launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, 1);
-        launch_pending_rows(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0);
+        launch_pending_rows(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, 1);
         launch_update(c, EKFSLAM_F_HI, 0);
     } else if (c->fuse_downdates) {
         // one pass over P per frame: the li update is computed (x_k_k, W_li) but its covariance downdate is

@@ -1270,7 +1270,7 @@ __global__ void __launch_bounds__(128) k_wfix(DevView v, int defer) {
 // part of (H J1) P J1' (columns 3..6 of the rows k_hp produced), and V = H_c W' into the Sb scratch.
 // k_gemm(mode 1) then subtracts V W'.  One block per filter.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid) {
+__global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid, int from_gate) {
     const int b = blockIdx.x;
     const int N = v.N, ld = v.ld, kmax = v.kmax;
     const int k1 = v.kpend[b];
@@ -1307,6 +1307,14 @@ __global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) gr[i] = g3 * J1[i * 4 + 0] + g4 * J1[i * 4 + 1] + g5 * J1[i * 4 + 2] + g6 * J1[i * 4 + 3];
     }
+    if (from_gate) {   // k_rescue_gate left H_c Wt' of every candidate in the Li scratch, rows 2i, 2i+1
+        const double* __restrict__ Vall = v.Li + (size_t)b * kmax * kmax;
+        for (int e = threadIdx.x; e < rows * k1; e += blockDim.x) {
+            const int r = e / k1, a = e - r * k1;
+            V[(size_t)r * kmax + a] = Vall[(size_t)(2 * sel[r >> 1] + (r & 1)) * kmax + a];
+        }
+        return;
+    }
     for (int e = threadIdx.x; e < rows * k1; e += blockDim.x) {
         const int r = e / k1, a = e - r * k1;
         const size_t t = (size_t)b * N + sel[r >> 1];
@@ -1330,7 +1338,7 @@ __global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid) {
 // One block per filter, one warp per candidate (round robin), fixed-order warp reductions.
 // ---------------------------------------------------------------------------------------
 #define RG_THREADS 256
-__global__ void __launch_bounds__(RG_THREADS, 4) k_rescue_gate(DevView v, ekfslam_params prm) {
+__global__ void __launch_bounds__(RG_THREADS, 4) k_rescue_gate(DevView v, ekfslam_params prm, int keep_v) {
     extern __shared__ double wcam[];   // [k1][7] camera columns of the pending rows
     const int b = blockIdx.x;
     const int N = v.N, ld = v.ld, kmax = v.kmax;
@@ -1408,6 +1416,11 @@ __global__ void __launch_bounds__(RG_THREADS, 4) k_rescue_gate(DevView v, ekfsla
                 if (m < w) { const double wv = W[w_at(kmax, a, off + m)]; v0 += hs[7 + m] * wv; v1 += hs[EKF_HC + 7 + m] * wv; }
             }
             q00 += v0 * v0; q01 += v0 * v1; q11 += v1 * v1;
+            if (keep_v) {   // rows 2i, 2i+1 of H_c Wt' for k_v (the hi inliers are a subset of the candidates): the Li scratch is free here
+                double* __restrict__ Vall = v.Li + (size_t)b * kmax * kmax;
+                Vall[(size_t)(2 * i) * kmax + a] = v0;
+                Vall[(size_t)(2 * i + 1) * kmax + a] = v1;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -1427,12 +1440,12 @@ __global__ void __launch_bounds__(RG_THREADS, 4) k_rescue_gate(DevView v, ekfsla
     }
 }
 
-void launch_rescue_gate(ekfslam_ctx* c) {
+void launch_rescue_gate(ekfslam_ctx* c, int keep_v) {
     DevView& v = c->v;
     const size_t sm = sizeof(double) * (size_t)v.kmax * 7;
     ENSURE_DYN_SMEM(k_rescue_gate, sm, c->device);
     KScope ks(c, KT_INNOV);
-    k_rescue_gate<<<v.B, RG_THREADS, sm, c->stream>>>(v, c->prm);
+    k_rescue_gate<<<v.B, RG_THREADS, sm, c->stream>>>(v, c->prm, keep_v);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1473,28 +1486,37 @@ __device__ __forceinline__ void g2_small_body(const DevView& v, int b, int r0, i
         }
         __syncthreads();
         if (c0 >= n) continue;   // warp-uniform; the warp still takes part in the barriers
-        const int nk4 = (min(G2S_VC, kk - a0) + 3) >> 2;
-        const double* ap = Vs + g * G2S_VP + q;
-        for (int k4 = 0; k4 < nk4; k4 += G2S_U) {
+        const int na = min(G2S_VC, kk - a0);
+        const int nfull = na >> 2;                      // K steps whose four pending rows all exist
+        const double* ap = Vs + g * G2S_VP + q;         // A fragment of K step s, tile mt: ap[mt * 8 * VP + 4 s]
+        const double* p0 = w0 + (size_t)(a0 + q) * EKF_WPAD;   // B fragments: row a0 + 4 s + q of the two column tiles
+        const double* p1 = w1 + (size_t)(a0 + q) * EKF_WPAD;   // (columns >= n read column 0 and are never stored)
+        int s4 = 0;
+        for (; s4 + G2S_U <= nfull; s4 += G2S_U) {      // G2S_U steps: all B fragments in flight, no predicates
             double b0[G2S_U], b1[G2S_U];
 #pragma unroll
-            for (int u = 0; u < G2S_U; ++u) {
-                const int a = a0 + 4 * (k4 + u) + q;
-                const bool va = (k4 + u < nk4) && a < kk;
-                b0[u] = (va && ok0) ? w0[(size_t)a * EKF_WPAD] : 0.0;
-                b1[u] = (va && ok1) ? w1[(size_t)a * EKF_WPAD] : 0.0;
-            }
+            for (int u = 0; u < G2S_U; ++u) { b0[u] = p0[(size_t)u * 4 * EKF_WPAD]; b1[u] = p1[(size_t)u * 4 * EKF_WPAD]; }
 #pragma unroll
             for (int u = 0; u < G2S_U; ++u) {
-                if (k4 + u < nk4) {
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const double af = ap[mt * 8 * G2S_VP + 4 * (k4 + u)];
-                        dmma(acc[mt][0], af, b0[u]);
-                        dmma(acc[mt][1], af, b1[u]);
-                    }
+                for (int mt = 0; mt < MT; ++mt) {
+                    const double af = ap[mt * 8 * G2S_VP + 4 * u];
+                    dmma(acc[mt][0], af, b0[u]);
+                    dmma(acc[mt][1], af, b1[u]);
                 }
             }
+            ap += 4 * G2S_U; p0 += (size_t)G2S_U * 4 * EKF_WPAD; p1 += (size_t)G2S_U * 4 * EKF_WPAD;
+        }
+        for (; s4 * 4 < na; ++s4) {                     // remaining steps one at a time; the last may be partial
+            const bool va = s4 * 4 + q < na;
+            const double b0 = va ? p0[0] : 0.0, b1 = va ? p1[0] : 0.0;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const double af = ap[mt * 8 * G2S_VP];   // V rows beyond kk were staged as zeros
+                dmma(acc[mt][0], af, b0);
+                dmma(acc[mt][1], af, b1);
+            }
+            ap += 4; p0 += 4 * EKF_WPAD; p1 += 4 * EKF_WPAD;
         }
     }
     if (c0 >= n) return;
@@ -1540,9 +1562,9 @@ static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
     ENSURE_DYN_SMEM(k_gemm, w_sm, c->device);
 }
 
-void launch_pending_rows(ekfslam_ctx* c, int need, int forbid) {
+void launch_pending_rows(ekfslam_ctx* c, int need, int forbid, int from_gate) {
     DevView& v = c->v;
-    { KScope ks(c, KT_V); k_v<<<v.B, 256, 0, c->stream>>>(v, need, forbid); }
+    { KScope ks(c, KT_V); k_v<<<v.B, 256, 0, c->stream>>>(v, need, forbid, from_gate); }
     dim3 gw((v.kmax + TM - 1) / TM, 2, v.B);   // (64-row tiles, column groups, filters)
     const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax + 256) + sizeof(int) * v.kmax;
     gemm_attr(c, w_sm);

@@ -85,6 +85,10 @@ struct ekfslam_ctx {
     // measurement model run (first needed by the matcher gate), x / flags / stats come down while the last covariance
     // downdate (which only touches P) is still running.
     cudaStream_t copy_stream;
+    // side stream for launches that would otherwise run nearly alone on the GPU (the large resident-Cholesky variant:
+    // a handful of filters, one CTA each, ~0.15 ms of latency) - forked / joined with ev_fork / ev_join
+    cudaStream_t aux_stream;
+    cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_in, ev_out, ev_main;
     int wait_inputs;     // ekfslam_step: make the stream wait for ev_in before the first kernel that reads zc / mflags / u
     int arm_out;         // launch_update(HI): record ev_out before the covariance downdate; cleared when recorded

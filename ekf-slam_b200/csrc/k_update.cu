@@ -1622,20 +1622,32 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
             static int mid = -1;
             if (mid < 0) { const char* e = getenv("EKFSLAM_CHOL_MID"); mid = (e && e[0] == '0') ? 0 : 1; }
             const bool use_mid = mid && v.kmax > CHS_KM;
-            if (hi) {   // few stacked rows are the rule: small variant first, then CHS_KS < k <= CHS_KM, then the rest
+            if (hi) {   // few stacked rows are the rule: k <= CHS_KS, CHS_KS < k <= CHS_KM, and the rest
+                if (use_mid) {
+                    // the 144-row variant rarely has more than a few filters to do (one CTA each, ~0.1 ms of latency):
+                    // it runs on the side stream, concurrently with the other two
+                    cudaEventRecord(c->ev_fork, st);
+                    cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0);
+                    k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, c->aux_stream>>>(v);
+                    cudaEventRecord(c->ev_join, c->aux_stream);
+                    c->launches++;
+                }
                 k_chol_sm<CHS_KS, 128, 0><<<v.B, 128, chss_sm, st>>>(v);
                 if (use_mid) {
                     k_chol_sm<CHS_KM, 256, CHS_KS, 3><<<v.B, 256, chsm_sm, st>>>(v);
-                    k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, st>>>(v);
-                    c->launches++;
+                    cudaStreamWaitEvent(st, c->ev_join, 0);
                 } else {
                     k_chol_sm<CHS_K, 256, CHS_KS, 2><<<v.B, 256, chs_sm, st>>>(v);
                 }
                 c->launches++;
             } else {
-                if (use_mid) {   // the common stacked sizes at 3 CTAs/SM, the rest in the large variant
+                if (use_mid) {   // the common stacked sizes at 3 CTAs/SM, the rest in the large variant on the side stream
+                    cudaEventRecord(c->ev_fork, st);
+                    cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0);
+                    k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, c->aux_stream>>>(v);
+                    cudaEventRecord(c->ev_join, c->aux_stream);
                     k_chol_sm<CHS_KM, 256, 0, 3><<<v.B, 256, chsm_sm, st>>>(v);
-                    k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, st>>>(v);
+                    cudaStreamWaitEvent(st, c->ev_join, 0);
                     c->launches++;
                 } else {
                     k_chol_sm<CHS_K, 256, 0, 2><<<v.B, 256, chs_sm, st>>>(v);

@@ -997,24 +997,34 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
     // this thread's two 16-byte pieces of an A stage (64 rows x 8 chunks) and of a B stage (16 rows x 32 chunks)
     const int ar = tid >> 3, acc2 = (tid & 7) * 2;
     const int br = tid >> 5, bcc = (tid & 31) * 2;
+    // per-thread invariants of a stage load (the address arithmetic of four copies was ~200 instructions per chunk:
+    // three times the tensor work of the chunk)
+    const bool aok0 = a0 + ar < k, aok1 = a0 + ar + 32 < k;
+    const double* ap0 = A + (size_t)(aok0 ? a0 + ar : 0) * kmax + acc2;
+    const double* ap1 = A + (size_t)(aok1 ? a0 + ar + 32 : 0) * kmax + acc2;
+    const double* gcol = G + bcc;
+    unsigned ad0 = (unsigned)__cvta_generic_to_shared(As + ar * APAD + acc2);   // + st * TM * APAD * 8; second piece + 32 rows
+    unsigned bd0 = (unsigned)__cvta_generic_to_shared(Bs + br * TPAD + bcc);    // + st * TK * TPAD * 8; second piece + 8 rows
+    // opaque to the optimiser: left alone it REMATERIALISES these (block index, 64-bit products, ...) at every use
+    asm volatile("" : "+l"(ap0), "+l"(ap1), "+l"(gcol), "+r"(ad0), "+r"(bd0));
+    auto cpa = [](unsigned dst, const double* src, int bytes) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    };
     auto load_stage = [&](int st, int cb, int it) {
         const int t0 = it * TK, c0 = cb * TM;
-        double* as = As + st * TM * APAD;
-        double* bs = Bs + st * TK * TPAD;
+        const unsigned ad = ad0 + st * (TM * APAD * 8);
+        const unsigned bd = bd0 + st * (TK * TPAD * 8);
+        const bool tok = t0 + acc2 < kk;
+        cpa(ad, (aok0 && tok) ? ap0 + t0 : ap0, (aok0 && tok) ? 16 : 0);
+        cpa(ad + 32 * APAD * 8, (aok1 && tok) ? ap1 + t0 : ap1, (aok1 && tok) ? 16 : 0);
+        const bool cok = c0 + bcc < ld;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            {   // A: rows ar, ar + 32
-                const int r = ar + 32 * j;
-                const bool ok = (a0 + r < k) && (t0 + acc2 < kk);
-                cp_async16(as + r * APAD + acc2, ok ? A + (size_t)(a0 + r) * kmax + t0 + acc2 : A, ok ? 16 : 0);
-            }
-            {   // B: rows br, br + 8
-                const int tt = t0 + br + 8 * j;
-                const bool ok = (tt < kk) && (c0 + bcc < ld);
-                const double* src = G;
-                if (ok) src = (mode == 0) ? G + (size_t)grow[tt] * ld + c0 + bcc : W + w_at(kmax, tt, c0 + bcc);
-                cp_async16(bs + (br + 8 * j) * TPAD + bcc, src, ok ? 16 : 0);
-            }
+        for (int j = 0; j < 2; ++j) {   // B: rows br, br + 8
+            const int tt = t0 + br + 8 * j;
+            const bool ok = cok && tt < kk;
+            const double* src = gcol;
+            if (ok) src = (mode == 0) ? gcol + (size_t)grow[tt] * ld + c0 : W + w_at(kmax, tt, c0 + bcc);
+            cpa(bd + j * (8 * TPAD * 8), src, ok ? 16 : 0);
         }
     };
     double acc[4][2][2];
@@ -1034,13 +1044,16 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
         cp_async_commit();
     }
     int cb = cb0, it = 0;
+    int cst = 0, lst = NSTAGE - 1;   // stage being consumed / stage being loaded (ring counters instead of j % NSTAGE)
     for (int j = 0; j < total; ++j) {
         cp_async_wait<NSTAGE - 2>();
         __syncthreads();
-        if (lcb < ncb) { load_stage((j + NSTAGE - 1) % NSTAGE, lcb, lit); if (++lit == nk) { lit = 0; ++lcb; } }
+        if (lcb < ncb) { load_stage(lst, lcb, lit); if (++lit == nk) { lit = 0; ++lcb; } }
         cp_async_commit();
-        const double* as = As + (j % NSTAGE) * TM * APAD;
-        const double* bs = Bs + (j % NSTAGE) * TK * TPAD;
+        if (++lst == NSTAGE) lst = 0;
+        const double* as = As + cst * TM * APAD;
+        const double* bs = Bs + cst * TK * TPAD;
+        if (++cst == NSTAGE) cst = 0;
         if (xrole) {
             // state update G_sel' inv(S) nu for this column tile: thread (column tid & 63, quarter tid >> 6) takes four
             // of the chunk's 16 rows; the four partial sums meet in shared memory at the end of the column tile
@@ -1057,7 +1070,11 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
         const double* ap = as + (wr * 32 + g) * APAD + q;
         const double* bp = bs + q * TPAD + wc * 16 + g;
         const int tb0 = it * TK;
-        if (mt_hi == 4 && tb0 + TK <= tmax_w && (mode != 0 || tb0 + TK - 4 < rbase + 8)) {
+        // Every chunk a warp needs runs the same branch-free block: all four 8-row tiles x all four K steps.  A has
+        // explicit zeros above the diagonal and zero-filled rows / columns beyond k, so the products the triangular
+        // dispatch used to skip (a jump table per K step: ~20 instructions and an indirect branch for <= 8 DMMAs) are
+        // multiplications by zero; the tensor pipe was 37 % busy and the issue slots 63 %, so trading issue for DMMAs wins.
+        if (mt_hi > 0 && tb0 < tmax_w) {
 #pragma unroll
             for (int k4 = 0; k4 < TK / 4; ++k4) {
                 double af[4], bf[2];
@@ -1069,30 +1086,6 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
                 for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
-            }
-        } else {
-#pragma unroll 1
-            for (int k4 = 0; k4 < TK / 4; ++k4) {
-                const int tb = tb0 + k4 * 4;
-                if (tb >= tmax_w) break;
-                const int mt_lo = (mode == 0) ? max(0, (tb - rbase) >> 3) : 0;
-                // real (warp-uniform) branches, one code block per range: a predicated-off mma.sync still occupies the
-                // tensor pipe (ncu: pipe-active time was twice the ideal DMMA time while this was a predicated loop)
-                const double* a4 = ap + k4 * 4;
-                const double* b4 = bp + k4 * 4 * TPAD;
-                switch (mt_lo * 5 + mt_hi) {
-                    case 0 * 5 + 1: gemm_step<0, 1>(a4, b4, acc); break;
-                    case 0 * 5 + 2: gemm_step<0, 2>(a4, b4, acc); break;
-                    case 0 * 5 + 3: gemm_step<0, 3>(a4, b4, acc); break;
-                    case 0 * 5 + 4: gemm_step<0, 4>(a4, b4, acc); break;
-                    case 1 * 5 + 2: gemm_step<1, 2>(a4, b4, acc); break;
-                    case 1 * 5 + 3: gemm_step<1, 3>(a4, b4, acc); break;
-                    case 1 * 5 + 4: gemm_step<1, 4>(a4, b4, acc); break;
-                    case 2 * 5 + 3: gemm_step<2, 3>(a4, b4, acc); break;
-                    case 2 * 5 + 4: gemm_step<2, 4>(a4, b4, acc); break;
-                    case 3 * 5 + 4: gemm_step<3, 4>(a4, b4, acc); break;
-                    default: break;
-                }
             }
         }
         if (++it < nk) continue;

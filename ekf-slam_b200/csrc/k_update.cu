@@ -955,7 +955,8 @@ __device__ __forceinline__ void gemm_step(const double* __restrict__ ap, const d
     }
 }
 
-__global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finalize, int kskip) {
+template <int mode>   // 0: W = inv(L) G_sel (the update), 1: G_sel -= V W (rows against a pending update); compile-time: no dead address paths
+__global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int kskip) {
     extern __shared__ __align__(16) double dsm[];
     const int b = blockIdx.z;
     const int k = 2 * v.ksel[b];                        // rows of the output
@@ -980,7 +981,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
     const bool xrole = (mode == 0) && (a0 + TM >= k);
     if (xrole)
         for (int t = tid; t < k; t += blockDim.x) cs[t] = v.cv[(size_t)b * kmax + t];
-    for (int t = tid; t < k; t += blockDim.x) grow[t] = 2 * sel[t >> 1] + (t & 1);
+    for (int t = tid; t < k; t += blockDim.x) grow[t] = (2 * sel[t >> 1] + (t & 1)) * ld;   // element offset of the G row of stacked row t
     __syncthreads();
 
     // One CTA owns a 64-row tile of the output for ALL column tiles: the cp.async ring runs over the flattened
@@ -1023,7 +1024,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
             const int tt = t0 + br + 8 * j;
             const bool ok = cok && tt < kk;
             const double* src = gcol;
-            if (ok) src = (mode == 0) ? gcol + (size_t)grow[tt] * ld + c0 : W + w_at(kmax, tt, c0 + bcc);
+            if (ok) src = (mode == 0) ? gcol + grow[tt] + c0 : W + w_at(kmax, tt, c0 + bcc);
             cpa(bd + j * (8 * TPAD * 8), src, ok ? 16 : 0);
         }
     };
@@ -1096,7 +1097,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int mode, int finali
             const int a = a0 + wr * 32 + mt * 8 + g;
             if (a < k) {
                 // the 64 output columns of a column tile are one panel of W
-                double* __restrict__ orow = (mode == 0) ? W + w_at(kmax, roff + a, c0) - c0 : G + (size_t)grow[a] * ld;
+                double* __restrict__ orow = (mode == 0) ? W + w_at(kmax, roff + a, c0) - c0 : G + grow[a];
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
                     const int c = c0 + wc * 16 + nt * 8 + 2 * q;
@@ -1552,7 +1553,8 @@ __global__ void __launch_bounds__(256, 3) k_g2_small(DevView v) {
 }
 
 static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
-    ENSURE_DYN_SMEM(k_gemm, w_sm, c->device);
+    ENSURE_DYN_SMEM(k_gemm<0>, w_sm, c->device);
+    ENSURE_DYN_SMEM(k_gemm<1>, w_sm, c->device);
 }
 
 void launch_pending_rows(ekfslam_ctx* c, int need, int forbid, int from_gate) {
@@ -1566,7 +1568,7 @@ void launch_pending_rows(ekfslam_ctx* c, int need, int forbid, int from_gate) {
         static int small = -1;
         if (small < 0) { const char* e = getenv("EKFSLAM_G2_SMALL"); small = (e && e[0] == '0') ? 0 : 1; }
         if (small) { dim3 gs((v.nmax + 127) / 128, v.B); k_g2_small<<<gs, 256, 0, c->stream>>>(v); c->launches++; }
-        k_gemm<<<gw, 256, w_sm, c->stream>>>(v, 1, 0, small ? G2S_ROWS : 0);
+        k_gemm<1><<<gw, 256, w_sm, c->stream>>>(v, 0, small ? G2S_ROWS : 0);
     }
 }
 
@@ -1676,7 +1678,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         if (small < 0) { const char* e = getenv("EKFSLAM_W_SMALL"); small = (e && e[0] == '0') ? 0 : 1; }
         const int fin = (flags & 2) ? 0 : 1;
         if (small) { k_w_small<<<v.B, 128, 0, st>>>(v, fin); c->launches++; }
-        k_gemm<<<gw, 256, w_sm, st>>>(v, 0, fin, small ? WS_K : 0);
+        k_gemm<0><<<gw, 256, w_sm, st>>>(v, fin, small ? WS_K : 0);
     }
     if (flags & 2) return;   // not the last iterate of an iterated update: W is recomputed, nothing pending
     { KScope ks(c, KT_WFIX); k_wfix<<<v.B, 128, 0, st>>>(v, (flags & 4) ? 1 : 0); }

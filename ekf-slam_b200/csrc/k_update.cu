@@ -1076,18 +1076,25 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
         // dispatch used to skip (a jump table per K step: ~20 instructions and an indirect branch for <= 8 DMMAs) are
         // multiplications by zero; the tensor pipe was 37 % busy and the issue slots 63 %, so trading issue for DMMAs wins.
         if (mt_hi > 0 && tb0 < tmax_w) {
-#pragma unroll
-            for (int k4 = 0; k4 < TK / 4; ++k4) {
-                double af[4], bf[2];
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * APAD + k4 * 4];
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) bf[nt] = bp[k4 * 4 * TPAD + nt * 8];
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+            // d = chunk start relative to the warp's first row (a multiple of 16).  Left of the diagonal (d < 0, or any
+            // chunk of mode 1) every product is needed.  On the diagonal only part is: d = 0 -> tile 0 needs K steps 0-1;
+            // d = 16 -> tiles 0, 1 need nothing, tile 2 needs K steps 0-1.  Three compile-time blocks, one warp-uniform
+            // branch per chunk (a jump table per K step cost more than the DMMAs it saved).
+            const int d = (mode == 0) ? tb0 - rbase : -16;
+#define GEMM_CHUNK(MT0, HALF)                                                                                   \
+            _Pragma("unroll") for (int k4 = 0; k4 < TK / 4; ++k4) {                                               \
+                double af[4], bf[2];                                                                              \
+                _Pragma("unroll") for (int mt = MT0; mt < 4; ++mt) af[mt] = ap[mt * 8 * APAD + k4 * 4];           \
+                _Pragma("unroll") for (int nt = 0; nt < 2; ++nt) bf[nt] = bp[k4 * 4 * TPAD + nt * 8];             \
+                _Pragma("unroll") for (int mt = MT0; mt < 4; ++mt) {                                              \
+                    if (mt == MT0 && HALF && k4 >= 2) continue;                                                   \
+                    _Pragma("unroll") for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);           \
+                }                                                                                                 \
             }
+            if (d < 0) { GEMM_CHUNK(0, false) }
+            else if (d == 0) { GEMM_CHUNK(0, true) }
+            else { GEMM_CHUNK(2, true) }
+#undef GEMM_CHUNK
         }
         if (++it < nk) continue;
         // ---- last chunk of column tile cb: store the 64x64 tile, fold the state update, restart the accumulators

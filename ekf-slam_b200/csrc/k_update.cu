@@ -939,22 +939,6 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
 //   mode 1:  G[candrow(a)] -= sum_t V[a][t] * W[t]            (pending-update correction of the rescue rows:
 //            H_c P_kk = H_c P - (H_c W') W for a deferred W; V = H_c W' lives in the Sb scratch).
 // ---------------------------------------------------------------------------------------
-// one K step (4 rows of the staged panels) of k_gemm for the 8-row tiles LO..HI-1 of this warp
-template <int LO, int HI>
-__device__ __forceinline__ void gemm_step(const double* __restrict__ ap, const double* __restrict__ bp, double (&acc)[4][2][2]) {
-    double bf[2];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) bf[nt] = bp[nt * 8];
-#pragma unroll
-    for (int mt = LO; mt < HI; ++mt) {
-        const double af = ap[mt * 8 * APAD];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            dmma(acc[mt][nt], af, bf[nt]);
-        }
-    }
-}
-
 template <int mode>   // 0: W = inv(L) G_sel (the update), 1: G_sel -= V W (rows against a pending update); compile-time: no dead address paths
 __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int kskip) {
     extern __shared__ __align__(16) double dsm[];

@@ -301,7 +301,17 @@ class FilterBank:
         for a, dt in ((zc, np.float64), (fl, np.uint8), (u, np.float64)):
             if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
                 raise ValueError("step_host takes C-contiguous arrays of the exact dtype (no hidden copies)")
-        if zc.shape != (self.B, self.N, 2) or fl.shape != (self.B, self.N) or u.shape[0] != self.B:
+        if zc.shape != (self.B, self.N, 2) or fl.shape != (self.B, self.N) or u.ndim != 2 or u.shape[0] != self.B:
             raise ValueError("step_host: bad shapes")
+        # the library writes B*n_max doubles, B*N bytes and B stats records straight into these
+        for name, a, dt, shape in (("x_out", x_out, np.float64, (self.B, self.n_max)),
+                                   ("flags_out", flags_out, np.uint8, (self.B, self.N)),
+                                   ("stats_out", stats_out, np.int32, (self.B, len(L.STATS_FIELDS)))):
+            if a is None:
+                continue
+            if not isinstance(a, np.ndarray) or a.dtype != dt or not a.flags["C_CONTIGUOUS"] or \
+                    not a.flags["WRITEABLE"] or tuple(a.shape) != shape:
+                raise ValueError("step_host: %s must be a writable C-contiguous %s array of shape %s"
+                                 % (name, np.dtype(dt).name, shape))
         L.check(self.lib.ekfslam_step_host(self._h, match_mode, _ptr(zc), _ptr(fl), _ptr(u), u.shape[1],
                                            _ptr(x_out), _ptr(flags_out), _ptr(stats_out)))

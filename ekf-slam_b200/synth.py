@@ -307,3 +307,155 @@ class SynthSequence:
         if n_u > self.n_u:
             raise ValueError("sequence was generated with n_u=%d" % self.n_u)
         return np.ascontiguousarray(self.U[:, t, :n_u])
+
+
+# ---------------------------------------------------------------------------- closed-loop world
+# A persistent synthetic WORLD (as opposed to SynthSequence's pre-drawn candidate arrays): M world
+# points per filter, a camera trajectory, and counter-based noise, so that candidate pixels for the
+# features currently in the map (whatever map management did to it) and corner detections for new
+# features can be produced per frame — on the device by k_synth_candidates / k_synth_detect
+# (csrc/k_map.cu), and here in numpy as their mirror.  A feature's identity is its world-point id,
+# carried in the per-feature `tag` (the stand-in for features_info(i).feature_when_initialized,
+# mc/add_feature_to_info_vector.m:10, which the reference's matcher uses to recognise a feature).
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+
+
+def _mix64(x):
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = x ^ (x >> np.uint64(30))
+        x = x * np.uint64(0xBF58476D1CE4E5B9)
+        x = x ^ (x >> np.uint64(27))
+        x = x * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return x
+
+
+def world_uniform(seed, b, t, w, c):
+    """Counter-based uniform in [0,1): key (seed, filter b, frame t, world point w, channel c).
+    Same integer arithmetic as `world_u01` in csrc/k_map.cu."""
+    with np.errstate(over="ignore"):
+        k = _mix64(np.uint64(seed) + _GOLD * (np.asarray(b, dtype=np.uint64) + np.uint64(1)))
+        k = _mix64(k + np.asarray(t, dtype=np.uint64))
+        k = _mix64(k + np.asarray(w, dtype=np.uint64))
+        k = _mix64(k + np.asarray(c, dtype=np.uint64))
+    return (k >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+class SynthWorld:
+    """M world points per filter, T+1 camera poses, counter-based measurement noise.
+
+    points [B,M,3], pose_r [B,T+1,3], pose_q [B,T+1,4].  World point w of filter b is *flaky* when
+    w % flaky_mod == flaky_mod - 1: its candidate is a gross outlier with probability p_flaky (such
+    features get deleted by the rule of `delete_features`).
+    """
+    BAND = 22   # excluded image band for new features (mc/initialize_a_feature.m:8: half patch 20 + 1)
+
+    def __init__(self, B, M, T, seed=0, b_offset=0, p_outlier=0.2, noise_px=0.5, gross_px=8.0, p_flaky=0.8,
+                 flaky_mod=7, cam=None, depth_range=(2.0, 10.0), spread_px=60.0):
+        self.B, self.M, self.T = B, M, T
+        self.seed, self.b_offset = int(seed), int(b_offset)
+        self.p_outlier, self.noise_px, self.gross_px = float(p_outlier), float(noise_px), float(gross_px)
+        self.p_flaky, self.flaky_mod = float(p_flaky), int(flaky_mod)
+        self.cam = cam or default_camera()
+        cam = self.cam
+        T1 = T + 1
+        uv = np.empty((B, M, 2))
+        depth = np.empty((B, M))
+        self.pose_r = np.empty((B, T1, 3))
+        self.pose_q = np.empty((B, T1, 4))
+        # undistorted-pixel extent of the image (the wide-angle lens pulls a much larger field into view)
+        ext = undistort(np.array([[0.0, 0.0], [float(cam.nCols), float(cam.nRows)]]), cam)
+        for b in range(B):
+            rng = np.random.RandomState((self.seed + self.b_offset + b) % (2 ** 32))
+            # points spread over a field wider than the image so that features enter and leave the view
+            uv[b, :, 0] = rng.uniform(ext[0, 0] - spread_px, ext[1, 0] + spread_px, M)
+            uv[b, :, 1] = rng.uniform(ext[0, 1] - spread_px, ext[1, 1] + spread_px, M)
+            depth[b] = rng.uniform(depth_range[0], depth_range[1], M)
+            vv = rng.uniform(-1, 1, 3)
+            v = vv / np.linalg.norm(vv) * rng.uniform(0.01, 0.03)
+            ww = rng.uniform(-1, 1, 3)
+            w = ww / np.linalg.norm(ww) * rng.uniform(0.003, 0.01)
+            dv = rng.normal(0, 0.002, (T1, 3))
+            dw = rng.normal(0, 0.001, (T1, 3))
+            r = np.zeros(3)
+            q = np.array([1.0, 0, 0, 0])
+            for t in range(T1):
+                self.pose_r[b, t] = r
+                self.pose_q[b, t] = q
+                v = v + dv[t] - 0.02 * r
+                w = np.clip(w + dw[t] - 0.04 * (2.0 * q[1:4]), -0.02, 0.02)
+                r = r + v
+                th = np.linalg.norm(w)
+                dq = np.concatenate([[np.cos(th / 2)], np.sin(th / 2) * w / th])
+                q = quat_mul(q, dq)
+                q = q / np.linalg.norm(q)
+        fku, fkv = cam.f / cam.dx, cam.f / cam.dy
+        ray = np.stack([(uv[..., 0] - cam.Cx) / fku, (uv[..., 1] - cam.Cy) / fkv, np.ones((B, M))], -1)
+        self.points = ray * depth[..., None]
+
+    # -- what a camera at frame t sees ----------------------------------------------------------
+    def truth_pixels(self, t):
+        """zt [B,M,2] distorted pixels of all world points at the true pose of frame t, vis [B,M]."""
+        zt, dep = project(self.points, self.pose_r[:, t], self.pose_q[:, t], self.cam)
+        cam = self.cam
+        with np.errstate(invalid="ignore"):
+            vis = (dep > 0) & (zt[..., 0] > 0) & (zt[..., 0] < cam.nCols) & (zt[..., 1] > 0) & (zt[..., 1] < cam.nRows)
+        return zt, vis
+
+    def _noise(self, b, t, w):
+        u = [world_uniform(self.seed, b + self.b_offset, t, w, c) for c in range(6)]
+        rad = np.sqrt(-2.0 * np.log(1.0 - u[1]))
+        n0, n1 = rad * np.cos(2.0 * np.pi * u[2]), rad * np.sin(2.0 * np.pi * u[2])
+        return u, n0, n1
+
+    def candidates(self, t, tags, nfeat):
+        """Candidate pixels at frame t for the features of the current maps.
+        tags [B,N] world ids, nfeat [B].  Returns zc [B,N,2], has [B,N] u8 (numpy mirror of
+        k_synth_candidates)."""
+        B, N = tags.shape
+        zt, vis = self.truth_pixels(t)
+        zc = np.zeros((B, N, 2))
+        has = np.zeros((B, N), dtype=np.uint8)
+        for b in range(B):
+            k = int(nfeat[b])
+            if k == 0:
+                continue
+            w = tags[b, :k].astype(np.int64)
+            u, n0, n1 = self._noise(b, t, w)
+            p_out = np.where(w % self.flaky_mod == self.flaky_mod - 1, self.p_flaky, self.p_outlier)
+            out = u[0] < p_out
+            zg = zt[b, w] + np.stack([(2 * u[3] - 1), (2 * u[4] - 1)], -1) * self.gross_px
+            zn = zt[b, w] + np.stack([n0, n1], -1) * self.noise_px
+            zc[b, :k] = np.where(out[:, None], zg, zn)
+            has[b, :k] = vis[b, w]
+            zc[b, :k][~vis[b, w]] = 0.0
+        return zc, has
+
+    def detections(self, t, tags, nfeat, K):
+        """Corner detections for new features in the image of frame t: the first K world points (by id)
+        that are visible inside the excluded band and not yet in the map, at integer pixels (FAST corners
+        are integer locations).  Returns uv [B,K,2], tag [B,K] (-1 = unused), n [B] (mirror of
+        k_synth_detect)."""
+        B = tags.shape[0]
+        zt, vis = self.truth_pixels(t)
+        cam = self.cam
+        uv = np.zeros((B, K, 2))
+        tg = np.full((B, K), -1, dtype=np.int32)
+        n = np.zeros(B, dtype=np.int32)
+        for b in range(B):
+            have = set(int(x) for x in tags[b, :int(nfeat[b])])
+            for w in range(self.M):
+                if n[b] >= K:
+                    break
+                if not vis[b, w] or w in have:
+                    continue
+                u, n0, n1 = self._noise(b, t, w)
+                px = np.floor(zt[b, w] + np.array([n0, n1]) * self.noise_px + 0.5)
+                if px[0] < self.BAND or px[0] > cam.nCols - self.BAND or px[1] < self.BAND or px[1] > cam.nRows - self.BAND:
+                    continue
+                uv[b, n[b]] = px
+                tg[b, n[b]] = w
+                n[b] += 1
+        return uv, tg, n

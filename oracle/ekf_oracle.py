@@ -1059,3 +1059,62 @@ def update_iterated(x_km1_k, p_km1_k, features_info, cam, flag, n_iter=3):
     p = J @ p @ J.T
     xj[3:7] = xj[3:7] / np.linalg.norm(xj[3:7])
     return xj, p
+
+
+# --------------------------------------------------------------------------
+# L4  map management: mc/map_management.m and what it calls.
+# Pinned by executing the reference's own map_management.m / inversedepth_2_cartesian.m /
+# delete_a_feature.m / add_features_inverse_depth.m / add_feature_to_info_vector.m /
+# update_features_info.m through oracle/mref (tests/test_oracle_map_ref.py).
+# --------------------------------------------------------------------------
+def delete_features(filter, features_info):
+    """``delete_features`` is called by mc/map_management.m:7 but is NOT shipped by the reference.
+    Rule of the published 1-point-RANSAC toolbox the reference derives from (same statement as the
+    harness shim baseline/octave/shims/delete_features.m): a feature predicted more than 5 times and
+    matched in fewer than half of its predictions is removed; highest index first."""
+    for i in range(len(features_info) - 1, -1, -1):
+        fi = features_info[i]
+        if fi.times_measured < 0.5 * fi.times_predicted and fi.times_predicted > 5:
+            filter.x_k_k, filter.p_k_k = delete_a_feature(filter.x_k_k, filter.p_k_k, i, features_info)
+            features_info = features_info[:i] + features_info[i + 1:]
+    return filter, features_info
+
+
+def initialize_features(step, cam, filter, features_info, num_features_to_initialize, im):
+    """mc/initialize_features.m:4-21 with the corner search of mc/initialize_a_feature.m:14-57 (CV
+    Toolbox) replaced by supplied detections ``im = (uv [K,2], tag [K])``, one attempt per detection;
+    the rest is mc/initialize_a_feature.m:60-70: add_features_inverse_depth with
+    initial_rho = 1, std_rho = 1, std_pxl = std_z, then add_feature_to_info_vector."""
+    uv_list, tags = im
+    max_attempts, attempts, initialized = 50, 0, 0
+    K = len(uv_list)
+    while initialized < num_features_to_initialize and attempts < max_attempts and attempts < K:
+        uv = np.asarray(uv_list[attempts], dtype=np.float64)
+        X_RES, P_RES, newFeature = add_features_inverse_depth(uv, filter.x_k_k, filter.p_k_k, cam,
+                                                              filter.std_z, 1.0, 1.0)
+        filter.x_k_k, filter.p_k_k = X_RES, P_RES
+        fi = new_feature_info(uv, X_RES, step, newFeature)
+        fi.feature_when_initialized = int(tags[attempts])
+        features_info = features_info + [fi]
+        attempts += 1
+        initialized += 1
+    return filter, features_info
+
+
+def map_management(filter, features_info, cam, im, min_number_of_features_in_image, step):
+    """mc/map_management.m:4-35: delete -> count measured -> update_features_info -> (at most one)
+    inverse-depth -> Cartesian conversion -> top up to min_number_of_features_in_image."""
+    filter, features_info = delete_features(filter, features_info)                       # :7
+    measured = 0
+    for fi in features_info:                                                              # :11-14
+        if fi.low_innovation_inlier or fi.high_innovation_inlier:
+            measured += 1
+    features_info = update_features_info(features_info)                                   # :17
+    filter, features_info = inversedepth_2_cartesian(filter, features_info)               # :22
+    if measured == 0:                                                                     # :27-35
+        filter, features_info = initialize_features(step, cam, filter, features_info,
+                                                    min_number_of_features_in_image, im)
+    elif measured < min_number_of_features_in_image:
+        filter, features_info = initialize_features(step, cam, filter, features_info,
+                                                    min_number_of_features_in_image - measured, im)
+    return filter, features_info

@@ -153,7 +153,7 @@ def test_step_host_equals_step(pkg, pinned):
         zc, has = seq.frame(t)
         u = seq.uniforms(t, n_u)
         zc_h[...] = zc
-        fl_h[...] = has
+        fl_h[...] = has * pkg.F_CAND          # step_host takes the staged flag bytes (candidate bit), like bind_frame
         u_h[...] = u
         banks[0].step_host(zc_h, fl_h, u_h, match_mode=1, x_out=x_out, flags_out=f_out, stats_out=s_out)
         banks[1].upload_candidates(zc, has)
@@ -175,7 +175,7 @@ def test_step_host_equals_step(pkg, pinned):
         zc, has = seq.frame(t)
         u = seq.uniforms(t, n_u)
         zc_h[...] = zc
-        fl_h[...] = has
+        fl_h[...] = has * pkg.F_CAND          # step_host takes the staged flag bytes (candidate bit), like bind_frame
         u_h[...] = u
         banks[0].step_host(zc_h, fl_h, u_h, match_mode=1)
         banks[1].upload_candidates(zc, has)

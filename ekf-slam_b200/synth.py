@@ -353,7 +353,7 @@ class SynthWorld:
     BAND = 22   # excluded image band for new features (mc/initialize_a_feature.m:8: half patch 20 + 1)
 
     def __init__(self, B, M, T, seed=0, b_offset=0, p_outlier=0.2, noise_px=0.5, gross_px=8.0, p_flaky=0.8,
-                 flaky_mod=7, cam=None, depth_range=(2.0, 10.0), spread_px=60.0):
+                 flaky_mod=7, cam=None, depth_range=(2.0, 10.0), spread_px=80.0, speed=(0.01, 0.03), spring=0.02):
         self.B, self.M, self.T = B, M, T
         self.seed, self.b_offset = int(seed), int(b_offset)
         self.p_outlier, self.noise_px, self.gross_px = float(p_outlier), float(noise_px), float(gross_px)
@@ -374,7 +374,7 @@ class SynthWorld:
             uv[b, :, 1] = rng.uniform(ext[0, 1] - spread_px, ext[1, 1] + spread_px, M)
             depth[b] = rng.uniform(depth_range[0], depth_range[1], M)
             vv = rng.uniform(-1, 1, 3)
-            v = vv / np.linalg.norm(vv) * rng.uniform(0.01, 0.03)
+            v = vv / np.linalg.norm(vv) * rng.uniform(speed[0], speed[1])
             ww = rng.uniform(-1, 1, 3)
             w = ww / np.linalg.norm(ww) * rng.uniform(0.003, 0.01)
             dv = rng.normal(0, 0.002, (T1, 3))
@@ -384,7 +384,7 @@ class SynthWorld:
             for t in range(T1):
                 self.pose_r[b, t] = r
                 self.pose_q[b, t] = q
-                v = v + dv[t] - 0.02 * r
+                v = v + dv[t] - spring * r
                 w = np.clip(w + dw[t] - 0.04 * (2.0 * q[1:4]), -0.02, 0.02)
                 r = r + v
                 th = np.linalg.norm(w)

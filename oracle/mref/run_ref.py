@@ -100,3 +100,73 @@ def run_sequence(x0, P0, types, zc, has, U, I=None, keep_P="last", on_frame=None
     out = dict(x=np.array(xs), flags=np.array(fls), nhyp=np.array(nh, dtype=np.int32), h=np.array(hs))
     out["P"] = np.array(Ps) if keep_P == "all" else np.array(filt.get("p_k_k"))
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# closed loop with map management (mono_slam.m:50-82): the reference's own map_management.m
+# ------------------------------------------------------------------------------------------
+def tags_of(features_info):
+    return np.array([int(np.asarray(e["feature_when_initialized"]).reshape(-1)[0]) for e in features_info.elems],
+                    dtype=np.int32)
+
+
+def run_closed_loop(world, b, frames, min_features=25, K=25, n_u=64, I=None, u_seed=0):
+    """Filter b of a SynthWorld through `frames` iterations of the mono_slam.m loop, reference code:
+    map_management.m (delete_features shim, update_features_info, inversedepth_2_cartesian,
+    initialize_features shim -> add_features_inverse_depth + add_feature_to_info_vector) then the
+    filter step of ref_frame.m.  Detections come from the image of the previous frame and the
+    candidates from the current one, exactly like `im` in mono_slam.m:47,53,59.
+    Returns per frame: x, types, tags, flags, nhyp, counters + the inputs that were fed (detections,
+    candidates, uniforms) so that the oracle / the GPU can be driven with the very same data."""
+    from .minterp import StructArr, mat
+    I = I or make_interp()
+    cam = I.call("initialize_cam")
+    x, P = I.call("initialize_x_and_p", nargout=2)
+    filt = make_filter(I, x, P)
+    fi = np.zeros((0, 0))
+    rng = np.random.RandomState(u_seed + 7919 * b)
+    out = dict(x=[], P=None, types=[], tags=[], flags=[], nhyp=[], counters=[], det_uv=[], det_tag=[], det_n=[],
+               zc=[], has=[], U=[], n_after_mm=[])
+    blank = np.zeros((int(world.cam.nRows), int(world.cam.nCols)))
+    for step in range(1, frames + 1):
+        nf = len(fi.elems) if isinstance(fi, StructArr) else 0
+        tags = tags_of(fi) if nf else np.zeros(0, dtype=np.int32)
+        # NOTE: the detector must not re-detect features already in the map; features deleted by
+        # map_management in THIS call are still excluded (they were in the map when the image was searched)
+        tg_in = np.full((world.B, max(nf, 1)), -1, dtype=np.int32)
+        nfa = np.zeros(world.B, dtype=np.int32)
+        tg_in[b, :nf] = tags
+        nfa[b] = nf
+        uv, tg, nd = world.detections(step - 1, tg_in, nfa, K)
+        im = StructArr(["uv", "tag", "img"], [{"uv": np.ascontiguousarray(uv[b, :nd[b]].T),
+                                                "tag": tg[b, :nd[b]].astype(np.float64).reshape(1, -1),
+                                                "img": blank}])
+        filt, fi = I.call("map_management", filt, fi, cam, im, float(min_features), float(step), nargout=2)
+        nf = len(fi.elems)
+        tags = tags_of(fi)
+        tg_in = np.full((world.B, max(nf, 1)), -1, dtype=np.int32)
+        nfa = np.zeros(world.B, dtype=np.int32)
+        tg_in[b, :nf] = tags
+        nfa[b] = nf
+        zc, has = world.candidates(step, tg_in, nfa)
+        u = rng.rand(n_u)
+        I.rand_stream = iter(u)
+        I.rand_drawn = 0
+        out["n_after_mm"].append(filt.get("x_k_k").shape[0])
+        filt, fi, _nic = I.call("ref_frame_nomm", filt, fi, cam, np.ascontiguousarray(zc[b, :nf].T),
+                                has[b, :nf].astype(np.float64).reshape(1, -1), nargout=3)
+        out["x"].append(filt.get("x_k_k").reshape(-1).copy())
+        out["types"].append(types_of(fi))
+        out["tags"].append(tags.copy())
+        out["flags"].append(flags_of(fi))
+        out["nhyp"].append(I.rand_drawn)
+        out["counters"].append(np.array([[float(np.asarray(e["times_predicted"]).reshape(-1)[0]),
+                                          float(np.asarray(e["times_measured"]).reshape(-1)[0])] for e in fi.elems]))
+        out["det_uv"].append(uv[b].copy())
+        out["det_tag"].append(tg[b].copy())
+        out["det_n"].append(int(nd[b]))
+        out["zc"].append(zc[b, :nf].copy())
+        out["has"].append(has[b, :nf].copy())
+        out["U"].append(u)
+    out["P"] = np.array(filt.get("p_k_k"))
+    return out

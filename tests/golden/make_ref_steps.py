@@ -195,7 +195,69 @@ def case_stale_h():
              extra=dict(stale_feature=d["feature"]))
 
 
-CASES = dict(cfg1=case_cfg1, outliers=case_outliers, mixed=case_mixed, n100=case_n100, stale_h=case_stale_h)
+MAP_WORLD = dict(M=150, depth_range=(1.0, 3.0), speed=(0.05, 0.08), spring=0.004)
+
+
+def pack_closed_loop(recs, NMAX, K):
+    """list (per filter) of closed-loop records -> padded arrays [B, T, ...]."""
+    B, Tn = len(recs), len(recs[0]["x"])
+    n_max = 13 + 6 * NMAX
+    d = dict(x=np.zeros((B, Tn, n_max)), nstate=np.zeros((B, Tn), dtype=np.int32), nfeat=np.zeros((B, Tn), dtype=np.int32),
+             n_after_mm=np.zeros((B, Tn), dtype=np.int32),
+             types=np.zeros((B, Tn, NMAX), dtype=np.uint8), tags=np.full((B, Tn, NMAX), -1, dtype=np.int32),
+             flags=np.zeros((B, Tn, NMAX), dtype=np.uint8), nhyp=np.zeros((B, Tn), dtype=np.int32),
+             counters=np.zeros((B, Tn, NMAX, 2), dtype=np.int32), det_uv=np.zeros((B, Tn, K, 2)),
+             det_tag=np.full((B, Tn, K), -1, dtype=np.int32), det_n=np.zeros((B, Tn), dtype=np.int32),
+             zc=np.zeros((B, Tn, NMAX, 2)), has=np.zeros((B, Tn, NMAX), dtype=np.uint8),
+             U=np.zeros((B, Tn, len(recs[0]["U"][0]))))
+    Ps = []
+    for b, r in enumerate(recs):
+        for t in range(Tn):
+            n, nf = len(r["x"][t]), len(r["types"][t])
+            assert nf <= NMAX
+            d["x"][b, t, :n] = r["x"][t]
+            d["nstate"][b, t], d["nfeat"][b, t], d["n_after_mm"][b, t] = n, nf, r["n_after_mm"][t]
+            d["types"][b, t, :nf] = r["types"][t]
+            d["tags"][b, t, :nf] = r["tags"][t]
+            d["flags"][b, t, :nf] = r["flags"][t]
+            d["nhyp"][b, t] = r["nhyp"][t]
+            d["counters"][b, t, :nf] = r["counters"][t]
+            d["det_uv"][b, t] = r["det_uv"][t]
+            d["det_tag"][b, t] = r["det_tag"][t]
+            d["det_n"][b, t] = r["det_n"][t]
+            d["zc"][b, t, :nf] = r["zc"][t]
+            d["has"][b, t, :nf] = r["has"][t]
+            d["U"][b, t] = r["U"][t]
+        P = np.zeros((n_max, n_max))
+        n = r["P"].shape[0]
+        P[:n, :n] = r["P"]
+        Ps.append(P)
+    d["P"] = np.array(Ps)
+    return d
+
+
+def case_map():
+    """mono_slam.m:50-82 closed loop WITH the reference's own map_management.m (feature initialisation,
+    inverse-depth -> Cartesian conversion, deletion, per-frame bookkeeping) over 80 frames."""
+    B, Tn, K, NMAX, seed = 2, 80, 20, 64, 2
+    world = synth.SynthWorld(B, T=Tn, seed=seed, **MAP_WORLD)
+    I = R.make_interp()
+    t0 = time.time()
+    recs = []
+    for b in range(B):
+        recs.append(R.run_closed_loop(world, b, Tn, min_features=20, K=K, I=I))
+        print("  ref_map: filter %d/%d done, %.1f s" % (b + 1, B, time.time() - t0), flush=True)
+    d = pack_closed_loop(recs, NMAX, K)
+    d.update(seed=seed, min_features=20, K=K)
+    d["ref_functions_run"] = np.array(sorted(k for k in I.call_counts if k in I.sources_used and
+                                             I.sources_used[k].startswith(R.REF_DIR)))
+    path = os.path.join(HERE, "ref_map_t80.npz")
+    np.savez_compressed(path, **d)
+    print("wrote %s (%.0f KB)" % (path, os.path.getsize(path) / 1024))
+    print("  conversions:", [(d["types"][b, -1] == 2).sum() for b in range(B)], "final nfeat", d["nfeat"][:, -1])
+
+
+CASES = dict(cfg1=case_cfg1, outliers=case_outliers, mixed=case_mixed, n100=case_n100, stale_h=case_stale_h, map=case_map)
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(CASES)

@@ -43,6 +43,11 @@ class Stats(C.Structure):
 
 STATS_FIELDS = [f[0] for f in Stats._fields_]
 
+
+class WorldParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("b_offset", C.c_int32), ("flaky_mod", C.c_int32), ("noise_px", C.c_double),
+                ("gross_px", C.c_double), ("p_outlier", C.c_double), ("p_flaky", C.c_double), ("band_px", C.c_double)]
+
 _P = C.c_void_p
 _I = C.c_int
 _SIGS = {
@@ -90,6 +95,17 @@ _SIGS = {
     "ekfslam_inversedepth_2_cartesian": (_I, [_P, C.c_double, _I, _P]),
     "ekfslam_delete_features": (_I, [_P, _I, _I, _P]),
     "ekfslam_add_features": (_I, [_P, _I, _I, _P, _P, C.c_double, C.c_double, C.c_double]),
+    "ekfslam_map_management": (_I, [_P, _I]),
+    "ekfslam_upload_detections": (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    "ekfslam_download_detections": (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    "ekfslam_upload_feature_meta": (_I, [_P, _I, _I, _P, _P]),
+    "ekfslam_download_feature_tags": (_I, [_P, _I, _I, _P]),
+    "ekfslam_download_candidates": (_I, [_P, _I, _I, _P, _P]),
+    "ekfslam_world_upload": (_I, [_P, _I, _I, _P, _P, C.POINTER(WorldParams)]),
+    "ekfslam_world_candidates": (_I, [_P, _I]),
+    "ekfslam_world_detect": (_I, [_P, _I, _I]),
+    "ekfslam_world_uniforms": (_I, [_P, _I, _I]),
+    "ekfslam_download_uniforms": (_I, [_P, _I, _I, _P, _I]),
     "ekfslam_device_ptr": (_P, [_P, C.c_char_p]),
     "ekfslam_enable_timing": (_I, [_P, _I]),
     "ekfslam_kernel_count": (_I, []),

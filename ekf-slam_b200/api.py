@@ -347,3 +347,172 @@ def filter_step(f, features_info, cam, im, u=None, fixed_hypotheses=0, info=None
     if info is not None:
         info.update({k: int(v[0]) for k, v in st.items()})
     return f, _pull_features(bank, features_info, n)
+
+
+# ------------------------------------------------------------------------------------------
+# map management: mc/map_management.m and the functions it calls, on the device ops
+# ekfslam_map_management / ekfslam_add_features / ekfslam_inversedepth_2_cartesian / ekfslam_delete_features
+# ------------------------------------------------------------------------------------------
+def _q2r(q):
+    r, x, y, z = q
+    return np.array([[r * r + x * x - y * y - z * z, 2 * (x * y - r * z), 2 * (z * x + r * y)],
+                     [2 * (x * y + r * z), r * r - x * x + y * y - z * z, 2 * (y * z - r * x)],
+                     [2 * (z * x - r * y), 2 * (y * z + r * x), r * r - x * x - y * y + z * z]])
+
+
+def _setup_map(features_info, x, P, extra, f=None, cam=None):
+    """Like _setup, but with room for `extra` new features; uploads (x, P) as (x_k_k, p_k_k)."""
+    n = _state_dim(features_info)
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    if x.shape[0] != n:
+        raise ValueError("state vector has %d entries, features_info implies %d" % (x.shape[0], n))
+    N = len(features_info) + int(extra)
+    n_max = 13 + 6 * max(N, 1)
+    bank = _bank(max(N, 1), n_max, f, cam)
+    t = np.zeros((1, bank.N), dtype=np.uint8)
+    t[0, :len(features_info)] = _types(features_info)[0, :len(features_info)]
+    bank.upload_feature_types(t, nfeat=np.array([len(features_info)], dtype=np.int32))
+    xs = np.zeros((1, n_max))
+    Ps = np.zeros((1, n_max, n_max))
+    xs[0, :n] = x
+    Ps[0, :n, :n] = np.asarray(P, dtype=np.float64)
+    bank.upload_state(x=xs, P=Ps, which=0)
+    return bank, n
+
+
+def _pull_map(bank):
+    x, P, ns = bank.download_state(which=0)
+    n = int(ns[0])
+    types, nf = bank.download_feature_types()
+    return x[0, :n].copy(), P[0, :n, :n].copy(), types[0, :int(nf[0])].copy()
+
+
+def add_features_inverse_depth(uvd, X, P, cam, std_pxl, initial_rho, std_rho):
+    """mc/add_features_inverse_depth.m:1-24 -> mc/hinv.m + mc/add_a_feature_covariance_inverse_depth.m.
+    uvd: [2] or [2, nNew] distorted pixels.  Returns (X_RES, P_RES, newFeature) (newFeature of the last one)."""
+    uvd = np.asarray(uvd, dtype=np.float64).reshape(2, -1)
+    X = np.asarray(X, dtype=np.float64).reshape(-1)
+    if uvd.shape[1] == 0:
+        return X, np.asarray(P, dtype=np.float64), None
+    if (X.shape[0] - 13) % 3:
+        raise ValueError("state size %d is not 13 + 6*N_id + 3*N_c" % X.shape[0])
+    # only the state SIZE matters for an append: describe the existing map as Cartesian triples
+    layout = [new_feature("cartesian") for _ in range((X.shape[0] - 13) // 3)]
+    bank, n = _setup_map(layout, X, P, extra=uvd.shape[1], cam=cam)
+    for j in range(uvd.shape[1]):
+        bank.add_features_inverse_depth(uvd[:, j][None], std_pxl=std_pxl, initial_rho=initial_rho, std_rho=std_rho)
+    x, Pn, _ = _pull_map(bank)
+    return x, Pn, x[-6:].copy()
+
+
+def inversedepth_2_cartesian(f, features_info):
+    """mc/inversedepth_2_cartesian.m:1-52 (at most one conversion per call, :49)."""
+    if not features_info:
+        return f, features_info
+    bank, n = _setup_map(features_info, f.x_k_k, f.p_k_k, extra=0, f=f)
+    conv = bank.inversedepth_2_cartesian(threshold=0.1)
+    if conv[0] >= 0:
+        f.x_k_k, f.p_k_k, _ = _pull_map(bank)
+        features_info[int(conv[0])].type = "cartesian"
+    return f, features_info
+
+
+def delete_a_feature(X_km1_km1, P_km1_km1, featToDelete, features_info):
+    """mc/delete_a_feature.m:1-25; featToDelete is the 0-based position in the Python list."""
+    bank, n = _setup_map(features_info, X_km1_km1, P_km1_km1, extra=0)
+    d = np.zeros((1, bank.N), dtype=np.uint8)
+    d[0, int(featToDelete)] = 1
+    bank.delete_features(d)
+    x, P, _ = _pull_map(bank)
+    return x, P
+
+
+def delete_features(f, features_info):
+    """Called by mc/map_management.m:7 but NOT shipped by the reference; rule of the published toolbox it derives
+    from: delete a feature predicted more than 5 times and matched in fewer than half of those predictions."""
+    dele = [fi.times_measured < 0.5 * fi.times_predicted and fi.times_predicted > 5 for fi in features_info]
+    if any(dele):
+        bank, n = _setup_map(features_info, f.x_k_k, f.p_k_k, extra=0, f=f)
+        d = np.zeros((1, bank.N), dtype=np.uint8)
+        d[0, :len(dele)] = dele
+        bank.delete_features(d)
+        f.x_k_k, f.p_k_k, _ = _pull_map(bank)
+        features_info = [fi for fi, dd in zip(features_info, dele) if not dd]
+    return f, features_info
+
+
+def add_feature_to_info_vector(uv, im_k, X_RES, features_info, step, newFeature, init_feature_descriptor):
+    """mc/add_feature_to_info_vector.m:1-32 (host bookkeeping; the image patch copy of :7 is dropped)."""
+    fi = new_feature("inversedepth", yi=newFeature, uv=uv, step=step)
+    X_RES = np.asarray(X_RES, dtype=np.float64).reshape(-1)
+    fi.r_wc_when_initialized = X_RES[0:3].copy()
+    fi.R_wc_when_initialized = _q2r(X_RES[3:7])
+    fi.init_measurement = np.asarray(uv, dtype=np.float64).reshape(2)
+    fi.feature_when_initialized = init_feature_descriptor
+    return list(features_info) + [fi]
+
+
+def _detections(im):
+    """`im` of the map functions: corner detections uv [K,2] or (uv [K,2], descriptors [K]) — the stand-in for the
+    image the reference searches with detectFASTFeatures (mc/initialize_a_feature.m:29)."""
+    if isinstance(im, tuple):
+        uv, desc = im
+    else:
+        uv, desc = im, None
+    uv = np.asarray(uv, dtype=np.float64).reshape(-1, 2)
+    desc = list(range(len(uv))) if desc is None else list(desc)
+    return uv, desc
+
+
+def initialize_features(step, cam, f, features_info, num_features_to_initialize, im):
+    """mc/initialize_features.m:1-21 with the corner search of mc/initialize_a_feature.m replaced by the supplied
+    detections (one attempt each, at most 50 attempts)."""
+    uv, desc = _detections(im)
+    k = int(min(num_features_to_initialize, len(uv), 50))
+    for j in range(k):
+        X_RES, P_RES, newFeature = add_features_inverse_depth(uv[j], f.x_k_k, f.p_k_k, cam, f.std_z, 1.0, 1.0)
+        f.x_k_k, f.p_k_k = X_RES, P_RES
+        features_info = add_feature_to_info_vector(uv[j], None, X_RES, features_info, step, newFeature, desc[j])
+    return f, features_info
+
+
+def map_management(f, features_info, cam, im, min_number_of_features_in_image, step):
+    """mc/map_management.m:1-35 in ONE device call (ekfslam_map_management): delete_features ->
+    count measured -> update_features_info -> inversedepth_2_cartesian -> initialize_features.
+    ``im`` = corner detections, see :func:`_detections`."""
+    uv, desc = _detections(im)
+    K = max(len(uv), 1)
+    nf0 = len(features_info)
+    bank, n = _setup_map(features_info, f.x_k_k, f.p_k_k, extra=min(K, 50), f=f, cam=cam)
+    _push_features(bank, features_info)
+    counters = np.zeros((1, bank.N, 2), dtype=np.int32)
+    tags = np.full((1, bank.N), -1, dtype=np.int32)
+    for i, fi in enumerate(features_info):
+        counters[0, i] = (fi.times_predicted, fi.times_measured)
+        tags[0, i] = i                                   # old features: position in the old list
+    bank.upload_feature_meta(counters=counters, tag=tags)
+    uvp = np.zeros((1, K, 2))
+    uvp[0, :len(uv)] = uv
+    dtag = (nf0 + np.arange(K, dtype=np.int32))[None]     # new features: nf0 + detection index
+    bank.upload_detections(uvp, np.array([len(uv)], dtype=np.int32), tag=dtag)
+    bank.map_management(int(min_number_of_features_in_image))
+    x, P, types = _pull_map(bank)
+    tg = bank.download_feature_tags()[0, :len(types)]
+    cnt = bank.download_features()["counters"][0]
+    out = []
+    pos = 13
+    for i, (ty, tag) in enumerate(zip(types, tg)):
+        w = 6 if ty == L.FEAT_INVERSEDEPTH else 3
+        if tag < nf0:
+            fi = features_info[int(tag)]
+            fi.type = "inversedepth" if ty == L.FEAT_INVERSEDEPTH else "cartesian"
+        else:
+            j = int(tag) - nf0
+            fi = add_feature_to_info_vector(uv[j], None, x, [], step, x[pos:pos + 6].copy(), desc[j])[0]
+        fi.times_predicted, fi.times_measured = int(cnt[i, 0]), int(cnt[i, 1])
+        fi.individually_compatible = fi.low_innovation_inlier = fi.high_innovation_inlier = 0
+        fi.h = fi.z = fi.H = fi.S = None
+        out.append(fi)
+        pos += w
+    f.x_k_k, f.p_k_k = x, P
+    return f, out

@@ -167,6 +167,7 @@ class FilterBank:
         if u.ndim != 2:
             raise ValueError("u must be [nb, n_u]")
         L.check(self.lib.ekfslam_upload_uniforms(self._h, b0, u.shape[0], _ptr(u), u.shape[1]))
+        self._n_u = u.shape[1]
 
     def upload_features(self, h=None, Hc=None, S=None, z=None, flags=None, b0=0):
         nb = None
@@ -246,6 +247,74 @@ class FilterBank:
         nf = np.empty(nb, dtype=np.int32)
         L.check(self.lib.ekfslam_download_feature_types(self._h, b0, nb, _ptr(t), _ptr(nf)))
         return t, nf
+
+    def map_management(self, min_number_of_features_in_image=25):
+        """mc/map_management.m:1-35 for every filter on the device (delete -> measured -> update_features_info ->
+        at most one inverse-depth -> Cartesian conversion -> top up from the detection list).  Follow it with
+        ``step(reset=False)``."""
+        L.check(self.lib.ekfslam_map_management(self._h, int(min_number_of_features_in_image)))
+
+    def upload_detections(self, uv, n, tag=None, b0=0):
+        """Detection list for map_management: uv [nb,K,2] corner pixels, n [nb] valid entries, tag [nb,K]."""
+        uv = _c(uv, np.float64)
+        nb, K = uv.shape[0], uv.shape[1]
+        uv = _c(uv, np.float64, (nb, K, 2))
+        n = _c(n, np.int32, (nb,))
+        tag = None if tag is None else _c(tag, np.int32, (nb, K))
+        L.check(self.lib.ekfslam_upload_detections(self._h, b0, nb, K, _ptr(uv), _ptr(tag), _ptr(n)))
+
+    def download_detections(self, K, b0=0, nb=None):
+        nb = self.B - b0 if nb is None else nb
+        uv, tag, n = np.empty((nb, K, 2)), np.empty((nb, K), dtype=np.int32), np.empty(nb, dtype=np.int32)
+        L.check(self.lib.ekfslam_download_detections(self._h, b0, nb, K, _ptr(uv), _ptr(tag), _ptr(n)))
+        return uv, tag, n
+
+    def upload_feature_meta(self, counters=None, tag=None, b0=0):
+        """times_predicted / times_measured [nb,N,2] and the feature identities tag [nb,N]."""
+        nb = len(counters) if counters is not None else len(tag)
+        counters = None if counters is None else _c(counters, np.int32, (nb, self.N, 2))
+        tag = None if tag is None else _c(tag, np.int32, (nb, self.N))
+        L.check(self.lib.ekfslam_upload_feature_meta(self._h, b0, nb, _ptr(counters), _ptr(tag)))
+
+    def download_feature_tags(self, b0=0, nb=None):
+        nb = self.B - b0 if nb is None else nb
+        tag = np.empty((nb, self.N), dtype=np.int32)
+        L.check(self.lib.ekfslam_download_feature_tags(self._h, b0, nb, _ptr(tag)))
+        return tag
+
+    def download_candidates(self, b0=0, nb=None):
+        """The staged candidates of the current frame: zc [nb,N,2], has [nb,N] (0/1)."""
+        nb = self.B - b0 if nb is None else nb
+        zc, fl = np.empty((nb, self.N, 2)), np.empty((nb, self.N), dtype=np.uint8)
+        L.check(self.lib.ekfslam_download_candidates(self._h, b0, nb, _ptr(zc), _ptr(fl)))
+        return zc, ((fl & L.F_CAND) != 0).astype(np.uint8)
+
+    # -- synthetic world on the device (stand-in for the image front-end) ---------------------
+    def world_upload(self, world, b0=0):
+        """world: synth.SynthWorld (filters [b0, b0+B) of it live in this bank)."""
+        pts = _c(world.points[b0:b0 + self.B], np.float64, (self.B, world.M, 3))
+        poses = np.concatenate([world.pose_r[b0:b0 + self.B], world.pose_q[b0:b0 + self.B]], axis=2)   # [B,T+1,7]
+        poses = _c(np.transpose(poses, (1, 0, 2)), np.float64, (world.T + 1, self.B, 7))
+        wp = L.WorldParams(seed=world.seed, b_offset=world.b_offset + b0, flaky_mod=world.flaky_mod,
+                           noise_px=world.noise_px, gross_px=world.gross_px, p_outlier=world.p_outlier,
+                           p_flaky=world.p_flaky, band_px=float(world.BAND))
+        L.check(self.lib.ekfslam_world_upload(self._h, world.M, world.T, _ptr(pts), _ptr(poses), C.byref(wp)))
+
+    def world_candidates(self, t):
+        L.check(self.lib.ekfslam_world_candidates(self._h, int(t)))
+
+    def world_uniforms(self, t, n_u):
+        L.check(self.lib.ekfslam_world_uniforms(self._h, int(t), int(n_u)))
+        self._n_u = int(n_u)
+
+    def download_uniforms(self, b0=0, nb=None):
+        nb = self.B - b0 if nb is None else nb
+        u = np.empty((nb, self._n_u))
+        L.check(self.lib.ekfslam_download_uniforms(self._h, b0, nb, _ptr(u), self._n_u))
+        return u
+
+    def world_detect(self, t, K):
+        L.check(self.lib.ekfslam_world_detect(self._h, int(t), int(K)))
 
     # -- stages (names follow the reference functions they replace) --------------------------
     def begin_frame(self):

@@ -79,7 +79,7 @@ static void kt_collect(ekfslam_ctx* c) {
 static const char* KT_NAMES[KT_COUNT] = {"k_begin_frame", "k_predict", "k_features", "k_hp", "k_innov", "k_ransac",
                                          "k_upd_S", "k_chol", "k_w", "k_downdate_hi", "k_downdate", "k_symmetrize",
                                          "k_add_features", "k_wfix", "k_v", "k_g2", "k_w_hi", "k_chol_hi", "k_upd_S_hi",
-                                         "k_hp_rescue"};
+                                         "k_hp_rescue", "k_world"};
 
 template <typename T>
 static cudaError_t dalloc(T** p, size_t count, int64_t* total) {
@@ -214,6 +214,10 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     DA(v.nstate, Bz);
     DA(v.nfeat, Bz);
     DA(v.counters, Bz * v.N * 2);
+    DA(v.tag, Bz * v.N);
+    DA(c->mm_del, Bz * v.N);
+    DA(c->mm_quota, Bz);
+    DA(c->det_n, Bz);
     DA(v.sel, Bz * v.N);
     DA(v.ksel, Bz);
     DA(v.stats, Bz);
@@ -261,7 +265,8 @@ int ekfslam_destroy(ekfslam_ctx* c) {
     if (c->own_zc) { c->v.zc = c->own_zc; c->v.mflags = c->own_mflags; c->v.u = c->own_u; c->own_zc = nullptr; }
     DevView& v = c->v;
     void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.jnt, v.jn1, v.kpend, v.roff, v.ktot, v.kmaxdev, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
-                    v.flags, v.mflags, v.foff, v.nstate, v.nfeat, v.counters, v.sel, v.ksel, v.stats, v.nhyp_tab};
+                    v.flags, v.mflags, v.foff, v.nstate, v.nfeat, v.counters, v.tag, v.sel, v.ksel, v.stats, v.nhyp_tab,
+                    c->mm_del, c->mm_quota, c->det_n, c->det_uv, c->det_tag, c->world_points, c->world_poses};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->timer) {
@@ -441,6 +446,7 @@ int ekfslam_download_state(ekfslam_ctx* c, int b0, int nb, int which, double* x,
 // ---- features_info <-> device --------------------------------------------------------------
 int ekfslam_upload_feature_types(ekfslam_ctx* c, int b0, int nb, const uint8_t* type, const int32_t* nfeat) {
     NEED_CTX(c);
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!type || !nfeat) return fail(EKFSLAM_ERR_INVALID, "type / nfeat is null");
     DevView& v = c->v;
@@ -466,6 +472,7 @@ int ekfslam_upload_feature_types(ekfslam_ctx* c, int b0, int nb, const uint8_t* 
     CK(cudaMemsetAsync(v.flags + o, 0, (size_t)nb * v.N, c->stream));
     CK(cudaMemsetAsync(v.mflags + o, 0, (size_t)nb * v.N, c->stream));
     CK(cudaMemsetAsync(v.counters + 2 * o, 0, sizeof(int32_t) * 2 * nb * v.N, c->stream));
+    CK(cudaMemsetAsync(v.tag + o, 0xff, sizeof(int32_t) * nb * v.N, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return EKFSLAM_OK;
 }
@@ -776,6 +783,7 @@ int ekfslam_step_host(ekfslam_ctx* c, int match_mode, const double* zc, const ui
 
 int ekfslam_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* xv, const double* Pxv) {
     NEED_CTX(c);
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!xv || !Pxv) return fail(EKFSLAM_ERR_INVALID, "xv / Pxv is null");
     DevView& v = c->v;
@@ -797,6 +805,7 @@ int ekfslam_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* xv, cons
     CK(cudaMemsetAsync(v.mflags + o, 0, (size_t)nb * v.N, c->stream));
     CK(cudaMemsetAsync(v.foff + o, 0, sizeof(int32_t) * nb * v.N, c->stream));
     CK(cudaMemsetAsync(v.counters + 2 * o, 0, sizeof(int32_t) * 2 * nb * v.N, c->stream));
+    CK(cudaMemsetAsync(v.tag + o, 0xff, sizeof(int32_t) * nb * v.N, c->stream));
     CK(cudaMemsetAsync(v.stats + b0, 0, sizeof(ekfslam_stats) * nb, c->stream));
     launch_reset_filters(c, b0, nb, d, d + 13);
     LAUNCHED();
@@ -807,6 +816,7 @@ int ekfslam_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* xv, cons
 int ekfslam_add_features(ekfslam_ctx* c, int b0, int nb, const double* uvd, const uint8_t* add, double std_pxl,
                          double initial_rho, double std_rho) {
     NEED_CTX(c);
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!uvd) return fail(EKFSLAM_ERR_INVALID, "uvd is null");
     // staging buffers for the pixels / mask (grown on demand, freed with the context)
@@ -821,7 +831,7 @@ int ekfslam_add_features(ekfslam_ctx* c, int b0, int nb, const double* uvd, cons
     CK(cudaMemcpyAsync(d_uvd, uvd, sizeof(double) * 2 * nb, cudaMemcpyHostToDevice, c->stream));
     if (add) CK(cudaMemcpyAsync(d_add, add, nb, cudaMemcpyHostToDevice, c->stream));
     ensure_upper(c);
-    launch_add_features(c, b0, nb, d_uvd, add ? d_add : nullptr, std_pxl, initial_rho, std_rho);
+    launch_add_features(c, b0, nb, d_uvd, 2, add ? d_add : nullptr, nullptr, 0, nullptr, 0, std_pxl, initial_rho, std_rho);
     LAUNCHED();
     CK(cudaStreamSynchronize(c->stream));
     return EKFSLAM_OK;
@@ -852,6 +862,7 @@ int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* c, double threshold, int force
 
 int ekfslam_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* del) {
     NEED_CTX(c);
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!del) return fail(EKFSLAM_ERR_INVALID, "del is null");
     DevView& v = c->v;
@@ -862,6 +873,163 @@ int ekfslam_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* del) 
     launch_delete_features(c, b0, nb, (const uint8_t*)c->pin);
     LAUNCHED();
     CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+// ---- closed loop: detection list, map management, synthetic world ------------------------------
+static int ensure_det(ekfslam_ctx* c, int K) {
+    if (K <= 0 || K > 1024) return fail(EKFSLAM_ERR_INVALID, "K must be in [1, 1024]");
+    if (c->det_uv && c->det_K == K) return EKFSLAM_OK;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->det_uv) { cudaFree(c->det_uv); cudaFree(c->det_tag); c->det_uv = nullptr; c->det_tag = nullptr; }
+    const size_t BK = (size_t)c->v.B * K;
+    CK(cudaMalloc((void**)&c->det_uv, sizeof(double) * 2 * BK));
+    CK(cudaMalloc((void**)&c->det_tag, sizeof(int32_t) * BK));
+    CK(cudaMemsetAsync(c->det_uv, 0, sizeof(double) * 2 * BK, c->stream));
+    CK(cudaMemsetAsync(c->det_tag, 0xff, sizeof(int32_t) * BK, c->stream));
+    CK(cudaMemsetAsync(c->det_n, 0, sizeof(int32_t) * c->v.B, c->stream));
+    c->det_K = K;
+    return EKFSLAM_OK;
+}
+
+int ekfslam_upload_detections(ekfslam_ctx* c, int b0, int nb, int K, const double* uv, const int32_t* tag,
+                              const int32_t* n) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!uv || !n) return fail(EKFSLAM_ERR_INVALID, "uv / n is null");
+    for (int i = 0; i < nb; ++i)
+        if (n[i] < 0 || n[i] > K) return fail(EKFSLAM_ERR_INVALID, "n out of [0, K]");
+    if (int r = ensure_det(c, K)) return r;
+    CK(cudaMemcpyAsync(c->det_uv + 2 * (size_t)b0 * K, uv, sizeof(double) * 2 * nb * K, cudaMemcpyHostToDevice, c->stream));
+    if (tag) CK(cudaMemcpyAsync(c->det_tag + (size_t)b0 * K, tag, sizeof(int32_t) * nb * K, cudaMemcpyHostToDevice, c->stream));
+    else CK(cudaMemsetAsync(c->det_tag + (size_t)b0 * K, 0xff, sizeof(int32_t) * nb * K, c->stream));
+    CK(cudaMemcpyAsync(c->det_n + b0, n, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_download_detections(ekfslam_ctx* c, int b0, int nb, int K, double* uv, int32_t* tag, int32_t* n) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!c->det_uv || K != c->det_K) return fail(EKFSLAM_ERR_STATE, "no detection list of this K on the device");
+    if (uv) CK(cudaMemcpyAsync(uv, c->det_uv + 2 * (size_t)b0 * K, sizeof(double) * 2 * nb * K, cudaMemcpyDeviceToHost, c->stream));
+    if (tag) CK(cudaMemcpyAsync(tag, c->det_tag + (size_t)b0 * K, sizeof(int32_t) * nb * K, cudaMemcpyDeviceToHost, c->stream));
+    if (n) CK(cudaMemcpyAsync(n, c->det_n + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_upload_feature_meta(ekfslam_ctx* c, int b0, int nb, const int32_t* counters, const int32_t* tag) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    DevView& v = c->v;
+    const size_t o = (size_t)b0 * v.N, cnt = (size_t)nb * v.N;
+    if (counters) CK(cudaMemcpyAsync(v.counters + 2 * o, counters, sizeof(int32_t) * 2 * cnt, cudaMemcpyHostToDevice, c->stream));
+    if (tag) CK(cudaMemcpyAsync(v.tag + o, tag, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_download_feature_tags(ekfslam_ctx* c, int b0, int nb, int32_t* tag) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!tag) return fail(EKFSLAM_ERR_INVALID, "tag is null");
+    CK(cudaMemcpyAsync(tag, c->v.tag + (size_t)b0 * c->v.N, sizeof(int32_t) * (size_t)nb * c->v.N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_download_candidates(ekfslam_ctx* c, int b0, int nb, double* zc, uint8_t* fl) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    DevView& v = c->v;
+    const size_t o = (size_t)b0 * v.N, cnt = (size_t)nb * v.N;
+    if (zc) CK(cudaMemcpyAsync(zc, v.zc + 2 * o, sizeof(double) * 2 * cnt, cudaMemcpyDeviceToHost, c->stream));
+    if (fl) CK(cudaMemcpyAsync(fl, v.mflags + o, cnt, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_map_management(ekfslam_ctx* c, int min_number_of_features_in_image) {
+    NEED_CTX(c);
+    DevView& v = c->v;
+    if (min_number_of_features_in_image < 0) return fail(EKFSLAM_ERR_INVALID, "min_number_of_features_in_image < 0");
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
+    if (!c->det_uv) return fail(EKFSLAM_ERR_STATE, "map_management: no detection list (ekfslam_upload_detections / ekfslam_world_detect)");
+    if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "map_management supports n_max <= 4096");
+    ensure_upper(c);
+    launch_mm_plan(c, min_number_of_features_in_image);           // deletion list, measured, quota     (:7-14, :27-35)
+    launch_delete_features(c, 0, v.B, c->mm_del);                  // delete_a_feature.m                 (:7)
+    launch_begin_frame(c);                                         // update_features_info.m             (:17)
+    launch_id2cart(c, 0.1, -1, nullptr);                           // inversedepth_2_cartesian.m         (:22)
+    const int K = c->det_K < 50 ? c->det_K : 50;
+    for (int j = 0; j < K; ++j)                                    // initialize_features                (:27-35)
+        launch_add_features(c, 0, v.B, c->det_uv + 2 * (size_t)j, 2 * c->det_K, nullptr, c->mm_quota, j,
+                            c->det_tag + j, c->det_K, c->prm.std_z, 1.0, 1.0);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_world_upload(ekfslam_ctx* c, int M, int T, const double* points, const double* poses,
+                         const ekfslam_world_params* wp) {
+    NEED_CTX(c);
+    if (!points || !poses || !wp) return fail(EKFSLAM_ERR_INVALID, "points / poses / params is null");
+    if (M <= 0 || M > 2048 || T < 0) return fail(EKFSLAM_ERR_INVALID, "M must be in [1, 2048] and T >= 0");
+    if (wp->flaky_mod <= 0) return fail(EKFSLAM_ERR_INVALID, "flaky_mod must be positive");
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->world_points) { cudaFree(c->world_points); cudaFree(c->world_poses); c->world_points = nullptr; c->world_poses = nullptr; }
+    const size_t np_ = (size_t)c->v.B * M * 3, nq = (size_t)(T + 1) * c->v.B * 7;
+    CK(cudaMalloc((void**)&c->world_points, sizeof(double) * np_));
+    CK(cudaMalloc((void**)&c->world_poses, sizeof(double) * nq));
+    CK(cudaMemcpyAsync(c->world_points, points, sizeof(double) * np_, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->world_poses, poses, sizeof(double) * nq, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    DevWorld& w = c->world;
+    w.M = M; w.T = T; w.points = c->world_points; w.poses = c->world_poses;
+    w.seed = wp->seed; w.b_offset = wp->b_offset; w.flaky_mod = wp->flaky_mod;
+    w.noise_px = wp->noise_px; w.gross_px = wp->gross_px; w.p_outlier = wp->p_outlier; w.p_flaky = wp->p_flaky;
+    w.band = wp->band_px;
+    return EKFSLAM_OK;
+}
+
+int ekfslam_world_candidates(ekfslam_ctx* c, int t) {
+    NEED_CTX(c);
+    if (!c->world_points) return fail(EKFSLAM_ERR_STATE, "no world uploaded (ekfslam_world_upload)");
+    if (t < 0 || t > c->world.T) return fail(EKFSLAM_ERR_INVALID, "frame index out of [0, T]");
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
+    launch_world_candidates(c, t);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_world_uniforms(ekfslam_ctx* c, int t, int n_u) {
+    NEED_CTX(c);
+    if (!c->world_points) return fail(EKFSLAM_ERR_STATE, "no world uploaded (ekfslam_world_upload)");
+    if (n_u <= 0) return fail(EKFSLAM_ERR_INVALID, "n_u <= 0");
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
+    if (int r = ensure_u(c, n_u)) return r;
+    c->v.n_u = n_u;
+    launch_world_uniforms(c, t);
+    LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_download_uniforms(ekfslam_ctx* c, int b0, int nb, double* u, int n_u) {
+    NEED_CTX(c);
+    if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
+    if (!u || n_u != c->v.n_u || n_u <= 0) return fail(EKFSLAM_ERR_INVALID, "u is null or n_u differs from the resident stream");
+    CK(cudaMemcpyAsync(u, c->v.u + (size_t)b0 * n_u, sizeof(double) * (size_t)nb * n_u, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFSLAM_OK;
+}
+
+int ekfslam_world_detect(ekfslam_ctx* c, int t, int K) {
+    NEED_CTX(c);
+    if (!c->world_points) return fail(EKFSLAM_ERR_STATE, "no world uploaded (ekfslam_world_upload)");
+    if (t < 0 || t > c->world.T) return fail(EKFSLAM_ERR_INVALID, "frame index out of [0, T]");
+    if (int r = ensure_det(c, K)) return r;
+    launch_world_detect(c, t);
+    LAUNCHED();
     return EKFSLAM_OK;
 }
 

@@ -45,6 +45,7 @@ struct DevView {
     int32_t* nstate;      // [B]
     int32_t* nfeat;       // [B]
     int32_t* counters;    // [B][N][2]
+    int32_t* tag;         // [B][N]   feature identity (stand-in for features_info(i).feature_when_initialized)
     int32_t* sel;         // [B][N]   selected feature list of the running update
     int32_t* ksel;        // [B]      number of selected features
     int32_t* kpend;       // [B]      rows of W left pending by a deferred update (0 = none)
@@ -55,10 +56,22 @@ struct DevView {
     ekfslam_stats* stats; // [B]
 };
 
+// The synthetic world of the closed loop (k_map.cu): resident world points, camera trajectory, noise model.
+struct DevWorld {
+    int M, T;                    // world points per filter, frames (poses 0..T)
+    const double* points;        // [B][M][3]
+    const double* poses;         // [T+1][B][7]  r (3), q (4)
+    unsigned long long seed;
+    int b_offset;                // filter index offset of this context inside a larger batch (sharding)
+    double noise_px, gross_px, p_outlier, p_flaky;
+    int flaky_mod;
+    double band;                 // excluded image band for new features
+};
+
 // per-kernel timing (ekfslam_enable_timing): every launch is bracketed by an event pair
 enum {
     KT_BEGIN_FRAME = 0, KT_PREDICT, KT_FEATURES, KT_HP, KT_INNOV, KT_RANSAC, KT_UPD_S, KT_CHOL, KT_W, KT_DOWNDATE_HI,
-    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_WFIX, KT_V, KT_G2, KT_W_HI, KT_CHOL_HI, KT_UPD_S_HI, KT_HP_RESCUE, KT_COUNT
+    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_WFIX, KT_V, KT_G2, KT_W_HI, KT_CHOL_HI, KT_UPD_S_HI, KT_HP_RESCUE, KT_WORLD, KT_COUNT
 };
 struct KTimer;
 
@@ -97,6 +110,11 @@ struct ekfslam_ctx {
     size_t pin_bytes;
     int u_cap;
     int32_t* kmax_host;  // pinned: host copy of *v.kmaxdev (lock-step Cholesky bounds its launch loops with it)
+    // closed loop: synthetic world + detection list + map-management scratch (k_map.cu)
+    DevWorld world;
+    double* world_points; double* world_poses;
+    double* det_uv; int32_t* det_tag; int32_t* det_n; int det_K;   // [B][K][2], [B][K], [B]
+    uint8_t* mm_del; int32_t* mm_quota;                             // [B][N], [B]
     // the context's own frame buffers while caller-owned ones are bound (ekfslam_bind_frame)
     double* own_zc; uint8_t* own_mflags; double* own_u; int own_n_u;
 };
@@ -150,5 +168,11 @@ void launch_downdate(ekfslam_ctx* c, int slot);
 void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv);
 void launch_id2cart(ekfslam_ctx* c, double threshold, int force_index, int32_t* d_conv);
 void launch_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* d_del);
-void launch_add_features(ekfslam_ctx* c, int b0, int nb, const double* d_uvd, const uint8_t* d_add,
+// one feature per filter from uvd[lb * uvd_stride .. +1]; add (mask) / quota (add iff j < quota[b]) / tag_src may be null
+void launch_add_features(ekfslam_ctx* c, int b0, int nb, const double* d_uvd, int uvd_stride, const uint8_t* d_add,
+                         const int32_t* d_quota, int j, const int32_t* d_tag, int tag_stride,
                          double std_pxl, double rho0, double std_rho);
+void launch_world_candidates(ekfslam_ctx* c, int t);
+void launch_world_detect(ekfslam_ctx* c, int t);
+void launch_world_uniforms(ekfslam_ctx* c, int t);
+void launch_mm_plan(ekfslam_ctx* c, int min_features);

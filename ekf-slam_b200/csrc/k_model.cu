@@ -744,11 +744,14 @@ void ensure_upper(ekfslam_ctx* c) {
 // One block per filter; operates on (x_k_k, p_k_k).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_add_feature(DevView v, DevCam cam, int b0, const double* __restrict__ uvd,
-                                                     const uint8_t* __restrict__ add, double std_pxl, double rho0,
-                                                     double std_rho) {
+                                                     int uvd_stride, const uint8_t* __restrict__ add,
+                                                     const int32_t* __restrict__ quota, int jq,
+                                                     const int32_t* __restrict__ tag_src, int tag_stride,
+                                                     double std_pxl, double rho0, double std_rho) {
     const int lb = blockIdx.x;
     const int b = b0 + lb;
     if (add && !add[lb]) return;
+    if (quota && jq >= quota[b]) return;
     const int n = v.nstate[b], nf = v.nfeat[b];
     if (n + 6 > v.nmax || nf >= v.N) {
         if (threadIdx.x == 0) atomicOr(&v.stats[b].status, 4);  // no room: reported, feature not added
@@ -760,7 +763,7 @@ __global__ void __launch_bounds__(128) k_add_feature(DevView v, DevCam cam, int 
     __shared__ double dth_dq[4], dph_dq[4], D[6][6], newf[6];
     if (threadIdx.x == 0) {
         const double fku = cam.f / cam.dx, fkv = cam.f / cam.dy;  // cam.K(1,1), cam.K(2,2)
-        const double ud = uvd[2 * lb], vd = uvd[2 * lb + 1];
+        const double ud = uvd[(size_t)lb * uvd_stride], vd = uvd[(size_t)lb * uvd_stride + 1];
         // mc/undistort_fm.m:18-27
         const double xd = (ud - cam.Cx) * cam.dx, yd = (vd - cam.Cy) * cam.dy;
         const double rd = sqrt(xd * xd + yd * yd);
@@ -856,15 +859,18 @@ __global__ void __launch_bounds__(128) k_add_feature(DevView v, DevCam cam, int 
         v.foff[t] = n;
         v.flags[t] = 0; v.mflags[t] = 0;
         v.counters[2 * t] = 0; v.counters[2 * t + 1] = 0;
+        v.tag[t] = tag_src ? tag_src[(size_t)lb * tag_stride] : -1;
         v.nstate[b] = n + 6;
         v.nfeat[b] = nf + 1;
     }
 }
 
-void launch_add_features(ekfslam_ctx* c, int b0, int nb, const double* d_uvd, const uint8_t* d_add, double std_pxl,
+void launch_add_features(ekfslam_ctx* c, int b0, int nb, const double* d_uvd, int uvd_stride, const uint8_t* d_add,
+                         const int32_t* d_quota, int j, const int32_t* d_tag, int tag_stride, double std_pxl,
                          double rho0, double std_rho) {
     KScope ks(c, KT_ADD_FEATURES);
-    k_add_feature<<<nb, 128, 0, c->stream>>>(c->v, c->cam, b0, d_uvd, d_add, std_pxl, rho0, std_rho);
+    k_add_feature<<<nb, 128, 0, c->stream>>>(c->v, c->cam, b0, d_uvd, uvd_stride, d_add, d_quota, j, d_tag, tag_stride,
+                                             std_pxl, rho0, std_rho);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1039,13 +1045,13 @@ __global__ void __launch_bounds__(512) k_delete_features(DevView v, int b0, cons
         if (threadIdx.x == 0) {
             for (int j = i; j < nf - 1; ++j) {
                 const size_t d = (size_t)b * N + j, sidx = d + 1;
-                v.ftype[d] = v.ftype[sidx]; v.foff[d] = v.foff[sidx] - w; v.flags[d] = v.flags[sidx]; v.mflags[d] = v.mflags[sidx];
+                v.ftype[d] = v.ftype[sidx]; v.foff[d] = v.foff[sidx] - w; v.flags[d] = v.flags[sidx]; v.mflags[d] = v.mflags[sidx]; v.tag[d] = v.tag[sidx];
                 for (int q = 0; q < 2; ++q) { v.h[2 * d + q] = v.h[2 * sidx + q]; v.z[2 * d + q] = v.z[2 * sidx + q]; v.zc[2 * d + q] = v.zc[2 * sidx + q]; v.counters[2 * d + q] = v.counters[2 * sidx + q]; }
                 for (int q = 0; q < 4; ++q) v.S[4 * d + q] = v.S[4 * sidx + q];
                 for (int q = 0; q < EKF_HSTRIDE; ++q) v.Hc[EKF_HSTRIDE * d + q] = v.Hc[EKF_HSTRIDE * sidx + q];
             }
             const size_t last = (size_t)b * N + nf - 1;
-            v.ftype[last] = EKFSLAM_FEAT_NONE; v.flags[last] = 0; v.mflags[last] = 0; v.foff[last] = 0;
+            v.ftype[last] = EKFSLAM_FEAT_NONE; v.flags[last] = 0; v.mflags[last] = 0; v.foff[last] = 0; v.tag[last] = -1;
             s_n = n - w; s_nf = nf - 1;
         }
         __syncthreads();

@@ -433,6 +433,11 @@ class SynthWorld:
             zc[b, :k][~vis[b, w]] = 0.0
         return zc, has
 
+    def uniforms(self, t, n_u):
+        """RANSAC uniform stream of frame t, [B, n_u] — bit-identical to k_synth_uniforms (integer hash, exact scaling)."""
+        b = (np.arange(self.B) + self.b_offset)[:, None]
+        return world_uniform(self.seed, b, t, np.arange(n_u)[None, :], 7)
+
     def detections(self, t, tags, nfeat, K):
         """Corner detections for new features in the image of frame t: the first K world points (by id)
         that are visible inside the excluded band and not yet in the map, at integer pixels (FAST corners

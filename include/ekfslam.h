@@ -232,6 +232,59 @@ int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* ctx, double threshold, int for
  * covariance and the features_info arrays are compacted. */
 int ekfslam_delete_features(ekfslam_ctx* ctx, int b0, int nb, const uint8_t* del);
 
+/* mc/map_management.m:1-35 for every filter, on the device, in the reference's order:
+ *   1. delete_features (:7; NOT shipped by the reference - rule of the published toolbox it derives from:
+ *      times_predicted > 5 and times_measured < 0.5*times_predicted) via mc/delete_a_feature.m:4-25
+ *   2. measured = #{low_innovation_inlier || high_innovation_inlier} over the survivors (:11-14)
+ *   3. mc/update_features_info.m:4-18 (:17)
+ *   4. mc/inversedepth_2_cartesian.m:3-52, at most one conversion (:22)
+ *   5. initialize_features (:27-35): min_n features if measured == 0, else min_n - measured if that is
+ *      positive; the corner search of mc/initialize_a_feature.m:22-57 (CV Toolbox) is replaced by the
+ *      context's DETECTION LIST (ekfslam_upload_detections or ekfslam_world_detect), one attempt per
+ *      detection, attempt cap 50 (mc/initialize_features.m:5); each accepted corner goes through
+ *      mc/add_features_inverse_depth.m (initial_rho = 1, std_rho = 1, std_pxl = std_z,
+ *      mc/initialize_a_feature.m:10-12).
+ * Operates on (x_k_k, p_k_k).  Follow it with ekfslam_step(reset = 0): step 3 already reset the frame. */
+int ekfslam_map_management(ekfslam_ctx* ctx, int min_number_of_features_in_image);
+/* detection list: uv [nb][K][2] distorted corner pixels, tag [nb][K] (may be NULL -> -1), n [nb] valid entries */
+int ekfslam_upload_detections(ekfslam_ctx* ctx, int b0, int nb, int K, const double* uv, const int32_t* tag,
+                              const int32_t* n);
+int ekfslam_download_detections(ekfslam_ctx* ctx, int b0, int nb, int K, double* uv, int32_t* tag, int32_t* n);
+/* features_info bookkeeping fields: counters [nb][N_max][2] = times_predicted, times_measured
+ * (mc/add_feature_to_info_vector.m:16-17) and tag [nb][N_max] = the feature's identity, the stand-in for
+ * feature_when_initialized (:10).  Either may be NULL. */
+int ekfslam_upload_feature_meta(ekfslam_ctx* ctx, int b0, int nb, const int32_t* counters, const int32_t* tag);
+int ekfslam_download_feature_tags(ekfslam_ctx* ctx, int b0, int nb, int32_t* tag);
+/* the staged candidates of the current frame: zc [nb][N_max][2], fl [nb][N_max] (EKFSLAM_F_CAND bit) */
+int ekfslam_download_candidates(ekfslam_ctx* ctx, int b0, int nb, double* zc, uint8_t* fl);
+
+/* ---- synthetic world on the device (stand-in for the image front-end) ---- */
+/* The reference's matcher (mc/matching.m:16-53: FAST corners in the search ellipse, FREAK match) and its feature
+ * detector (mc/initialize_a_feature.m:22-57) need MATLAB's CV Toolbox and an image sequence that is not in the
+ * repository.  Their stand-in keeps resident: M world points per filter and the true camera trajectory; per
+ * frame it produces (i) for every feature in every map the candidate pixel z = distort(project(point(tag))) +
+ * noise (or a gross outlier), staged exactly like ekfslam_upload_candidates, and (ii) the detection list for
+ * ekfslam_map_management.  Noise is counter-based (seed, filter, frame, point), so a frame can be regenerated. */
+typedef struct {
+    uint64_t seed;
+    int32_t b_offset;     /* index of this context's filter 0 inside a larger sharded batch       */
+    int32_t flaky_mod;    /* point w is flaky when w % flaky_mod == flaky_mod - 1                  */
+    double noise_px;      /* std of the pixel noise                                                */
+    double gross_px;      /* gross outliers are uniform in +-gross_px                              */
+    double p_outlier;     /* outlier probability of an ordinary point                              */
+    double p_flaky;       /* outlier probability of a flaky point                                  */
+    double band_px;       /* excluded image band for new features (reference: 21)                  */
+} ekfslam_world_params;
+/* points [B][M][3], poses [T+1][B][7] = r (3), q (4, scalar first); M <= 2048 */
+int ekfslam_world_upload(ekfslam_ctx* ctx, int M, int T, const double* points, const double* poses,
+                         const ekfslam_world_params* wp);
+int ekfslam_world_candidates(ekfslam_ctx* ctx, int t);      /* stage the candidates of frame t        */
+int ekfslam_world_detect(ekfslam_ctx* ctx, int t, int K);   /* fill the detection list from frame t   */
+/* RANSAC uniform stream of frame t, n_u per filter (stands in for the rand(1) of mc/select_random_match.m:12) */
+int ekfslam_world_uniforms(ekfslam_ctx* ctx, int t, int n_u);
+/* the resident uniform stream, u [nb][n_u] (n_u must equal the resident stream's length) */
+int ekfslam_download_uniforms(ekfslam_ctx* ctx, int b0, int nb, double* u, int n_u);
+
 /* ---- measurement hooks ------------------------------------------------------ */
 /* bracket every kernel launch with a CUDA event pair on the context's stream and accumulate the
  * elapsed time per kernel; enabling again resets the accumulators, on=0 removes the events */

@@ -8,9 +8,10 @@
  *       sizes where the numpy loops are slow, and
  *   (2) by bench.py as the multi-threaded CPU baseline (`cpu_baseline.kind = "port"`,
  *       `--impl reference`): OpenMP over independent filters, all host cores.
- * The product package never links or loads this file.  Parity status is the numpy oracle's:
- * pinned by the reference's features_information.mat for h/H/S (through tests that compare the two
- * oracles on the golden frame), unpinned for RANSAC/update/rescue (no reference artefact exists).
+ * The product package never links or loads this file.  Parity status: pinned by the reference's
+ * features_information.mat for h/H/S and, since round 2, by the reference's OWN EXECUTION for
+ * RANSAC / update / rescue / the Cartesian model (tests/golden/ref_*.npz, produced by running the
+ * unmodified matlab_code/*.m through oracle/mref; tests/test_oracle_ref.py::test_c_oracle_matches_reference_execution).
  *
  * Build: make -C oracle   ->  oracle/libekf_oracle.so
  */

@@ -15,12 +15,15 @@ the MATLAB hot path of diwakar-vsingh/EKF-SLAM (``matlab_code/*.m``; cited as
   ``predict_state_and_covariance``, ``hi_inverse_depth``,
   ``calculate_Hi_inverse_depth`` and ``S_i = H P H' + R`` reproduce the stored
   ``yi``/``h``/``H``/``S`` of all 13 features to <= 1e-12.
-* PARITY UNPINNED (no golden vector exists in the reference and GNU Octave is
-  not installed here, so the reference itself cannot be executed): the RANSAC
-  selection, ``update``, ``rescue_hi_inliers``, the Cartesian model and the
-  prediction at a non-identity pose.  They are transcriptions of the cited
-  lines, cross-checked by finite differences (tests/test_oracle_jacobians.py)
-  and against the independent C restatement ``oracle/ekf_oracle.c``.
+* PINNED by the reference's own EXECUTION (round 2): the unmodified ``matlab_code/*.m`` sources are
+  run through ``oracle/mref`` (mini MATLAB interpreter) over synthetic frames; its outputs are the
+  fixtures ``tests/golden/ref_*.npz`` (``tests/golden/make_ref_steps.py``).  Against them this file
+  reproduces the RANSAC selection and adaptive hypothesis count, ``update`` / ``normJac``,
+  ``rescue_hi_inliers`` (incl. the stale-``h`` edge), the hi update, the Cartesian model and the map
+  management functions: flags / counts exact, x and P <= 1e-11 over 200 free-running frames
+  (tests/test_oracle_ref.py, tests/test_oracle_map_ref.py).
+* PARITY UNPINNED by construction: ``update_iterated`` only (the reference names it but ships no
+  implementation, so there is nothing to execute).
 
 Two functions the reference calls but does not ship are restated from their
 published definitions: ``quaternions(v, theta)`` (mc/v2q.m:15) and

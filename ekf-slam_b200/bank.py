@@ -360,9 +360,16 @@ class FilterBank:
         """Iterated EKF update (extension; see ekfslam_update_iterated)."""
         L.check(self.lib.ekfslam_update_iterated(self._h, mask, which_prior, n_iter))
 
-    def step(self, reset=True, match_mode=1):
-        """One filter step on resident data (mc/mono_slam.m:56-74)."""
-        L.check(self.lib.ekfslam_step(self._h, 1 if reset else 0, match_mode))
+    def step(self, reset=True, match_mode=1, graph=False):
+        """One filter step on resident data (mc/mono_slam.m:56-74).  graph=True replays it from a captured CUDA
+        graph (latency path; see ekfslam_step_graph)."""
+        fn = self.lib.ekfslam_step_graph if graph else self.lib.ekfslam_step
+        L.check(fn(self._h, 1 if reset else 0, match_mode))
+
+    def stage_frame(self, d_zc, d_fl, d_u, n_u):
+        """Device pointers (ints) of a resident frame, copied into the context's own frame buffers."""
+        L.check(self.lib.ekfslam_stage_frame(self._h, C.c_void_p(d_zc), C.c_void_p(d_fl), C.c_void_p(d_u), int(n_u)))
+        self._n_u = int(n_u)
 
     def step_host(self, zc, fl, u, match_mode=1, x_out=None, flags_out=None, stats_out=None):
         """The per-frame call with HOST buffers (pinned buffers make the copies asynchronous).

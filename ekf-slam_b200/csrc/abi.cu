@@ -13,6 +13,7 @@
 #include "common.cuh"
 
 static thread_local std::string g_err;
+extern "C" { static void step_graph_destroy(ekfslam_ctx* c); }   // defined with ekfslam_step_graph
 
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -45,23 +46,41 @@ struct KTimer {
 
 static cudaEvent_t kt_event(KTimer* t) {
     if (!t->pool.empty()) { cudaEvent_t e = t->pool.back(); t->pool.pop_back(); return e; }
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }   // this launch goes untimed
     return e;
 }
 
 void kt_begin(ekfslam_ctx* c, int slot) {
     KTimer* t = c->timer;
     t->cur[slot] = kt_event(t);
-    cudaEventRecord(t->cur[slot], c->stream);
+    if (t->cur[slot]) cudaEventRecord(t->cur[slot], c->stream);
+}
+
+// completed pairs at the head of the list are folded into the totals as soon as the list grows: a long run that never
+// queries ekfslam_kernel_time keeps a bounded number of events alive
+static void kt_drain_completed(KTimer* t) {
+    size_t done = 0;
+    while (done < t->pending.size() && cudaEventQuery(t->pending[done].b) == cudaSuccess) {
+        KTimer::Rec& r = t->pending[done];
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { t->ms[r.slot] += ms; t->count[r.slot]++; }
+        t->pool.push_back(r.a);
+        t->pool.push_back(r.b);
+        ++done;
+    }
+    cudaGetLastError();   // cudaErrorNotReady of the first unfinished pair is not an error
+    if (done) t->pending.erase(t->pending.begin(), t->pending.begin() + done);
 }
 
 void kt_end(ekfslam_ctx* c, int slot) {
     KTimer* t = c->timer;
     KTimer::Rec r;
-    r.a = t->cur[slot]; r.b = kt_event(t); r.slot = slot;
+    r.a = t->cur[slot]; r.b = r.a ? kt_event(t) : nullptr; r.slot = slot;
+    if (!r.a || !r.b) { if (r.a) t->pool.push_back(r.a); return; }
     cudaEventRecord(r.b, c->stream);
     t->pending.push_back(r);
+    if (t->pending.size() > 1024) kt_drain_completed(t);
 }
 
 static void kt_collect(ekfslam_ctx* c) {
@@ -244,6 +263,8 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
         return fail(EKFSLAM_ERR_CUDA, std::string("context init: ") + cudaGetErrorString(e));
     }
     c->stream = c->own_stream;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (c->sm_count <= 0) c->sm_count = 148;
     {
         // EKFSLAM_FUSE=1: one covariance pass per frame (deferred li downdate, see ekfslam_step).  Off by
         // default: at N=100 the rescue-row correction GEMM costs as much as the saved pass.
@@ -276,6 +297,7 @@ int ekfslam_destroy(ekfslam_ctx* c) {
         delete c->timer;
         c->timer = nullptr;
     }
+    step_graph_destroy(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -743,6 +765,82 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
         launch_update(c, EKFSLAM_F_HI, 0);
     }
     LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+// ---- the filter step as a CUDA graph (latency path: few filters, ~25 small launches per frame) -----------------
+struct StepGraph {
+    cudaGraphExec_t exec;
+    DevView v; ekfslam_params prm; DevCam cam;
+    int reset, match_mode, fuse, rescue_gather;
+    int64_t launches;
+};
+
+static void step_graph_destroy(ekfslam_ctx* c) {
+    StepGraph* g = (StepGraph*)c->step_graph;
+    if (g) { if (g->exec) cudaGraphExecDestroy(g->exec); delete g; c->step_graph = nullptr; }
+}
+
+int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
+    NEED_CTX(c);
+    DevView& v = c->v;
+    // not capturable: per-kernel timing (event queries), the lock-step Cholesky (host read-back of the largest stacked
+    // size), the host-buffer step's cross-stream events, the lower-triangle mode's host-side state
+    const bool lockstep_shape = v.B < 128 && v.kmax >= 256;
+    if (c->timer || lockstep_shape || c->tri || c->wait_inputs || c->arm_out) return ekfslam_step(c, reset, match_mode);
+    if (match_mode < 0 || match_mode > 2) return fail(EKFSLAM_ERR_INVALID, "match_mode must be 0, 1 or 2");
+    if (v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "step: no uniform stream uploaded");
+    StepGraph* g = (StepGraph*)c->step_graph;
+    if (g && (memcmp(&g->v, &v, sizeof(DevView)) || memcmp(&g->prm, &c->prm, sizeof(ekfslam_params)) ||
+              memcmp(&g->cam, &c->cam, sizeof(DevCam)) || g->reset != reset || g->match_mode != match_mode ||
+              g->fuse != c->fuse_downdates || g->rescue_gather != c->rescue_gather)) {
+        step_graph_destroy(c);
+        g = nullptr;
+    }
+    if (!g) {
+        g = new (std::nothrow) StepGraph();
+        if (!g) return fail(EKFSLAM_ERR_NOMEM, "host allocation failed");
+        memset(g, 0, sizeof(*g));
+        memcpy(&g->v, &v, sizeof(DevView)); memcpy(&g->prm, &c->prm, sizeof(ekfslam_params)); memcpy(&g->cam, &c->cam, sizeof(DevCam));
+        g->reset = reset; g->match_mode = match_mode; g->fuse = c->fuse_downdates; g->rescue_gather = c->rescue_gather;
+        const int64_t l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
+        if (e != cudaSuccess) { delete g; return fail(EKFSLAM_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e)); }
+        const int rs = ekfslam_step(c, reset, match_mode);
+        e = cudaStreamEndCapture(c->stream, &graph);
+        g->launches = c->launches - l0;
+        c->launches = l0;                                  // nothing has executed yet
+        if (rs != EKFSLAM_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            delete g;
+            cudaGetLastError();
+            if (rs != EKFSLAM_OK) return rs;
+            return fail(EKFSLAM_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        }
+        e = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { delete g; return fail(EKFSLAM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+        c->step_graph = g;
+    }
+    CK(cudaGraphLaunch(g->exec, c->stream));
+    c->launches += g->launches;
+    return EKFSLAM_OK;
+}
+
+// device-resident frame -> the context's OWN frame buffers by copy (unlike ekfslam_bind_frame the buffer addresses the
+// kernels see do not change, so a captured step graph stays valid)
+int ekfslam_stage_frame(ekfslam_ctx* c, const void* d_zc, const void* d_fl, const void* d_u, int n_u) {
+    NEED_CTX(c);
+    if (!d_zc || !d_fl || !d_u || n_u <= 0) return fail(EKFSLAM_ERR_INVALID, "stage_frame: null pointer or n_u <= 0");
+    if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
+    DevView& v = c->v;
+    if (int r = ensure_u(c, n_u)) return r;
+    v.n_u = n_u;
+    const size_t bn = (size_t)v.B * v.N;
+    CK(cudaMemcpyAsync(v.zc, d_zc, sizeof(double) * 2 * bn, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(v.mflags, d_fl, bn, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(v.u, d_u, sizeof(double) * (size_t)v.B * n_u, cudaMemcpyDeviceToDevice, c->stream));
     return EKFSLAM_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include "../../include/ekfslam.h"
 
 #define EKF_XV 13        // camera state size, mc/fv.m:3-6
@@ -109,6 +110,8 @@ struct ekfslam_ctx {
     void* pin;
     size_t pin_bytes;
     int u_cap;
+    void* step_graph;    // captured CUDA graph of the filter step (ekfslam_step_graph), opaque here
+    int sm_count;        // multiprocessors of THIS context's device (persistent-kernel grid sizes)
     int32_t* kmax_host;  // pinned: host copy of *v.kmaxdev (lock-step Cholesky bounds its launch loops with it)
     // closed loop: synthetic world + detection list + map-management scratch (k_map.cu)
     DevWorld world;
@@ -129,6 +132,9 @@ __host__ __device__ __forceinline__ size_t w_at(int kmax, int t, int c) {
 
 #define EKF_TRI(nic, s) (((nic) * ((nic) + 1)) / 2 + (s))
 
+// one process-wide lock for the per-device function-attribute high-water marks (ENSURE_DYN_SMEM)
+inline std::mutex& ekf_attr_mutex() { static std::mutex m; return m; }
+
 // timing hooks (abi.cu): no-ops unless timing is enabled
 void kt_begin(ekfslam_ctx* c, int slot);
 void kt_end(ekfslam_ctx* c, int slot);
@@ -146,9 +152,12 @@ struct KScope {
         static size_t _hw[64];                                                                               \
         const size_t _b = (size_t)(bytes);                                                                   \
         const int _d = (dev) & 63;                                                                           \
-        if (_b > 48 * 1024 && _b > _hw[_d]) {                                                                \
-            cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)_b);                \
-            _hw[_d] = _b;                                                                                    \
+        if (_b > 48 * 1024) {                                                                                \
+            std::lock_guard<std::mutex> _g(ekf_attr_mutex());   /* host threads driving different contexts */ \
+            if (_b > _hw[_d]) {                                                                              \
+                cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)_b);            \
+                _hw[_d] = _b;                                                                                \
+            }                                                                                                \
         }                                                                                                    \
     } while (0)
 

@@ -621,12 +621,12 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
 
 void launch_downdate(ekfslam_ctx* c, int slot) {
     DevView& v = c->v;
-    static int mode = -1, sms = 0;
+    static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("EKFSLAM_DOWNDATE");
         mode = (e && !strcmp(e, "tile")) ? 0 : 2;  // default: persistent warp-specialised kernel
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     }
+    const int sms = c->sm_count;   // of the context's own device (a process may drive several GPUs)
     const int nt = (v.nmax + TM - 1) / TM;
     const int T = nt * (nt + 1) / 2;
     KScope ks(c, slot);

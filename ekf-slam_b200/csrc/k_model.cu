@@ -80,7 +80,16 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
         const double sn = sin(om * dt / 2.0), cs = cos(om * dt / 2.0);
         const double w[3] = {wx, wy, wz};
         double dq[4][3];
+        // The reference divides by |omega| (mc/dqomegadt_by_domega.m:33,37-48) and only avoids 0/0 because it seeds
+        // omega with 1e-15 (mc/initialize_x_and_p.m:6).  An EXACTLY zero angular velocity (caller-supplied state) gets
+        // the analytic limit instead of NaNs: dq0/domega = 0, dq_i/domega_i = dt/2, cross terms 0.
+        const bool om_zero = !(om > 0.0);
         for (int a = 0; a < 3; ++a) {
+            if (om_zero) {
+                dq[0][a] = 0.0;
+                for (int c2 = 0; c2 < 3; ++c2) dq[1 + a][c2] = (a == c2) ? dt / 2.0 : 0.0;
+                continue;
+            }
             dq[0][a] = (-dt / 2.0) * (w[a] / om) * sn;
             for (int c2 = 0; c2 < 3; ++c2) {
                 if (a == c2)

@@ -10,7 +10,9 @@
 // After each round thread 0 replays the reference's sequential loop over those draws:
 // "first strictly greater support wins" (:37), the adaptive hypothesis count (:40-41, from a
 // host-libm table), the n_hyp==0 break (:42) and the i>n_hyp break (:45).
+#include <cooperative_groups.h>
 #include "model.cuh"
+namespace cg = cooperative_groups;
 
 #define RANSAC_WARPS 8
 #define RANSAC_THREADS (RANSAC_WARPS * 32)
@@ -253,15 +255,180 @@ __global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Latency path (few filters, fixed hypothesis budget - BASELINE config 2: ONE filter, 256 hypotheses per frame):
+// a thread-block CLUSTER of RANSAC_CLUSTER CTAs per filter.  Every CTA builds the (identical) match / draw lists, the
+// distinct drawn features are dealt round robin to the CTAs of the cluster (8 warps each), and CTA 0 collects the
+// supports and the winner's inlier mask through distributed shared memory (cluster.map_shared_rank) - no global
+// scratch, no second launch.  Same outcome as the fixed-budget branch of k_ransac: "the earliest draw that reaches
+// the maximum support" (mc/ransac_hypotheses.m:37 with :41-45 disabled).
+// ---------------------------------------------------------------------------------------
+#define RANSAC_CLUSTER 8
+__global__ void __launch_bounds__(RANSAC_THREADS) k_ransac_fixed_cluster(DevView v, DevCam cam, ekfslam_params prm) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    extern __shared__ unsigned char smem_raw[];
+    const int b = blockIdx.x / C;
+    const int n = v.nstate[b], nf = v.nfeat[b], N = v.N, ld = v.ld;
+    const int nwords = (N + 31) / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* xs = reinterpret_cast<double*>(smem_raw);              // [ld]
+    double* zs = xs + ld;                                          // [N][2]
+    int* mlist = reinterpret_cast<int*>(zs + 2 * N);               // [N]
+    int* moff = mlist + N;                                         // [N]
+    int* mtype = moff + N;                                         // [N]
+    int* iclist = mtype + N;                                       // [N]
+    int* need = iclist + N;                                        // [N] drawn flag, then support (of the features this CTA scored)
+    int* dl = need + N;                                            // [N] distinct drawn features, feature order
+    int* own = dl + N;                                             // [N] cluster rank that scores feature i
+    unsigned* masks = reinterpret_cast<unsigned*>(own + N);        // [N][nwords] inlier mask per scored feature
+    __shared__ int s_nm, s_nic, s_nd;
+    __shared__ unsigned long long s_key;
+
+    const double* __restrict__ xp = v.xp + (size_t)b * ld;
+    const double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
+    const uint8_t* __restrict__ fl = v.flags + (size_t)b * N;
+    for (int j = tid; j < n; j += blockDim.x) xs[j] = xp[j];
+    for (int j = tid; j < N; j += blockDim.x) { need[j] = 0; own[j] = 0; }
+    if (tid == 0) { s_nd = 0; s_key = 0ull; }
+    if (warp == 0) {
+        int nm = 0, nic = 0;
+        for (int i0 = 0; i0 < nf; i0 += 32) {
+            const int i = i0 + lane;
+            const uint8_t f = (i < nf) ? fl[i] : 0;
+            const bool hz = (f & EKFSLAM_F_HAS_Z) != 0, ic = (f & EKFSLAM_F_IC) != 0;
+            const unsigned mz = __ballot_sync(0xffffffffu, hz), mi = __ballot_sync(0xffffffffu, ic);
+            const unsigned below = (1u << lane) - 1u;
+            if (hz) {
+                const int s2 = nm + __popc(mz & below);
+                mlist[s2] = i; moff[s2] = v.foff[b * N + i]; mtype[s2] = v.ftype[b * N + i];
+                zs[2 * s2] = v.z[2 * (b * N + i)]; zs[2 * s2 + 1] = v.z[2 * (b * N + i) + 1];
+            }
+            if (ic) iclist[nic + __popc(mi & below)] = i;
+            nm += __popc(mz); nic += __popc(mi);
+        }
+        if (lane == 0) { s_nm = nm; s_nic = nic; }
+    }
+    __syncthreads();
+    const int nm = s_nm, nic = s_nic;
+    const int n_loop = prm.fixed_hyp;
+    const int ndraw = min(n_loop, v.n_u);
+    const double thr = prm.std_z;
+    const double* __restrict__ ub = v.u + (size_t)b * v.n_u;
+    if (nic > 0) {
+        for (int it = tid; it < ndraw; it += blockDim.x) {
+            int r = (int)floor(ub[it] * (double)nic);
+            r = min(r, nic - 1);
+            need[iclist[r]] = 1;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int nd = 0;
+            for (int i0 = 0; i0 < nf; i0 += 32) {
+                const int i = i0 + lane;
+                const bool on = (i < nf) && need[i] != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                    const int d = nd + __popc(m & ((1u << lane) - 1u));
+                    dl[d] = i;
+                    own[i] = (d / RANSAC_WARPS) % C;
+                }
+                nd += __popc(m);
+            }
+            if (lane == 0) s_nd = nd;
+        }
+        __syncthreads();
+        const int nd = s_nd;
+        for (int d = rank * RANSAC_WARPS + warp; d < nd; d += C * RANSAC_WARPS) {
+            const int pos = dl[d];
+            const int support = score_hypothesis(v, cam, b, pos, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane);
+            if (lane == 0) need[pos] = support;
+        }
+    }
+    cluster.sync();                                                // every CTA's supports / masks are in its shared memory
+    if (rank == 0) {
+        int best = 0;
+        if (nic > 0) {
+            const int nd = s_nd;
+            for (int d = tid; d < nd; d += blockDim.x) {
+                const int pos = dl[d], o = own[pos];
+                if (o != 0) need[pos] = cluster.map_shared_rank(need, o)[pos];
+            }
+            __syncthreads();
+            unsigned long long key = 0ull;
+            for (int it = tid; it < ndraw; it += blockDim.x) {
+                int r = (int)floor(ub[it] * (double)nic);
+                r = min(r, nic - 1);
+                const unsigned long long kq = ((unsigned long long)(unsigned)need[iclist[r]] << 32) | (unsigned long long)(0xffffffffu - (unsigned)it);
+                key = kq > key ? kq : key;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other > key ? other : key;
+            }
+            if (lane == 0) atomicMax(&s_key, key);
+            __syncthreads();
+            best = (int)(s_key >> 32);
+            if (best > 0) {
+                const int bestit = (int)(0xffffffffu - (unsigned)(s_key & 0xffffffffull));
+                int r = (int)floor(ub[bestit] * (double)nic);
+                r = min(r, nic - 1);
+                const int bp = iclist[r];
+                const unsigned* bm = cluster.map_shared_rank(masks, own[bp]) + bp * nwords;
+                // mc/set_as_most_supported_hypothesis.m:6-27
+                for (int j = tid; j < nm; j += blockDim.x) {
+                    const int i = mlist[j];
+                    const bool inl = (bm[j >> 5] >> (j & 31)) & 1u;
+                    uint8_t f = v.flags[(size_t)b * N + i];
+                    f = inl ? (f | EKFSLAM_F_LI) : (f & ~EKFSLAM_F_LI);
+                    v.flags[(size_t)b * N + i] = f;
+                }
+            }
+        }
+        if (tid == 0) {
+            ekfslam_stats& st = v.stats[b];
+            st.n_ic = nic; st.ransac_iters = nic > 0 ? ndraw : 0; st.ransac_scored = nic > 0 ? s_nd : 0; st.max_support = best;
+            st.status = (nic > 0 && n_loop > v.n_u) ? 1 : 0; st.n_li = 0; st.n_hi = 0; st.reserved = 0;
+        }
+    }
+    cluster.sync();                                                // remote shared memory stays valid until CTA 0 is done
+}
+
 static size_t ransac_smem_bytes(const DevView& v) {
     const int nwords = (v.N + 31) / 32;
     return sizeof(double) * (v.ld + 2 * v.N) + sizeof(int) * (6 * v.N) +
            sizeof(unsigned) * ((RANSAC_WARPS + 1) * nwords + v.N * nwords) + 16;
 }
 
+static size_t ransac_cluster_smem_bytes(const DevView& v) {
+    const int nwords = (v.N + 31) / 32;
+    return sizeof(double) * (v.ld + 2 * v.N) + sizeof(int) * (7 * v.N) + sizeof(unsigned) * (v.N * nwords) + 16;
+}
+
 void launch_ransac(ekfslam_ctx* c) {
+    static int use_cluster = -1;
+    if (use_cluster < 0) { const char* e = getenv("EKFSLAM_RANSAC_CLUSTER"); use_cluster = (e && e[0] == '0') ? 0 : 1; }
+    KScope ks(c, KT_RANSAC);
+    // few filters + fixed hypothesis budget (the latency path): one cluster of CTAs per filter
+    if (use_cluster && c->prm.fixed_hyp > 0 && (long long)c->v.B * RANSAC_CLUSTER <= 2LL * c->sm_count) {
+        const size_t sm = ransac_cluster_smem_bytes(c->v);
+        ENSURE_DYN_SMEM(k_ransac_fixed_cluster, sm, c->device);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(c->v.B * RANSAC_CLUSTER));
+        cfg.blockDim = dim3(RANSAC_THREADS);
+        cfg.dynamicSmemBytes = sm;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = RANSAC_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_ransac_fixed_cluster, c->v, c->cam, c->prm);
+        return;
+    }
     const size_t sm = ransac_smem_bytes(c->v);
     ENSURE_DYN_SMEM(k_ransac, sm, c->device);
-    KScope ks(c, KT_RANSAC);
     k_ransac<<<c->v.B, RANSAC_THREADS, sm, c->stream>>>(c->v, c->cam, c->prm);
 }

@@ -202,6 +202,17 @@ int ekfslam_update_iterated(ekfslam_ctx* ctx, int mask, int which_prior, int n_i
  * ransac, update_li, rescue, update_hi */
 int ekfslam_step(ekfslam_ctx* ctx, int reset, int match_mode);
 
+/* ekfslam_step replayed from a captured CUDA graph (latency path: a single filter's step is ~25 small launches).
+ * The graph is captured on first use and re-captured whenever anything the kernels see changes (buffers, parameters,
+ * camera, reset / match_mode).  Falls back to ekfslam_step where capture is not possible (per-kernel timing enabled,
+ * few filters with N_max >= 128: the lock-step Cholesky reads a size back to the host).  Stage frames with
+ * ekfslam_upload_candidates / ekfslam_upload_uniforms or ekfslam_stage_frame (NOT ekfslam_bind_frame, which changes
+ * the buffer addresses and forces a re-capture). */
+int ekfslam_step_graph(ekfslam_ctx* ctx, int reset, int match_mode);
+/* copy a device-resident frame (zc [B][N_max][2], staged flag bytes [B][N_max], uniforms [B][n_u]) into the
+ * context's own frame buffers, stream-ordered */
+int ekfslam_stage_frame(ekfslam_ctx* ctx, const void* d_zc, const void* d_fl, const void* d_u, int n_u);
+
 /* the same step fed from HOST buffers (the drop-in call a per-frame driver makes):
  * copies this frame's pixels zc [B][N_max][2] and flag bytes fl [B][N_max] (match_mode 1:
  * candidates, EKFSLAM_F_CAND bit; match_mode 2: explicit matches, HAS_Z|IC bits) and the

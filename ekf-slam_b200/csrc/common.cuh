@@ -174,6 +174,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags = 0);
 void launch_pending_rows(ekfslam_ctx* c, int need, int forbid, int from_gate = 0);   // from_gate: V rows were left in the Li scratch by launch_rescue_gate(c, 1)
 void launch_rescue_gate(ekfslam_ctx* c, int keep_v = 0);  // rescue gate against a pending update, from 13x13 gathers (no candidate G rows)  // G rows of the selected features against the pending update
 void launch_downdate(ekfslam_ctx* c, int slot);
+void launch_chol_blocked64(ekfslam_ctx* c, int kact);   // k_chol_big.cu: S = L L', X = inv(L) for few filters with large k
 void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv);
 void launch_id2cart(ekfslam_ctx* c, double threshold, int force_index, int32_t* d_conv);
 void launch_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* d_del);

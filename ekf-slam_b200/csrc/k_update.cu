@@ -575,252 +575,10 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Batched lock-step factorisation (large batches).  The single-block kernel above leaves most threads
-// waiting at block barriers while one warp factors a 16x16 diagonal block (clock64 profile: ~570 k cycles
-// per filter at k = 98, dominated by serial phases).  Here every phase is its own kernel over ALL filters,
-// with the thread count that phase can use: diagonal block = one warp per filter, panel = one thread per
-// row, trailing update = 32x32 tiles, inverse = one thread per column.  Filters whose k is smaller than the
-// current panel offset simply exit.  Same arithmetic as k_chol (right-looking, NB = 16, rsqrt pivots).
+// Few filters with a large stacked innovation (large maps): the factorisation S = L L' and X = inv(L) run as the
+// 64-wide blocked DMMA path of k_chol_big.cu (launch_chol_blocked64); the kernels below finish the job with
+// y = X nu and inv(S) nu = X' y, spread over the whole GPU.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_mk_diag(DevView v, int j0) {
-    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (b >= v.B) return;
-    const int k = 2 * v.ksel[b];
-    if (j0 >= k) return;
-    const int kmax = v.kmax, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nb = min(NB, k - j0);
-    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
-    double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
-    __shared__ double Dsh[4][NB][NB + 1];
-    const unsigned full_mask = 0xffffffffu;
-    const int i = lane & (NB - 1);
-    double a[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) a[c] = (i < nb && c <= i) ? S[(size_t)(j0 + i) * kmax + j0 + c] : ((i >= nb && c == i) ? 1.0 : 0.0);
-    bool bad = false;
-    double rdiag[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        const double piv = __shfl_sync(full_mask, a[c], c);
-        bad = bad || !(piv > 0.0);
-        const double rs = rsqrt(piv);
-        rdiag[c] = rs;
-        const double lic = (i == c) ? piv * rs : a[c] * rs;
-        a[c] = lic;
-#pragma unroll
-        for (int j = c + 1; j < NB; ++j) {
-            const double ljc = __shfl_sync(full_mask, lic, j);
-            a[j] -= lic * ljc;
-        }
-    }
-    if (bad && lane == 0) atomicOr(&v.stats[b].status, 2);
-    if (lane < NB) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) Dsh[w][i][c] = (c <= i) ? a[c] : 0.0;
-    }
-    __syncwarp();
-    const int c = i;
-    double x[NB];
-#pragma unroll
-    for (int ii = 0; ii < NB; ++ii) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int t = 0; t < ii; ++t) sacc += Dsh[w][ii][t] * x[t];
-        x[ii] = (ii == c) ? rdiag[ii] : ((ii > c) ? -sacc * rdiag[ii] : 0.0);
-    }
-    if (lane < nb) {
-#pragma unroll
-        for (int cc = 0; cc < NB; ++cc)
-            if (cc <= i) S[(size_t)(j0 + i) * kmax + j0 + cc] = a[cc];          // L_jj (row i)
-#pragma unroll
-        for (int ii = 0; ii < NB; ++ii)
-            if (ii < nb && ii >= c) X[(size_t)(j0 + ii) * kmax + j0 + c] = x[ii];  // inv(L_jj) (column c)
-    }
-}
-
-// panel rows i in [j0+nb, k): L[i][j0+c] = sum_{t<=c} S[i][j0+t] * Dinv[c][t].  grid = (row chunks of 128, B)
-__global__ void __launch_bounds__(128) k_mk_panel(DevView v, int j0) {
-    const int b = blockIdx.y;
-    const int k = 2 * v.ksel[b];
-    if (j0 >= k) return;
-    const int nb = min(NB, k - j0);
-    const int i1 = j0 + nb;
-    if (i1 + (int)(blockIdx.x * blockDim.x) >= k) return;
-    const int i = i1 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int kmax = v.kmax;
-    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
-    const double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
-    __shared__ double Di[NB][NB + 1];
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-        const int r = e / NB, cc = e - r * NB;
-        Di[r][cc] = (r < nb && cc <= r) ? X[(size_t)(j0 + r) * kmax + j0 + cc] : 0.0;
-    }
-    __syncthreads();
-    if (i >= k) return;
-    double row[NB];
-#pragma unroll
-    for (int t = 0; t < NB; ++t) row[t] = (t < nb) ? S[(size_t)i * kmax + j0 + t] : 0.0;
-#pragma unroll
-    for (int cc = 0; cc < NB; ++cc) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int t = 0; t <= cc; ++t) sacc += row[t] * Di[cc][t];
-        if (cc < nb) S[(size_t)i * kmax + j0 + cc] = sacc;
-    }
-}
-
-// trailing update S[i][c] -= sum_t L[i][j0+t] L[c][j0+t] on 32x32 tiles of the lower triangle behind the panel.
-// grid = (tile index, B), 64 threads, 4x4 per thread.
-__global__ void __launch_bounds__(64) k_mk_trail(DevView v, int j0) {
-    const int b = blockIdx.y;
-    const int k = 2 * v.ksel[b];
-    if (j0 >= k) return;
-    const int nb = min(NB, k - j0);
-    const int i1 = j0 + nb;
-    const int m = k - i1;
-    if (m <= 0) return;
-    const int e = blockIdx.x;
-    int ti = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
-    while (ti * (ti + 1) / 2 > e) --ti;
-    const int tj = e - ti * (ti + 1) / 2;
-    if (ti * 32 >= m) return;
-    const int kmax = v.kmax;
-    double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
-    __shared__ double Pa[32][NB + 1], Pb[32][NB + 1];
-    for (int q = threadIdx.x; q < 32 * NB; q += blockDim.x) {
-        const int r = q / NB, t = q - r * NB;
-        const int ia = ti * 32 + r, ib = tj * 32 + r;
-        Pa[r][t] = (ia < m && t < nb) ? S[(size_t)(i1 + ia) * kmax + j0 + t] : 0.0;
-        Pb[r][t] = (ib < m && t < nb) ? S[(size_t)(i1 + ib) * kmax + j0 + t] : 0.0;
-    }
-    __syncthreads();
-    const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) acc[a][cc] = 0.0;
-#pragma unroll
-    for (int t = 0; t < NB; ++t) {
-        double ra[4], rc[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { ra[a] = Pa[ty * 4 + a][t]; rc[a] = Pb[tx * 4 + a][t]; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) acc[a][cc] += ra[a] * rc[cc];
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int ia = ti * 32 + ty * 4 + a, ic = tj * 32 + tx * 4 + cc;
-            if (ia < m && ic <= ia) S[(size_t)(i1 + ia) * kmax + i1 + ic] -= acc[a][cc];
-        }
-}
-
-// block row I0 of X = inv(L):  X[I0+r][c] = -sum_j Dinv_I[r][j] * sum_{t=c}^{I0-1} L[I0+j][t] X[t][c].
-// grid = (column chunks of 128, B); the 16 x I0 row panel of L is staged in shared memory.
-__global__ void __launch_bounds__(128) k_mk_linv(DevView v, int I0) {
-    extern __shared__ double sm[];
-    const int b = blockIdx.y;
-    const int k = 2 * v.ksel[b];
-    if (I0 >= k || (int)(blockIdx.x * blockDim.x) >= I0) return;
-    const int nb = min(NB, k - I0);
-    const int kmax = v.kmax;
-    const double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
-    double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
-    double* Pn = sm;                          // [I0][NB+1]  Pn[t][r] = L[I0+r][t]
-    double* Di = sm + (size_t)I0 * (NB + 1);  // [NB][NB+1]
-    for (int e = threadIdx.x; e < NB * I0; e += blockDim.x) {
-        const int r = e / I0, t = e - r * I0;
-        Pn[t * (NB + 1) + r] = (r < nb) ? S[(size_t)(I0 + r) * kmax + t] : 0.0;
-    }
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-        const int r = e / NB, cc = e - r * NB;
-        Di[r * (NB + 1) + cc] = (r < nb && cc <= r) ? X[(size_t)(I0 + r) * kmax + I0 + cc] : 0.0;
-    }
-    __syncthreads();
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= I0) return;
-    double y[NB];
-#pragma unroll
-    for (int r = 0; r < NB; ++r) y[r] = 0.0;
-    for (int t = c; t < I0; ++t) {
-        const double xv = X[(size_t)t * kmax + c];
-#pragma unroll
-        for (int r = 0; r < NB; ++r) y[r] += Pn[t * (NB + 1) + r] * xv;
-    }
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int j = 0; j <= r; ++j) sacc += Di[r * (NB + 1) + j] * y[j];
-        if (r < nb) X[(size_t)(I0 + r) * kmax + c] = -sacc;
-    }
-}
-
-// X = inv(L) by block COLUMNS: column J of X solves L X_J = E_J by forward substitution, independently of every
-// other column:  X_JJ = Dinv_J,  X_IJ = -Dinv_I * sum_{J<=K<I} L_IK X_KJ.  One launch, grid = (block columns, B),
-// instead of one launch per block row (k_mk_linv: 62 dependent launches per update at N = 500, each a long serial
-// loop per thread - 10 of the 12.6 ms of a large-map step).  The CTA keeps its block column (k x 16) in shared
-// memory and streams the rows of L in chunks of INVC_CH columns; thread (r, c) owns entry (r, c) of the 16 x 16 block.
-#define INVC_CH 128
-__global__ void __launch_bounds__(256) k_mk_invcols(DevView v) {
-    extern __shared__ double sm[];
-    const int b = blockIdx.y;
-    const int k = 2 * v.ksel[b];
-    const int j0 = blockIdx.x * NB;
-    if (j0 >= k) return;
-    const int kmax = v.kmax;
-    const double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
-    double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
-    double* Xc = sm;                                        // [kmax][NB+1]  rows j0.. of block column J
-    double* Lc = Xc + (size_t)kmax * (NB + 1);              // [NB][INVC_CH+1]
-    double* Di = Lc + NB * (INVC_CH + 1);                   // [NB][NB+1]
-    double* Ys = Di + NB * (NB + 1);                        // [NB][NB+1]
-    const int tid = threadIdx.x, r = tid >> 4, c = tid & 15;
-    {
-        const int nbj = min(NB, k - j0);
-        Xc[r * (NB + 1) + c] = (r < nbj && c <= r && c < nbj) ? X[(size_t)(j0 + r) * kmax + j0 + c] : 0.0;
-    }
-    __syncthreads();
-    for (int i0 = j0 + NB; i0 < k; i0 += NB) {
-        const int nb = min(NB, k - i0);
-        Di[r * (NB + 1) + c] = (r < nb && c <= r) ? X[(size_t)(i0 + r) * kmax + i0 + c] : 0.0;
-        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-        for (int t0 = j0; t0 < i0; t0 += INVC_CH) {
-            const int len = min(INVC_CH, i0 - t0);
-            for (int e = tid; e < NB * INVC_CH; e += blockDim.x) {
-                const int rr = e / INVC_CH, tt = e - rr * INVC_CH;
-                Lc[rr * (INVC_CH + 1) + tt] = (rr < nb && tt < len) ? S[(size_t)(i0 + rr) * kmax + t0 + tt] : 0.0;
-            }
-            __syncthreads();
-            const double* lr = Lc + r * (INVC_CH + 1);
-            const double* xc = Xc + (size_t)(t0 - j0) * (NB + 1) + c;
-            const int len4 = (len + 3) & ~3;   // len is a multiple of 16 except possibly... rows of Xc beyond are zero-initialised below
-            for (int tt = 0; tt < len4; tt += 4) {
-                y0 += lr[tt] * xc[(size_t)tt * (NB + 1)];
-                y1 += lr[tt + 1] * xc[(size_t)(tt + 1) * (NB + 1)];
-                y2 += lr[tt + 2] * xc[(size_t)(tt + 2) * (NB + 1)];
-                y3 += lr[tt + 3] * xc[(size_t)(tt + 3) * (NB + 1)];
-            }
-            __syncthreads();
-        }
-        Ys[r * (NB + 1) + c] = (y0 + y1) + (y2 + y3);
-        __syncthreads();
-        double sacc = 0.0;
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-            if (j <= r) sacc += Di[r * (NB + 1) + j] * Ys[j * (NB + 1) + c];
-        const double xv = (r < nb) ? -sacc : 0.0;
-        Xc[(size_t)(i0 - j0 + r) * (NB + 1) + c] = xv;
-        if (r < nb && j0 + c < k) X[(size_t)(i0 + r) * kmax + j0 + c] = xv;
-        __syncthreads();
-    }
-}
-
 // y = X nu (one warp per row) and the explicit zeros k_gemm needs above the diagonal of X: k_gemm streams the rows of
 // a 64-row tile up to the tile's last column, so only columns r < c < 64 (r / 64 + 1) are ever read.
 // grid = (row chunks of 8, B); the result goes to cv as scratch (yv still holds nu for the other blocks).
@@ -841,40 +599,49 @@ __global__ void __launch_bounds__(256) k_mk_y(DevView v) {
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) v.cv[(size_t)b * kmax + a] = s;
 }
-// cv = X' y = inv(S) nu, one thread per column (rows a >= t, coalesced across the threads); y is read from the cv
-// scratch of k_mk_y into shared memory first and also stored to yv.  grid = (column chunks of 128, B).
-__global__ void __launch_bounds__(128) k_mk_cv(DevView v, double* __restrict__ out) {
-    extern __shared__ double ysh[];   // [k]
-    const int b = blockIdx.y;
+// cv = X' y = inv(S) nu.  Column t needs sum_{a >= t} X[a][t] y[a]: one thread per column (coalesced across the
+// threads), the row range split in chunks of CV_ROWS over grid.y (one CTA per column chunk was 0.2 ms of serial loop
+// per update at k = 1000).  y is read from the cv scratch of k_mk_y; partial sums go to out[chunk][kmax] and are added
+// up in a fixed order by k_mk_fin.  grid = (column chunks of 128, row chunks, B).
+#define CV_ROWS 64
+__global__ void __launch_bounds__(128) k_mk_cv(DevView v, double* __restrict__ out, long long out_stride) {
+    __shared__ double ysh[CV_ROWS];
+    const int b = blockIdx.z;
     const int k = 2 * v.ksel[b];
-    if (k == 0 || (int)(blockIdx.x * blockDim.x) >= k) return;
+    const int a0 = blockIdx.y * CV_ROWS;
+    const int t0 = blockIdx.x * blockDim.x;
+    if (k == 0 || t0 >= k || a0 >= k) return;
     const int kmax = v.kmax;
     const double* __restrict__ X = v.Li + (size_t)b * kmax * kmax;
     const double* __restrict__ y = v.cv + (size_t)b * kmax;
-    for (int a = threadIdx.x; a < k; a += blockDim.x) ysh[a] = y[a];
+    const int a1 = min(k, a0 + CV_ROWS);
+    for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) ysh[a - a0] = y[a];
     __syncthreads();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = t0 + threadIdx.x;
     if (t >= k) return;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int a = t;
-    for (; a + 3 < k; a += 4) {
-        s0 += X[(size_t)a * kmax + t] * ysh[a];
-        s1 += X[(size_t)(a + 1) * kmax + t] * ysh[a + 1];
-        s2 += X[(size_t)(a + 2) * kmax + t] * ysh[a + 2];
-        s3 += X[(size_t)(a + 3) * kmax + t] * ysh[a + 3];
+    int a = max(a0, t);
+    for (; a + 3 < a1; a += 4) {
+        s0 += X[(size_t)a * kmax + t] * ysh[a - a0];
+        s1 += X[(size_t)(a + 1) * kmax + t] * ysh[a + 1 - a0];
+        s2 += X[(size_t)(a + 2) * kmax + t] * ysh[a + 2 - a0];
+        s3 += X[(size_t)(a + 3) * kmax + t] * ysh[a + 3 - a0];
     }
-    for (; a < k; ++a) s0 += X[(size_t)a * kmax + t] * ysh[a];
-    out[(size_t)b * kmax + t] = (s0 + s1) + (s2 + s3);
+    for (; a < a1; ++a) s0 += X[(size_t)a * kmax + t] * ysh[a - a0];
+    out[(size_t)b * out_stride + (size_t)blockIdx.y * kmax + t] = (s0 + s1) + (s2 + s3);
 }
-// yv <- y, cv <- inv(S) nu (both were staged: y in cv, inv(S) nu in the tail of the Sb row scratch)
-__global__ void k_mk_fin(DevView v, const double* __restrict__ tmp) {
+// yv <- y, cv <- inv(S) nu = sum over the row chunks of k_mk_cv (chunks below column t's own chunk hold nothing)
+__global__ void k_mk_fin(DevView v, const double* __restrict__ tmp, long long tmp_stride) {
     const int b = blockIdx.y;
     const int k = 2 * v.ksel[b];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= k) return;
     const size_t o = (size_t)b * v.kmax + t;
-    v.yv[o] = v.cv[o];
-    v.cv[o] = tmp[o];
+    const double yt = v.cv[o];
+    double sacc = 0.0;
+    for (int ch = t / CV_ROWS; ch * CV_ROWS < k; ++ch) sacc += tmp[(size_t)b * tmp_stride + (size_t)ch * v.kmax + t];
+    v.yv[o] = yt;
+    v.cv[o] = sacc;
 }
 
 static void launch_chol_lockstep(ekfslam_ctx* c) {
@@ -882,50 +649,22 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
     cudaStream_t st = c->stream;
     const int kmax = v.kmax;
     // the launch loops only need to cover the largest stacked update of the batch: read it back (one small
-    // synchronous copy; this path is for few filters with large maps, where ~100 empty launches cost more)
+    // synchronous copy; this path is for few filters with large maps, where empty launches cost more)
     cudaMemcpyAsync(c->kmax_host, v.kmaxdev, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     const int kact = min(v.kmax, max(0, (int)*c->kmax_host));
     KScope ks(c, KT_CHOL);  // timed as one stage; every launch is counted
-    for (int j0 = 0; j0 < kact; j0 += NB) {
-        k_mk_diag<<<(v.B + 3) / 4, 128, 0, st>>>(v, j0);
-        c->launches += 1;
-        const int rows = kact - j0 - 1;
-        if (rows > 0) {
-            c->launches += 2;
-            dim3 gp((rows + 127) / 128, v.B);
-            k_mk_panel<<<gp, 128, 0, st>>>(v, j0);
-            const int mt = (rows + 31) / 32;
-            dim3 gt(mt * (mt + 1) / 2, v.B);
-            k_mk_trail<<<gt, 64, 0, st>>>(v, j0);
-        }
-    }
-    const size_t linv_max = sizeof(double) * ((size_t)kmax * (NB + 1) + NB * (NB + 1));
-    // inverse: one launch over block columns when the column fits shared memory, else block row by block row
-    const size_t invc_sm = sizeof(double) * ((size_t)kmax * (NB + 1) + NB * (INVC_CH + 1) + 2 * NB * (NB + 1));
-    if (invc_sm <= 200 * 1024) {
-        ENSURE_DYN_SMEM(k_mk_invcols, invc_sm, c->device);
-        dim3 gi((kact + NB - 1) / NB, v.B);
-        if (gi.x == 0) gi.x = 1;
-        k_mk_invcols<<<gi, 256, invc_sm, st>>>(v);
-        c->launches += 1;
-    } else {
-        ENSURE_DYN_SMEM(k_mk_linv, linv_max, c->device);
-        for (int I0 = NB; I0 < kmax; I0 += NB) {
-            dim3 gl((I0 + 127) / 128, v.B);
-            k_mk_linv<<<gl, 128, sizeof(double) * ((size_t)I0 * (NB + 1) + NB * (NB + 1)), st>>>(v, I0);
-            c->launches += 1;
-        }
-    }
-    // y = X nu, cv = X' y: rows / columns spread over the whole GPU (was one block per filter: 0.3 ms per update at cfg4)
+    launch_chol_blocked64(c, kact);   // 64-wide panels, panel / trailing / triangular-inverse products on the tensor pipe
     if (kact > 0) {
-        double* tmp = v.Sb;  // [B][kmax] scratch: the factor L in Sb is dead once inv(L) exists (W may hold pending rows)
-        dim3 gy((kact + 7) / 8, v.B), gc((kact + 127) / 128, v.B);
+        // scratch [row chunks][kmax] per filter at the head of its Sb block: the factor L (and the parked T blocks of the
+        // blocked inverse) are dead once inv(L) exists (W may hold pending rows, G the H P rows)
+        double* tmp = v.Sb;
+        const long long tstride = (long long)kmax * kmax;
+        const int nch = (kact + CV_ROWS - 1) / CV_ROWS;
+        dim3 gy((kact + 7) / 8, v.B), gc((kact + 127) / 128, nch, v.B), gf((kact + 127) / 128, v.B);
         k_mk_y<<<gy, 256, 0, st>>>(v);
-        const size_t cv_sm = sizeof(double) * (size_t)kact;
-        ENSURE_DYN_SMEM(k_mk_cv, cv_sm, c->device);
-        k_mk_cv<<<gc, 128, cv_sm, st>>>(v, tmp);
-        k_mk_fin<<<gc, 128, 0, st>>>(v, tmp);
+        k_mk_cv<<<gc, 128, 0, st>>>(v, tmp, tstride);
+        k_mk_fin<<<gf, 128, 0, st>>>(v, tmp, tstride);
         c->launches += 2;
     }
 }

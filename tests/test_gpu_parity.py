@@ -213,3 +213,11 @@ def test_n100_many_inliers_large_k(ekf):
     global-memory kernel (k_chol) instead of the shared-memory resident one, and the W GEMM spans three row tiles."""
     worst, tot = _run_sequence(ekf, B=2, N=100, frames=3, seed=820, p_outlier=0.0, noise_px=0.15)
     assert tot["li"] > 2 * 3 * 72, tot
+
+
+def test_blocked64_cholesky_ragged_k(ekf):
+    """Few filters with N_max >= 128 take the 64-wide blocked DMMA factorisation (k_chol_big.cu): three filters with
+    different map sizes, so the stacked innovation sizes differ per filter and are not multiples of 64."""
+    nf = [140, 97, 33]
+    worst, tot = _run_sequence(ekf, B=3, N=140, frames=3, seed=850, nfeat=nf, p_outlier=0.1)
+    assert tot["li"] > 300, tot

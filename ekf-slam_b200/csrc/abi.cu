@@ -97,7 +97,7 @@ static void kt_collect(ekfslam_ctx* c) {
 
 static const char* KT_NAMES[KT_COUNT] = {"k_begin_frame", "k_predict", "k_features", "k_hp", "k_innov", "k_ransac",
                                          "k_upd_S", "k_chol", "k_w", "k_downdate_hi", "k_downdate", "k_symmetrize",
-                                         "k_add_features", "k_wfix", "k_v", "k_g2", "k_w_hi", "k_chol_hi", "k_upd_S_hi",
+                                         "k_add_features", "k_wfix", "k_w_hi", "k_chol_hi", "k_upd_S_hi",
                                          "k_hp_rescue", "k_world"};
 
 template <typename T>
@@ -266,15 +266,8 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (c->sm_count <= 0) c->sm_count = 148;
     {
-        // EKFSLAM_FUSE=1: one covariance pass per frame (deferred li downdate, see ekfslam_step).  Off by
-        // default: at N=100 the rescue-row correction GEMM costs as much as the saved pass.
-        const char* e = getenv("EKFSLAM_FUSE");
-        c->fuse_downdates = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
         const char* e2 = getenv("EKFSLAM_RESCUE_GATHER");
         c->rescue_gather = (e2 && e2[0] == '0') ? 0 : 1;   // default on: gate 0.36 + rows of the hi inliers 0.61 ms vs 1.15 ms
-        const char* e3 = getenv("EKFSLAM_TRI");
-        c->tri = (e3 && e3[0] == '1') ? 1 : 0;   // opt-in: k_hp_tri is still slower than the full-row k_hp
-        c->upper_valid = 1;
     }
     *out = c;
     return EKFSLAM_OK;
@@ -456,7 +449,6 @@ int ekfslam_download_state(ekfslam_ctx* c, int b0, int nb, int which, double* x,
                              cudaMemcpyDeviceToHost, c->stream));
     }
     if (P) {
-        ensure_upper(c);
         const double* src = v.P + (size_t)b0 * v.nmax * v.ld;
         CK(cudaMemcpy2DAsync(P, sizeof(double) * v.nmax, src, sizeof(double) * v.ld, sizeof(double) * v.nmax,
                              (size_t)nb * v.nmax, cudaMemcpyDeviceToHost, c->stream));
@@ -732,34 +724,15 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
     if (c->wait_inputs) { cudaStreamWaitEvent(c->stream, c->ev_in, 0); c->wait_inputs = 0; }
     if (match_mode) launch_innov(c, match_mode);
     launch_ransac(c);
-    if (c->fuse_downdates == 2) {
-        // as below, but the rescue gate works from 13x13 gathers of P and of the pending rows (k_rescue_gate), so
-        // full rows H p_k_k are only produced for the candidates that passed (the hi inliers)
-        launch_update(c, EKFSLAM_F_LI, 1, 4);
-        launch_features(c, 0, 3);
-        launch_rescue_gate(c, 1);
-        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, 1);
-        launch_pending_rows(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, 1);
-        launch_update(c, EKFSLAM_F_HI, 0);
-    } else if (c->fuse_downdates) {
-        // one pass over P per frame: the li update is computed (x_k_k, W_li) but its covariance downdate is
-        // deferred; the rescue stage works on the implied p_k_k = Jn (P - W_li' W_li) Jn' through
-        // G = H P - (H W_li') W_li; the hi update stacks its W below and a single downdate applies both.
-        launch_update(c, EKFSLAM_F_LI, 1, 4);
-        launch_features(c, 0, 3);
-        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI, 1);
-        launch_pending_rows(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);
-        launch_innov(c, 3);
-        launch_update(c, EKFSLAM_F_HI, 0);
-    } else {
+    {
         launch_update(c, EKFSLAM_F_LI, 1);
         launch_features(c, 0, 3);
         if (c->rescue_gather) {
             // chi2 gate from 13x13 gathers of p_k_k (no pending update here), then G rows only for the hi inliers
             launch_rescue_gate(c);
-            launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, 0, KT_HP_RESCUE);
+            launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, KT_HP_RESCUE);
         } else {
-            launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI, 0, KT_HP_RESCUE);
+            launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI, KT_HP_RESCUE);
             launch_innov(c, 3);
         }
         launch_update(c, EKFSLAM_F_HI, 0);
@@ -772,7 +745,7 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
 struct StepGraph {
     cudaGraphExec_t exec;
     DevView v; ekfslam_params prm; DevCam cam;
-    int reset, match_mode, fuse, rescue_gather;
+    int reset, match_mode, rescue_gather;
     int64_t launches;
 };
 
@@ -787,13 +760,13 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
     // not capturable: per-kernel timing (event queries), the lock-step Cholesky (host read-back of the largest stacked
     // size), the host-buffer step's cross-stream events, the lower-triangle mode's host-side state
     const bool lockstep_shape = v.B < 128 && v.kmax >= 256;
-    if (c->timer || lockstep_shape || c->tri || c->wait_inputs || c->arm_out) return ekfslam_step(c, reset, match_mode);
+    if (c->timer || lockstep_shape || c->wait_inputs || c->arm_out) return ekfslam_step(c, reset, match_mode);
     if (match_mode < 0 || match_mode > 2) return fail(EKFSLAM_ERR_INVALID, "match_mode must be 0, 1 or 2");
     if (v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "step: no uniform stream uploaded");
     StepGraph* g = (StepGraph*)c->step_graph;
     if (g && (memcmp(&g->v, &v, sizeof(DevView)) || memcmp(&g->prm, &c->prm, sizeof(ekfslam_params)) ||
               memcmp(&g->cam, &c->cam, sizeof(DevCam)) || g->reset != reset || g->match_mode != match_mode ||
-              g->fuse != c->fuse_downdates || g->rescue_gather != c->rescue_gather)) {
+              g->rescue_gather != c->rescue_gather)) {
         step_graph_destroy(c);
         g = nullptr;
     }
@@ -802,7 +775,7 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
         if (!g) return fail(EKFSLAM_ERR_NOMEM, "host allocation failed");
         memset(g, 0, sizeof(*g));
         memcpy(&g->v, &v, sizeof(DevView)); memcpy(&g->prm, &c->prm, sizeof(ekfslam_params)); memcpy(&g->cam, &c->cam, sizeof(DevCam));
-        g->reset = reset; g->match_mode = match_mode; g->fuse = c->fuse_downdates; g->rescue_gather = c->rescue_gather;
+        g->reset = reset; g->match_mode = match_mode; g->rescue_gather = c->rescue_gather;
         const int64_t l0 = c->launches;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
@@ -928,7 +901,6 @@ int ekfslam_add_features(ekfslam_ctx* c, int b0, int nb, const double* uvd, cons
     uint8_t* d_add = (uint8_t*)(d_uvd + 2 * (size_t)nb);
     CK(cudaMemcpyAsync(d_uvd, uvd, sizeof(double) * 2 * nb, cudaMemcpyHostToDevice, c->stream));
     if (add) CK(cudaMemcpyAsync(d_add, add, nb, cudaMemcpyHostToDevice, c->stream));
-    ensure_upper(c);
     launch_add_features(c, b0, nb, d_uvd, 2, add ? d_add : nullptr, nullptr, 0, nullptr, 0, std_pxl, initial_rho, std_rho);
     LAUNCHED();
     CK(cudaStreamSynchronize(c->stream));
@@ -950,7 +922,6 @@ int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* c, double threshold, int force
     if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "inversedepth_2_cartesian supports n_max <= 4096");
     if (force_index >= v.N) return fail(EKFSLAM_ERR_INVALID, "force_index out of range");
     if (int r = ensure_scratch(c, sizeof(int32_t) * (size_t)v.B)) return r;
-    ensure_upper(c);
     launch_id2cart(c, threshold, force_index, (int32_t*)c->pin);
     LAUNCHED();
     if (converted) CK(cudaMemcpyAsync(converted, c->pin, sizeof(int32_t) * v.B, cudaMemcpyDeviceToHost, c->stream));
@@ -967,7 +938,6 @@ int ekfslam_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* del) 
     if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "delete_features supports n_max <= 4096");
     if (int r = ensure_scratch(c, (size_t)nb * v.N)) return r;
     CK(cudaMemcpyAsync(c->pin, del, (size_t)nb * v.N, cudaMemcpyHostToDevice, c->stream));
-    ensure_upper(c);
     launch_delete_features(c, b0, nb, (const uint8_t*)c->pin);
     LAUNCHED();
     CK(cudaStreamSynchronize(c->stream));
@@ -1055,7 +1025,6 @@ int ekfslam_map_management(ekfslam_ctx* c, int min_number_of_features_in_image) 
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (!c->det_uv) return fail(EKFSLAM_ERR_STATE, "map_management: no detection list (ekfslam_upload_detections / ekfslam_world_detect)");
     if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "map_management supports n_max <= 4096");
-    ensure_upper(c);
     launch_mm_plan(c, min_number_of_features_in_image);           // deletion list, measured, quota     (:7-14, :27-35)
     launch_delete_features(c, 0, v.B, c->mm_del);                  // delete_a_feature.m                 (:7)
     launch_begin_frame(c);                                         // update_features_info.m             (:17)
@@ -1134,7 +1103,6 @@ int ekfslam_world_detect(ekfslam_ctx* c, int t, int K) {
 void* ekfslam_device_ptr(ekfslam_ctx* c, const char* name) {
     if (!c || !name) return nullptr;
     DevView& v = c->v;
-    if (!strcmp(name, "P")) { cudaSetDevice(c->device); ensure_upper(c); }
     struct { const char* n; void* p; } tab[] = {
         {"x", v.x}, {"xp", v.xp}, {"P", v.P}, {"G", v.G}, {"W", v.W}, {"h", v.h}, {"Hc", v.Hc}, {"S", v.S},
         {"z", v.z}, {"zc", v.zc}, {"flags", v.flags}, {"mflags", v.mflags}, {"u", v.u}, {"stats", v.stats},

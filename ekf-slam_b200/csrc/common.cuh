@@ -72,7 +72,7 @@ struct DevWorld {
 // per-kernel timing (ekfslam_enable_timing): every launch is bracketed by an event pair
 enum {
     KT_BEGIN_FRAME = 0, KT_PREDICT, KT_FEATURES, KT_HP, KT_INNOV, KT_RANSAC, KT_UPD_S, KT_CHOL, KT_W, KT_DOWNDATE_HI,
-    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_WFIX, KT_V, KT_G2, KT_W_HI, KT_CHOL_HI, KT_UPD_S_HI, KT_HP_RESCUE, KT_WORLD, KT_COUNT
+    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_WFIX, KT_W_HI, KT_CHOL_HI, KT_UPD_S_HI, KT_HP_RESCUE, KT_WORLD, KT_COUNT
 };
 struct KTimer;
 
@@ -87,14 +87,7 @@ struct ekfslam_ctx {
     int64_t bytes;
     int64_t launches;
     int stage;  // call-order tracking
-    int fuse_downdates;  // ekfslam_step: defer the li covariance downdate and apply it together with the hi one
     int rescue_gather;   // ekfslam_step: rescue gate from 13x13 gathers of P, G rows only for the hi inliers
-    // Lower-triangle-authoritative covariance (EKFSLAM_TRI=1, opt-in): the persistent downdate stores only the lower
-    // 64x64 tiles (diagonal tiles in full), every per-frame reader (k_predict, k_hp_tri, k_rescue_gate) takes
-    // P[max(r,c)][min(r,c)].  upper_valid = 0 once a downdate has skipped the mirror images; the rare full-matrix users
-    // (map management, P download) call ensure_upper() first.
-    int tri;
-    int upper_valid;
     // ekfslam_step_host overlaps its PCIe copies with the step: inputs go up on copy_stream while prediction and the
     // measurement model run (first needed by the matcher gate), x / flags / stats come down while the last covariance
     // downdate (which only touches P) is still running.
@@ -165,14 +158,12 @@ struct KScope {
 void launch_begin_frame(ekfslam_ctx* c);
 void launch_predict(ekfslam_ctx* c);
 void launch_features(ekfslam_ctx* c, int which, int parts);  // parts: 1 = h, 2 = H, 3 = both
-void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending = 0, int slot = KT_HP);  // G rows for features with (flags&need)==need && !(flags&forbid)
+void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot = KT_HP);  // G rows for features with (flags&need)==need && !(flags&forbid)
 void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gate / explicit matches / rescue gate
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
-void ensure_upper(ekfslam_ctx* c);   // mirror the lower triangle of every filter's P into the upper one if a downdate left it stale
 void launch_ransac(ekfslam_ctx* c);
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags = 0);
-void launch_pending_rows(ekfslam_ctx* c, int need, int forbid, int from_gate = 0);   // from_gate: V rows were left in the Li scratch by launch_rescue_gate(c, 1)
-void launch_rescue_gate(ekfslam_ctx* c, int keep_v = 0);  // rescue gate against a pending update, from 13x13 gathers (no candidate G rows)  // G rows of the selected features against the pending update
+void launch_rescue_gate(ekfslam_ctx* c, int keep_v = 0);  // rescue gate from 13x13 gathers of P (no candidate G rows)
 void launch_downdate(ekfslam_ctx* c, int slot);
 void launch_chol_blocked64(ekfslam_ctx* c, int kact);   // k_chol_big.cu: S = L L', X = inv(L) for few filters with large k
 void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv);

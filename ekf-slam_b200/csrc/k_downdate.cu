@@ -638,13 +638,12 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
             const char* e = getenv("EKFSLAM_DD_CFG");
             cfgsel = (e && e[0] == 'A') ? 1 : (e && e[0] == 'B') ? 2 : 0;
         }
-        const bool cfgB = cfgsel ? (cfgsel == 2) : (slot == KT_DOWNDATE_HI && !c->fuse_downdates);   // fused: the one downdate carries the li rows too
+        const bool cfgB = cfgsel ? (cfgsel == 2) : (slot == KT_DOWNDATE_HI);
         const int S = cfgB ? 2 : 4, NX = cfgB ? 2 : 1;
         // filters are processed in groups small enough for the per-CTA tile metadata (8 B per tile) to stay
         // within the shared-memory budget of two CTAs per SM
         const long long ctas_full = (long long)sms * 2;
-        const int mirror = c->tri ? 0 : 1;
-        if (!mirror) c->upper_valid = 0;
+        const int mirror = 1;   // P is kept exactly symmetric in memory: every off-diagonal tile is stored with its mirror image
         const size_t fixed = sizeof(double) * (2 * S * TK * TPAD + NX * TM * XP) + sizeof(unsigned long long) * (2 * S + 2 * NX) +
                              sizeof(unsigned) * T;
         const size_t budget = 111 * 1024;

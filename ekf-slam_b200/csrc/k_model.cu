@@ -238,7 +238,7 @@ void launch_features(ekfslam_ctx* c, int which, int parts) {
 // K = P H_i' inv(S_i) (mc/ransac_hypotheses.m:24-25) and P H' of the update (mc/update.m:8-9).
 // ---------------------------------------------------------------------------------------
 #define HP_CHUNK 64
-__global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int use_pending) {
+__global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid) {
     const int b = blockIdx.y;
     const int n = v.nstate[b];
     const int ld = v.ld;
@@ -294,18 +294,6 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int
             sH[s][k] = v.Hc[((size_t)b * v.N + sIdx[s]) * EKF_HSTRIDE + k];
         }
         __syncthreads();
-        if (use_pending && v.kpend[b] > 0) {
-            // a deferred update is pending: the covariance in memory is still P, the current one is
-            // J1 (P - W'W) J1'.  This pass produces (H J1) P; k_v / k_gemm(mode 1) finish the job.
-            const double* __restrict__ J1 = v.jn1 + (size_t)b * 16;
-            for (int e = threadIdx.x; e < cnt * 2; e += blockDim.x) {
-                double* Hr = &sH[e >> 1][(e & 1) * EKF_HC + 3];
-                const double h3 = Hr[0], h4 = Hr[1], h5 = Hr[2], h6 = Hr[3];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) Hr[a] = h3 * J1[0 * 4 + a] + h4 * J1[1 * 4 + a] + h5 * J1[2 * 4 + a] + h6 * J1[3 * 4 + a];
-            }
-            __syncthreads();
-        }
         if (!active) continue;
         for (int s = 0; s < cnt; ++s) {
             const double* Hs = sH[s];
@@ -344,276 +332,7 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// G = H * P reading ONLY the lower triangle of P (EKFSLAM_TRI=1): half the covariance traffic of k_hp.
-// Invariant of that mode: the lower triangle and the 64x64 DIAGONAL tiles (both halves) are valid, nothing else.
-//
-// k_hp_tri (every predicted feature selected: the pass that feeds S_i, RANSAC and the li update)
-// grid = (64-column chunks, B), 8 warps; lane l of every warp owns columns j0+l and j0+l+32 of the chunk, the warps
-// take the selected features round robin.  Row rho of P restricted to the chunk's columns j comes from
-//   rho >= j0      : P[rho][j]   direct, coalesced along j (rows inside the diagonal tile included: it is stored in full)
-//   rho <  j0      : P[j][rho]   the chunk's OWN 64 rows, staged 64 columns at a time by 16-byte cp.async (row-major
-//                                copy, double buffered), read transposed from shared memory (pitch 66: 2-way conflicts).
-// Offsets are cumulative in feature index, so a warp walks its features once while the CTA walks the column blocks
-// 0..J-1; a feature cut by a block boundary keeps its partial sums in registers.  Every lower-triangle element is read
-// once per filter.
-//
-// k_hp_tri_sparse (few selected features: rescue rows, iterated-update rows): one thread per column, no staging;
-// element (rho, j) is read where it is valid, P[max][min].
-// ---------------------------------------------------------------------------------------
-#define HT_C 64
-#define HT_P 65
-#define HT_NW 8
-
-// selected features of filter b, compacted in index (= offset) order by all NW warps of the CTA (32 features per warp
-// and round, prefix over the warps).  sIdx[slot] = feature index | (inverse depth ? 1 << 30 : 0), sOff[slot] = state offset.
-template <int NW>
-__device__ __forceinline__ int hp_select(const DevView& v, int b, int nf, int need, int forbid, int* sIdx, int* sOff, int (*sWc)[2]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, N = v.N;
-    int cnt = 0;
-    for (int fb = 0; fb < nf; fb += NW * 32) {
-        const int i = fb + warp * 32 + lane;
-        bool selq = false;
-        int ty = 0, of = 0;
-        if (i < nf) {
-            const int t = b * N + i;
-            const uint8_t fl = v.flags[t];
-            ty = v.ftype[t];
-            of = v.foff[t];
-            selq = (ty != EKFSLAM_FEAT_NONE) && ((fl & need) == need) && ((fl & forbid) == 0);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, selq);
-        if (lane == 0) sWc[warp][0] = __popc(m);
-        __syncthreads();
-        int pcn = cnt;
-#pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) {
-            const int c_ = sWc[w2][0];
-            if (w2 < warp) pcn += c_;
-            cnt += c_;
-        }
-        if (selq) {
-            const int slot = pcn + __popc(m & ((1u << lane) - 1u));
-            sIdx[slot] = i | (ty == EKFSLAM_FEAT_INVERSEDEPTH ? (1 << 30) : 0);
-            sOff[slot] = of;
-        }
-        __syncthreads();
-    }
-    return cnt;
-}
-
-// camera columns of the two Jacobian rows of a feature, times J1 when a deferred update is pending (see k_hp)
-__device__ __forceinline__ void hp_cam_rows(const double* __restrict__ H, bool pend, const double* sJ1, double* h0, double* h1) {
-#pragma unroll
-    for (int k = 0; k < 7; ++k) { h0[k] = H[k]; h1[k] = H[EKF_HC + k]; }
-    if (pend) {
-        double t0[4], t1[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            t0[a] = h0[3] * sJ1[0 * 4 + a] + h0[4] * sJ1[1 * 4 + a] + h0[5] * sJ1[2 * 4 + a] + h0[6] * sJ1[3 * 4 + a];
-            t1[a] = h1[3] * sJ1[0 * 4 + a] + h1[4] * sJ1[1 * 4 + a] + h1[5] * sJ1[2 * 4 + a] + h1[6] * sJ1[3 * 4 + a];
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { h0[3 + a] = t0[a]; h1[3 + a] = t1[a]; }
-    }
-}
-
-#define HT_P2 66   // pitch of the staged block (row-major copy of P rows, 16-byte cp.async): transposed reads are 2-way conflicted
-__global__ void __launch_bounds__(HT_NW * 32, 3) k_hp_tri(DevView v, int need, int forbid, int use_pending) {
-    extern __shared__ __align__(16) unsigned char hp_sm[];
-    const int b = blockIdx.y;
-    const int n = v.nstate[b];
-    const int J = blockIdx.x, j0 = J * HT_C;
-    if (j0 >= n) return;
-    const int ld = v.ld, N = v.N;
-    const int nf = v.nfeat[b];
-    double* T = reinterpret_cast<double*>(hp_sm);              // [2][64][66]: T[buf][jj][cc] = P[j0 + jj][c0 + cc]
-    int* sIdx = reinterpret_cast<int*>(T + 2 * HT_C * HT_P2);  // [N]
-    int* sOff = sIdx + N;                                      // [N]
-    __shared__ double sPc[7][HT_C];                            // camera rows 0..6 of P at the chunk's columns
-    __shared__ int sWc[HT_NW][2];
-    __shared__ double sJ1[16];
-    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
-    double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
-    const double* __restrict__ Hb = v.Hc + (size_t)b * N * EKF_HSTRIDE;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // block c of the chunk's own rows: 64 rows x 32 sixteen-byte pieces, 8 per thread, lanes along the row
-    auto stage = [&](int c, int buf) {
-        double* Tb = T + buf * HT_C * HT_P2;
-        const double* src0 = P + (size_t)j0 * ld + c * HT_C + 2 * lane;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int jj = warp + HT_NW * u;
-            const bool ok = j0 + jj < n;
-            cp_async16(Tb + jj * HT_P2 + 2 * lane, ok ? src0 + (size_t)jj * ld : P, ok ? 16 : 0);
-        }
-    };
-    if (J > 0) stage(0, 0);
-    cp_async_commit();
-    if (J > 1) stage(1, 1);
-    cp_async_commit();
-
-    const int jA = j0 + lane, jB = jA + 32;
-    const bool okA = jA < n, okB = jB < n;
-    for (int e = tid; e < 7 * HT_C; e += HT_NW * 32) {
-        const int jj = e / 7, k = e - jj * 7;
-        sPc[k][jj] = (j0 + jj < n) ? P[(size_t)(j0 + jj) * ld + k] : 0.0;
-    }
-    const bool pend = use_pending && v.kpend[b] > 0;
-    if (tid < 16) sJ1[tid] = pend ? v.jn1[(size_t)b * 16 + tid] : 0.0;
-    const int cnt = hp_select<HT_NW>(v, b, nf, need, forbid, sIdx, sOff, sWc);
-
-    int s = warp, r = 0;
-    double g0A = 0.0, g0B = 0.0, g1A = 0.0, g1B = 0.0;
-
-    for (int c = 0; c < J; ++c) {
-        cp_async_wait<1>();
-        __syncthreads();
-        const int c0 = c * HT_C, hi = c0 + HT_C;
-        const double* Ta = T + (c & 1) * HT_C * HT_P2 + lane * HT_P2 - c0;   // element (own row lane, column rho) at Ta[rho]
-        const double* Tb2 = Ta + 32 * HT_P2;
-        while (s < cnt) {
-            const int off = sOff[s];
-            if (off + r >= hi) break;
-            const int idx = sIdx[s], w = (idx >> 30) ? 6 : 3, i = idx & 0x3fffffff;
-            const double* __restrict__ H = Hb + (size_t)i * EKF_HSTRIDE;
-            if (r == 0) {
-                double h0[7], h1[7];
-                hp_cam_rows(H, pend, sJ1, h0, h1);
-                g0A = g0B = g1A = g1B = 0.0;
-#pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                    const double pa = sPc[k][lane], pb = sPc[k][lane + 32];
-                    g0A += h0[k] * pa; g0B += h0[k] * pb;
-                    g1A += h1[k] * pa; g1B += h1[k] * pb;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                if (q >= r && q < w && off + q < hi) {
-                    const double pA = Ta[off + q], pB = Tb2[off + q];
-                    const double h0 = H[7 + q], h1 = H[EKF_HC + 7 + q];
-                    g0A += h0 * pA; g0B += h0 * pB; g1A += h1 * pA; g1B += h1 * pB;
-                }
-            }
-            r = min(w, hi - off);
-            if (r < w) break;   // continues in the next block / in the direct region
-            double* go0 = G + (size_t)(2 * i) * ld;
-            double* go1 = go0 + ld;
-            if (okA) { go0[jA] = g0A; go1[jA] = g1A; }
-            if (okB) { go0[jB] = g0B; go1[jB] = g1B; }
-            s += HT_NW; r = 0;
-        }
-        __syncthreads();   // every warp is done with this buffer
-        if (c + 2 < J) stage(c + 2, c & 1);
-        cp_async_commit();
-    }
-    // rows from the diagonal tile downwards: direct, coalesced
-    while (s < cnt) {
-        const int off = sOff[s];
-        const int idx = sIdx[s], w = (idx >> 30) ? 6 : 3, i = idx & 0x3fffffff;
-        const double* __restrict__ H = Hb + (size_t)i * EKF_HSTRIDE;
-        const double* __restrict__ Pr = P + (size_t)off * ld;
-        double pA[6], pB[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const bool use = q >= r && q < w;
-            pA[q] = (use && okA) ? Pr[(size_t)q * ld + jA] : 0.0;
-            pB[q] = (use && okB) ? Pr[(size_t)q * ld + jB] : 0.0;
-        }
-        if (r == 0) {
-            double h0[7], h1[7];
-            hp_cam_rows(H, pend, sJ1, h0, h1);
-            g0A = g0B = g1A = g1B = 0.0;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const double pa = sPc[k][lane], pb = sPc[k][lane + 32];
-                g0A += h0[k] * pa; g0B += h0[k] * pb;
-                g1A += h1[k] * pa; g1B += h1[k] * pb;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const bool use = q >= r && q < w;
-            const double hr0 = use ? H[7 + q] : 0.0, hr1 = use ? H[EKF_HC + 7 + q] : 0.0;
-            g0A += hr0 * pA[q]; g0B += hr0 * pB[q]; g1A += hr1 * pA[q]; g1B += hr1 * pB[q];
-        }
-        double* go0 = G + (size_t)(2 * i) * ld;
-        double* go1 = go0 + ld;
-        if (okA) { go0[jA] = g0A; go1[jA] = g1A; }
-        if (okB) { go0[jB] = g0B; go1[jB] = g1B; }
-        s += HT_NW; r = 0;
-    }
-}
-
-#define HTS_NW 4
-__global__ void __launch_bounds__(HTS_NW * 32, 6) k_hp_tri_sparse(DevView v, int need, int forbid, int use_pending) {
-    extern __shared__ __align__(16) unsigned char hp_sm[];
-    const int b = blockIdx.y;
-    const int n = v.nstate[b];
-    if (blockIdx.x * (HTS_NW * 32) >= n) return;
-    const int ld = v.ld, N = v.N;
-    const int nf = v.nfeat[b];
-    int* sIdx = reinterpret_cast<int*>(hp_sm);   // [N]
-    int* sOff = sIdx + N;                        // [N]
-    __shared__ int sWc[HTS_NW][2];
-    __shared__ double sJ1[16];
-    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
-    double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
-    const double* __restrict__ Hb = v.Hc + (size_t)b * N * EKF_HSTRIDE;
-    const int tid = threadIdx.x;
-    const int j = blockIdx.x * (HTS_NW * 32) + tid;
-    const bool ok = j < n;
-    const int jc = ok ? j : 0;
-    const double* __restrict__ Pj = P + (size_t)jc * ld;   // this column's own row
-    double pc[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) pc[k] = (jc >= k) ? Pj[k] : P[(size_t)k * ld + jc];
-    const bool pend = use_pending && v.kpend[b] > 0;
-    if (tid < 16) sJ1[tid] = pend ? v.jn1[(size_t)b * 16 + tid] : 0.0;
-    const int cnt = hp_select<HTS_NW>(v, b, nf, need, forbid, sIdx, sOff, sWc);
-    for (int s = 0; s < cnt; ++s) {
-        const int off = sOff[s];
-        const int idx = sIdx[s], w = (idx >> 30) ? 6 : 3, i = idx & 0x3fffffff;
-        const double* __restrict__ H = Hb + (size_t)i * EKF_HSTRIDE;
-        double p[6], hr0[6], hr1[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const int rho = off + q;
-            p[q] = (q < w) ? ((rho >= jc) ? P[(size_t)rho * ld + jc] : Pj[rho]) : 0.0;
-            hr0[q] = (q < w) ? H[7 + q] : 0.0;
-            hr1[q] = (q < w) ? H[EKF_HC + 7 + q] : 0.0;
-        }
-        double h0[7], h1[7];
-        hp_cam_rows(H, pend, sJ1, h0, h1);
-        double g0 = 0.0, g1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) { g0 += h0[k] * pc[k]; g1 += h1[k] * pc[k]; }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) { g0 += hr0[q] * p[q]; g1 += hr1[q] * p[q]; }
-        if (ok) {
-            G[(size_t)(2 * i) * ld + j] = g0;
-            G[(size_t)(2 * i + 1) * ld + j] = g1;
-        }
-    }
-}
-
-void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending, int slot) {
-    if (c->tri) {
-        KScope ks(c, slot);
-        if (slot == KT_HP) {   // every predicted feature: stream the lower triangle once
-            dim3 grid((c->v.nmax + HT_C - 1) / HT_C, c->v.B);
-            const size_t sm = sizeof(double) * 2 * HT_C * HT_P2 + sizeof(int) * 2 * (size_t)c->v.N;
-            ENSURE_DYN_SMEM(k_hp_tri, sm, c->device);
-            k_hp_tri<<<grid, HT_NW * 32, sm, c->stream>>>(c->v, need, forbid, use_pending);
-        } else {               // a few features (rescue rows)
-            dim3 grid((c->v.nmax + HTS_NW * 32 - 1) / (HTS_NW * 32), c->v.B);
-            const size_t sm = sizeof(int) * 2 * (size_t)c->v.N;
-            k_hp_tri_sparse<<<grid, HTS_NW * 32, sm, c->stream>>>(c->v, need, forbid, use_pending);
-        }
-        return;
-    }
+void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot) {
     const int colchunks = (c->v.nmax + 255) / 256;
     const int fchunks = (c->v.N + HP_CHUNK - 1) / HP_CHUNK;
     int fz = 1;   // feature-chunk groups: only when the (column chunk, filter) grid cannot fill the GPU
@@ -621,7 +340,7 @@ void launch_hp(ekfslam_ctx* c, int need, int forbid, int use_pending, int slot) 
     if (fz > fchunks) fz = fchunks;
     dim3 grid(colchunks, c->v.B, fz);
     KScope ks(c, slot);
-    k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid, use_pending);
+    k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -736,12 +455,6 @@ void launch_symmetrize(ekfslam_ctx* c, int b0, int nb) {
     dim3 grid(nt * nt, nb), block(32, 8);
     KScope ks(c, KT_SYMMETRIZE);
     k_symmetrize<<<grid, block, 0, c->stream>>>(c->v, b0);
-}
-
-void ensure_upper(ekfslam_ctx* c) {
-    if (c->upper_valid) return;
-    for (int b0 = 0; b0 < c->v.B; b0 += 32768) launch_symmetrize(c, b0, c->v.B - b0 < 32768 ? c->v.B - b0 : 32768);
-    c->upper_valid = 1;
 }
 
 // ---------------------------------------------------------------------------------------

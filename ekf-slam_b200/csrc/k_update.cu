@@ -670,29 +670,27 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Tensor-core GEMM of the update, 64x64 tiles, grid = (row tiles, B), each CTA walking all column tiles; two uses:
-//   mode 0:  W[roff + a] = sum_t X[a][t] * G[selrow(t)]       (X = inv(L), lower triangular, explicit zeros
-//            above the diagonal; G_sel = the selected rows of G).  The last row tile also accumulates the
-//            state update x+ = x + G_sel' inv(S) nu (mc/update.m:12) for its 64 columns, and column tile 0
-//            then computes normJac(q+) and normalises the quaternion (mc/update.m:18,24) when `finalize`.
-//   mode 1:  G[candrow(a)] -= sum_t V[a][t] * W[t]            (pending-update correction of the rescue rows:
-//            H_c P_kk = H_c P - (H_c W') W for a deferred W; V = H_c W' lives in the Sb scratch).
+// Tensor-core GEMM of the update, 64x64 tiles, grid = (row tiles, column groups, B), each CTA walking its column tiles:
+//   W[roff + a] = sum_t X[a][t] * G[selrow(t)]       (X = inv(L), lower triangular, explicit zeros above the
+//   diagonal; G_sel = the selected rows of G).  The last row tile also accumulates the state update
+//   x+ = x + G_sel' inv(S) nu (mc/update.m:12) for its 64 columns, and column tile 0 then computes normJac(q+) and
+//   normalises the quaternion (mc/update.m:18,24) when `finalize`.
 // ---------------------------------------------------------------------------------------
-template <int mode>   // 0: W = inv(L) G_sel (the update), 1: G_sel -= V W (rows against a pending update); compile-time: no dead address paths
+template <int mode>   // only mode 0 exists (the name k_gemm<0> is what the committed ncu profiles show)
 __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int kskip) {
     extern __shared__ __align__(16) double dsm[];
     const int b = blockIdx.z;
     const int k = 2 * v.ksel[b];                        // rows of the output
-    const int kk = (mode == 0) ? k : v.kpend[b];        // contraction length
+    const int kk = k;                                   // contraction length
     const int a0 = blockIdx.x * TM;
     if (a0 >= k || kk == 0 || k <= kskip) return;       // k <= kskip: handled by k_w_small
     const int n = v.nstate[b];
     const int ld = v.ld, kmax = v.kmax;
-    const double* __restrict__ A = (mode == 0 ? v.Li : v.Sb) + (size_t)b * kmax * kmax;
+    const double* __restrict__ A = v.Li + (size_t)b * kmax * kmax;
     double* __restrict__ G = v.G + (size_t)b * kmax * ld;
     double* __restrict__ W = v.W + (size_t)b * v.wstride;
     const int* __restrict__ sel = v.sel + (size_t)b * v.N;
-    const int roff = (mode == 0) ? v.roff[b] : 0;
+    const int roff = v.roff[b];
 
     double* As = dsm;                           // [NSTAGE][64][APAD]   As[i][t] = A[a0+i][t0+t]
     double* Bs = dsm + NSTAGE * TM * APAD;      // [NSTAGE][TK][TPAD]   Bs[t][j] = B[t0+t][c0+j]
@@ -701,7 +699,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
     int* grow = reinterpret_cast<int*>(xred + 256);  // [kmax]  G row of stacked row t: 2 sel[t/2] + (t&1)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, q = lane & 3;
-    const bool xrole = (mode == 0) && (a0 + TM >= k);
+    const bool xrole = a0 + TM >= k;
     if (xrole)
         for (int t = tid; t < k; t += blockDim.x) cs[t] = v.cv[(size_t)b * kmax + t];
     for (int t = tid; t < k; t += blockDim.x) grow[t] = (2 * sel[t >> 1] + (t & 1)) * ld;   // element offset of the G row of stacked row t
@@ -710,7 +708,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
     // One CTA owns a 64-row tile of the output for ALL column tiles: the cp.async ring runs over the flattened
     // (column tile, K chunk) sequence, so the pipeline fills once per CTA instead of once per 64x64 tile (short K
     // loops - few stacked rows - were all pipeline fill).
-    const int tend = (mode == 0) ? min(k, a0 + TM) : kk;  // mode 0: X[a][t] = 0 for t > a
+    const int tend = min(k, a0 + TM);  // X[a][t] = 0 for t > a
     const int nk = (tend + TK - 1) / TK;
     // column tiles [cb0, cb1) of this CTA: gridDim.y CTAs share the column tiles of one row tile (1 = the CTA walks them
     // all; more = shorter CTAs, for launches where few filters have work)
@@ -747,7 +745,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
             const int tt = t0 + br + 8 * j;
             const bool ok = cok && tt < kk;
             const double* src = gcol;
-            if (ok) src = (mode == 0) ? gcol + grow[tt] + c0 : W + w_at(kmax, tt, c0 + bcc);
+            if (ok) src = gcol + grow[tt] + c0;
             cpa(bd + j * (8 * TPAD * 8), src, ok ? 16 : 0);
         }
     };
@@ -757,7 +755,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     double xacc = 0.0;
-    const int tmax_w = (mode == 0) ? min(k, a0 + wr * 32 + 32) : kk;
+    const int tmax_w = min(k, a0 + wr * 32 + 32);
     const int rbase = a0 + wr * 32;
     const int mt_hi = max(0, min(4, (k - rbase + 7) >> 3));
 
@@ -803,7 +801,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
             // chunk of mode 1) every product is needed.  On the diagonal only part is: d = 0 -> tile 0 needs K steps 0-1;
             // d = 16 -> tiles 0, 1 need nothing, tile 2 needs K steps 0-1.  Three compile-time blocks, one warp-uniform
             // branch per chunk (a jump table per K step cost more than the DMMAs it saved).
-            const int d = (mode == 0) ? tb0 - rbase : -16;
+            const int d = tb0 - rbase;
 #define GEMM_CHUNK(MT0, HALF)                                                                                   \
             _Pragma("unroll") for (int k4 = 0; k4 < TK / 4; ++k4) {                                               \
                 double af[4], bf[2];                                                                              \
@@ -827,20 +825,14 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
             const int a = a0 + wr * 32 + mt * 8 + g;
             if (a < k) {
                 // the 64 output columns of a column tile are one panel of W
-                double* __restrict__ orow = (mode == 0) ? W + w_at(kmax, roff + a, c0) - c0 : G + grow[a];
+                double* __restrict__ orow = W + w_at(kmax, roff + a, c0) - c0;
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
                     const int c = c0 + wc * 16 + nt * 8 + 2 * q;
                     if (c < ld) {  // ld is even: c+1 < ld as well; the padding columns [n, ld) are kept zero
                         double2 o;
-                        if (mode == 0) {
-                            o.x = (c < n) ? acc[mt][nt][0] : 0.0;
-                            o.y = (c + 1 < n) ? acc[mt][nt][1] : 0.0;
-                        } else {
-                            o = *reinterpret_cast<const double2*>(orow + c);
-                            o.x = (c < n) ? o.x - acc[mt][nt][0] : 0.0;
-                            o.y = (c + 1 < n) ? o.y - acc[mt][nt][1] : 0.0;
-                        }
+                        o.x = (c < n) ? acc[mt][nt][0] : 0.0;
+                        o.y = (c + 1 < n) ? acc[mt][nt][1] : 0.0;
                         *reinterpret_cast<double2*>(orow + c) = o;
                     }
                 }
@@ -990,75 +982,10 @@ __global__ void __launch_bounds__(128) k_wfix(DevView v, int defer) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Rescue rows against a pending update (only filters with kpend > 0): candidate list, the column
-// part of (H J1) P J1' (columns 3..6 of the rows k_hp produced), and V = H_c W' into the Sb scratch.
-// k_gemm(mode 1) then subtracts V W'.  One block per filter.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_v(DevView v, int need, int forbid, int from_gate) {
-    const int b = blockIdx.x;
-    const int N = v.N, ld = v.ld, kmax = v.kmax;
-    const int k1 = v.kpend[b];
-    __shared__ int s_cnt;
-    int* __restrict__ sel = v.sel + (size_t)b * N;
-    if (threadIdx.x < 32) {
-        int cnt = 0;
-        if (k1 > 0) {
-            const int nf = v.nfeat[b];
-            for (int i0 = 0; i0 < nf; i0 += 32) {
-                const int i = i0 + threadIdx.x;
-                bool on = false;
-                if (i < nf) {
-                    const uint8_t fl = v.flags[(size_t)b * N + i];
-                    on = v.ftype[(size_t)b * N + i] != EKFSLAM_FEAT_NONE && (fl & need) == need && (fl & forbid) == 0;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, on);
-                if (on) sel[cnt + __popc(m & ((1u << threadIdx.x) - 1u))] = i;
-                cnt += __popc(m);
-            }
-        }
-        if (threadIdx.x == 0) { v.ksel[b] = cnt; s_cnt = cnt; }
-    }
-    __syncthreads();
-    const int rows = 2 * s_cnt;
-    if (rows == 0) return;
-    double* __restrict__ G = v.G + (size_t)b * kmax * ld;
-    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
-    double* __restrict__ V = v.Sb + (size_t)b * kmax * kmax;
-    const double* __restrict__ J1 = v.jn1 + (size_t)b * 16;
-    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-        double* gr = G + (size_t)(2 * sel[r >> 1] + (r & 1)) * ld + 3;
-        const double g3 = gr[0], g4 = gr[1], g5 = gr[2], g6 = gr[3];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) gr[i] = g3 * J1[i * 4 + 0] + g4 * J1[i * 4 + 1] + g5 * J1[i * 4 + 2] + g6 * J1[i * 4 + 3];
-    }
-    if (from_gate) {   // k_rescue_gate left H_c Wt' of every candidate in the Li scratch, rows 2i, 2i+1
-        const double* __restrict__ Vall = v.Li + (size_t)b * kmax * kmax;
-        for (int e = threadIdx.x; e < rows * k1; e += blockDim.x) {
-            const int r = e / k1, a = e - r * k1;
-            V[(size_t)r * kmax + a] = Vall[(size_t)(2 * sel[r >> 1] + (r & 1)) * kmax + a];
-        }
-        return;
-    }
-    for (int e = threadIdx.x; e < rows * k1; e += blockDim.x) {
-        const int r = e / k1, a = e - r * k1;
-        const size_t t = (size_t)b * N + sel[r >> 1];
-        const double* __restrict__ H = v.Hc + t * EKF_HSTRIDE + (r & 1) * EKF_HC;
-        const int off = v.foff[t];
-        const int w = (v.ftype[t] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
-        double s = 0.0;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) s += H[c] * W[w_at(kmax, a, c)];
-        for (int c = 0; c < w; ++c) s += H[7 + c] * W[w_at(kmax, a, off + c)];
-        V[(size_t)r * kmax + a] = s;
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// Rescue gate, mc/rescue_hi_inliers.m:11-20, WITHOUT the G rows of the candidates (default rescue path; with a
-// pending / deferred li update under EKFSLAM_FUSE=2, without one otherwise: k1 = 0, J1 = I): the 2x2  S_c = H_c p_k_k H_c'  with  p_k_k = J1 (P - W'W) J1' = J1 P J1' - Wt'Wt  (Wt = W J1', what
-// k_wfix leaves in memory) is   (H_c J1) P[c,c] (H_c J1)' - (H_c Wt')(H_c Wt')'   where c are the 13 (10) columns
-// H_c touches: a 13x13 gather of the stored covariance and 13 columns of the k1 pending rows.  Only the
-// candidates that pass (HI) then need full rows H p_k_k (k_hp + k_v + k_gemm mode 1 on those rows).
+// Rescue gate, mc/rescue_hi_inliers.m:11-20, WITHOUT the G rows of the candidates: the 2x2  S_c = H_c p_k_k H_c'  only
+// needs the 13x13 (10x10) gather P[c,c] of the columns H_c touches.  Only the candidates that pass (HI) then need
+// full rows H p_k_k (k_hp on those rows).  The kernel is written for a covariance p_k_k = J1 (P - W'W) J1' with k1 rows
+// of a not-yet-applied update pending in W (k1 = kpend; the step never leaves one pending: k1 = 0, J1 = I).
 // One block per filter, one warp per candidate (round robin), fixed-order warp reductions.
 // ---------------------------------------------------------------------------------------
 #define RG_THREADS 256
@@ -1172,134 +1099,8 @@ void launch_rescue_gate(ekfslam_ctx* c, int keep_v) {
     k_rescue_gate<<<v.B, RG_THREADS, sm, c->stream>>>(v, c->prm, keep_v);
 }
 
-// ---------------------------------------------------------------------------------------
-// G[rows of the selection] -= V W  for filters with FEW selected rows (<= G2S_ROWS, in groups of G2S_M; the hi inliers of a frame are
-// typically ~12 features).  The DMMA tile kernel (k_gemm mode 1, which keeps the filters with more rows) spends a 64-row
-// tile, a cp.async ring and a pipeline fill on these.  Here: grid = (128-column chunks, B), 8 warps x 16 columns; a
-// warp holds MT (1..4) 8-row tiles x 2 column tiles of accumulators on DMMA m8n8k4, the A fragments (V, staged 128
-// pending rows at a time, pitch 132: conflict-free) come from shared memory, the B fragments (W, panel-major: a
-// fragment is four 64-byte runs) straight from global memory, four K steps in flight.
-// (A DFMA version with V broadcast from shared memory was shared-memory-bound: 1.7 ms vs 1.57 ms for k_gemm.)
-// ---------------------------------------------------------------------------------------
-#define G2S_M 32      // rows per group
-#define G2S_ROWS 128  // filters with more selected rows go to k_gemm
-#define G2S_VC 128
-#define G2S_VP 132
-#define G2S_U 8       // K steps (of 4 pending rows) whose B fragments are in flight per warp
-template <int MT>
-__device__ __forceinline__ void g2_small_body(const DevView& v, int b, int r0, int rows, int kk, double* Vs, const int* grow) {
-    const int n = v.nstate[b], ld = v.ld, kmax = v.kmax;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-    const int c0 = blockIdx.x * 128 + warp * 16;
-    const double* __restrict__ V = v.Sb + (size_t)b * kmax * kmax;
-    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
-    double* __restrict__ G = v.G + (size_t)b * kmax * ld;
-    const bool ok0 = c0 + g < n, ok1 = c0 + 8 + g < n;
-    const double* __restrict__ w0 = W + w_at(kmax, 0, ok0 ? c0 + g : 0);       // row a at + a * EKF_WPAD
-    const double* __restrict__ w1 = W + w_at(kmax, 0, ok1 ? c0 + 8 + g : 0);
-    double acc[MT][2][2];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-    for (int a0 = 0; a0 < kk; a0 += G2S_VC) {
-        __syncthreads();
-        for (int e = tid; e < MT * 8 * G2S_VC; e += 256) {
-            const int r = e / G2S_VC, a = e - r * G2S_VC;
-            Vs[r * G2S_VP + a] = (r0 + r < rows && a0 + a < kk) ? V[(size_t)(r0 + r) * kmax + a0 + a] : 0.0;
-        }
-        __syncthreads();
-        if (c0 >= n) continue;   // warp-uniform; the warp still takes part in the barriers
-        const int na = min(G2S_VC, kk - a0);
-        const int nfull = na >> 2;                      // K steps whose four pending rows all exist
-        const double* ap = Vs + g * G2S_VP + q;         // A fragment of K step s, tile mt: ap[mt * 8 * VP + 4 s]
-        const double* p0 = w0 + (size_t)(a0 + q) * EKF_WPAD;   // B fragments: row a0 + 4 s + q of the two column tiles
-        const double* p1 = w1 + (size_t)(a0 + q) * EKF_WPAD;   // (columns >= n read column 0 and are never stored)
-        int s4 = 0;
-        for (; s4 + G2S_U <= nfull; s4 += G2S_U) {      // G2S_U steps: all B fragments in flight, no predicates
-            double b0[G2S_U], b1[G2S_U];
-#pragma unroll
-            for (int u = 0; u < G2S_U; ++u) { b0[u] = p0[(size_t)u * 4 * EKF_WPAD]; b1[u] = p1[(size_t)u * 4 * EKF_WPAD]; }
-#pragma unroll
-            for (int u = 0; u < G2S_U; ++u) {
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const double af = ap[mt * 8 * G2S_VP + 4 * u];
-                    dmma(acc[mt][0], af, b0[u]);
-                    dmma(acc[mt][1], af, b1[u]);
-                }
-            }
-            ap += 4 * G2S_U; p0 += (size_t)G2S_U * 4 * EKF_WPAD; p1 += (size_t)G2S_U * 4 * EKF_WPAD;
-        }
-        for (; s4 * 4 < na; ++s4) {                     // remaining steps one at a time; the last may be partial
-            const bool va = s4 * 4 + q < na;
-            const double b0 = va ? p0[0] : 0.0, b1 = va ? p1[0] : 0.0;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const double af = ap[mt * 8 * G2S_VP];   // V rows beyond kk were staged as zeros
-                dmma(acc[mt][0], af, b0);
-                dmma(acc[mt][1], af, b1);
-            }
-            ap += 4; p0 += 4 * EKF_WPAD; p1 += 4 * EKF_WPAD;
-        }
-    }
-    if (c0 >= n) return;
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-        const int r = r0 + mt * 8 + g;
-        if (r < rows) {
-            double* gr = G + (size_t)grow[r] * ld;
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                const int c = c0 + nt * 8 + 2 * q;
-                if (c + 1 < n) {
-                    double2* p2 = reinterpret_cast<double2*>(gr + c);
-                    double2 t = *p2;
-                    t.x -= acc[mt][nt][0]; t.y -= acc[mt][nt][1];
-                    *p2 = t;
-                } else if (c < n) {
-                    gr[c] -= acc[mt][nt][0];
-                }
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256, 3) k_g2_small(DevView v) {
-    __shared__ __align__(16) double Vs[G2S_M * G2S_VP];
-    __shared__ int grow[G2S_ROWS];
-    const int b = blockIdx.y;
-    const int rows = 2 * v.ksel[b], kk = v.kpend[b];
-    if (rows == 0 || rows > G2S_ROWS || kk == 0 || blockIdx.x * 128 >= v.nstate[b]) return;
-    if (threadIdx.x < rows) grow[threadIdx.x] = 2 * v.sel[(size_t)b * v.N + (threadIdx.x >> 1)] + (threadIdx.x & 1);
-    // (the first __syncthreads of the body orders grow before its use)
-    for (int r0 = 0; r0 < rows; r0 += G2S_M) {   // 32-row groups; W is re-read from L2 for every group
-        const int left = rows - r0;
-        if (left <= 8) g2_small_body<1>(v, b, r0, rows, kk, Vs, grow);
-        else if (left <= 16) g2_small_body<2>(v, b, r0, rows, kk, Vs, grow);
-        else if (left <= 24) g2_small_body<3>(v, b, r0, rows, kk, Vs, grow);
-        else g2_small_body<4>(v, b, r0, rows, kk, Vs, grow);
-    }
-}
-
 static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
     ENSURE_DYN_SMEM(k_gemm<0>, w_sm, c->device);
-    ENSURE_DYN_SMEM(k_gemm<1>, w_sm, c->device);
-}
-
-void launch_pending_rows(ekfslam_ctx* c, int need, int forbid, int from_gate) {
-    DevView& v = c->v;
-    { KScope ks(c, KT_V); k_v<<<v.B, 256, 0, c->stream>>>(v, need, forbid, from_gate); }
-    dim3 gw((v.kmax + TM - 1) / TM, 2, v.B);   // (64-row tiles, column groups, filters)
-    const size_t w_sm = sizeof(double) * (NSTAGE * (TM * APAD + TK * TPAD) + v.kmax + 256) + sizeof(int) * v.kmax;
-    gemm_attr(c, w_sm);
-    {
-        KScope ks(c, KT_G2);
-        static int small = -1;
-        if (small < 0) { const char* e = getenv("EKFSLAM_G2_SMALL"); small = (e && e[0] == '0') ? 0 : 1; }
-        if (small) { dim3 gs((v.nmax + 127) / 128, v.B); k_g2_small<<<gs, 256, 0, c->stream>>>(v); c->launches++; }
-        k_gemm<1><<<gw, 256, w_sm, c->stream>>>(v, 0, small ? G2S_ROWS : 0);
-    }
 }
 
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {

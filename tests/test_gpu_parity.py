@@ -160,43 +160,12 @@ def test_large_map_n500(ekf):
     assert tot["li"] > 200
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_fused_single_pass_mode(ekf, monkeypatch, mode):
-    """EKFSLAM_FUSE=1/2: the li covariance downdate is deferred and applied together with the hi one (one pass
-    over P per frame); the rescue stage then works on the implied p_k_k (2: gate from 13x13 gathers, full rows
-    only for the hi inliers).  Same parity bar."""
-    monkeypatch.setenv("EKFSLAM_FUSE", mode)
-    worst, tot = _run_sequence(ekf, B=3, N=40, frames=5, seed=800)
-    assert tot["li"] > 40 and tot["hi"] > 0
-    worst, tot = _run_sequence(ekf, B=2, N=20, frames=4, seed=801, cart=[0, 3, 4, 9, 15, 19])
-    assert tot["li"] > 0
-
-
-def test_lower_triangle_mode(ekf, monkeypatch):
-    """EKFSLAM_TRI=1: only the lower triangle (and the diagonal 64x64 tiles) of P is kept current between frames - the
-    downdate stores no mirror images, k_hp_tri / k_hp_tri_sparse / k_predict / k_rescue_gate read P[max][min]; the
-    upper triangle is rebuilt on demand for the download.  Same parity bar, and N=100 spans several 64-column chunks."""
-    monkeypatch.setenv("EKFSLAM_TRI", "1")
-    worst, tot = _run_sequence(ekf, B=2, N=100, frames=3, seed=830)
-    assert tot["li"] > 100 and tot["hi"] > 0
-    worst, tot = _run_sequence(ekf, B=2, N=20, frames=4, seed=831, cart=[0, 3, 4, 9, 15, 19])
-    assert tot["li"] > 0
-
-
 def test_ragged_batch_and_unpredicted_features(ekf):
     """Filters of one batch with different map sizes (24, 17, 5 and 0 features: n = 157, 115, 43, 13) and features that
-    are never predicted (ray pointing away from the camera: h / H / S stay empty, mc/predict_camera_measurements.m:14-16),
-    in the default and in the lower-triangle mode."""
+    are never predicted (ray pointing away from the camera: h / H / S stay empty, mc/predict_camera_measurements.m:14-16)."""
     nf = [24, 17, 5, 0]
     worst, tot = _run_sequence(ekf, B=4, N=24, frames=4, seed=840, nfeat=nf, behind=[(0, 3), (0, 11), (1, 0), (2, 4)])
     assert tot["li"] > 20 and tot["ic"] > 40
-
-
-def test_ragged_batch_lower_triangle_mode(ekf, monkeypatch):
-    monkeypatch.setenv("EKFSLAM_TRI", "1")
-    nf = [24, 17, 5, 0]
-    worst, tot = _run_sequence(ekf, B=4, N=24, frames=4, seed=841, nfeat=nf, behind=[(0, 3), (1, 16)])
-    assert tot["li"] > 20
 
 
 def test_downdate_filter_groups(ekf, monkeypatch):

@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 i=0
 for e in "$@"; do
 i=$((i+1))
-env $e EKFSLAM_FUSE=0 timeout 900 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err
+env $e timeout 900 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err
 python - <<PY
 import json
 d=json.load(open("gpurun_out/ab_$i.json"))

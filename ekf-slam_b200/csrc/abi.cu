@@ -34,6 +34,15 @@ static int fail(int code, const std::string& msg) {
         CK(cudaSetDevice((c)->device));                                 \
     } while (0)
 
+// Entry points that read or write P, W or the pending-row bookkeeping outside ekfslam_step first materialise the
+// covariance a deferred hi update left as "P_mem + pending rows" (flush_pending below).
+static int flush_pending(ekfslam_ctx* c);
+#define NEED_P(c)                                                       \
+    do {                                                                \
+        NEED_CTX(c);                                                    \
+        if ((c)->pending) { if (int _r = flush_pending(c)) return _r; } \
+    } while (0)
+
 // ---- per-kernel timing ---------------------------------------------------------------------
 struct KTimer {
     struct Rec { cudaEvent_t a, b; int slot; };
@@ -98,7 +107,7 @@ static void kt_collect(ekfslam_ctx* c) {
 static const char* KT_NAMES[KT_COUNT] = {"k_begin_frame", "k_predict", "k_features", "k_hp", "k_innov", "k_ransac",
                                          "k_upd_S", "k_chol", "k_w", "k_downdate_hi", "k_downdate", "k_symmetrize",
                                          "k_add_features", "k_wfix", "k_w_hi", "k_chol_hi", "k_upd_S_hi",
-                                         "k_hp_rescue", "k_world"};
+                                         "k_hp_rescue", "k_world", "k_vpend"};
 
 template <typename T>
 static cudaError_t dalloc(T** p, size_t count, int64_t* total) {
@@ -109,6 +118,16 @@ static cudaError_t dalloc(T** p, size_t count, int64_t* total) {
         e = cudaMemset(*p, 0, bytes ? bytes : 1);
     }
     return e;
+}
+
+static int flush_pending(ekfslam_ctx* c) {
+    // p_k_k = jn1 P_mem jn1' - Wp'Wp for every filter with pending rows (the others: ktot = 0, untouched)
+    launch_flush_prep(c);
+    launch_downdate(c, KT_DOWNDATE_HI);
+    c->pending = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(EKFSLAM_ERR_CUDA, std::string("flush_pending: ") + cudaGetErrorString(e));
+    return EKFSLAM_OK;
 }
 
 extern "C" {
@@ -208,7 +227,8 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     DA(v.xp, Bz * v.ld);
     DA(v.P, Bz * v.nmax * v.ld);
     DA(v.G, Bz * v.kmax * v.ld);
-    v.wstride = (long long)((v.ld + 63) / 64) * v.kmax * EKF_WPAD;
+    v.wrows = 2 * v.kmax;
+    v.wstride = (long long)((v.ld + 63) / 64) * v.wrows * EKF_WPAD;
     DA(v.W, Bz * (size_t)v.wstride);
     DA(v.Sb, Bz * v.kmax * v.kmax);
     DA(v.Li, Bz * v.kmax * v.kmax);
@@ -268,6 +288,8 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     {
         const char* e2 = getenv("EKFSLAM_RESCUE_GATHER");
         c->rescue_gather = (e2 && e2[0] == '0') ? 0 : 1;   // default on: gate 0.36 + rows of the hi inliers 0.61 ms vs 1.15 ms
+        const char* e3 = getenv("EKFSLAM_DEFER_HI");
+        c->defer_hi = (e3 && e3[0] == '0') ? 0 : 1;        // default on: one covariance pass per frame (see ekfslam_step)
     }
     *out = c;
     return EKFSLAM_OK;
@@ -414,7 +436,7 @@ static int check_range(const ekfslam_ctx* c, int b0, int nb) {
 // ---- filter struct <-> device ------------------------------------------------------------
 int ekfslam_upload_state(ekfslam_ctx* c, int b0, int nb, int which, const double* x, const double* P,
                          const int32_t* nstate) {
-    NEED_CTX(c);
+    NEED_P(c);
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     DevView& v = c->v;
     if (nstate) {
@@ -440,6 +462,7 @@ int ekfslam_upload_state(ekfslam_ctx* c, int b0, int nb, int which, const double
 
 int ekfslam_download_state(ekfslam_ctx* c, int b0, int nb, int which, double* x, double* P, int32_t* nstate) {
     NEED_CTX(c);
+    if (P && c->pending) { if (int r = flush_pending(c)) return r; }   // x_k_k is always current; only P can be pending
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     DevView& v = c->v;
     if (nstate) CK(cudaMemcpyAsync(nstate, v.nstate + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, c->stream));
@@ -459,7 +482,7 @@ int ekfslam_download_state(ekfslam_ctx* c, int b0, int nb, int which, double* x,
 
 // ---- features_info <-> device --------------------------------------------------------------
 int ekfslam_upload_feature_types(ekfslam_ctx* c, int b0, int nb, const uint8_t* type, const int32_t* nfeat) {
-    NEED_CTX(c);
+    NEED_P(c);
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!type || !nfeat) return fail(EKFSLAM_ERR_INVALID, "type / nfeat is null");
@@ -611,7 +634,7 @@ int ekfslam_begin_frame(ekfslam_ctx* c) {
 }
 
 int ekfslam_predict(ekfslam_ctx* c) {
-    NEED_CTX(c);
+    NEED_P(c);
     launch_predict(c);
     LAUNCHED();
     return EKFSLAM_OK;
@@ -626,21 +649,21 @@ int ekfslam_features(ekfslam_ctx* c, int which, int parts) {
 }
 
 int ekfslam_hp(ekfslam_ctx* c, int need, int forbid) {
-    NEED_CTX(c);
+    NEED_P(c);
     launch_hp(c, need, forbid);
     LAUNCHED();
     return EKFSLAM_OK;
 }
 
 int ekfslam_innovation(ekfslam_ctx* c) {
-    NEED_CTX(c);
+    NEED_P(c);
     launch_innov(c, 0);
     LAUNCHED();
     return EKFSLAM_OK;
 }
 
 int ekfslam_measure(ekfslam_ctx* c, int which) {
-    NEED_CTX(c);
+    NEED_P(c);
     launch_features(c, which ? 1 : 0, 3);
     launch_hp(c, EKFSLAM_F_HAS_H, 0);
     launch_innov(c, 0);
@@ -656,7 +679,7 @@ static int gate_mode(ekfslam_ctx* c, int mode) {
 }
 
 int ekfslam_gate(ekfslam_ctx* c) {
-    NEED_CTX(c);
+    NEED_P(c);
     return gate_mode(c, 1);
 }
 
@@ -666,7 +689,7 @@ int ekfslam_apply_matches(ekfslam_ctx* c) {
 }
 
 int ekfslam_ransac(ekfslam_ctx* c) {
-    NEED_CTX(c);
+    NEED_P(c);
     if (c->v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "ransac: no uniform stream uploaded (ekfslam_upload_uniforms)");
     launch_ransac(c);
     LAUNCHED();
@@ -674,7 +697,7 @@ int ekfslam_ransac(ekfslam_ctx* c) {
 }
 
 int ekfslam_update_masked(ekfslam_ctx* c, int mask, int which_prior) {
-    NEED_CTX(c);
+    NEED_P(c);
     if (!(mask & 0xff)) return fail(EKFSLAM_ERR_INVALID, "empty mask");
     launch_update(c, mask, which_prior ? 1 : 0);
     LAUNCHED();
@@ -684,7 +707,7 @@ int ekfslam_update_masked(ekfslam_ctx* c, int mask, int which_prior) {
 int ekfslam_update_li(ekfslam_ctx* c) { return ekfslam_update_masked(c, EKFSLAM_F_LI, 1); }
 
 int ekfslam_update_iterated(ekfslam_ctx* c, int mask, int which_prior, int n_iter) {
-    NEED_CTX(c);
+    NEED_P(c);
     if (!(mask & 0xff)) return fail(EKFSLAM_ERR_INVALID, "empty mask");
     if (n_iter < 1 || n_iter > 64) return fail(EKFSLAM_ERR_INVALID, "n_iter must be in [1, 64]");
     DevView& v = c->v;
@@ -702,7 +725,7 @@ int ekfslam_update_iterated(ekfslam_ctx* c, int mask, int which_prior, int n_ite
 }
 
 int ekfslam_rescue(ekfslam_ctx* c) {
-    NEED_CTX(c);
+    NEED_P(c);
     launch_features(c, 0, 3);                            // h, H of ALL features at x_k_k (:6-7)
     launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);  // G rows of the candidates (IC && !LI)
     launch_innov(c, 3);                                 // chi2 gate -> HI (:11-20)
@@ -716,10 +739,16 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
     NEED_CTX(c);
     if (match_mode < 0 || match_mode > 2) return fail(EKFSLAM_ERR_INVALID, "match_mode must be 0, 1 or 2");
     if (c->v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "step: no uniform stream uploaded");
+    // defer_hi: the covariance downdate of the hi update is NOT applied at the end of the frame; its rows stay pending in
+    // W and ride along with the next frame's li downdate (P crosses HBM once per frame for the downdates instead of
+    // twice).  In between, k_predict carries the pending rows through F and k_hp_pend subtracts (H Wp') Wp from
+    // G = H P_mem while it streams P_mem.
+    const int defer = c->defer_hi;
     if (reset) launch_begin_frame(c);
     launch_predict(c);
     launch_features(c, 1, 3);
-    launch_hp(c, EKFSLAM_F_HAS_H, 0);
+    if (defer) launch_hp_pend(c, EKFSLAM_F_HAS_H, 0);   // (bit-identical to k_hp for a filter without pending rows)
+    else launch_hp(c, EKFSLAM_F_HAS_H, 0);
     launch_innov(c, 0);
     if (c->wait_inputs) { cudaStreamWaitEvent(c->stream, c->ev_in, 0); c->wait_inputs = 0; }
     if (match_mode) launch_innov(c, match_mode);
@@ -735,9 +764,21 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
             launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI, KT_HP_RESCUE);
             launch_innov(c, 3);
         }
-        launch_update(c, EKFSLAM_F_HI, 0);
+        launch_update(c, EKFSLAM_F_HI, 0, defer ? 4 : 0);
+        c->pending = defer;   // (the li downdate above has consumed whatever was pending before)
     }
     LAUNCHED();
+    return EKFSLAM_OK;
+}
+
+int ekfslam_flush(ekfslam_ctx* c) {
+    NEED_P(c);
+    return EKFSLAM_OK;
+}
+
+int ekfslam_set_defer_hi(ekfslam_ctx* c, int on) {
+    NEED_P(c);
+    c->defer_hi = on ? 1 : 0;
     return EKFSLAM_OK;
 }
 
@@ -745,7 +786,7 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
 struct StepGraph {
     cudaGraphExec_t exec;
     DevView v; ekfslam_params prm; DevCam cam;
-    int reset, match_mode, rescue_gather;
+    int reset, match_mode, rescue_gather, defer_hi;
     int64_t launches;
 };
 
@@ -766,7 +807,7 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
     StepGraph* g = (StepGraph*)c->step_graph;
     if (g && (memcmp(&g->v, &v, sizeof(DevView)) || memcmp(&g->prm, &c->prm, sizeof(ekfslam_params)) ||
               memcmp(&g->cam, &c->cam, sizeof(DevCam)) || g->reset != reset || g->match_mode != match_mode ||
-              g->rescue_gather != c->rescue_gather)) {
+              g->rescue_gather != c->rescue_gather || g->defer_hi != c->defer_hi)) {
         step_graph_destroy(c);
         g = nullptr;
     }
@@ -776,6 +817,7 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
         memset(g, 0, sizeof(*g));
         memcpy(&g->v, &v, sizeof(DevView)); memcpy(&g->prm, &c->prm, sizeof(ekfslam_params)); memcpy(&g->cam, &c->cam, sizeof(DevCam));
         g->reset = reset; g->match_mode = match_mode; g->rescue_gather = c->rescue_gather;
+        g->defer_hi = c->defer_hi;
         const int64_t l0 = c->launches;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
@@ -798,6 +840,7 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
     }
     CK(cudaGraphLaunch(g->exec, c->stream));
     c->launches += g->launches;
+    c->pending = c->defer_hi;
     return EKFSLAM_OK;
 }
 
@@ -853,7 +896,7 @@ int ekfslam_step_host(ekfslam_ctx* c, int match_mode, const double* zc, const ui
 }
 
 int ekfslam_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* xv, const double* Pxv) {
-    NEED_CTX(c);
+    NEED_P(c);
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!xv || !Pxv) return fail(EKFSLAM_ERR_INVALID, "xv / Pxv is null");
@@ -886,7 +929,7 @@ int ekfslam_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* xv, cons
 
 int ekfslam_add_features(ekfslam_ctx* c, int b0, int nb, const double* uvd, const uint8_t* add, double std_pxl,
                          double initial_rho, double std_rho) {
-    NEED_CTX(c);
+    NEED_P(c);
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!uvd) return fail(EKFSLAM_ERR_INVALID, "uvd is null");
@@ -917,7 +960,7 @@ static int ensure_scratch(ekfslam_ctx* c, size_t need) {
 }
 
 int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* c, double threshold, int force_index, int32_t* converted) {
-    NEED_CTX(c);
+    NEED_P(c);
     DevView& v = c->v;
     if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "inversedepth_2_cartesian supports n_max <= 4096");
     if (force_index >= v.N) return fail(EKFSLAM_ERR_INVALID, "force_index out of range");
@@ -930,7 +973,7 @@ int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* c, double threshold, int force
 }
 
 int ekfslam_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* del) {
-    NEED_CTX(c);
+    NEED_P(c);
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!del) return fail(EKFSLAM_ERR_INVALID, "del is null");
@@ -1019,7 +1062,7 @@ int ekfslam_download_candidates(ekfslam_ctx* c, int b0, int nb, double* zc, uint
 }
 
 int ekfslam_map_management(ekfslam_ctx* c, int min_number_of_features_in_image) {
-    NEED_CTX(c);
+    NEED_P(c);
     DevView& v = c->v;
     if (min_number_of_features_in_image < 0) return fail(EKFSLAM_ERR_INVALID, "min_number_of_features_in_image < 0");
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256, 3) k_downdate_tile(DevView v) {
     const int tj = e - ti * (ti + 1) / 2;
     const int i0 = ti * TM, j0 = tj * TM;
     if (i0 >= n) return;
-    const int ld = v.ld, kmax = v.kmax;
+    const int ld = v.ld, kmax = v.wrows;   // W panel stride (rows)
     const double* __restrict__ W = v.W + (size_t)b * v.wstride;
     double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
     const bool diag = (ti == tj);
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(WS2_THREADS, 2) k_downdate_ws2(DevView v, int 
     unsigned long long* cfull = pfull + NX;  // [NX] X[j] holds P - acc
     int2* meta = reinterpret_cast<int2*>(cfull + NX);                                  // [M]  {ktot, n}
     unsigned* lut = reinterpret_cast<unsigned*>(meta + M);                            // [T]  ti<<16|tj
-    const int ld = v.ld, kmax = v.kmax;
+    const int ld = v.ld, kmax = v.wrows;   // W panel stride (rows)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long G = gridDim.x;
     for (int m = tid; m < M; m += blockDim.x) {

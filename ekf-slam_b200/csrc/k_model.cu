@@ -41,8 +41,15 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
     __shared__ double Pxx[13][13];
     __shared__ double T[13][13];
     __shared__ double Fqq[4][4], Fqw[4][3];
+    __shared__ double Jh[4][4];
 
     const int tid = threadIdx.x;
+    // Rows a deferred hi update left pending (ekfslam_step, defer_hi): the covariance in memory is P_mem with
+    //   p_k_k = Jh P_mem Jh' - Wp'Wp,   Jh = blkdiag(I3, jn1, I),  Wp = W[0:kp)
+    // so  p_k+1_k = F p_k_k F' + Q = (F Jh) P_mem (F Jh)' + Q - (Wp F')'(Wp F'):  Jh is applied to P_mem here, in
+    // front of F, the pending rows are carried through F', and jn1 goes back to the identity.
+    const int kp = v.kpend[b];
+    if (kp > 0 && tid < 16) Jh[tid >> 2][tid & 3] = v.jn1[(size_t)b * 16 + tid];
     for (int e = tid; e < 169; e += blockDim.x) {
         const int r = e / 13, cc = e - r * 13;
         Pxx[r][cc] = P[(size_t)r * ld + cc];
@@ -50,6 +57,22 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
         Q[r][cc] = 0.0;
     }
     __syncthreads();
+    if (kp > 0) {   // Pxx <- Jh Pxx Jh' (rows / columns 3..6)
+        for (int e = tid; e < 169; e += blockDim.x) {
+            const int r = e / 13, cc = e - r * 13;
+            double s = Pxx[r][cc];
+            if (r >= 3 && r < 7) s = Jh[r - 3][0] * Pxx[3][cc] + Jh[r - 3][1] * Pxx[4][cc] + Jh[r - 3][2] * Pxx[5][cc] + Jh[r - 3][3] * Pxx[6][cc];
+            T[r][cc] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < 169; e += blockDim.x) {
+            const int r = e / 13, cc = e - r * 13;
+            double s = T[r][cc];
+            if (cc >= 3 && cc < 7) s = T[r][3] * Jh[cc - 3][0] + T[r][4] * Jh[cc - 3][1] + T[r][5] * Jh[cc - 3][2] + T[r][6] * Jh[cc - 3][3];
+            Pxx[r][cc] = s;
+        }
+        __syncthreads();
+    }
     if (tid == 0) {
         const double dt = prm.delta_t;
         const double q0 = x[3], qx = x[4], qy = x[5], qz = x[6];
@@ -143,6 +166,11 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
         double c[13];
 #pragma unroll
         for (int r = 0; r < 13; ++r) c[r] = P[(size_t)j * ld + r];   // lower triangle (authoritative): P[r][j] = P[j][r], j >= 13 > r
+        if (kp > 0) {   // pending normalisation Jacobian first: c[3..6] <- Jh c[3..6]
+            const double c3 = c[3], c4 = c[4], c5 = c[5], c6 = c[6];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) c[3 + r] = Jh[r][0] * c3 + Jh[r][1] * c4 + Jh[r][2] * c5 + Jh[r][3] * c6;
+        }
         double o[7];
         const double dt = prm.delta_t;
         o[0] = c[0] + dt * c[7]; o[1] = c[1] + dt * c[8]; o[2] = c[2] + dt * c[9];
@@ -172,6 +200,23 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
         s += Q[r][cc];
         P[(size_t)r * ld + cc] = s;
         P[(size_t)cc * ld + r] = s;
+    }
+    if (kp > 0) {
+        // pending rows through the prediction: Wp <- Wp F' (only columns 0..6 change; they live in panel 0 of W)
+        double* __restrict__ W = v.W + (size_t)b * v.wstride;
+        const double dt = prm.delta_t;
+        for (int m = tid; m < kp; m += blockDim.x) {
+            double* w = W + w_at(v.wrows, m, 0);
+            double c[13];
+#pragma unroll
+            for (int r = 0; r < 13; ++r) c[r] = w[r];
+            w[0] = c[0] + dt * c[7]; w[1] = c[1] + dt * c[8]; w[2] = c[2] + dt * c[9];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                w[3 + r] = Fqq[r][0] * c[3] + Fqq[r][1] * c[4] + Fqq[r][2] * c[5] + Fqq[r][3] * c[6] +
+                           Fqw[r][0] * c[10] + Fqw[r][1] * c[11] + Fqw[r][2] * c[12];
+        }
+        if (tid < 16) v.jn1[(size_t)b * 16 + tid] = ((tid >> 2) == (tid & 3)) ? 1.0 : 0.0;
     }
 }
 
@@ -341,6 +386,261 @@ void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot) {
     dim3 grid(colchunks, c->v.B, fz);
     KScope ks(c, slot);
     k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid);
+}
+
+// ---------------------------------------------------------------------------------------
+// G = H P with rows of a deferred update pending in W (ekfslam_step, defer_hi):  the covariance is
+//   P = P_mem - Wp'Wp   (Wp = W[0:kp), already carried through the prediction by k_predict)
+// so  G = H P_mem - V Wp  with  V = H Wp'  (2N x kp, k_vpend).  The correction is folded into the pass that streams
+// P_mem: one state column per thread, the column of Wp (blocks of 32 pending rows) in registers, V broadcast from
+// global memory / L1.  kp <= 32 (the rule for a hi update): one sweep over the features; every further block of 32
+// pending rows is a read-modify-write sweep over the G rows this thread wrote itself.
+// Same summation order for H P_mem as k_hp, so a filter without pending rows gets bit-identical G rows.
+// ---------------------------------------------------------------------------------------
+#define HPP_T 160
+#define HPP_KB 32
+#define HPP_D 8      // features in flight per thread (cp.async ring depth)
+#define VP_PITCH 33  // shared tile pitch of k_vpend (doubles)
+// V = H Wp' (rows 2i, 2i+1 <- feature i; kp columns), into the inv(L) scratch (dead between two updates).
+// One warp per group of 32 features, lanes along the features (the feature blocks of 32 consecutive features are one
+// contiguous range of a W row), 32 pending rows at a time; the 64 x 32 result goes through shared memory so that the
+// rows of V are written coalesced.
+__global__ void __launch_bounds__(64) k_vpend(DevView v, int need, int forbid) {
+    const int b = blockIdx.x;
+    const int kp = v.kpend[b];
+    if (kp == 0) return;
+    const int nf = v.nfeat[b], N = v.N, kmax = v.kmax;
+    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
+    double* __restrict__ V = v.Li + (size_t)b * kmax * kmax;
+    __shared__ double tile[2][64][VP_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kp4 = (kp + 3) & ~3;   // k_hp_pend reads V in groups of four columns: zero-fill up to the next multiple
+    for (int f0 = warp * 32; f0 < nf; f0 += 2 * 32) {
+        const int i = f0 + lane;
+        bool on = false;
+        int off = 0, w = 0;
+        double H[EKF_HSTRIDE];
+        if (i < nf) {
+            const size_t t = (size_t)b * N + i;
+            const int ty = v.ftype[t];
+            const uint8_t fl = v.flags[t];
+            on = ty != EKFSLAM_FEAT_NONE && (fl & need) == need && !(fl & forbid);
+            if (on) {
+                off = v.foff[t];
+                w = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+#pragma unroll
+                for (int k = 0; k < EKF_HSTRIDE; ++k) H[k] = v.Hc[t * EKF_HSTRIDE + k];
+            }
+        }
+        for (int m0 = 0; m0 < kp4; m0 += 32) {
+            const int mb = min(32, kp4 - m0);
+            for (int j = 0; j < mb; ++j) {
+                const int m = m0 + j;
+                double a0 = 0.0, a1 = 0.0;
+                if (on && m < kp) {
+                    const double* __restrict__ wc = W + w_at(v.wrows, m, 0);
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) { const double wv = wc[r]; a0 += H[r] * wv; a1 += H[EKF_HC + r] * wv; }
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+                        if (r < w) { const double wv = W[w_at(v.wrows, m, off + r)]; a0 += H[7 + r] * wv; a1 += H[EKF_HC + 7 + r] * wv; }
+                }
+                tile[warp][2 * lane][j] = a0;
+                tile[warp][2 * lane + 1][j] = a1;
+            }
+            __syncwarp();
+            const int nrow = 2 * min(32, nf - f0);
+            for (int r = 0; r < nrow; ++r)
+                if (lane < mb) V[(size_t)(2 * f0 + r) * kmax + m0 + lane] = tile[warp][r][lane];
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(HPP_T, 3) k_hp_pend(DevView v, int need, int forbid) {
+    const int b = blockIdx.y;
+    const int n = v.nstate[b];
+    const int ld = v.ld, kmax = v.kmax;
+    if (blockIdx.x * HPP_T >= n) return;
+    const int c = blockIdx.x * HPP_T + threadIdx.x;
+    const int nf = v.nfeat[b];
+    const int kp = v.kpend[b];
+    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    double* __restrict__ G = v.G + (size_t)b * kmax * ld;
+    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
+    const double* __restrict__ V = v.Li + (size_t)b * kmax * kmax;
+
+    __shared__ double sH[HP_CHUNK][EKF_HSTRIDE];
+    __shared__ int sOff[HP_CHUNK];
+    __shared__ int sIdx[HP_CHUNK];
+    __shared__ int sW[HP_CHUNK];
+    __shared__ int sCnt;
+    // thread-private ring of feature rows in flight: slot d holds P[off .. off+5][c] of one feature.  Asynchronous
+    // copies keep HPP_D features (48 bytes each) per thread in flight without holding registers: the column of Wp
+    // already takes 64 of them, and with ordinary loads the kernel was latency-bound (5x slower than k_hp).
+    extern __shared__ __align__(16) double ring[];   // [HPP_D][6][HPP_T]
+
+    const bool active = c < n;
+    double pc[7];
+    double wp[HPP_KB];
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r) pc[r] = P[(size_t)r * ld + c];
+    }
+    const int kb0 = min(kp, HPP_KB);
+#pragma unroll
+    for (int j = 0; j < HPP_KB; ++j) wp[j] = (active && j < kb0) ? W[w_at(v.wrows, j, c)] : 0.0;
+    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring + threadIdx.x);
+    const double* __restrict__ Pc = P + (active ? c : 0);
+    auto fetch = [&](int s) {   // rows of selected feature s of the chunk -> ring slot s % HPP_D (always commits a group)
+        if (active) {
+            const double* src = Pc + (size_t)sOff[s] * ld;
+            const unsigned dst = ring0 + (unsigned)((s % HPP_D) * 6 * HPP_T * 8);
+            const int w = sW[s];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+                if (r < w)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + r * HPP_T * 8), "l"(src + (size_t)r * ld) : "memory");
+        }
+    };
+    for (int f0 = 0; f0 < nf; f0 += HP_CHUNK) {
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int base = 0;
+#pragma unroll
+            for (int h2 = 0; h2 < HP_CHUNK / 32; ++h2) {
+                const int i = f0 + h2 * 32 + threadIdx.x;
+                bool selq = false;
+                int ty = 0, of = 0;
+                if (i < nf) {
+                    const int t = b * v.N + i;
+                    const uint8_t fl = v.flags[t];
+                    ty = v.ftype[t];
+                    of = v.foff[t];
+                    selq = (ty != EKFSLAM_FEAT_NONE) && ((fl & need) == need) && ((fl & forbid) == 0);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, selq);
+                if (selq) {
+                    const int slot = base + __popc(m & ((1u << threadIdx.x) - 1u));
+                    sIdx[slot] = i; sOff[slot] = of; sW[slot] = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+                }
+                base += __popc(m);
+            }
+            if (threadIdx.x == 0) sCnt = base;
+        }
+        __syncthreads();
+        const int cnt = sCnt;
+        for (int e = threadIdx.x; e < cnt * EKF_HSTRIDE; e += blockDim.x) {
+            const int s = e / EKF_HSTRIDE, k = e - s * EKF_HSTRIDE;
+            sH[s][k] = v.Hc[((size_t)b * v.N + sIdx[s]) * EKF_HSTRIDE + k];
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int s = 0; s < HPP_D - 1; ++s) {
+            if (s < cnt) fetch(s);
+            cp_async_commit();
+        }
+#pragma unroll 1
+        for (int s = 0; s < cnt; ++s) {
+            if (s + HPP_D - 1 < cnt) fetch(s + HPP_D - 1);
+            cp_async_commit();
+            cp_async_wait<HPP_D - 1>();     // the group of feature s has landed (own copies only: no barrier needed)
+            if (!active) continue;
+            const double* Hs = sH[s];
+            const double* pr = ring + (s % HPP_D) * 6 * HPP_T + threadIdx.x;
+            double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) { g0 += Hs[r] * pc[r]; g1 += Hs[EKF_HC + r] * pc[r]; }
+            if (sW[s] == 6) {
+                double pf[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) pf[r] = pr[r * HPP_T];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) { g0 += Hs[7 + r] * pf[r]; g1 += Hs[EKF_HC + 7 + r] * pf[r]; }
+            } else {
+                double pf[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) pf[r] = pr[r * HPP_T];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { g0 += Hs[7 + r] * pf[r]; g1 += Hs[EKF_HC + 7 + r] * pf[r]; }
+            }
+            const int i = sIdx[s];
+            if (kb0 > 0) {
+                const double2* __restrict__ va = reinterpret_cast<const double2*>(V + (size_t)(2 * i) * kmax);
+                const double2* __restrict__ vb = reinterpret_cast<const double2*>(V + (size_t)(2 * i + 1) * kmax);
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int j4 = 0; j4 < HPP_KB / 4; ++j4) {
+                    if (j4 * 4 < kb0) {   // V is zero-filled up to the next multiple of 4 (k_vpend), wp beyond kp is 0
+                        const double2 a01 = __ldg(va + 2 * j4), a23 = __ldg(va + 2 * j4 + 1);
+                        const double2 b01 = __ldg(vb + 2 * j4), b23 = __ldg(vb + 2 * j4 + 1);
+                        c0 += a01.x * wp[4 * j4] + a01.y * wp[4 * j4 + 1] + a23.x * wp[4 * j4 + 2] + a23.y * wp[4 * j4 + 3];
+                        c1 += b01.x * wp[4 * j4] + b01.y * wp[4 * j4 + 1] + b23.x * wp[4 * j4 + 2] + b23.y * wp[4 * j4 + 3];
+                    }
+                }
+                g0 -= c0; g1 -= c1;
+            }
+            G[(size_t)(2 * i) * ld + c] = g0;
+            G[(size_t)(2 * i + 1) * ld + c] = g1;
+        }
+        cp_async_wait<0>();
+    }
+    // further blocks of pending rows (unusual: more than 16 features in a deferred update): read-modify-write sweeps
+    for (int m0 = HPP_KB; m0 < kp; m0 += HPP_KB) {
+        if (!active) break;
+        const int kb = min(kp - m0, HPP_KB);
+#pragma unroll
+        for (int j = 0; j < HPP_KB; ++j) wp[j] = (j < kb) ? W[w_at(v.wrows, m0 + j, c)] : 0.0;
+        for (int i = 0; i < nf; ++i) {
+            const int t = b * v.N + i;
+            const uint8_t fl = v.flags[t];
+            if (v.ftype[t] == EKFSLAM_FEAT_NONE || (fl & need) != need || (fl & forbid)) continue;
+            const double2* __restrict__ va = reinterpret_cast<const double2*>(V + (size_t)(2 * i) * kmax + m0);
+            const double2* __restrict__ vb = reinterpret_cast<const double2*>(V + (size_t)(2 * i + 1) * kmax + m0);
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int j4 = 0; j4 < HPP_KB / 4; ++j4) {
+                if (j4 * 4 < kb) {
+                    const double2 a01 = __ldg(va + 2 * j4), a23 = __ldg(va + 2 * j4 + 1);
+                    const double2 b01 = __ldg(vb + 2 * j4), b23 = __ldg(vb + 2 * j4 + 1);
+                    c0 += a01.x * wp[4 * j4] + a01.y * wp[4 * j4 + 1] + a23.x * wp[4 * j4 + 2] + a23.y * wp[4 * j4 + 3];
+                    c1 += b01.x * wp[4 * j4] + b01.y * wp[4 * j4 + 1] + b23.x * wp[4 * j4 + 2] + b23.y * wp[4 * j4 + 3];
+                }
+            }
+            G[(size_t)(2 * i) * ld + c] -= c0;
+            G[(size_t)(2 * i + 1) * ld + c] -= c1;
+        }
+    }
+}
+
+void launch_hp_pend(ekfslam_ctx* c, int need, int forbid) {
+    {
+        KScope ks(c, KT_VPEND);
+        k_vpend<<<c->v.B, 64, 0, c->stream>>>(c->v, need, forbid);
+    }
+    dim3 grid((c->v.nmax + HPP_T - 1) / HPP_T, c->v.B);
+    KScope ks(c, KT_HP);
+    const size_t sm = sizeof(double) * HPP_D * 6 * HPP_T;
+    ENSURE_DYN_SMEM(k_hp_pend, sm, c->device);
+    k_hp_pend<<<grid, HPP_T, sm, c->stream>>>(c->v, need, forbid);
+}
+
+// pending rows -> the inputs of a stand-alone covariance downdate: P <- jn1 P jn1' - Wp'Wp
+__global__ void k_flush_prep(DevView v) {
+    const int b = blockIdx.x * (blockDim.x / 16) + threadIdx.x / 16;
+    if (b >= v.B) return;
+    const int e = threadIdx.x & 15;
+    const int kp = v.kpend[b];
+    const bool id = (e >> 2) == (e & 3);
+    v.jn[(size_t)b * 16 + e] = (kp > 0) ? v.jn1[(size_t)b * 16 + e] : (id ? 1.0 : 0.0);
+    v.jn1[(size_t)b * 16 + e] = id ? 1.0 : 0.0;
+    __syncwarp();
+    if (e == 0) { v.ktot[b] = kp; v.kpend[b] = 0; }
+}
+
+void launch_flush_prep(ekfslam_ctx* c) {
+    c->launches++;
+    k_flush_prep<<<(c->v.B + 7) / 8, 128, 0, c->stream>>>(c->v);
 }
 
 // ---------------------------------------------------------------------------------------

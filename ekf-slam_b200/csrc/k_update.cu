@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
             const int a = a0 + wr * 32 + mt * 8 + g;
             if (a < k) {
                 // the 64 output columns of a column tile are one panel of W
-                double* __restrict__ orow = W + w_at(kmax, roff + a, c0) - c0;
+                double* __restrict__ orow = W + w_at(v.wrows, roff + a, c0) - c0;
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
                     const int c = c0 + wc * 16 + nt * 8 + 2 * q;
@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(128, 4) k_w_small(DevView v, int finalize) {
         double xs = 0.0;
 #pragma unroll
         for (int t = 0; t < WS_K; ++t) xs += g[t] * cs[t];
-        double* __restrict__ wcol = W + w_at(kmax, roff, c);
+        double* __restrict__ wcol = W + w_at(v.wrows, roff, c);
 #pragma unroll
         for (int a = 0; a < WS_K; ++a) {
             if (a < k) {
@@ -956,7 +956,7 @@ __global__ void __launch_bounds__(128) k_wfix(DevView v, int defer) {
     __syncthreads();
     if (k > 0) {
         for (int a = threadIdx.x; a < rows; a += blockDim.x) {
-            double* w = W + w_at(v.kmax, a, 3);
+            double* w = W + w_at(v.wrows, a, 3);
             const double w3 = w[0], w4 = w[1], w5 = w[2], w6 = w[3];
 #pragma unroll
             for (int i = 0; i < 4; ++i) w[i] = w3 * Jt[i * 4 + 0] + w4 * Jt[i * 4 + 1] + w5 * Jt[i * 4 + 2] + w6 * Jt[i * 4 + 3];
@@ -1003,7 +1003,7 @@ __global__ void __launch_bounds__(RG_THREADS, 4) k_rescue_gate(DevView v, ekfsla
     if (tid < 16) J1[tid] = (k1 > 0) ? v.jn1[(size_t)b * 16 + tid] : ((tid >> 2) == (tid & 3) ? 1.0 : 0.0);
     for (int e = tid; e < k1 * 7; e += blockDim.x) {
         const int a = e / 7, m = e - a * 7;
-        wcam[e] = W[w_at(kmax, a, m)];
+        wcam[e] = W[w_at(v.wrows, a, m)];
     }
     __syncthreads();
     for (int i = warp; i < nf; i += (blockDim.x >> 5)) {
@@ -1064,7 +1064,7 @@ __global__ void __launch_bounds__(RG_THREADS, 4) k_rescue_gate(DevView v, ekfsla
             for (int m = 0; m < 7; ++m) { const double wv = wcam[a * 7 + m]; v0 += hs[m] * wv; v1 += hs[EKF_HC + m] * wv; }
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
-                if (m < w) { const double wv = W[w_at(kmax, a, off + m)]; v0 += hs[7 + m] * wv; v1 += hs[EKF_HC + 7 + m] * wv; }
+                if (m < w) { const double wv = W[w_at(v.wrows, a, off + m)]; v0 += hs[7 + m] * wv; v1 += hs[EKF_HC + 7 + m] * wv; }
             }
             q00 += v0 * v0; q01 += v0 * v1; q11 += v1 * v1;
             if (keep_v) {   // rows 2i, 2i+1 of H_c Wt' for k_v (the hi inliers are a subset of the candidates): the Li scratch is free here
@@ -1213,7 +1213,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     }
     if (flags & 2) return;   // not the last iterate of an iterated update: W is recomputed, nothing pending
     { KScope ks(c, KT_WFIX); k_wfix<<<v.B, 128, 0, st>>>(v, (flags & 4) ? 1 : 0); }
-    if (flags & 4) return;   // deferred: the covariance downdate happens with the next (non-deferred) update
     if (c->arm_out && (mask & EKFSLAM_F_HI)) { cudaEventRecord(c->ev_out, st); c->arm_out = 0; }  // x, flags, stats are final
+    if (flags & 4) return;   // deferred: the covariance downdate happens with the next (non-deferred) update
     launch_downdate(c, (mask & EKFSLAM_F_HI) ? KT_DOWNDATE_HI : KT_DOWNDATE);
 }

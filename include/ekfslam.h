@@ -202,6 +202,18 @@ int ekfslam_update_iterated(ekfslam_ctx* ctx, int mask, int which_prior, int n_i
  * ransac, update_li, rescue, update_hi */
 int ekfslam_step(ekfslam_ctx* ctx, int reset, int match_mode);
 
+/* One covariance pass per frame.  By default ekfslam_step (and _step_graph / _step_host) does NOT apply the
+ * covariance downdate of the hi update (mc/update.m:13-14 inside mc/ekf_update_hi_inliers.m:21) at the end of the
+ * frame: x_k_k, the flags and the stats are final, the rows W = inv(L) H p_k_k stay pending on the device and are
+ * applied together with the NEXT frame's li downdate (prediction carries them through F, mc/predict_state_and_
+ * covariance.m:26-27, and G = H P is corrected by -(H W')W while P is streamed).  Every other entry point that reads
+ * or writes the covariance (download_state, the stage-level calls, map management ...) materialises p_k_k first, so
+ * the deferral is not observable through the API - only as rounding (<= 1e-13 relative, tests/test_gpu_defer.py).
+ * ekfslam_flush materialises p_k_k explicitly; ekfslam_set_defer_hi(ctx, 0) restores the two-pass step
+ * (environment: EKFSLAM_DEFER_HI=0). */
+int ekfslam_flush(ekfslam_ctx* ctx);
+int ekfslam_set_defer_hi(ekfslam_ctx* ctx, int on);
+
 /* ekfslam_step replayed from a captured CUDA graph (latency path: a single filter's step is ~25 small launches).
  * The graph is captured on first use and re-captured whenever anything the kernels see changes (buffers, parameters,
  * camera, reset / match_mode).  Falls back to ekfslam_step where capture is not possible (per-kernel timing enabled,

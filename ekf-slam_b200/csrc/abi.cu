@@ -107,7 +107,7 @@ static void kt_collect(ekfslam_ctx* c) {
 static const char* KT_NAMES[KT_COUNT] = {"k_begin_frame", "k_predict", "k_features", "k_hp", "k_innov", "k_ransac",
                                          "k_upd_S", "k_chol", "k_w", "k_downdate_hi", "k_downdate", "k_symmetrize",
                                          "k_add_features", "k_wfix", "k_w_hi", "k_chol_hi", "k_upd_S_hi",
-                                         "k_hp_rescue", "k_world", "k_vpend"};
+                                         "k_hp_rescue", "k_world", "k_vpend", "k_gcorr"};
 
 template <typename T>
 static cudaError_t dalloc(T** p, size_t count, int64_t* total) {
@@ -232,6 +232,8 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     DA(v.W, Bz * (size_t)v.wstride);
     DA(v.Sb, Bz * v.kmax * v.kmax);
     DA(v.Li, Bz * v.kmax * v.kmax);
+    v.vld = (v.kmax + 7) & ~7;
+    DA(v.V, Bz * v.kmax * v.vld);
     DA(v.yv, Bz * v.kmax);
     DA(v.jn, Bz * 16);
     DA(v.jnt, Bz * 16);
@@ -300,7 +302,7 @@ int ekfslam_destroy(ekfslam_ctx* c) {
     cudaSetDevice(c->device);
     if (c->own_zc) { c->v.zc = c->own_zc; c->v.mflags = c->own_mflags; c->v.u = c->own_u; c->own_zc = nullptr; }
     DevView& v = c->v;
-    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.jnt, v.jn1, v.kpend, v.roff, v.ktot, v.kmaxdev, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
+    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.V, v.yv, v.jn, v.jnt, v.jn1, v.kpend, v.roff, v.ktot, v.kmaxdev, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
                     v.flags, v.mflags, v.foff, v.nstate, v.nfeat, v.counters, v.tag, v.sel, v.ksel, v.stats, v.nhyp_tab,
                     c->mm_del, c->mm_quota, c->det_n, c->det_uv, c->det_tag, c->world_points, c->world_poses};
     for (void* p : ptrs)
@@ -657,7 +659,7 @@ int ekfslam_hp(ekfslam_ctx* c, int need, int forbid) {
 
 int ekfslam_innovation(ekfslam_ctx* c) {
     NEED_P(c);
-    launch_innov(c, 0);
+    launch_innov_gather(c);
     LAUNCHED();
     return EKFSLAM_OK;
 }
@@ -665,9 +667,8 @@ int ekfslam_innovation(ekfslam_ctx* c) {
 int ekfslam_measure(ekfslam_ctx* c, int which) {
     NEED_P(c);
     launch_features(c, which ? 1 : 0, 3);
-    launch_hp(c, EKFSLAM_F_HAS_H, 0);
-    launch_innov(c, 0);
-    LAUNCHED();
+    launch_innov_gather(c);   // S_i from 13x13 gathers of P: the full rows H P are built where they are consumed
+    LAUNCHED();               // (ekfslam_ransac: per hypothesis; ekfslam_update_li / ekfslam_hp: per update)
     return EKFSLAM_OK;
 }
 
@@ -704,7 +705,11 @@ int ekfslam_update_masked(ekfslam_ctx* c, int mask, int which_prior) {
     return EKFSLAM_OK;
 }
 
-int ekfslam_update_li(ekfslam_ctx* c) { return ekfslam_update_masked(c, EKFSLAM_F_LI, 1); }
+int ekfslam_update_li(ekfslam_ctx* c) {
+    NEED_P(c);
+    launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);   // G rows of the low-innovation inliers
+    return ekfslam_update_masked(c, EKFSLAM_F_LI, 1);
+}
 
 int ekfslam_update_iterated(ekfslam_ctx* c, int mask, int which_prior, int n_iter) {
     NEED_P(c);
@@ -741,19 +746,20 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
     if (c->v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "step: no uniform stream uploaded");
     // defer_hi: the covariance downdate of the hi update is NOT applied at the end of the frame; its rows stay pending in
     // W and ride along with the next frame's li downdate (P crosses HBM once per frame for the downdates instead of
-    // twice).  In between, k_predict carries the pending rows through F and k_hp_pend subtracts (H Wp') Wp from
-    // G = H P_mem while it streams P_mem.
+    // twice).  In between, k_predict carries the pending rows through F and every product with the covariance picks up
+    // the rank-kp correction (k_vpend / k_innov_gather / k_ransac / k_gcorr, see k_model.cu).
     const int defer = c->defer_hi;
     if (reset) launch_begin_frame(c);
     launch_predict(c);
     launch_features(c, 1, 3);
-    if (defer) launch_hp_pend(c, EKFSLAM_F_HAS_H, 0);   // (bit-identical to k_hp for a filter without pending rows)
-    else launch_hp(c, EKFSLAM_F_HAS_H, 0);
-    launch_innov(c, 0);
+    if (defer) launch_vpend(c, EKFSLAM_F_HAS_H, 0);     // Vn = -H Wp' (no-op for a filter without pending rows)
+    launch_innov_gather(c);
     if (c->wait_inputs) { cudaStreamWaitEvent(c->stream, c->ev_in, 0); c->wait_inputs = 0; }
     if (match_mode) launch_innov(c, match_mode);
-    launch_ransac(c);
+    launch_ransac(c);                                    // builds the G rows of the hypotheses it scores
     {
+        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);                  // G rows of the low-innovation inliers: H P_mem ...
+        if (defer) launch_gcorr(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);   // ... + Vn Wp
         launch_update(c, EKFSLAM_F_LI, 1);
         launch_features(c, 0, 3);
         if (c->rescue_gather) {

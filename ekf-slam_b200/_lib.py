@@ -91,8 +91,6 @@ _SIGS = {
     "ekfslam_update_iterated": (_I, [_P, _I, _I, _I]),
     "ekfslam_step": (_I, [_P, _I, _I]),
     "ekfslam_step_graph": (_I, [_P, _I, _I]),
-    "ekfslam_flush": (_I, [_P]),
-    "ekfslam_set_defer_hi": (_I, [_P, _I]),
     "ekfslam_stage_frame": (_I, [_P, _P, _P, _P, _I]),
     "ekfslam_step_host": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "ekfslam_reset_filters": (_I, [_P, _I, _I, _P, _P]),

@@ -246,7 +246,6 @@ def ransac_hypotheses(f, features_info, cam, u=None, fixed_hypotheses=0, info=No
         u = np.random.rand(fixed_hypotheses if fixed_hypotheses > 0 else 1000)
     bank.set_params(fixed_hyp=int(fixed_hypotheses))
     bank.upload_uniforms(np.asarray(u, dtype=np.float64)[None])
-    bank.hp(need=L.F_HAS_H | L.F_IC)
     bank.ransac_hypotheses()
     st = bank.download_stats()
     bank.set_params(fixed_hyp=0)

@@ -366,15 +366,6 @@ class FilterBank:
         fn = self.lib.ekfslam_step_graph if graph else self.lib.ekfslam_step
         L.check(fn(self._h, 1 if reset else 0, match_mode))
 
-    def flush(self):
-        """Materialise p_k_k (apply the covariance rows a step left pending; see ekfslam_flush).  Implicit in every
-        call that reads or writes the covariance - only needed to time or order the work explicitly."""
-        L.check(self.lib.ekfslam_flush(self._h))
-
-    def set_defer_hi(self, on):
-        """One covariance pass per frame (default) / the two-pass step (see ekfslam_set_defer_hi)."""
-        L.check(self.lib.ekfslam_set_defer_hi(self._h, 1 if on else 0))
-
     def stage_frame(self, d_zc, d_fl, d_u, n_u):
         """Device pointers (ints) of a resident frame, copied into the context's own frame buffers."""
         L.check(self.lib.ekfslam_stage_frame(self._h, C.c_void_p(d_zc), C.c_void_p(d_fl), C.c_void_p(d_u), int(n_u)))

@@ -34,15 +34,6 @@ static int fail(int code, const std::string& msg) {
         CK(cudaSetDevice((c)->device));                                 \
     } while (0)
 
-// Entry points that read or write P, W or the pending-row bookkeeping outside ekfslam_step first materialise the
-// covariance a deferred hi update left as "P_mem + pending rows" (flush_pending below).
-static int flush_pending(ekfslam_ctx* c);
-#define NEED_P(c)                                                       \
-    do {                                                                \
-        NEED_CTX(c);                                                    \
-        if ((c)->pending) { if (int _r = flush_pending(c)) return _r; } \
-    } while (0)
-
 // ---- per-kernel timing ---------------------------------------------------------------------
 struct KTimer {
     struct Rec { cudaEvent_t a, b; int slot; };
@@ -107,7 +98,7 @@ static void kt_collect(ekfslam_ctx* c) {
 static const char* KT_NAMES[KT_COUNT] = {"k_begin_frame", "k_predict", "k_features", "k_hp", "k_innov", "k_ransac",
                                          "k_upd_S", "k_chol", "k_w", "k_downdate_hi", "k_downdate", "k_symmetrize",
                                          "k_add_features", "k_wfix", "k_w_hi", "k_chol_hi", "k_upd_S_hi",
-                                         "k_hp_rescue", "k_world", "k_vpend", "k_gcorr"};
+                                         "k_hp_rescue", "k_world"};
 
 template <typename T>
 static cudaError_t dalloc(T** p, size_t count, int64_t* total) {
@@ -118,16 +109,6 @@ static cudaError_t dalloc(T** p, size_t count, int64_t* total) {
         e = cudaMemset(*p, 0, bytes ? bytes : 1);
     }
     return e;
-}
-
-static int flush_pending(ekfslam_ctx* c) {
-    // p_k_k = jn1 P_mem jn1' - Wp'Wp for every filter with pending rows (the others: ktot = 0, untouched)
-    launch_flush_prep(c);
-    launch_downdate(c, KT_DOWNDATE_HI);
-    c->pending = 0;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(EKFSLAM_ERR_CUDA, std::string("flush_pending: ") + cudaGetErrorString(e));
-    return EKFSLAM_OK;
 }
 
 extern "C" {
@@ -227,13 +208,11 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     DA(v.xp, Bz * v.ld);
     DA(v.P, Bz * v.nmax * v.ld);
     DA(v.G, Bz * v.kmax * v.ld);
-    v.wrows = 2 * v.kmax;
+    v.wrows = v.kmax;
     v.wstride = (long long)((v.ld + 63) / 64) * v.wrows * EKF_WPAD;
     DA(v.W, Bz * (size_t)v.wstride);
     DA(v.Sb, Bz * v.kmax * v.kmax);
     DA(v.Li, Bz * v.kmax * v.kmax);
-    v.vld = (v.kmax + 7) & ~7;
-    DA(v.V, Bz * v.kmax * v.vld);
     DA(v.yv, Bz * v.kmax);
     DA(v.jn, Bz * 16);
     DA(v.jnt, Bz * 16);
@@ -290,8 +269,6 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     {
         const char* e2 = getenv("EKFSLAM_RESCUE_GATHER");
         c->rescue_gather = (e2 && e2[0] == '0') ? 0 : 1;   // default on: gate 0.36 + rows of the hi inliers 0.61 ms vs 1.15 ms
-        const char* e3 = getenv("EKFSLAM_DEFER_HI");
-        c->defer_hi = (e3 && e3[0] == '0') ? 0 : 1;        // default on: one covariance pass per frame (see ekfslam_step)
     }
     *out = c;
     return EKFSLAM_OK;
@@ -302,7 +279,7 @@ int ekfslam_destroy(ekfslam_ctx* c) {
     cudaSetDevice(c->device);
     if (c->own_zc) { c->v.zc = c->own_zc; c->v.mflags = c->own_mflags; c->v.u = c->own_u; c->own_zc = nullptr; }
     DevView& v = c->v;
-    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.V, v.yv, v.jn, v.jnt, v.jn1, v.kpend, v.roff, v.ktot, v.kmaxdev, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
+    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.jnt, v.jn1, v.kpend, v.roff, v.ktot, v.kmaxdev, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
                     v.flags, v.mflags, v.foff, v.nstate, v.nfeat, v.counters, v.tag, v.sel, v.ksel, v.stats, v.nhyp_tab,
                     c->mm_del, c->mm_quota, c->det_n, c->det_uv, c->det_tag, c->world_points, c->world_poses};
     for (void* p : ptrs)
@@ -438,7 +415,7 @@ static int check_range(const ekfslam_ctx* c, int b0, int nb) {
 // ---- filter struct <-> device ------------------------------------------------------------
 int ekfslam_upload_state(ekfslam_ctx* c, int b0, int nb, int which, const double* x, const double* P,
                          const int32_t* nstate) {
-    NEED_P(c);
+    NEED_CTX(c);
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     DevView& v = c->v;
     if (nstate) {
@@ -464,7 +441,6 @@ int ekfslam_upload_state(ekfslam_ctx* c, int b0, int nb, int which, const double
 
 int ekfslam_download_state(ekfslam_ctx* c, int b0, int nb, int which, double* x, double* P, int32_t* nstate) {
     NEED_CTX(c);
-    if (P && c->pending) { if (int r = flush_pending(c)) return r; }   // x_k_k is always current; only P can be pending
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     DevView& v = c->v;
     if (nstate) CK(cudaMemcpyAsync(nstate, v.nstate + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, c->stream));
@@ -484,7 +460,7 @@ int ekfslam_download_state(ekfslam_ctx* c, int b0, int nb, int which, double* x,
 
 // ---- features_info <-> device --------------------------------------------------------------
 int ekfslam_upload_feature_types(ekfslam_ctx* c, int b0, int nb, const uint8_t* type, const int32_t* nfeat) {
-    NEED_P(c);
+    NEED_CTX(c);
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!type || !nfeat) return fail(EKFSLAM_ERR_INVALID, "type / nfeat is null");
@@ -636,7 +612,7 @@ int ekfslam_begin_frame(ekfslam_ctx* c) {
 }
 
 int ekfslam_predict(ekfslam_ctx* c) {
-    NEED_P(c);
+    NEED_CTX(c);
     launch_predict(c);
     LAUNCHED();
     return EKFSLAM_OK;
@@ -651,21 +627,21 @@ int ekfslam_features(ekfslam_ctx* c, int which, int parts) {
 }
 
 int ekfslam_hp(ekfslam_ctx* c, int need, int forbid) {
-    NEED_P(c);
+    NEED_CTX(c);
     launch_hp(c, need, forbid);
     LAUNCHED();
     return EKFSLAM_OK;
 }
 
 int ekfslam_innovation(ekfslam_ctx* c) {
-    NEED_P(c);
+    NEED_CTX(c);
     launch_innov_gather(c);
     LAUNCHED();
     return EKFSLAM_OK;
 }
 
 int ekfslam_measure(ekfslam_ctx* c, int which) {
-    NEED_P(c);
+    NEED_CTX(c);
     launch_features(c, which ? 1 : 0, 3);
     launch_innov_gather(c);   // S_i from 13x13 gathers of P: the full rows H P are built where they are consumed
     LAUNCHED();               // (ekfslam_ransac: per hypothesis; ekfslam_update_li / ekfslam_hp: per update)
@@ -680,7 +656,7 @@ static int gate_mode(ekfslam_ctx* c, int mode) {
 }
 
 int ekfslam_gate(ekfslam_ctx* c) {
-    NEED_P(c);
+    NEED_CTX(c);
     return gate_mode(c, 1);
 }
 
@@ -690,7 +666,7 @@ int ekfslam_apply_matches(ekfslam_ctx* c) {
 }
 
 int ekfslam_ransac(ekfslam_ctx* c) {
-    NEED_P(c);
+    NEED_CTX(c);
     if (c->v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "ransac: no uniform stream uploaded (ekfslam_upload_uniforms)");
     launch_ransac(c);
     LAUNCHED();
@@ -698,7 +674,7 @@ int ekfslam_ransac(ekfslam_ctx* c) {
 }
 
 int ekfslam_update_masked(ekfslam_ctx* c, int mask, int which_prior) {
-    NEED_P(c);
+    NEED_CTX(c);
     if (!(mask & 0xff)) return fail(EKFSLAM_ERR_INVALID, "empty mask");
     launch_update(c, mask, which_prior ? 1 : 0);
     LAUNCHED();
@@ -706,13 +682,13 @@ int ekfslam_update_masked(ekfslam_ctx* c, int mask, int which_prior) {
 }
 
 int ekfslam_update_li(ekfslam_ctx* c) {
-    NEED_P(c);
+    NEED_CTX(c);
     launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);   // G rows of the low-innovation inliers
     return ekfslam_update_masked(c, EKFSLAM_F_LI, 1);
 }
 
 int ekfslam_update_iterated(ekfslam_ctx* c, int mask, int which_prior, int n_iter) {
-    NEED_P(c);
+    NEED_CTX(c);
     if (!(mask & 0xff)) return fail(EKFSLAM_ERR_INVALID, "empty mask");
     if (n_iter < 1 || n_iter > 64) return fail(EKFSLAM_ERR_INVALID, "n_iter must be in [1, 64]");
     DevView& v = c->v;
@@ -730,7 +706,7 @@ int ekfslam_update_iterated(ekfslam_ctx* c, int mask, int which_prior, int n_ite
 }
 
 int ekfslam_rescue(ekfslam_ctx* c) {
-    NEED_P(c);
+    NEED_CTX(c);
     launch_features(c, 0, 3);                            // h, H of ALL features at x_k_k (:6-7)
     launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);  // G rows of the candidates (IC && !LI)
     launch_innov(c, 3);                                 // chi2 gate -> HI (:11-20)
@@ -744,22 +720,15 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
     NEED_CTX(c);
     if (match_mode < 0 || match_mode > 2) return fail(EKFSLAM_ERR_INVALID, "match_mode must be 0, 1 or 2");
     if (c->v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "step: no uniform stream uploaded");
-    // defer_hi: the covariance downdate of the hi update is NOT applied at the end of the frame; its rows stay pending in
-    // W and ride along with the next frame's li downdate (P crosses HBM once per frame for the downdates instead of
-    // twice).  In between, k_predict carries the pending rows through F and every product with the covariance picks up
-    // the rank-kp correction (k_vpend / k_innov_gather / k_ransac / k_gcorr, see k_model.cu).
-    const int defer = c->defer_hi;
     if (reset) launch_begin_frame(c);
     launch_predict(c);
     launch_features(c, 1, 3);
-    if (defer) launch_vpend(c, EKFSLAM_F_HAS_H, 0);     // Vn = -H Wp' (no-op for a filter without pending rows)
-    launch_innov_gather(c);
+    launch_innov_gather(c);                              // S_i from 13x13 gathers of P: no G rows needed yet
     if (c->wait_inputs) { cudaStreamWaitEvent(c->stream, c->ev_in, 0); c->wait_inputs = 0; }
     if (match_mode) launch_innov(c, match_mode);
     launch_ransac(c);                                    // builds the G rows of the hypotheses it scores
     {
-        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);                  // G rows of the low-innovation inliers: H P_mem ...
-        if (defer) launch_gcorr(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);   // ... + Vn Wp
+        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);   // G rows of the low-innovation inliers only
         launch_update(c, EKFSLAM_F_LI, 1);
         launch_features(c, 0, 3);
         if (c->rescue_gather) {
@@ -770,21 +739,9 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
             launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI, KT_HP_RESCUE);
             launch_innov(c, 3);
         }
-        launch_update(c, EKFSLAM_F_HI, 0, defer ? 4 : 0);
-        c->pending = defer;   // (the li downdate above has consumed whatever was pending before)
+        launch_update(c, EKFSLAM_F_HI, 0);
     }
     LAUNCHED();
-    return EKFSLAM_OK;
-}
-
-int ekfslam_flush(ekfslam_ctx* c) {
-    NEED_P(c);
-    return EKFSLAM_OK;
-}
-
-int ekfslam_set_defer_hi(ekfslam_ctx* c, int on) {
-    NEED_P(c);
-    c->defer_hi = on ? 1 : 0;
     return EKFSLAM_OK;
 }
 
@@ -792,7 +749,7 @@ int ekfslam_set_defer_hi(ekfslam_ctx* c, int on) {
 struct StepGraph {
     cudaGraphExec_t exec;
     DevView v; ekfslam_params prm; DevCam cam;
-    int reset, match_mode, rescue_gather, defer_hi;
+    int reset, match_mode, rescue_gather;
     int64_t launches;
 };
 
@@ -813,7 +770,7 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
     StepGraph* g = (StepGraph*)c->step_graph;
     if (g && (memcmp(&g->v, &v, sizeof(DevView)) || memcmp(&g->prm, &c->prm, sizeof(ekfslam_params)) ||
               memcmp(&g->cam, &c->cam, sizeof(DevCam)) || g->reset != reset || g->match_mode != match_mode ||
-              g->rescue_gather != c->rescue_gather || g->defer_hi != c->defer_hi)) {
+              g->rescue_gather != c->rescue_gather)) {
         step_graph_destroy(c);
         g = nullptr;
     }
@@ -823,7 +780,6 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
         memset(g, 0, sizeof(*g));
         memcpy(&g->v, &v, sizeof(DevView)); memcpy(&g->prm, &c->prm, sizeof(ekfslam_params)); memcpy(&g->cam, &c->cam, sizeof(DevCam));
         g->reset = reset; g->match_mode = match_mode; g->rescue_gather = c->rescue_gather;
-        g->defer_hi = c->defer_hi;
         const int64_t l0 = c->launches;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
@@ -846,7 +802,6 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
     }
     CK(cudaGraphLaunch(g->exec, c->stream));
     c->launches += g->launches;
-    c->pending = c->defer_hi;
     return EKFSLAM_OK;
 }
 
@@ -902,7 +857,7 @@ int ekfslam_step_host(ekfslam_ctx* c, int match_mode, const double* zc, const ui
 }
 
 int ekfslam_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* xv, const double* Pxv) {
-    NEED_P(c);
+    NEED_CTX(c);
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!xv || !Pxv) return fail(EKFSLAM_ERR_INVALID, "xv / Pxv is null");
@@ -935,7 +890,7 @@ int ekfslam_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* xv, cons
 
 int ekfslam_add_features(ekfslam_ctx* c, int b0, int nb, const double* uvd, const uint8_t* add, double std_pxl,
                          double initial_rho, double std_rho) {
-    NEED_P(c);
+    NEED_CTX(c);
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!uvd) return fail(EKFSLAM_ERR_INVALID, "uvd is null");
@@ -966,7 +921,7 @@ static int ensure_scratch(ekfslam_ctx* c, size_t need) {
 }
 
 int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* c, double threshold, int force_index, int32_t* converted) {
-    NEED_P(c);
+    NEED_CTX(c);
     DevView& v = c->v;
     if (v.nmax > 512 * 8) return fail(EKFSLAM_ERR_INVALID, "inversedepth_2_cartesian supports n_max <= 4096");
     if (force_index >= v.N) return fail(EKFSLAM_ERR_INVALID, "force_index out of range");
@@ -979,7 +934,7 @@ int ekfslam_inversedepth_2_cartesian(ekfslam_ctx* c, double threshold, int force
 }
 
 int ekfslam_delete_features(ekfslam_ctx* c, int b0, int nb, const uint8_t* del) {
-    NEED_P(c);
+    NEED_CTX(c);
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");
     if (check_range(c, b0, nb)) return EKFSLAM_ERR_INVALID;
     if (!del) return fail(EKFSLAM_ERR_INVALID, "del is null");
@@ -1068,7 +1023,7 @@ int ekfslam_download_candidates(ekfslam_ctx* c, int b0, int nb, double* zc, uint
 }
 
 int ekfslam_map_management(ekfslam_ctx* c, int min_number_of_features_in_image) {
-    NEED_P(c);
+    NEED_CTX(c);
     DevView& v = c->v;
     if (min_number_of_features_in_image < 0) return fail(EKFSLAM_ERR_INVALID, "min_number_of_features_in_image < 0");
     if (c->own_zc) return fail(EKFSLAM_ERR_STATE, "frame buffers are bound to caller memory (ekfslam_unbind_frame first)");

@@ -26,15 +26,13 @@ struct DevView {
     double* G;            // [B][kmax][ld] rows 2i,2i+1 = H_i * P
     double* W;            // [B][ncb][wrows][EKF_WPAD] W = inv(L) * G_sel, stored by 64-column panels (see w_at)
     long long wstride;    // doubles per filter in W = ncb * wrows * EKF_WPAD, ncb = ceil(ld / 64)
-    int wrows;            // rows per panel of W = 2 * kmax: the rows a deferred hi update left pending + the li rows stacked behind them
+    int wrows;            // rows per panel of W (= kmax)
     double* Sb;           // [B][kmax][kmax] stacked innovation covariance / its Cholesky factor
     double* Li;           // [B][kmax][kmax] inverse of the Cholesky factor
-    double* V;            // [B][kmax][vld] Vn = -H Wp' for the rows a deferred update left pending (k_vpend -> k_hp_pend)
-    int vld;              // row pitch of V: kmax rounded up to 8 (rows are zero-filled to the next multiple of 8 pending rows)
     double* yv;           // [B][kmax]     inv(L)*(z-h)
     double* jn;           // [B][16]       normalisation Jacobian the covariance downdate applies (product over the pending updates)
     double* jnt;          // [B][16]       normJac(q+) of the update being computed
-    double* jn1;          // [B][16]       normJac of a deferred (not yet applied) update; k_predict folds it into F and resets it to I
+    double* jn1;          // [B][16]       normJac of a deferred (not yet applied) update
     double* cv;           // [B][kmax]     inv(S)*(z-h) = inv(L)' * yv
     double* h;            // [B][N][2]
     double* Hc;           // [B][N][26]
@@ -75,8 +73,7 @@ struct DevWorld {
 // per-kernel timing (ekfslam_enable_timing): every launch is bracketed by an event pair
 enum {
     KT_BEGIN_FRAME = 0, KT_PREDICT, KT_FEATURES, KT_HP, KT_INNOV, KT_RANSAC, KT_UPD_S, KT_CHOL, KT_W, KT_DOWNDATE_HI,
-    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_WFIX, KT_W_HI, KT_CHOL_HI, KT_UPD_S_HI, KT_HP_RESCUE, KT_WORLD, KT_VPEND, KT_GCORR,
-    KT_COUNT
+    KT_DOWNDATE, KT_SYMMETRIZE, KT_ADD_FEATURES, KT_WFIX, KT_W_HI, KT_CHOL_HI, KT_UPD_S_HI, KT_HP_RESCUE, KT_WORLD, KT_COUNT
 };
 struct KTimer;
 
@@ -92,12 +89,6 @@ struct ekfslam_ctx {
     int64_t launches;
     int stage;  // call-order tracking
     int rescue_gather;   // ekfslam_step: rescue gate from 13x13 gathers of P, G rows only for the hi inliers
-    // ekfslam_step defers the covariance downdate of the hi update into the NEXT frame's li downdate (one pass over P
-    // per frame instead of two): the hi rows stay pending in W (kpend / jn1 on the device), prediction carries them
-    // through F, k_hp_pend corrects G = H P while it streams P.  `pending` = some filter may hold pending rows: every
-    // other entry point that reads or writes P materialises it first (flush_pending, abi.cu).
-    int defer_hi;
-    int pending;
     // ekfslam_step_host overlaps its PCIe copies with the step: inputs go up on copy_stream while prediction and the
     // measurement model run (first needed by the matcher gate), x / flags / stats come down while the last covariance
     // downdate (which only touches P) is still running.
@@ -169,10 +160,7 @@ void launch_begin_frame(ekfslam_ctx* c);
 void launch_predict(ekfslam_ctx* c);
 void launch_features(ekfslam_ctx* c, int which, int parts);  // parts: 1 = h, 2 = H, 3 = both
 void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot = KT_HP);  // G rows for features with (flags&need)==need && !(flags&forbid)
-void launch_vpend(ekfslam_ctx* c, int need, int forbid);     // Vn = -H Wp' for the rows a deferred update left pending
-void launch_gcorr(ekfslam_ctx* c, int need, int forbid);     // G rows of the selection += Vn Wp (after launch_hp on the same selection)
 void launch_innov_gather(ekfslam_ctx* c);                    // S_i (+R) of every predicted feature from 13x13 gathers of P (no G rows)
-void launch_flush_prep(ekfslam_ctx* c);                      // pending rows -> ktot / jn for a stand-alone covariance downdate
 void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gate / explicit matches / rescue gate
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
 void launch_ransac(ekfslam_ctx* c);

@@ -42,15 +42,8 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
     __shared__ double Pxx[13][13];
     __shared__ double T[13][13];
     __shared__ double Fqq[4][4], Fqw[4][3];
-    __shared__ double Jh[4][4];
 
     const int tid = threadIdx.x;
-    // Rows a deferred hi update left pending (ekfslam_step, defer_hi): the covariance in memory is P_mem with
-    //   p_k_k = Jh P_mem Jh' - Wp'Wp,   Jh = blkdiag(I3, jn1, I),  Wp = W[0:kp)
-    // so  p_k+1_k = F p_k_k F' + Q = (F Jh) P_mem (F Jh)' + Q - (Wp F')'(Wp F'):  Jh is applied to P_mem here, in
-    // front of F, the pending rows are carried through F', and jn1 goes back to the identity.
-    const int kp = v.kpend[b];
-    if (kp > 0 && tid < 16) Jh[tid >> 2][tid & 3] = v.jn1[(size_t)b * 16 + tid];
     for (int e = tid; e < 169; e += blockDim.x) {
         const int r = e / 13, cc = e - r * 13;
         Pxx[r][cc] = P[(size_t)r * ld + cc];
@@ -58,22 +51,6 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
         Q[r][cc] = 0.0;
     }
     __syncthreads();
-    if (kp > 0) {   // Pxx <- Jh Pxx Jh' (rows / columns 3..6)
-        for (int e = tid; e < 169; e += blockDim.x) {
-            const int r = e / 13, cc = e - r * 13;
-            double s = Pxx[r][cc];
-            if (r >= 3 && r < 7) s = Jh[r - 3][0] * Pxx[3][cc] + Jh[r - 3][1] * Pxx[4][cc] + Jh[r - 3][2] * Pxx[5][cc] + Jh[r - 3][3] * Pxx[6][cc];
-            T[r][cc] = s;
-        }
-        __syncthreads();
-        for (int e = tid; e < 169; e += blockDim.x) {
-            const int r = e / 13, cc = e - r * 13;
-            double s = T[r][cc];
-            if (cc >= 3 && cc < 7) s = T[r][3] * Jh[cc - 3][0] + T[r][4] * Jh[cc - 3][1] + T[r][5] * Jh[cc - 3][2] + T[r][6] * Jh[cc - 3][3];
-            Pxx[r][cc] = s;
-        }
-        __syncthreads();
-    }
     if (tid == 0) {
         const double dt = prm.delta_t;
         const double q0 = x[3], qx = x[4], qy = x[5], qz = x[6];
@@ -167,11 +144,6 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
         double c[13];
 #pragma unroll
         for (int r = 0; r < 13; ++r) c[r] = P[(size_t)j * ld + r];   // lower triangle (authoritative): P[r][j] = P[j][r], j >= 13 > r
-        if (kp > 0) {   // pending normalisation Jacobian first: c[3..6] <- Jh c[3..6]
-            const double c3 = c[3], c4 = c[4], c5 = c[5], c6 = c[6];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) c[3 + r] = Jh[r][0] * c3 + Jh[r][1] * c4 + Jh[r][2] * c5 + Jh[r][3] * c6;
-        }
         double o[7];
         const double dt = prm.delta_t;
         o[0] = c[0] + dt * c[7]; o[1] = c[1] + dt * c[8]; o[2] = c[2] + dt * c[9];
@@ -201,23 +173,6 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
         s += Q[r][cc];
         P[(size_t)r * ld + cc] = s;
         P[(size_t)cc * ld + r] = s;
-    }
-    if (kp > 0) {
-        // pending rows through the prediction: Wp <- Wp F' (only columns 0..6 change; they live in panel 0 of W)
-        double* __restrict__ W = v.W + (size_t)b * v.wstride;
-        const double dt = prm.delta_t;
-        for (int m = tid; m < kp; m += blockDim.x) {
-            double* w = W + w_at(v.wrows, m, 0);
-            double c[13];
-#pragma unroll
-            for (int r = 0; r < 13; ++r) c[r] = w[r];
-            w[0] = c[0] + dt * c[7]; w[1] = c[1] + dt * c[8]; w[2] = c[2] + dt * c[9];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                w[3 + r] = Fqq[r][0] * c[3] + Fqq[r][1] * c[4] + Fqq[r][2] * c[5] + Fqq[r][3] * c[6] +
-                           Fqw[r][0] * c[10] + Fqw[r][1] * c[11] + Fqw[r][2] * c[12];
-        }
-        if (tid < 16) v.jn1[(size_t)b * 16 + tid] = ((tid >> 2) == (tid & 3)) ? 1.0 : 0.0;
     }
 }
 
@@ -390,183 +345,8 @@ void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Rows of a deferred update pending in W (ekfslam_step, defer_hi).  The covariance is
-//   P = P_mem - Wp'Wp   (Wp = W[0:kp), already carried through the prediction by k_predict)
-// so every product with P picks up a rank-kp correction through  V = H Wp'  (2N x kp; stored negated, Vn = -V):
-//   S_i = H_i P_mem H_i' - V_i V_i'                      (k_innov_gather)
-//   G   = H P_mem + Vn Wp                                 (hypothesis rows: k_ransac; update rows: k_hp + k_gcorr)
-// Folding the correction into the k_hp pass for ALL 2N rows was tried three ways (a DFMA version with a column of Wp in
-// registers, two DMMA versions with the accumulator layout as lane mapping): every one was latency-bound at 12 warps
-// per SM and 3-6x slower than k_hp, which owes its 94 % of the HBM roofline to 64 resident warps.  So the full rows
-// are only produced where they are needed - the handful of RANSAC hypotheses and the features of the update - by
-// the unchanged k_hp on those rows, and the correction is a small tensor-core pass over the same rows.
-// ---------------------------------------------------------------------------------------
-// Vn = -H Wp' (rows 2i, 2i+1 <- feature i; kp columns, zero-filled up to the next multiple of 8; row pitch vld).
-// grid (groups of 32 features, B), 4 warps: lanes along the features (the feature blocks of 32 consecutive features
-// are one contiguous range of a W row, the camera columns a broadcast), warps along the pending rows.
-__global__ void __launch_bounds__(128) k_vpend(DevView v, int need, int forbid) {
-    const int b = blockIdx.y;
-    const int kp = v.kpend[b];
-    if (kp == 0) return;
-    const int nf = v.nfeat[b], N = v.N, vld = v.vld;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + lane;
-    if (i >= nf) return;
-    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
-    double* __restrict__ V0 = v.V + ((size_t)b * v.kmax + 2 * i) * vld;
-    double* __restrict__ V1 = V0 + vld;
-    const int kp8 = (kp + 7) & ~7;
-    const size_t t = (size_t)b * N + i;
-    const int ty = v.ftype[t];
-    const uint8_t fl = v.flags[t];
-    const bool on = ty != EKFSLAM_FEAT_NONE && (fl & need) == need && !(fl & forbid);
-    if (!on) {
-        for (int m = warp; m < kp8; m += 4) { V0[m] = 0.0; V1[m] = 0.0; }
-        return;
-    }
-    const int off = v.foff[t];
-    const bool id = ty == EKFSLAM_FEAT_INVERSEDEPTH;
-    double H[EKF_HSTRIDE];
-#pragma unroll
-    for (int k = 0; k < EKF_HSTRIDE; ++k) H[k] = v.Hc[t * EKF_HSTRIDE + k];   // (Cartesian: columns 10..12 are zero)
-    const int o3 = id ? off + 3 : off;          // Cartesian features re-read their first rows for the three missing ones
-    for (int m = warp; m < kp8; m += 4) {
-        double a0 = 0.0, a1 = 0.0;
-        if (m < kp) {
-            const double* __restrict__ wc = W + w_at(v.wrows, m, 0);
-            const double* __restrict__ wf = W + w_at(v.wrows, m, off);       // a feature block may straddle two panels:
-            const double* __restrict__ wg = W + w_at(v.wrows, m, o3);        // two base pointers, element-wise w_at below
-            double wv[13];
-#pragma unroll
-            for (int r = 0; r < 7; ++r) wv[r] = wc[r];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) wv[7 + r] = ((off & 63) + r < 64) ? wf[r] : W[w_at(v.wrows, m, off + r)];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) wv[10 + r] = ((o3 & 63) + r < 64) ? wg[r] : W[w_at(v.wrows, m, o3 + r)];
-#pragma unroll
-            for (int r = 0; r < 13; ++r) { a0 += H[r] * wv[r]; a1 += H[EKF_HC + r] * wv[r]; }
-        }
-        V0[m] = -a0;
-        V1[m] = -a1;
-    }
-}
-
-void launch_vpend(ekfslam_ctx* c, int need, int forbid) {
-    KScope ks(c, KT_VPEND);
-    dim3 gv((c->v.N + 31) / 32, c->v.B);
-    k_vpend<<<gv, 128, 0, c->stream>>>(c->v, need, forbid);
-}
-
-// ---------------------------------------------------------------------------------------
-// G rows of the selected features += Vn Wp  (read-modify-write, after k_hp on the same selection).  A dense
-// (rows x kp) x (kp x n) product per filter on the fp64 tensor pipe: grid (64-column panels, B), 4 warps x 16 columns.
-// The B fragments (Wp, 32 pending rows per pass) of a warp's 16 columns do not depend on the row group: they are
-// loaded once into registers; a warp then walks the selected features four at a time (8 G rows = one DMMA tile row)
-// with the two accumulator tiles (from G) and the A fragments (Vn) of the pass all requested before the first use -
-// one memory round trip per group, no shared-memory staging, one barrier (the selection list).
-// ---------------------------------------------------------------------------------------
-#define GC_KB 32
-__global__ void __launch_bounds__(128, 5) k_gcorr(DevView v, int need, int forbid) {
-    extern __shared__ int gc_sel[];                    // [N] selected features (feature order)
-    __shared__ int s_cnt;
-    const int b = blockIdx.y;
-    const int kp = v.kpend[b];
-    if (kp == 0) return;
-    const int n = v.nstate[b];
-    const int c00 = blockIdx.x * 64;
-    if (c00 >= n) return;
-    const int ld = v.ld, vld = v.vld, nf = v.nfeat[b];
-    double* __restrict__ G = v.G + (size_t)b * v.kmax * ld;
-    const double* __restrict__ Wpan = v.W + (size_t)b * v.wstride + (size_t)blockIdx.x * v.wrows * EKF_WPAD;
-    const double* __restrict__ V = v.V + (size_t)b * v.kmax * vld;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, q = lane & 3;
-    if (warp == 0) {
-        int cnt = 0;
-        for (int i0 = 0; i0 < nf; i0 += 32) {
-            const int i = i0 + lane;
-            bool on = false;
-            if (i < nf) {
-                const uint8_t fl = v.flags[(size_t)b * v.N + i];
-                on = v.ftype[(size_t)b * v.N + i] != EKFSLAM_FEAT_NONE && (fl & need) == need && (fl & forbid) == 0;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, on);
-            if (on) gc_sel[cnt + __popc(m & ((1u << lane) - 1u))] = i;
-            cnt += __popc(m);
-        }
-        if (lane == 0) s_cnt = cnt;
-    }
-    __syncthreads();
-    const int rows = 2 * s_cnt;
-    const int cbase = c00 + warp * 16 + 2 * q;
-    const int cl0 = min(cbase, ld - 2), cl1 = min(cbase + 8, ld - 2);
-    const bool st0 = cbase < n, st1 = cbase + 8 < n;
-    for (int m0 = 0; m0 < kp; m0 += GC_KB) {
-        const int kb8 = (min(kp - m0, GC_KB) + 7) & ~7;
-        const int nks = kb8 >> 2;
-        double bf[2][GC_KB / 4];
-#pragma unroll
-        for (int ks = 0; ks < GC_KB / 4; ++ks) {
-            const int m = m0 + 4 * ks + q;             // rows at and beyond kp belong to another update: zeros
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-                bf[nt][ks] = (m < kp) ? Wpan[(size_t)m * EKF_WPAD + min(warp * 16 + 8 * nt + g, 63)] : 0.0;
-        }
-#pragma unroll 1
-        for (int r0 = 0; r0 < rows; r0 += 8) {
-            const bool valid = r0 + g < rows;
-            const int t = valid ? r0 + g : 0;
-            const int row = 2 * gc_sel[t >> 1] + (t & 1);
-            double* __restrict__ grow = G + (size_t)row * ld;
-            const double* __restrict__ vrow = V + (size_t)row * vld + m0 + q;
-            const double2 c0v = *reinterpret_cast<const double2*>(grow + cl0);
-            const double2 c1v = *reinterpret_cast<const double2*>(grow + cl1);
-            double af[GC_KB / 4];
-#pragma unroll
-            for (int ks = 0; ks < GC_KB / 4; ++ks) af[ks] = (ks < nks) ? __ldg(vrow + 4 * ks) : 0.0;
-            double acc0[2] = {c0v.x, c0v.y}, acc1[2] = {c1v.x, c1v.y};
-#pragma unroll
-            for (int ks = 0; ks < GC_KB / 4; ++ks) {
-                if (ks < nks) {
-                    dmma(acc0, af[ks], bf[0][ks]);
-                    dmma(acc1, af[ks], bf[1][ks]);
-                }
-            }
-            if (valid) {
-                if (st0) *reinterpret_cast<double2*>(grow + cbase) = make_double2(acc0[0], acc0[1]);
-                if (st1) *reinterpret_cast<double2*>(grow + cbase + 8) = make_double2(acc1[0], acc1[1]);
-            }
-        }
-    }
-}
-
-void launch_gcorr(ekfslam_ctx* c, int need, int forbid) {
-    dim3 grid((c->v.nmax + 63) / 64, c->v.B);
-    KScope ks(c, KT_GCORR);
-    k_gcorr<<<grid, 128, sizeof(int) * c->v.N, c->stream>>>(c->v, need, forbid);
-}
-
-// pending rows -> the inputs of a stand-alone covariance downdate: P <- jn1 P jn1' - Wp'Wp
-__global__ void k_flush_prep(DevView v) {
-    const int b = blockIdx.x * (blockDim.x / 16) + threadIdx.x / 16;
-    if (b >= v.B) return;
-    const int e = threadIdx.x & 15;
-    const int kp = v.kpend[b];
-    const bool id = (e >> 2) == (e & 3);
-    v.jn[(size_t)b * 16 + e] = (kp > 0) ? v.jn1[(size_t)b * 16 + e] : (id ? 1.0 : 0.0);
-    v.jn1[(size_t)b * 16 + e] = id ? 1.0 : 0.0;
-    __syncwarp();
-    if (e == 0) { v.ktot[b] = kp; v.kpend[b] = 0; }
-}
-
-void launch_flush_prep(ekfslam_ctx* c) {
-    c->launches++;
-    k_flush_prep<<<(c->v.B + 7) / 8, 128, 0, c->stream>>>(c->v);
-}
-
-// ---------------------------------------------------------------------------------------
 // Per-feature 2x2 innovation covariance from G, and the match gates.  One thread per feature.
-//   mode 0: S_i = H_i P H_i' + R_i for every predicted feature (mc/search_IC_matches.m:6-10)
+//   (S_i = H_i P H_i' + R_i of every predicted feature, mc/search_IC_matches.m:6-10: k_innov_gather below)
 //   mode 1: synthetic matcher gate (mc/matching.m:16,38) on candidates  -> z, HAS_Z, IC
 //   mode 2: explicit matches (what mc/matching.m:52-53 would have written) -> z, HAS_Z, IC
 //   mode 3: rescue gate (mc/rescue_hi_inliers.m:11-20): S_i = H_i P H_i' (no R) for IC && !LI,
@@ -612,11 +392,6 @@ __global__ void __launch_bounds__(128) k_innov(DevView v, ekfslam_params prm, in
             const double a0 = g0[off + k], a1 = g1[off + k], h0 = H[7 + k], h1 = H[EKF_HC + 7 + k];
             s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
         }
-        if (mode == 0) {  // + R_i = eye(2), mc/add_feature_to_info_vector.m:32
-            s00 += 1.0; s11 += 1.0;
-            v.S[4 * t] = s00; v.S[4 * t + 1] = s01; v.S[4 * t + 2] = s10; v.S[4 * t + 3] = s11;
-            return;
-        }
     }
     const double zu = (mode == 1) ? v.zc[2 * t] : v.z[2 * t];
     const double zv = (mode == 1) ? v.zc[2 * t + 1] : v.z[2 * t + 1];
@@ -644,7 +419,7 @@ __global__ void __launch_bounds__(128) k_innov(DevView v, ekfslam_params prm, in
 // needs the 13x13 (10x10) block P[c,c] of the columns H_i touches - 6 short row segments per feature (columns 0..6
 // and the feature's own block of rows off..off+5, read from the authoritative lower triangle) plus the 7x7 camera
 // block shared by all features of a filter.  One thread per feature; ~25 sectors of DRAM traffic per feature instead
-// of 2 x n doubles of G.  With rows of a deferred update pending (kp > 0):  S_i -= V_i V_i'  (Vn rows, k_vpend).
+// of 2 x n doubles of G.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_innov_gather(DevView v) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -697,14 +472,6 @@ __global__ void __launch_bounds__(128) k_innov_gather(DevView v) {
             }
             s00 += t0 * H[7 + jj]; s01 += t0 * H[EKF_HC + 7 + jj]; s10 += t1 * H[7 + jj]; s11 += t1 * H[EKF_HC + 7 + jj];
         }
-    }
-    const int kp = v.kpend[b];
-    if (kp > 0) {
-        const double* __restrict__ v0 = v.V + ((size_t)b * v.kmax + 2 * i) * v.vld;
-        const double* __restrict__ v1 = v0 + v.vld;
-        double q00 = 0.0, q01 = 0.0, q11 = 0.0;
-        for (int m = 0; m < kp; ++m) { const double a0 = v0[m], a1 = v1[m]; q00 += a0 * a0; q01 += a0 * a1; q11 += a1 * a1; }
-        s00 -= q00; s01 -= q01; s10 -= q01; s11 -= q11;
     }
     s00 += 1.0; s11 += 1.0;   // + R_i = eye(2), mc/add_feature_to_info_vector.m:32
     v.S[4 * t] = s00; v.S[4 * t + 1] = s01; v.S[4 * t + 2] = s10; v.S[4 * t + 3] = s11;

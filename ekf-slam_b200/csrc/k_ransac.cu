@@ -24,9 +24,8 @@ namespace cg = cooperative_groups;
 //   xi - x = P H_pos' inv(S_pos) (z_pos - h_pos) = (g' H_pos) P          g = inv(S_pos) nu  (2-vector)
 // i.e. ONE combination of the 13 rows of P that H_pos touches.  An adaptive RANSAC scores ~7 of 100 features per frame,
 // so the 2N-row product G = H P that used to be computed up front for this (k_hp over all features) is gone.
-// With rows of a deferred update pending (P = P_mem - Wp'Wp):  + (g' Vn_pos) Wp.
-// Lanes along the columns (coalesced rows of P / of the W panels); the kp coefficients g'Vn are spread over the lanes
-// and broadcast by shuffles.  The row lands in row 2 pos of the G buffer, where score_hypothesis reads it.
+// Lanes along the columns (coalesced rows of P).  The row lands in row 2 pos of the G buffer, where score_hypothesis
+// reads it.
 __device__ __forceinline__ void build_hyp_row(const DevView& v, int b, int pos, int n, double g0, double g1, double* G, int lane) {
     const int ld = v.ld;
     const size_t t = (size_t)b * v.N + pos;
@@ -34,7 +33,6 @@ __device__ __forceinline__ void build_hyp_row(const DevView& v, int b, int pos, 
     const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
     const int off = v.foff[t];
     const bool id = v.ftype[t] == EKFSLAM_FEAT_INVERSEDEPTH;
-    const int kp = v.kpend[b];
     // the 13 coefficients g'H live in this warp's slice of shared memory (the kernel runs at 64 registers)
     __shared__ double s_hrow[RANSAC_WARPS][16];
     double* hs = s_hrow[(threadIdx.x >> 5) % RANSAC_WARPS];
@@ -42,8 +40,6 @@ __device__ __forceinline__ void build_hyp_row(const DevView& v, int b, int pos, 
     if (lane < 13) hs[lane] = g0 * H[lane] + g1 * H[EKF_HC + lane];   // (Cartesian: columns 10..12 of H are zero)
     __syncwarp();
     double* Ga = G + (size_t)(2 * pos) * ld;
-    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
-    const double* __restrict__ Vn = v.V + ((size_t)b * v.kmax + 2 * pos) * v.vld;
     const double* __restrict__ Pf = P + (size_t)off * ld;
     const size_t r3 = id ? 3 : 0;              // Cartesian features re-read their first rows for the three missing ones
     for (int c0 = 0; c0 < n; c0 += 32) {
@@ -57,17 +53,6 @@ __device__ __forceinline__ void build_hyp_row(const DevView& v, int b, int pos, 
         double d = 0.0;
 #pragma unroll
         for (int r = 0; r < 13; ++r) d += hs[r] * p[r];
-        for (int m0 = 0; m0 < kp; m0 += 32) {
-            const int mm = m0 + lane;
-            const double vv = (mm < kp) ? g0 * Vn[mm] + g1 * Vn[v.vld + mm] : 0.0;
-            const int mb = min(32, kp - m0);                  // (kp is even)
-            const double* __restrict__ wcol = W + w_at(v.wrows, m0, cc);
-            for (int j = 0; j < mb; j += 2) {
-                const double w0 = wcol[(size_t)j * EKF_WPAD], w1 = wcol[(size_t)(j + 1) * EKF_WPAD];
-                d += __shfl_sync(0xffffffffu, vv, j) * w0;
-                d += __shfl_sync(0xffffffffu, vv, j + 1) * w1;
-            }
-        }
         if (c < n) Ga[c] = d;
     }
     __syncwarp();

@@ -159,14 +159,19 @@ int ekfslam_begin_frame(ekfslam_ctx* ctx);
 int ekfslam_predict(ekfslam_ctx* ctx);
 /* mc/search_IC_matches.m:4-10 = mc/predict_camera_measurements.m:4-28 (hi_inverse_depth,
  * hi_cartesian, hu, distort_fm) + mc/calculate_derivatives.m:3-28 (calculate_Hi_*) +
- * S_i = H_i P H_i' + R_i.  which: 1 = at (x_k_km1,p_k_km1), 0 = at (x_k_k,p_k_k). */
+ * S_i = H_i P H_i' + R_i.  which: 1 = at (x_k_km1,p_k_km1), 0 = at (x_k_k,p_k_k).
+ * S_i only needs the 13x13 block of P that H_i touches; the full rows P H_i' (2 x n per feature) are
+ * built where they are consumed: per scored hypothesis inside ekfslam_ransac, per update by ekfslam_hp. */
 int ekfslam_measure(ekfslam_ctx* ctx, int which);
-/* the three kernels of ekfslam_measure, separately callable:
+/* the kernels of ekfslam_measure, separately callable, and the row product of the updates:
  * ekfslam_features: parts&1 = mc/predict_camera_measurements.m (h), parts&2 =
  *                   mc/calculate_derivatives.m (H, linearised at the stored h);
- * ekfslam_hp:       rows 2i,2i+1 of G = H_i * P for every feature whose flag byte f has
- *                   (f & need) == need && (f & forbid) == 0 — the P H' every later stage uses;
- * ekfslam_innovation: S_i = H_i P H_i' + R_i from G (mc/search_IC_matches.m:6-10). */
+ * ekfslam_innovation: S_i = H_i P H_i' + R_i (mc/search_IC_matches.m:6-10) from 13x13 gathers of P;
+ * ekfslam_hp:       rows 2i,2i+1 of G = H_i * P (= (P H_i')', mc/update.m:8-9) for every feature whose
+ *                   flag byte f has (f & need) == need && (f & forbid) == 0.  ekfslam_update_masked /
+ *                   ekfslam_update_iterated read these rows for the features they stack;
+ *                   ekfslam_update_li, ekfslam_rescue (+ ekfslam_update_hi) and ekfslam_step call it
+ *                   themselves for exactly the rows they need. */
 int ekfslam_features(ekfslam_ctx* ctx, int which, int parts);
 int ekfslam_hp(ekfslam_ctx* ctx, int need, int forbid);
 int ekfslam_innovation(ekfslam_ctx* ctx);
@@ -177,7 +182,8 @@ int ekfslam_gate(ekfslam_ctx* ctx);
  * (what mc/matching.m:52-53 writes: z and individually_compatible) */
 int ekfslam_apply_matches(ekfslam_ctx* ctx);
 /* mc/ransac_hypotheses.m:3-47 (select_random_match, generate_state_vector_pattern,
- * compute_hypothesis_support_fast, set_as_most_supported_hypothesis) */
+ * compute_hypothesis_support_fast, set_as_most_supported_hypothesis).  Needs S_i (ekfslam_measure /
+ * ekfslam_innovation) and the matches; the gain P H_p' inv(S_p) of a hypothesis (:24-25) is formed on demand. */
 int ekfslam_ransac(ekfslam_ctx* ctx);
 /* mc/ekf_update_li_inliers.m:4-21 -> mc/update.m:3-32 (+normJac) from (x_k_km1,p_k_km1) */
 int ekfslam_update_li(ekfslam_ctx* ctx);
@@ -201,18 +207,6 @@ int ekfslam_update_iterated(ekfslam_ctx* ctx, int mask, int which_prior, int n_i
  * candidates, 2 = apply the staged explicit matches, 0 = flags already on the device),
  * ransac, update_li, rescue, update_hi */
 int ekfslam_step(ekfslam_ctx* ctx, int reset, int match_mode);
-
-/* One covariance pass per frame.  By default ekfslam_step (and _step_graph / _step_host) does NOT apply the
- * covariance downdate of the hi update (mc/update.m:13-14 inside mc/ekf_update_hi_inliers.m:21) at the end of the
- * frame: x_k_k, the flags and the stats are final, the rows W = inv(L) H p_k_k stay pending on the device and are
- * applied together with the NEXT frame's li downdate (prediction carries them through F, mc/predict_state_and_
- * covariance.m:26-27, and G = H P is corrected by -(H W')W while P is streamed).  Every other entry point that reads
- * or writes the covariance (download_state, the stage-level calls, map management ...) materialises p_k_k first, so
- * the deferral is not observable through the API - only as rounding (<= 1e-13 relative, tests/test_gpu_defer.py).
- * ekfslam_flush materialises p_k_k explicitly; ekfslam_set_defer_hi(ctx, 0) restores the two-pass step
- * (environment: EKFSLAM_DEFER_HI=0). */
-int ekfslam_flush(ekfslam_ctx* ctx);
-int ekfslam_set_defer_hi(ekfslam_ctx* ctx, int on);
 
 /* ekfslam_step replayed from a captured CUDA graph (latency path: a single filter's step is ~25 small launches).
  * The graph is captured on first use and re-captured whenever anything the kernels see changes (buffers, parameters,

@@ -479,7 +479,6 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         feats_upload(&f);
         state_upload(prhs[1], "x_k_km1", "p_k_km1", 1, f.n);
         ck(ekfslam_upload_uniforms(g_ctx, 0, 1, mxGetPr(prhs[4]), (int)mxGetNumberOfElements(prhs[4])), "ekfslam_upload_uniforms");
-        ck(ekfslam_hp(g_ctx, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, 0), "ekfslam_hp");
         ck(ekfslam_ransac(g_ctx), "ekfslam_ransac");
         plhs[0] = feats_download(prhs[2], &f, 16);
     } else if (!strcmp(cmd, "ekf_update_li_inliers") || !strcmp(cmd, "ekf_update_hi_inliers")) {  /* mc/update.m */

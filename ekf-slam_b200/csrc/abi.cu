@@ -216,9 +216,6 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     DA(v.yv, Bz * v.kmax);
     DA(v.jn, Bz * 16);
     DA(v.jnt, Bz * 16);
-    DA(v.jn1, Bz * 16);
-    DA(v.kpend, Bz);
-    DA(v.roff, Bz);
     DA(v.ktot, Bz);
     DA(v.kmaxdev, 1);
     DA(v.cv, Bz * v.kmax);
@@ -279,7 +276,7 @@ int ekfslam_destroy(ekfslam_ctx* c) {
     cudaSetDevice(c->device);
     if (c->own_zc) { c->v.zc = c->own_zc; c->v.mflags = c->own_mflags; c->v.u = c->own_u; c->own_zc = nullptr; }
     DevView& v = c->v;
-    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.jnt, v.jn1, v.kpend, v.roff, v.ktot, v.kmaxdev, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
+    void* ptrs[] = {v.x, v.xp, v.P, v.G, v.W, v.Sb, v.Li, v.yv, v.jn, v.jnt, v.ktot, v.kmaxdev, v.cv, v.h, v.Hc, v.S, v.z, v.zc, v.u, v.ftype,
                     v.flags, v.mflags, v.foff, v.nstate, v.nfeat, v.counters, v.tag, v.sel, v.ksel, v.stats, v.nhyp_tab,
                     c->mm_del, c->mm_quota, c->det_n, c->det_uv, c->det_tag, c->world_points, c->world_poses};
     for (void* p : ptrs)
@@ -635,7 +632,7 @@ int ekfslam_hp(ekfslam_ctx* c, int need, int forbid) {
 
 int ekfslam_innovation(ekfslam_ctx* c) {
     NEED_CTX(c);
-    launch_innov_gather(c);
+    launch_innov_gather(c, 0);
     LAUNCHED();
     return EKFSLAM_OK;
 }
@@ -643,7 +640,7 @@ int ekfslam_innovation(ekfslam_ctx* c) {
 int ekfslam_measure(ekfslam_ctx* c, int which) {
     NEED_CTX(c);
     launch_features(c, which ? 1 : 0, 3);
-    launch_innov_gather(c);   // S_i from 13x13 gathers of P: the full rows H P are built where they are consumed
+    launch_innov_gather(c, 0);   // S_i from 13x13 gathers of P: the full rows H P are built where they are consumed
     LAUNCHED();               // (ekfslam_ransac: per hypothesis; ekfslam_update_li / ekfslam_hp: per update)
     return EKFSLAM_OK;
 }
@@ -723,17 +720,19 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
     if (reset) launch_begin_frame(c);
     launch_predict(c);
     launch_features(c, 1, 3);
-    launch_innov_gather(c);                              // S_i from 13x13 gathers of P: no G rows needed yet
+    launch_innov_gather(c, 0);                              // S_i from 13x13 gathers of P: no G rows needed yet
     if (c->wait_inputs) { cudaStreamWaitEvent(c->stream, c->ev_in, 0); c->wait_inputs = 0; }
     if (match_mode) launch_innov(c, match_mode);
     launch_ransac(c);                                    // builds the G rows of the hypotheses it scores
     {
-        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);   // G rows of the low-innovation inliers only
+        // G rows of the low-innovation inliers only (with a fixed hypothesis budget launch_ransac has already built the
+        // rows of every individually compatible feature, a superset)
+        if (c->prm.fixed_hyp <= 0) launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);
         launch_update(c, EKFSLAM_F_LI, 1);
         launch_features(c, 0, 3);
         if (c->rescue_gather) {
-            // chi2 gate from 13x13 gathers of p_k_k (no pending update here), then G rows only for the hi inliers
-            launch_rescue_gate(c);
+            // chi2 gate from 13x13 gathers of p_k_k, then G rows only for the hi inliers
+            launch_innov_gather(c, 3);
             launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, KT_HP_RESCUE);
         } else {
             launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI, KT_HP_RESCUE);

@@ -30,9 +30,8 @@ struct DevView {
     double* Sb;           // [B][kmax][kmax] stacked innovation covariance / its Cholesky factor
     double* Li;           // [B][kmax][kmax] inverse of the Cholesky factor
     double* yv;           // [B][kmax]     inv(L)*(z-h)
-    double* jn;           // [B][16]       normalisation Jacobian the covariance downdate applies (product over the pending updates)
+    double* jn;           // [B][16]       normalisation Jacobian the covariance downdate applies
     double* jnt;          // [B][16]       normJac(q+) of the update being computed
-    double* jn1;          // [B][16]       normJac of a deferred (not yet applied) update
     double* cv;           // [B][kmax]     inv(S)*(z-h) = inv(L)' * yv
     double* h;            // [B][N][2]
     double* Hc;           // [B][N][26]
@@ -50,8 +49,6 @@ struct DevView {
     int32_t* tag;         // [B][N]   feature identity (stand-in for features_info(i).feature_when_initialized)
     int32_t* sel;         // [B][N]   selected feature list of the running update
     int32_t* ksel;        // [B]      number of selected features
-    int32_t* kpend;       // [B]      rows of W left pending by a deferred update (0 = none)
-    int32_t* roff;        // [B]      row offset of the running update inside W (= pending rows before it)
     int32_t* ktot;        // [B]      rows of W the covariance downdate has to apply
     int32_t* kmaxdev;     // [1]      max over the filters of the stacked rows of the running update (k_upd_S)
     int32_t* nhyp_tab;    // [(N+1)(N+2)/2] adaptive hypothesis count, host libm (see abi.cu)
@@ -160,12 +157,11 @@ void launch_begin_frame(ekfslam_ctx* c);
 void launch_predict(ekfslam_ctx* c);
 void launch_features(ekfslam_ctx* c, int which, int parts);  // parts: 1 = h, 2 = H, 3 = both
 void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot = KT_HP);  // G rows for features with (flags&need)==need && !(flags&forbid)
-void launch_innov_gather(ekfslam_ctx* c);                    // S_i (+R) of every predicted feature from 13x13 gathers of P (no G rows)
+void launch_innov_gather(ekfslam_ctx* c, int mode);          // S_i from 13x13 gathers of P (no G rows): 0 = S_i + R stored, 3 = rescue gate
 void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gate / explicit matches / rescue gate
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
 void launch_ransac(ekfslam_ctx* c);
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags = 0);
-void launch_rescue_gate(ekfslam_ctx* c, int keep_v = 0);  // rescue gate from 13x13 gathers of P (no candidate G rows)
 void launch_downdate(ekfslam_ctx* c, int slot);
 void launch_chol_blocked64(ekfslam_ctx* c, int kact);   // k_chol_big.cu: S = L L', X = inv(L) for few filters with large k
 void launch_reset_filters(ekfslam_ctx* c, int b0, int nb, const double* d_xv, const double* d_Pxv);

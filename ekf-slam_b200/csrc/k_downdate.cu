@@ -1,8 +1,7 @@
 // Covariance downdate  P <- J P J' - W'W  (mc/update.m:13-22) on 64x64 tiles of the lower triangle.
 //
-// W holds ktot rows per filter: the rows of one update, or of a deferred li update followed by the hi
-// update ([W_li; W_hi], one pass over P per frame instead of two).  Every row already carries the
-// normalisation Jacobians (W <- W J', k_wfix), so J = blkdiag(I3, Jn, I) only has to be applied to the P
+// W holds the ktot rows of one update per filter.  Every row already carries the normalisation
+// Jacobian (W <- W J', k_wfix), so J = blkdiag(I3, Jn, I) only has to be applied to the P
 // tile itself: columns 3..6 of tile column 0 and rows 3..6 of tile (0,0).  0.5P + 0.5P' (:14) is the identity
 // because the lower triangle is authoritative and every tile is stored together with its mirror image.
 //

@@ -415,20 +415,25 @@ __global__ void __launch_bounds__(128) k_innov(DevView v, ekfslam_params prm, in
 }
 
 // ---------------------------------------------------------------------------------------
-// S_i = H_i P H_i' + R_i for every predicted feature (mc/search_IC_matches.m:6-10) WITHOUT the G rows: the 2x2 only
-// needs the 13x13 (10x10) block P[c,c] of the columns H_i touches - 6 short row segments per feature (columns 0..6
-// and the feature's own block of rows off..off+5, read from the authoritative lower triangle) plus the 7x7 camera
-// block shared by all features of a filter.  One thread per feature; ~25 sectors of DRAM traffic per feature instead
-// of 2 x n doubles of G.
+// The 2x2 innovation covariance of a feature WITHOUT the G rows: S_i only needs the 13x13 (10x10) block P[c,c] of the
+// columns H_i touches - 6 short row segments per feature (columns 0..6 and the feature's own block of rows
+// off..off+5, read from the authoritative lower triangle) plus the 7x7 camera block shared by all features of a
+// filter.  One thread per feature; ~25 sectors of DRAM traffic per feature instead of 2 x n doubles of G.
+//   mode 0: S_i = H_i P H_i' + R_i for every predicted feature (mc/search_IC_matches.m:6-10), stored;
+//   mode 3: rescue gate (mc/rescue_hi_inliers.m:11-20): S_i = H_i p_k_k H_i' (no R) for IC && !LI,
+//           nu' inv(S_i) nu < chi2 -> HI.  S is not stored (it is a local in the reference).  Only the features that
+//           pass then need full rows H p_k_k (k_hp on the HI rows).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_innov_gather(DevView v) {
+__global__ void __launch_bounds__(128, 4) k_innov_gather(DevView v, ekfslam_params prm, int mode) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= v.B * v.N) return;
     const int b = t / v.N, i = t - b * v.N;
     if (i >= v.nfeat[b]) return;
     const int type = v.ftype[t];
     if (type == EKFSLAM_FEAT_NONE) return;
-    if (!(v.flags[t] & EKFSLAM_F_HAS_H)) return;
+    uint8_t f = v.flags[t];
+    if (!(f & EKFSLAM_F_HAS_H)) return;
+    if (mode == 3 && !((f & EKFSLAM_F_IC) && !(f & EKFSLAM_F_LI))) return;
     const int ld = v.ld;
     const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
     const double* __restrict__ Hp = v.Hc + (size_t)t * EKF_HSTRIDE;
@@ -473,14 +478,22 @@ __global__ void __launch_bounds__(128) k_innov_gather(DevView v) {
             s00 += t0 * H[7 + jj]; s01 += t0 * H[EKF_HC + 7 + jj]; s10 += t1 * H[7 + jj]; s11 += t1 * H[EKF_HC + 7 + jj];
         }
     }
-    s00 += 1.0; s11 += 1.0;   // + R_i = eye(2), mc/add_feature_to_info_vector.m:32
-    v.S[4 * t] = s00; v.S[4 * t + 1] = s01; v.S[4 * t + 2] = s10; v.S[4 * t + 3] = s11;
+    if (mode == 0) {
+        s00 += 1.0; s11 += 1.0;   // + R_i = eye(2), mc/add_feature_to_info_vector.m:32
+        v.S[4 * t] = s00; v.S[4 * t + 1] = s01; v.S[4 * t + 2] = s10; v.S[4 * t + 3] = s11;
+        return;
+    }
+    const double n0 = v.z[2 * t] - v.h[2 * t], n1 = v.z[2 * t + 1] - v.h[2 * t + 1];
+    const double det = s00 * s11 - s01 * s10;
+    const double d2 = (n0 * (s11 * n0 - s01 * n1) + n1 * (-s10 * n0 + s00 * n1)) / det;
+    if (d2 < prm.chi2_gate) f |= EKFSLAM_F_HI; else f &= ~EKFSLAM_F_HI;
+    v.flags[t] = f;
 }
 
-void launch_innov_gather(ekfslam_ctx* c) {
+void launch_innov_gather(ekfslam_ctx* c, int mode) {
     const int tot = c->v.B * c->v.N;
     KScope ks(c, KT_INNOV);
-    k_innov_gather<<<(tot + 127) / 128, 128, 0, c->stream>>>(c->v);
+    k_innov_gather<<<(tot + 127) / 128, 128, 0, c->stream>>>(c->v, c->prm, mode);
 }
 
 void launch_innov(ekfslam_ctx* c, int mode) {

@@ -20,62 +20,71 @@ namespace cg = cooperative_groups;
 #define RANSAC_MINB 4   // 64 registers: the kernel is latency-bound, 4 CTAs/SM instead of 2
 #endif
 
-// The state correction of ONE hypothesis, built on demand by the warp that scores it (mc/ransac_hypotheses.m:22-26):
+// The state corrections of the hypotheses of ONE round (adaptive rule: 8 draws per round, ~7 scored per frame), built on
+// demand by the whole block (mc/ransac_hypotheses.m:22-26):
 //   xi - x = P H_pos' inv(S_pos) (z_pos - h_pos) = (g' H_pos) P          g = inv(S_pos) nu  (2-vector)
-// i.e. ONE combination of the 13 rows of P that H_pos touches.  An adaptive RANSAC scores ~7 of 100 features per frame,
-// so the 2N-row product G = H P that used to be computed up front for this (k_hp over all features) is gone.
-// Lanes along the columns (coalesced rows of P).  The row lands in row 2 pos of the G buffer, where score_hypothesis
-// reads it.
-__device__ __forceinline__ void build_hyp_row(const DevView& v, int b, int pos, int n, double g0, double g1, double* G, int lane) {
-    const int ld = v.ld;
-    const size_t t = (size_t)b * v.N + pos;
-    const double* __restrict__ H = v.Hc + t * EKF_HSTRIDE;
-    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
-    const int off = v.foff[t];
-    const bool id = v.ftype[t] == EKFSLAM_FEAT_INVERSEDEPTH;
-    // the 13 coefficients g'H live in this warp's slice of shared memory (the kernel runs at 64 registers)
-    __shared__ double s_hrow[RANSAC_WARPS][16];
-    double* hs = s_hrow[(threadIdx.x >> 5) % RANSAC_WARPS];
-    __syncwarp();
-    if (lane < 13) hs[lane] = g0 * H[lane] + g1 * H[EKF_HC + lane];   // (Cartesian: columns 10..12 of H are zero)
-    __syncwarp();
-    double* Ga = G + (size_t)(2 * pos) * ld;
-    const double* __restrict__ Pf = P + (size_t)off * ld;
-    const size_t r3 = id ? 3 : 0;              // Cartesian features re-read their first rows for the three missing ones
-    for (int c0 = 0; c0 < n; c0 += 32) {
-        const int c = c0 + lane;
-        const int cc = min(c, n - 1);
-        double p[13];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) p[r] = P[(size_t)r * ld + cc];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) { p[7 + r] = Pf[(size_t)r * ld + cc]; p[10 + r] = Pf[(r3 + r) * ld + cc]; }
-        double d = 0.0;
-#pragma unroll
-        for (int r = 0; r < 13; ++r) d += hs[r] * p[r];
-        if (c < n) Ga[c] = d;
-    }
-    __syncwarp();
-}
-
-// Support of the hypothesis drawn at feature `pos` (mc/ransac_hypotheses.m:22-33), one warp: the state correction
-// (build_hyp_row), then lanes re-project the matched features at xi; the inlier mask goes to mask[nwords].
-// Returns the support (same value in every lane).
-__device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& cam, int b, int pos, int n, const double* xs,
-                                                double* G, const int* moff, const int* mtype,
-                                                const double* zs, int nm, double thr, unsigned* mask, int lane) {
-    const int N = v.N, ld = v.ld;
-    const size_t t = (size_t)b * N + pos;
+// i.e. ONE combination of the 13 rows of P that H_pos touches, so the 2N-row product G = H P that used to be computed up
+// front for this (k_hp over all features) is gone.  Threads along the columns (coalesced rows of P); the 7 camera rows
+// are loaded once per column and shared by the round's hypotheses; every load of a column is independent, so a round
+// costs ~3 memory round trips (a warp per hypothesis walking its 613 columns took 20).  The combined row lands in row
+// 2 pos of the G buffer, where score_hypothesis reads it.
+struct HypRound {
+    double coef[RANSAC_WARPS][16];   // g'H of the hypothesis of warp w (13 used; Cartesian: columns 10..12 of H are zero)
+    int pos[RANSAC_WARPS];           // feature it draws, -1 = nothing to build
+    int off[RANSAC_WARPS];           // state offset | Cartesian << 30
+};
+__device__ __forceinline__ void hyp_gain(const DevView& v, size_t t, double& g0, double& g1) {
     const double s00 = v.S[4 * t], s01 = v.S[4 * t + 1], s10 = v.S[4 * t + 2], s11 = v.S[4 * t + 3];
     const double n0 = v.z[2 * t] - v.h[2 * t], n1 = v.z[2 * t + 1] - v.h[2 * t + 1];
     const double det = s00 * s11 - s01 * s10;
-    const double g0 = (s11 * n0 - s01 * n1) / det;
-    const double g1 = (-s10 * n0 + s00 * n1) / det;
-    build_hyp_row(v, b, pos, n, g0, g1, G, lane);
-    const double* Ga = G + (size_t)(2 * pos) * ld;   // written by this warp just before: plain loads
+    g0 = (s11 * n0 - s01 * n1) / det;
+    g1 = (-s10 * n0 + s00 * n1) / det;
+}
+__device__ __forceinline__ void build_round_rows(const DevView& v, int b, int n, const HypRound& hr, double* G) {
+    const int ld = v.ld;
+    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        double cam[7];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) cam[r] = P[(size_t)r * ld + c];
+#pragma unroll
+        for (int w = 0; w < RANSAC_WARPS; ++w) {
+            const int pos = hr.pos[w];
+            if (pos < 0) continue;
+            const int off = hr.off[w] & 0x3fffffff;
+            const size_t r3 = (hr.off[w] >> 30) ? 0 : 3;   // Cartesian features re-read their first rows for the three missing ones
+            const double* __restrict__ Pf = P + (size_t)off * ld + c;
+            const double* hs = hr.coef[w];
+            double p6[6];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { p6[r] = Pf[(size_t)r * ld]; p6[3 + r] = Pf[(r3 + r) * ld]; }
+            double d = 0.0;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) d += hs[r] * cam[r];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) d += hs[7 + r] * p6[r];
+            G[(size_t)(2 * pos) * ld + c] = d;
+        }
+    }
+}
+
+// Support of the hypothesis drawn at feature `pos` (mc/ransac_hypotheses.m:22-33), one warp: lanes re-project the
+// matched features at xi; the inlier mask goes to mask[nwords].  Returns the support (same value in every lane).
+// rows == 2: rows 2 pos, 2 pos + 1 of G = H P are there (k_hp over the IC features - the fixed-budget configurations
+//            score nearly every matched feature, one batched pass beats ~90 row builds):  xi = x + g0 Ga + g1 Gb;
+// rows == 1: row 2 pos holds the combined correction (build_round_rows):                  xi = x + Ga.
+__device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& cam, int b, int pos, const double* xs,
+                                                const double* G, const int* moff, const int* mtype,
+                                                const double* zs, int nm, double thr, unsigned* mask, int lane, int rows) {
+    const int N = v.N, ld = v.ld;
+    double f0 = 1.0, f1 = 0.0;
+    if (rows == 2) hyp_gain(v, (size_t)b * N + pos, f0, f1);
+    const double* Ga = G + (size_t)(2 * pos) * ld;   // (rows == 1: written by this block just before - plain loads)
+    const double* Gb = Ga + ld;
+    const bool two = rows == 2;
     double c7[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) c7[k] = xs[k] + Ga[k];
+    for (int k = 0; k < 7; ++k) c7[k] = two ? xs[k] + (Ga[k] * f0 + Gb[k] * f1) : xs[k] + Ga[k];
     double R[9];
     q2r_dev(c7 + 3, R);
     int support = 0;
@@ -89,7 +98,7 @@ __device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& 
             double y[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k)
-                y[k] = (k < w) ? xs[off + k] + Ga[off + k] : 0.0;
+                y[k] = (k < w) ? (two ? xs[off + k] + (Ga[off + k] * f0 + Gb[off + k] * f1) : xs[off + k] + Ga[off + k]) : 0.0;
             const double res = support_residual_dev(cam, c7, R, y, ty, zs[2 * j], zs[2 * j + 1]);
             inl = res < thr;
         }
@@ -100,7 +109,7 @@ __device__ __forceinline__ int score_hypothesis(const DevView& v, const DevCam& 
     return support;
 }
 
-__global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView v, DevCam cam, ekfslam_params prm) {
+__global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView v, DevCam cam, ekfslam_params prm, int prebuilt) {
     extern __shared__ unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int n = v.nstate[b];
@@ -123,6 +132,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView 
     int* dl = reinterpret_cast<int*>(bestmask + nwords + N * nwords);  // [N] distinct drawn features (fixed-budget path)
     __shared__ int s_nm, s_nic, s_done, s_best, s_roundbest, s_nhyp, s_iters, s_scored, s_status;
     __shared__ int rpos[RANSAC_WARPS], rsup[RANSAC_WARPS];
+    __shared__ HypRound hround;
 
     const double* __restrict__ xp = v.xp + (size_t)b * ld;
     double* G = v.G + (size_t)b * v.kmax * ld;
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView 
         const int nd = s_nd;
         for (int d = warp; d < nd; d += RANSAC_WARPS) {
             const int pos = dl[d];
-            const int support = score_hypothesis(v, cam, b, pos, n, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane);
+            const int support = score_hypothesis(v, cam, b, pos, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane, 2);
             if (lane == 0) need[pos] = support;             // need[] now holds the support of every drawn feature
         }
         __syncthreads();
@@ -239,8 +249,22 @@ __global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView 
         bool score = (pos >= 0) && (memo[pos] < 0);
         for (int w2 = 0; w2 < warp && score; ++w2)
             if (rpos[w2] == pos) score = false;
+        if (!prebuilt) {
+            // the round's state corrections, built by the whole block
+            if (score) {
+                const size_t t = (size_t)b * N + pos;
+                double g0, g1;
+                hyp_gain(v, t, g0, g1);
+                const double* __restrict__ H = v.Hc + t * EKF_HSTRIDE;
+                if (lane < 13) hround.coef[warp][lane] = g0 * H[lane] + g1 * H[EKF_HC + lane];
+                if (lane == 0) { hround.pos[warp] = pos; hround.off[warp] = v.foff[t] | (v.ftype[t] == EKFSLAM_FEAT_INVERSEDEPTH ? 0 : (1 << 30)); }
+            } else if (lane == 0) hround.pos[warp] = -1;
+            __syncthreads();
+            build_round_rows(v, b, n, hround, G);
+            __syncthreads();
+        }
         if (score) {
-            const int support = score_hypothesis(v, cam, b, pos, n, xs, G, moff, mtype, zs, nm, thr, rmask + warp * nwords, lane);
+            const int support = score_hypothesis(v, cam, b, pos, xs, G, moff, mtype, zs, nm, thr, rmask + warp * nwords, lane, prebuilt ? 2 : 1);
             if (lane == 0) rsup[warp] = support;
         }
         __syncthreads();
@@ -303,7 +327,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS, RANSAC_MINB) k_ransac(DevView 
 // the maximum support" (mc/ransac_hypotheses.m:37 with :41-45 disabled).
 // ---------------------------------------------------------------------------------------
 #define RANSAC_CLUSTER 8
-__global__ void __launch_bounds__(RANSAC_THREADS) k_ransac_fixed_cluster(DevView v, DevCam cam, ekfslam_params prm) {
+__global__ void __launch_bounds__(RANSAC_THREADS) k_ransac_fixed_cluster(DevView v, DevCam cam, ekfslam_params prm, int prebuilt) {
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -381,7 +405,7 @@ __global__ void __launch_bounds__(RANSAC_THREADS) k_ransac_fixed_cluster(DevView
         const int nd = s_nd;
         for (int d = rank * RANSAC_WARPS + warp; d < nd; d += C * RANSAC_WARPS) {
             const int pos = dl[d];
-            const int support = score_hypothesis(v, cam, b, pos, n, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane);
+            const int support = score_hypothesis(v, cam, b, pos, xs, G, moff, mtype, zs, nm, thr, masks + pos * nwords, lane, 2);
             if (lane == 0) need[pos] = support;
         }
     }
@@ -449,6 +473,10 @@ static size_t ransac_cluster_smem_bytes(const DevView& v) {
 void launch_ransac(ekfslam_ctx* c) {
     static int use_cluster = -1;
     if (use_cluster < 0) { const char* e = getenv("EKFSLAM_RANSAC_CLUSTER"); use_cluster = (e && e[0] == '0') ? 0 : 1; }
+    // fixed hypothesis budget (BASELINE configs 2 / 5: 256 / 512 draws): nearly every matched feature is drawn, so the
+    // rows H P of the IC features come from one k_hp pass; adaptive rule (~7 scored hypotheses): built on demand
+    const int prebuilt = c->prm.fixed_hyp > 0 ? 1 : 0;
+    if (prebuilt) launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, 0);
     KScope ks(c, KT_RANSAC);
     // few filters + fixed hypothesis budget (the latency path): one cluster of CTAs per filter
     if (use_cluster && c->prm.fixed_hyp > 0 && (long long)c->v.B * RANSAC_CLUSTER <= 2LL * c->sm_count) {
@@ -464,10 +492,10 @@ void launch_ransac(ekfslam_ctx* c) {
         at[0].val.clusterDim.x = RANSAC_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_ransac_fixed_cluster, c->v, c->cam, c->prm);
+        cudaLaunchKernelEx(&cfg, k_ransac_fixed_cluster, c->v, c->cam, c->prm, prebuilt);
         return;
     }
     const size_t sm = ransac_smem_bytes(c->v);
     ENSURE_DYN_SMEM(k_ransac, sm, c->device);
-    k_ransac<<<c->v.B, RANSAC_THREADS, sm, c->stream>>>(c->v, c->cam, c->prm);
+    k_ransac<<<c->v.B, RANSAC_THREADS, sm, c->stream>>>(c->v, c->cam, c->prm, prebuilt);
 }

@@ -59,7 +59,7 @@ __device__ __forceinline__ void upd_S_pairs(const DevView& v, int b, int ns, int
 // ---------------------------------------------------------------------------------------
 // select + S + nu.  One block per filter.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_prior, int iter_nu, int defer, int do_pairs) {
+__global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_prior, int iter_nu, int do_pairs) {
     const int b = blockIdx.x;
     const int N = v.N, ld = v.ld, kmax = v.kmax;
     const int nf = v.nfeat[b];
@@ -80,9 +80,6 @@ __global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_pr
         if (tid == 0) {
             v.ksel[b] = cnt;
             s_k = cnt;
-            // rows a deferred update left in W come first; this update appends behind them
-            v.roff[b] = v.kpend[b];
-            v.kpend[b] = defer ? 2 * cnt : 0;
             if (mask & EKFSLAM_F_LI) v.stats[b].n_li = cnt;
             if (mask & EKFSLAM_F_HI) v.stats[b].n_hi = cnt;
             if (cnt > 0) atomicMax(v.kmaxdev, 2 * cnt);
@@ -671,7 +668,7 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
 
 // ---------------------------------------------------------------------------------------
 // Tensor-core GEMM of the update, 64x64 tiles, grid = (row tiles, column groups, B), each CTA walking its column tiles:
-//   W[roff + a] = sum_t X[a][t] * G[selrow(t)]       (X = inv(L), lower triangular, explicit zeros above the
+//   W[a] = sum_t X[a][t] * G[selrow(t)]       (X = inv(L), lower triangular, explicit zeros above the
 //   diagonal; G_sel = the selected rows of G).  The last row tile also accumulates the state update
 //   x+ = x + G_sel' inv(S) nu (mc/update.m:12) for its 64 columns, and column tile 0 then computes normJac(q+) and
 //   normalises the quaternion (mc/update.m:18,24) when `finalize`.
@@ -690,7 +687,6 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
     double* __restrict__ G = v.G + (size_t)b * kmax * ld;
     double* __restrict__ W = v.W + (size_t)b * v.wstride;
     const int* __restrict__ sel = v.sel + (size_t)b * v.N;
-    const int roff = v.roff[b];
 
     double* As = dsm;                           // [NSTAGE][64][APAD]   As[i][t] = A[a0+i][t0+t]
     double* Bs = dsm + NSTAGE * TM * APAD;      // [NSTAGE][TK][TPAD]   Bs[t][j] = B[t0+t][c0+j]
@@ -825,7 +821,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
             const int a = a0 + wr * 32 + mt * 8 + g;
             if (a < k) {
                 // the 64 output columns of a column tile are one panel of W
-                double* __restrict__ orow = W + w_at(v.wrows, roff + a, c0) - c0;
+                double* __restrict__ orow = W + w_at(v.wrows, a, c0) - c0;
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
                     const int c = c0 + wc * 16 + nt * 8 + 2 * q;
@@ -886,7 +882,6 @@ __global__ void __launch_bounds__(128, 4) k_w_small(DevView v, int finalize) {
     const double* __restrict__ G = v.G + (size_t)b * kmax * ld;
     double* __restrict__ W = v.W + (size_t)b * v.wstride;
     const int* __restrict__ sel = v.sel + (size_t)b * v.N;
-    const int roff = v.roff[b];
     __shared__ double Xs[WS_K][WS_K + 1];
     __shared__ double cs[WS_K];
     __shared__ int grow[WS_K];
@@ -909,7 +904,7 @@ __global__ void __launch_bounds__(128, 4) k_w_small(DevView v, int finalize) {
         double xs = 0.0;
 #pragma unroll
         for (int t = 0; t < WS_K; ++t) xs += g[t] * cs[t];
-        double* __restrict__ wcol = W + w_at(v.wrows, roff, c);
+        double* __restrict__ wcol = W + w_at(v.wrows, 0, c);
 #pragma unroll
         for (int a = 0; a < WS_K; ++a) {
             if (a < k) {
@@ -940,163 +935,26 @@ __global__ void __launch_bounds__(128, 4) k_w_small(DevView v, int finalize) {
 }
 
 // ---------------------------------------------------------------------------------------
-// After k_gemm(mode 0): fold this update's normalisation Jacobian Jt into W and do the bookkeeping.
+// After k_gemm: fold this update's normalisation Jacobian Jt into W and do the bookkeeping.
 //   mc/update.m:20-22 is  P+ = J (P - W'W) J' = J P J' - (W J')' (W J')  with J = blkdiag(I3, Jt, I): only columns
-//   3..6 of W change.  Rows left pending by a deferred update are multiplied as well (the product of both
-//   Jacobians then applies to P in the single covariance downdate).
+//   3..6 of W change; the covariance downdate applies J to the P tiles themselves.
 // One block per filter.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_wfix(DevView v, int defer) {
+__global__ void __launch_bounds__(128) k_wfix(DevView v) {
     const int b = blockIdx.x;
-    const int k = 2 * v.ksel[b], roff = v.roff[b];
-    const int rows = roff + k;
+    const int k = 2 * v.ksel[b];
     double* __restrict__ W = v.W + (size_t)b * v.wstride;
     __shared__ double Jt[16];
     if (threadIdx.x < 16) Jt[threadIdx.x] = v.jnt[(size_t)b * 16 + threadIdx.x];
     __syncthreads();
-    if (k > 0) {
-        for (int a = threadIdx.x; a < rows; a += blockDim.x) {
-            double* w = W + w_at(v.wrows, a, 3);
-            const double w3 = w[0], w4 = w[1], w5 = w[2], w6 = w[3];
+    for (int a = threadIdx.x; a < k; a += blockDim.x) {
+        double* w = W + w_at(v.wrows, a, 3);
+        const double w3 = w[0], w4 = w[1], w5 = w[2], w6 = w[3];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) w[i] = w3 * Jt[i * 4 + 0] + w4 * Jt[i * 4 + 1] + w5 * Jt[i * 4 + 2] + w6 * Jt[i * 4 + 3];
-        }
+        for (int i = 0; i < 4; ++i) w[i] = w3 * Jt[i * 4 + 0] + w4 * Jt[i * 4 + 1] + w5 * Jt[i * 4 + 2] + w6 * Jt[i * 4 + 3];
     }
-    if (threadIdx.x < 16) {
-        const int i = threadIdx.x >> 2, j = threadIdx.x & 3;
-        double* jn = v.jn + (size_t)b * 16;
-        double* jn1 = v.jn1 + (size_t)b * 16;
-        if (defer) {
-            if (k > 0) jn1[threadIdx.x] = Jt[threadIdx.x];
-        } else if (k > 0 && roff > 0) {
-            double s = 0.0;
-            for (int m = 0; m < 4; ++m) s += Jt[i * 4 + m] * jn1[m * 4 + j];   // J_total = Jt * J_pending
-            jn[threadIdx.x] = s;
-        } else if (k > 0) {
-            jn[threadIdx.x] = Jt[threadIdx.x];
-        } else if (roff > 0) {
-            jn[threadIdx.x] = jn1[threadIdx.x];
-        }
-    }
-    if (threadIdx.x == 0 && !defer) v.ktot[b] = rows;
-}
-
-// ---------------------------------------------------------------------------------------
-// Rescue gate, mc/rescue_hi_inliers.m:11-20, WITHOUT the G rows of the candidates: the 2x2  S_c = H_c p_k_k H_c'  only
-// needs the 13x13 (10x10) gather P[c,c] of the columns H_c touches.  Only the candidates that pass (HI) then need
-// full rows H p_k_k (k_hp on those rows).  The kernel is written for a covariance p_k_k = J1 (P - W'W) J1' with k1 rows
-// of a not-yet-applied update pending in W (k1 = kpend; the step never leaves one pending: k1 = 0, J1 = I).
-// One block per filter, one warp per candidate (round robin), fixed-order warp reductions.
-// ---------------------------------------------------------------------------------------
-#define RG_THREADS 256
-__global__ void __launch_bounds__(RG_THREADS, 4) k_rescue_gate(DevView v, ekfslam_params prm, int keep_v) {
-    extern __shared__ double wcam[];   // [k1][7] camera columns of the pending rows
-    const int b = blockIdx.x;
-    const int N = v.N, ld = v.ld, kmax = v.kmax;
-    const int k1 = v.kpend[b];
-    const int nf = v.nfeat[b];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* __restrict__ W = v.W + (size_t)b * v.wstride;
-    const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
-    __shared__ double J1[16];
-    __shared__ double hsm[(RG_THREADS / 32) * 4 * EKF_HC];
-    if (tid < 16) J1[tid] = (k1 > 0) ? v.jn1[(size_t)b * 16 + tid] : ((tid >> 2) == (tid & 3) ? 1.0 : 0.0);
-    for (int e = tid; e < k1 * 7; e += blockDim.x) {
-        const int a = e / 7, m = e - a * 7;
-        wcam[e] = W[w_at(v.wrows, a, m)];
-    }
-    __syncthreads();
-    for (int i = warp; i < nf; i += (blockDim.x >> 5)) {
-        const size_t t = (size_t)b * N + i;
-        const int type = v.ftype[t];
-        uint8_t f = v.flags[t];
-        if (type == EKFSLAM_FEAT_NONE || !(f & EKFSLAM_F_HAS_H) || !(f & EKFSLAM_F_IC) || (f & EKFSLAM_F_LI)) continue;
-        const double* __restrict__ H = v.Hc + t * EKF_HSTRIDE;
-        const int off = v.foff[t];
-        const int w = (type == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
-        const int nc = 7 + w;
-        // H_c (for the W part) and H_c J1 (for the P part: columns 3..6 mix) in this warp's shared scratch
-        double* hs = hsm + warp * 4 * EKF_HC;          // [2][13] H_c, [2][13] H_c J1
-        __syncwarp();
-        if (lane < 2 * EKF_HC) {
-            const int rr = lane / EKF_HC, m = lane - rr * EKF_HC;
-            const double hv = (m < nc) ? H[rr * EKF_HC + m] : 0.0;
-            hs[rr * EKF_HC + m] = hv;
-            hs[(2 + rr) * EKF_HC + m] = hv;
-        }
-        __syncwarp();
-        if (lane < 8) {
-            const int rr = lane >> 2, a = lane & 3;
-            const double* hr = hs + rr * EKF_HC;
-            hs[(2 + rr) * EKF_HC + 3 + a] = hr[3] * J1[0 * 4 + a] + hr[4] * J1[1 * 4 + a] + hr[5] * J1[2 * 4 + a] + hr[6] * J1[3 * 4 + a];
-        }
-        __syncwarp();
-        const double* j0 = hs + 2 * EKF_HC;
-        const double* j1 = hs + 3 * EKF_HC;
-        // (H J1) P[c,c] (H J1)': the <= 169 entries of the gather spread over the lanes, all loads issued before use
-        double pvs[6];
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-            const int e = lane + 32 * u;
-            double pv = 0.0;
-            if (e < nc * nc) {
-                const int r = e / nc, cc = e - r * nc;
-                const int gr = (r < 7) ? r : off + r - 7, gc = (cc < 7) ? cc : off + cc - 7;
-                pv = (gr >= gc) ? P[(size_t)gr * ld + gc] : P[(size_t)gc * ld + gr];   // lower triangle is authoritative
-            }
-            pvs[u] = pv;
-        }
-        double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-            const int e = lane + 32 * u;
-            if (e < nc * nc) {
-                const int r = e / nc, cc = e - r * nc;
-                const double a0 = j0[r], a1 = j1[r], c0 = j0[cc], c1 = j1[cc], pv = pvs[u];
-                s00 += a0 * pv * c0; s01 += a0 * pv * c1; s10 += a1 * pv * c0; s11 += a1 * pv * c1;
-            }
-        }
-        // (H Wt') over the pending rows, lanes along the rows
-        double q00 = 0.0, q01 = 0.0, q11 = 0.0;
-        for (int a = lane; a < k1; a += 32) {
-            double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-            for (int m = 0; m < 7; ++m) { const double wv = wcam[a * 7 + m]; v0 += hs[m] * wv; v1 += hs[EKF_HC + m] * wv; }
-#pragma unroll
-            for (int m = 0; m < 6; ++m) {
-                if (m < w) { const double wv = W[w_at(v.wrows, a, off + m)]; v0 += hs[7 + m] * wv; v1 += hs[EKF_HC + 7 + m] * wv; }
-            }
-            q00 += v0 * v0; q01 += v0 * v1; q11 += v1 * v1;
-            if (keep_v) {   // rows 2i, 2i+1 of H_c Wt' for k_v (the hi inliers are a subset of the candidates): the Li scratch is free here
-                double* __restrict__ Vall = v.Li + (size_t)b * kmax * kmax;
-                Vall[(size_t)(2 * i) * kmax + a] = v0;
-                Vall[(size_t)(2 * i + 1) * kmax + a] = v1;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s00 += __shfl_xor_sync(0xffffffffu, s00, o); s01 += __shfl_xor_sync(0xffffffffu, s01, o);
-            s10 += __shfl_xor_sync(0xffffffffu, s10, o); s11 += __shfl_xor_sync(0xffffffffu, s11, o);
-            q00 += __shfl_xor_sync(0xffffffffu, q00, o); q01 += __shfl_xor_sync(0xffffffffu, q01, o);
-            q11 += __shfl_xor_sync(0xffffffffu, q11, o);
-        }
-        if (lane == 0) {
-            s00 -= q00; s01 -= q01; s10 -= q01; s11 -= q11;
-            const double n0 = v.z[2 * t] - v.h[2 * t], n1 = v.z[2 * t + 1] - v.h[2 * t + 1];
-            const double det = s00 * s11 - s01 * s10;
-            const double d2 = (n0 * (s11 * n0 - s01 * n1) + n1 * (-s10 * n0 + s00 * n1)) / det;
-            if (d2 < prm.chi2_gate) f |= EKFSLAM_F_HI; else f &= ~EKFSLAM_F_HI;
-            v.flags[t] = f;
-        }
-    }
-}
-
-void launch_rescue_gate(ekfslam_ctx* c, int keep_v) {
-    DevView& v = c->v;
-    const size_t sm = sizeof(double) * (size_t)v.kmax * 7;
-    ENSURE_DYN_SMEM(k_rescue_gate, sm, c->device);
-    KScope ks(c, KT_INNOV);
-    k_rescue_gate<<<v.B, RG_THREADS, sm, c->stream>>>(v, c->prm, keep_v);
+    if (threadIdx.x < 16 && k > 0) v.jn[(size_t)b * 16 + threadIdx.x] = Jt[threadIdx.x];
+    if (threadIdx.x == 0) v.ktot[b] = k;
 }
 
 static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
@@ -1105,7 +963,7 @@ static void gemm_attr(ekfslam_ctx* c, size_t w_sm) {
 
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     // flags: 1 = iterated-update innovation (see k_upd_S), 2 = not the final iteration (no quaternion
-    // normalisation, no covariance downdate), 4 = deferred (x and W now, covariance with the next update)
+    // normalisation, no covariance downdate)
     DevView& v = c->v;
     cudaStream_t st = c->stream;
     const bool hi = (mask & EKFSLAM_F_HI) != 0;
@@ -1113,7 +971,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     {
         KScope ks(c, hi ? KT_UPD_S_HI : KT_UPD_S);
         const int slices = (v.B < 296) ? (int)((8 * 148 + v.B - 1) / v.B) : 1;   // few filters: spread the pair loop
-        k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, (flags & 4) ? 1 : 0, slices == 1);
+        k_upd_S<<<v.B, 256, 0, st>>>(v, mask, which_prior, flags & 1, slices == 1);
         if (slices > 1) { dim3 gp(slices, v.B); k_upd_pairs<<<gp, 256, 0, st>>>(v); c->launches++; }
     }
     const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
@@ -1212,8 +1070,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         k_gemm<0><<<gw, 256, w_sm, st>>>(v, fin, small ? WS_K : 0);
     }
     if (flags & 2) return;   // not the last iterate of an iterated update: W is recomputed, nothing pending
-    { KScope ks(c, KT_WFIX); k_wfix<<<v.B, 128, 0, st>>>(v, (flags & 4) ? 1 : 0); }
+    { KScope ks(c, KT_WFIX); k_wfix<<<v.B, 128, 0, st>>>(v); }
     if (c->arm_out && (mask & EKFSLAM_F_HI)) { cudaEventRecord(c->ev_out, st); c->arm_out = 0; }  // x, flags, stats are final
-    if (flags & 4) return;   // deferred: the covariance downdate happens with the next (non-deferred) update
     launch_downdate(c, (mask & EKFSLAM_F_HI) ? KT_DOWNDATE_HI : KT_DOWNDATE);
 }

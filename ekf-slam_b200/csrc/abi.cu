@@ -263,10 +263,6 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     c->stream = c->own_stream;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (c->sm_count <= 0) c->sm_count = 148;
-    {
-        const char* e2 = getenv("EKFSLAM_RESCUE_GATHER");
-        c->rescue_gather = (e2 && e2[0] == '0') ? 0 : 1;   // default on: gate 0.36 + rows of the hi inliers 0.61 ms vs 1.15 ms
-    }
     *out = c;
     return EKFSLAM_OK;
 }
@@ -705,8 +701,8 @@ int ekfslam_update_iterated(ekfslam_ctx* c, int mask, int which_prior, int n_ite
 int ekfslam_rescue(ekfslam_ctx* c) {
     NEED_CTX(c);
     launch_features(c, 0, 3);                            // h, H of ALL features at x_k_k (:6-7)
-    launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI);  // G rows of the candidates (IC && !LI)
-    launch_innov(c, 3);                                 // chi2 gate -> HI (:11-20)
+    launch_innov_gather(c, 3);                           // chi2 gate of the candidates (IC && !LI) -> HI (:11-20)
+    launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, KT_HP_RESCUE);   // G rows of the rescued features for ekfslam_update_hi
     LAUNCHED();
     return EKFSLAM_OK;
 }
@@ -730,14 +726,8 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
         if (c->prm.fixed_hyp <= 0) launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_LI, 0);
         launch_update(c, EKFSLAM_F_LI, 1);
         launch_features(c, 0, 3);
-        if (c->rescue_gather) {
-            // chi2 gate from 13x13 gathers of p_k_k, then G rows only for the hi inliers
-            launch_innov_gather(c, 3);
-            launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, KT_HP_RESCUE);
-        } else {
-            launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_IC, EKFSLAM_F_LI, KT_HP_RESCUE);
-            launch_innov(c, 3);
-        }
+        launch_innov_gather(c, 3);                                        // chi2 gate from 13x13 gathers of p_k_k
+        launch_hp(c, EKFSLAM_F_HAS_H | EKFSLAM_F_HI, 0, KT_HP_RESCUE);    // G rows only for the hi inliers
         launch_update(c, EKFSLAM_F_HI, 0);
     }
     LAUNCHED();
@@ -748,7 +738,7 @@ int ekfslam_step(ekfslam_ctx* c, int reset, int match_mode) {
 struct StepGraph {
     cudaGraphExec_t exec;
     DevView v; ekfslam_params prm; DevCam cam;
-    int reset, match_mode, rescue_gather;
+    int reset, match_mode;
     int64_t launches;
 };
 
@@ -768,8 +758,7 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
     if (v.n_u <= 0) return fail(EKFSLAM_ERR_STATE, "step: no uniform stream uploaded");
     StepGraph* g = (StepGraph*)c->step_graph;
     if (g && (memcmp(&g->v, &v, sizeof(DevView)) || memcmp(&g->prm, &c->prm, sizeof(ekfslam_params)) ||
-              memcmp(&g->cam, &c->cam, sizeof(DevCam)) || g->reset != reset || g->match_mode != match_mode ||
-              g->rescue_gather != c->rescue_gather)) {
+              memcmp(&g->cam, &c->cam, sizeof(DevCam)) || g->reset != reset || g->match_mode != match_mode)) {
         step_graph_destroy(c);
         g = nullptr;
     }
@@ -778,7 +767,7 @@ int ekfslam_step_graph(ekfslam_ctx* c, int reset, int match_mode) {
         if (!g) return fail(EKFSLAM_ERR_NOMEM, "host allocation failed");
         memset(g, 0, sizeof(*g));
         memcpy(&g->v, &v, sizeof(DevView)); memcpy(&g->prm, &c->prm, sizeof(ekfslam_params)); memcpy(&g->cam, &c->cam, sizeof(DevCam));
-        g->reset = reset; g->match_mode = match_mode; g->rescue_gather = c->rescue_gather;
+        g->reset = reset; g->match_mode = match_mode;
         const int64_t l0 = c->launches;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);

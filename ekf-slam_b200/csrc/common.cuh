@@ -85,7 +85,6 @@ struct ekfslam_ctx {
     int64_t bytes;
     int64_t launches;
     int stage;  // call-order tracking
-    int rescue_gather;   // ekfslam_step: rescue gate from 13x13 gathers of P, G rows only for the hi inliers
     // ekfslam_step_host overlaps its PCIe copies with the step: inputs go up on copy_stream while prediction and the
     // measurement model run (first needed by the matcher gate), x / flags / stats come down while the last covariance
     // downdate (which only touches P) is still running.
@@ -158,7 +157,7 @@ void launch_predict(ekfslam_ctx* c);
 void launch_features(ekfslam_ctx* c, int which, int parts);  // parts: 1 = h, 2 = H, 3 = both
 void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot = KT_HP);  // G rows for features with (flags&need)==need && !(flags&forbid)
 void launch_innov_gather(ekfslam_ctx* c, int mode);          // S_i from 13x13 gathers of P (no G rows): 0 = S_i + R stored, 3 = rescue gate
-void launch_innov(ekfslam_ctx* c, int mode);           // S_i (+R) / matcher gate / explicit matches / rescue gate
+void launch_innov(ekfslam_ctx* c, int mode);           // matcher gate (1) / explicit matches (2)
 void launch_symmetrize(ekfslam_ctx* c, int b0, int nb);
 void launch_ransac(ekfslam_ctx* c);
 void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags = 0);

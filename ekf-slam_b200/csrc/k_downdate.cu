@@ -641,9 +641,7 @@ void launch_downdate(ekfslam_ctx* c, int slot) {
         const int S = cfgB ? 2 : 4, NX = cfgB ? 2 : 1;
         // filters are processed in groups small enough for the per-CTA tile metadata (8 B per tile) to stay
         // within the shared-memory budget of two CTAs per SM
-        static int per_sm = -1;
-        if (per_sm < 0) { const char* e = getenv("EKFSLAM_DD_CTAS_PER_SM"); per_sm = (e && e[0] == '1') ? 1 : 2; }
-        const long long ctas_full = (long long)sms * per_sm;
+        const long long ctas_full = (long long)sms * 2;
         const int mirror = 1;   // P is kept exactly symmetric in memory: every off-diagonal tile is stored with its mirror image
         const size_t fixed = sizeof(double) * (2 * S * TK * TPAD + NX * TM * XP) + sizeof(unsigned long long) * (2 * S + 2 * NX) +
                              sizeof(unsigned) * T;

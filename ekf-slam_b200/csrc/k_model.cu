@@ -345,21 +345,17 @@ void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Per-feature 2x2 innovation covariance from G, and the match gates.  One thread per feature.
-//   (S_i = H_i P H_i' + R_i of every predicted feature, mc/search_IC_matches.m:6-10: k_innov_gather below)
-//   mode 1: synthetic matcher gate (mc/matching.m:16,38) on candidates  -> z, HAS_Z, IC
+// The match gates.  One thread per feature.
+//   mode 1: synthetic matcher gate (mc/matching.m:16,38) on candidates  -> z, HAS_Z, IC  (S_i from k_innov_gather)
 //   mode 2: explicit matches (what mc/matching.m:52-53 would have written) -> z, HAS_Z, IC
-//   mode 3: rescue gate (mc/rescue_hi_inliers.m:11-20): S_i = H_i P H_i' (no R) for IC && !LI,
-//           nu' inv(S_i) nu < chi2 -> HI.  S is not stored (it is a local in the reference).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_innov(DevView v, ekfslam_params prm, int mode) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= v.B * v.N) return;
     const int b = t / v.N, i = t - b * v.N;
     if (i >= v.nfeat[b]) return;
-    const int type = v.ftype[t];
-    if (type == EKFSLAM_FEAT_NONE) return;
-    uint8_t f = v.flags[t];
+    if (v.ftype[t] == EKFSLAM_FEAT_NONE) return;
+    const uint8_t f = v.flags[t];
     if (mode == 2) {
         const uint8_t m = v.mflags[t] & (EKFSLAM_F_HAS_Z | EKFSLAM_F_IC);
         if (m) {
@@ -368,49 +364,20 @@ __global__ void __launch_bounds__(128) k_innov(DevView v, ekfslam_params prm, in
         }
         return;
     }
-    if (!(f & EKFSLAM_F_HAS_H)) return;
-    if (mode == 1 && !(v.mflags[t] & EKFSLAM_F_CAND)) return;
-    if (mode == 3 && !((f & EKFSLAM_F_IC) && !(f & EKFSLAM_F_LI))) return;
-
-    double s00, s01, s10, s11;
-    if (mode == 1) {
-        s00 = v.S[4 * t]; s01 = v.S[4 * t + 1]; s10 = v.S[4 * t + 2]; s11 = v.S[4 * t + 3];
-    } else {
-        const int ld = v.ld;
-        const double* __restrict__ g0 = v.G + ((size_t)b * v.kmax + 2 * i) * ld;
-        const double* __restrict__ g1 = g0 + ld;
-        const double* __restrict__ H = v.Hc + (size_t)t * EKF_HSTRIDE;
-        const int off = v.foff[t];
-        const int w = (type == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
-        s00 = s01 = s10 = s11 = 0.0;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const double a0 = g0[k], a1 = g1[k], h0 = H[k], h1 = H[EKF_HC + k];
-            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
-        }
-        for (int k = 0; k < w; ++k) {
-            const double a0 = g0[off + k], a1 = g1[off + k], h0 = H[7 + k], h1 = H[EKF_HC + 7 + k];
-            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
-        }
-    }
-    const double zu = (mode == 1) ? v.zc[2 * t] : v.z[2 * t];
-    const double zv = (mode == 1) ? v.zc[2 * t + 1] : v.z[2 * t + 1];
+    if (!(f & EKFSLAM_F_HAS_H) || !(v.mflags[t] & EKFSLAM_F_CAND)) return;
+    const double s00 = v.S[4 * t], s01 = v.S[4 * t + 1], s10 = v.S[4 * t + 2], s11 = v.S[4 * t + 3];
+    const double zu = v.zc[2 * t], zv = v.zc[2 * t + 1];
     const double n0 = zu - v.h[2 * t], n1 = zv - v.h[2 * t + 1];
     const double det = s00 * s11 - s01 * s10;
     // nu' inv(S) nu with inv(S) = [s11 -s01; -s10 s00]/det
     const double d2 = (n0 * (s11 * n0 - s01 * n1) + n1 * (-s10 * n0 + s00 * n1)) / det;
-    if (mode == 1) {
-        // all(eig(S) < 100): the larger eigenvalue of the 2x2
-        const double tr = s00 + s11;
-        const double disc = sqrt((s00 - s11) * (s00 - s11) + 4.0 * s01 * s10);
-        const double lmax = 0.5 * (tr + disc);
-        if (lmax < 100.0 && d2 < prm.chi2_gate) {
-            v.z[2 * t] = zu; v.z[2 * t + 1] = zv;
-            v.flags[t] = f | EKFSLAM_F_HAS_Z | EKFSLAM_F_IC;
-        }
-    } else {  // mode 3
-        if (d2 < prm.chi2_gate) f |= EKFSLAM_F_HI; else f &= ~EKFSLAM_F_HI;
-        v.flags[t] = f;
+    // all(eig(S) < 100): the larger eigenvalue of the 2x2
+    const double tr = s00 + s11;
+    const double disc = sqrt((s00 - s11) * (s00 - s11) + 4.0 * s01 * s10);
+    const double lmax = 0.5 * (tr + disc);
+    if (lmax < 100.0 && d2 < prm.chi2_gate) {
+        v.z[2 * t] = zu; v.z[2 * t + 1] = zv;
+        v.flags[t] = f | EKFSLAM_F_HAS_Z | EKFSLAM_F_IC;
     }
 }
 

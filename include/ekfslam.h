@@ -187,7 +187,8 @@ int ekfslam_apply_matches(ekfslam_ctx* ctx);
 int ekfslam_ransac(ekfslam_ctx* ctx);
 /* mc/ekf_update_li_inliers.m:4-21 -> mc/update.m:3-32 (+normJac) from (x_k_km1,p_k_km1) */
 int ekfslam_update_li(ekfslam_ctx* ctx);
-/* mc/rescue_hi_inliers.m:3-22 */
+/* mc/rescue_hi_inliers.m:3-22: h, H of every feature at x_k_k, chi2 gate of the candidates (IC && !LI) from
+ * 13x13 gathers of p_k_k, then the rows H p_k_k of the rescued features (for ekfslam_update_hi) */
 int ekfslam_rescue(ekfslam_ctx* ctx);
 /* mc/ekf_update_hi_inliers.m:4-21 -> mc/update.m from (x_k_k,p_k_k) */
 int ekfslam_update_hi(ekfslam_ctx* ctx);

@@ -654,7 +654,7 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
     launch_chol_blocked64(c, kact);   // 64-wide panels, panel / trailing / triangular-inverse products on the tensor pipe
     if (kact > 0) {
         // scratch [row chunks][kmax] per filter at the head of its Sb block: the factor L (and the parked T blocks of the
-        // blocked inverse) are dead once inv(L) exists (W may hold pending rows, G the H P rows)
+        // blocked inverse) are dead once inv(L) exists (G holds the H P rows)
         double* tmp = v.Sb;
         const long long tstride = (long long)kmax * kmax;
         const int nch = (kact + CV_ROWS - 1) / CV_ROWS;
@@ -1069,7 +1069,7 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         if (small) { k_w_small<<<v.B, 128, 0, st>>>(v, fin); c->launches++; }
         k_gemm<0><<<gw, 256, w_sm, st>>>(v, fin, small ? WS_K : 0);
     }
-    if (flags & 2) return;   // not the last iterate of an iterated update: W is recomputed, nothing pending
+    if (flags & 2) return;   // not the last iterate of an iterated update: W is recomputed
     { KScope ks(c, KT_WFIX); k_wfix<<<v.B, 128, 0, st>>>(v); }
     if (c->arm_out && (mask & EKFSLAM_F_HI)) { cudaEventRecord(c->ev_out, st); c->arm_out = 0; }  // x, flags, stats are final
     launch_downdate(c, (mask & EKFSLAM_F_HI) ? KT_DOWNDATE_HI : KT_DOWNDATE);

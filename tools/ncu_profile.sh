@@ -8,5 +8,5 @@ BENCH="python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu-baseline"
 $BENCH > gpurun_out/plain_$R.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$R.csv $BENCH > gpurun_out/ncu_list_$R.log 2>&1
 $BENCH > gpurun_out/plain2_$R.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k_downdate|k_hp|k_chol|k_gemm|k_w_small|k_wfix|k_ransac|k_upd_S|k_predict|k_features|k_innov|k_rescue_gate" -s 52 -c 26 -o gpurun_out/prof_$R $BENCH > gpurun_out/ncu_full_$R.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_downdate|k_hp|k_chol|k_gemm|k_w_small|k_wfix|k_ransac|k_upd_S|k_predict|k_features|k_innov" -s ${SKIP:-54} -c ${CNT:-27} -o gpurun_out/prof_$R $BENCH > gpurun_out/ncu_full_$R.log 2>&1
 tail -n 2 gpurun_out/ncu_list_$R.log gpurun_out/ncu_full_$R.log

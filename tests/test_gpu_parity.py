@@ -190,3 +190,62 @@ def test_blocked64_cholesky_ragged_k(ekf):
     nf = [140, 97, 33]
     worst, tot = _run_sequence(ekf, B=3, N=140, frames=3, seed=850, nfeat=nf, p_outlier=0.1)
     assert tot["li"] > 300, tot
+
+
+def test_innovation_gather_mixed_ragged_map(ekf):
+    """S_i = H_i P H_i' + R_i from 13x13 / 10x10 gathers of P (k_innov_gather; mc/search_IC_matches.m:6-10) on a mixed
+    inverse-depth / Cartesian, ragged batch with a fully dense covariance, against the oracle's dense
+    H P H' + R: h, the compact Jacobian and S to 1e-12; the G rows are never formed on this path."""
+    pkg, synth = ekf
+    B, N = 4, 30
+    seq = synth.SynthSequence(B=B, N=N, T=2, seed=321, n_u=16)
+    x0, P0, types = seq.initial_state()
+    n_max = 13 + 6 * N
+    nfeat = [30, 30, 11, 1]
+    cart = [0, 3, 4, 9, 17, 29]
+    xs, Ps, ts, ns = [], [], [], []
+    rng = np.random.RandomState(7)
+    for b in range(B):
+        tb = types[b].copy()
+        nb_ = 13 + 6 * nfeat[b]
+        tb[nfeat[b]:] = 0
+        xb, Pb = x0[b, :nb_].copy(), P0[b, :nb_, :nb_].copy()
+        A = rng.normal(0, 1e-3, (nb_, nb_))           # fill in every cross-covariance block
+        Pb = Pb + A @ A.T
+        if b < 2:
+            xb, Pb, tb2 = synth.convert_to_cartesian(np.pad(xb, (0, n_max - nb_)), np.pad(Pb, ((0, n_max - nb_),) * 2),
+                                                     np.pad(tb[:N], (0, 0)), cart)
+            tb = tb2
+            nb_ = 13 + 6 * int((tb == 1).sum()) + 3 * int((tb == 2).sum())
+            xb, Pb = xb[:nb_], Pb[:nb_, :nb_]
+        xs.append(np.pad(xb, (0, n_max - nb_)))
+        Ps.append(np.pad(Pb, ((0, n_max - nb_), (0, n_max - nb_))))
+        ts.append(tb)
+        ns.append(nb_)
+    xs, Ps, ts = np.stack(xs), np.stack(Ps), np.stack(ts)
+    bank = pkg.FilterBank(B, N, n_max)
+    bank.upload_feature_types(ts)
+    bank.upload_state(xs, Ps)
+    bank.begin_frame()
+    bank.ekf_prediction()
+    bank.measure(1)
+    d = bank.download_features()
+    cam = O.initialize_cam()
+    checked = 0
+    for b in range(B):
+        f = T.oracle_filter(xs[b, :ns[b]], Ps[b, :ns[b], :ns[b]])
+        fi = T.oracle_features(ts[b])
+        f, fi = O.ekf_prediction(f, fi)
+        fi = O.predict_and_derive(f, fi, cam)
+        Hc = T.compact_H(fi)
+        for i, a in enumerate(fi):
+            has_h = bool(d["flags"][b, i] & T.F_HAS_H)
+            assert has_h == (a.h is not None), (b, i)
+            if a.h is None:
+                continue
+            np.testing.assert_allclose(d["h"][b, i], a.h, rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(d["Hc"][b, i], Hc[i], rtol=1e-11, atol=1e-11 * np.abs(Hc[i]).max())
+            np.testing.assert_allclose(d["S"][b, i], a.S, rtol=1e-12, atol=1e-12 * np.abs(a.S).max())
+            checked += 1
+    assert checked >= 60
+    bank.close()

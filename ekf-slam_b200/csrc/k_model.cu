@@ -239,7 +239,7 @@ void launch_features(ekfslam_ctx* c, int which, int parts) {
 // K = P H_i' inv(S_i) (mc/ransac_hypotheses.m:24-25) and P H' of the update (mc/update.m:8-9).
 // ---------------------------------------------------------------------------------------
 #define HP_CHUNK 64
-__global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid) {
+__global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int fch) {
     const int b = blockIdx.y;
     const int n = v.nstate[b];
     const int ld = v.ld;
@@ -261,18 +261,20 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid) {
 #pragma unroll
         for (int r = 0; r < 7; ++r) pc[r] = *reinterpret_cast<const double2*>(P + (size_t)r * ld + c0);
     }
-    // blockIdx.z splits the feature chunks among CTAs (few filters with large maps would otherwise leave most SMs idle)
-    for (int f0 = blockIdx.z * HP_CHUNK; f0 < nf; f0 += gridDim.z * HP_CHUNK) {
+    // blockIdx.z splits the feature chunks (fch <= HP_CHUNK features each) among CTAs: few filters would otherwise leave
+    // most SMs idle (one filter of N = 100: 6 CTAs streaming 3 MB)
+    for (int f0 = blockIdx.z * fch; f0 < nf; f0 += gridDim.z * fch) {
         __syncthreads();
         if (threadIdx.x < 32) {
             // warp 0 compacts the selected features of this chunk (ballot + prefix popcount)
             int base = 0;
 #pragma unroll
             for (int h2 = 0; h2 < HP_CHUNK / 32; ++h2) {
-                const int i = f0 + h2 * 32 + threadIdx.x;
+                const int j = h2 * 32 + threadIdx.x;
+                const int i = f0 + j;
                 bool selq = false;
                 int ty = 0, of = 0;
-                if (i < nf) {
+                if (j < fch && i < nf) {
                     const int t = b * v.N + i;
                     const uint8_t fl = v.flags[t];
                     ty = v.ftype[t];
@@ -335,13 +337,18 @@ __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid) {
 
 void launch_hp(ekfslam_ctx* c, int need, int forbid, int slot) {
     const int colchunks = (c->v.nmax + 255) / 256;
-    const int fchunks = (c->v.N + HP_CHUNK - 1) / HP_CHUNK;
-    int fz = 1;   // feature-chunk groups: only when the (column chunk, filter) grid cannot fill the GPU
-    if ((long long)colchunks * c->v.B < 4 * 148) fz = (int)((4LL * 148 + (long long)colchunks * c->v.B - 1) / ((long long)colchunks * c->v.B));
-    if (fz > fchunks) fz = fchunks;
+    // feature-chunk groups (blockIdx.z): only when the (column chunk, filter) grid cannot fill the GPU; the chunk shrinks
+    // from 64 features down to 8 until there are ~4 CTAs per SM
+    const long long base = (long long)colchunks * c->v.B;
+    const long long want = 4LL * c->sm_count;
+    int fch = HP_CHUNK;
+    while (fch > 8 && base * ((c->v.N + fch - 1) / fch) < want) fch >>= 1;
+    int fz = (c->v.N + fch - 1) / fch;
+    if (base >= want) fz = 1;
+    else if (base * fz > want) fz = (int)((want + base - 1) / base);
     dim3 grid(colchunks, c->v.B, fz);
     KScope ks(c, slot);
-    k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid);
+    k_hp<<<grid, 128, 0, c->stream>>>(c->v, need, forbid, fch);
 }
 
 // ---------------------------------------------------------------------------------------

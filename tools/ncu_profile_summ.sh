@@ -3,7 +3,7 @@
 # are written as text; the .ncu-rep itself is kept only if it is small enough.
 mkdir -p gpurun_out
 R=${ROUND:-r1}
-BENCH="python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu-baseline"
+BENCH="python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-extra"
 $BENCH > gpurun_out/plain2_$R.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"k_downdate|k_hp|k_chol|k_gemm|k_w_small|k_wfix|k_ransac|k_upd_S|k_predict|k_features|k_innov" -s ${SKIP:-54} -c ${CNT:-27} -o /tmp/prof_$R $BENCH > gpurun_out/ncu_full_$R.log 2>&1
 tail -n 2 gpurun_out/ncu_full_$R.log

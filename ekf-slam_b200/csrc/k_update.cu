@@ -356,13 +356,96 @@ __global__ void __launch_bounds__(128) k_chol(DevView v, int kskip) {
 // stalls were half of its issue stalls) and stays as the path for larger k.  Same blocked algorithm and pivots.
 // ---------------------------------------------------------------------------------------
 #define CHS_K 144   // large variant: KMIN < k <= 144, 256 threads, 2 CTAs/SM
-#define CHS_KM 112  // middle variant (li update at N = 100: k ~ 100): 256 threads, <= 85 registers, 70 KB -> 3 CTAs/SM (EKFSLAM_CHOL_MID=0 disables)
-#define CHS_KS 48   // small variant (hi update: k ~ 24): k <= 48, 128 threads, 20 KB of shared memory -> many CTAs/SM
-__device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
+#define CHS_KM 112  // middle variant (li update at N = 100: k ~ 100): 256 threads, <= 85 registers, 72 KB -> 3 CTAs/SM (EKFSLAM_CHOL_MID=0 disables)
+#define CHS_KS 48   // small variant (hi update: k ~ 24): k <= 48, 128 threads, 21 KB of shared memory -> many CTAs/SM
+// Packed lower triangle whose rows start on an even index (16-byte aligned): the trailing update reads and writes four
+// neighbouring columns of a row as two 128-bit accesses.
+__device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + ((r + 1) >> 1) + c; }
+#define CHS_TRI(K) (((K) * ((K) + 1)) / 2 + ((K) + 1) / 2)
+#define CHS_PRS 18  // row stride of the staged row panel of the inverse phase: 16-byte aligned rows, four consecutive rows in disjoint banks
+#define CHS_SMEM(K) (sizeof(double) * (CHS_TRI(K) + 3 * NB * (NB + 1) + (size_t)(K) * CHS_PRS))
 
+// Shared-memory traffic decides this kernel (ncu, round 2: 102 M shared wavefronts per launch of 4096 filters, 39 % of
+// them in the inner loop of the inverse phase, 28 % in the trailing update, both with one 8-byte load per FMA and every
+// lane on its own row).  Both loops now read operands that are staged so that a warp's lanes either share an address
+// (broadcast) or sit next to each other, as 128-bit loads:
+//   * trailing update: the solved panel is kept TRANSPOSED (PT[t][row]), a 4x4 micro tile reads its four rows / four
+//     columns at one t as two double2 each; the tile goes back to the packed triangle as double2 read-modify-writes;
+//   * inverse phase: the row panel L[I0..I0+16)[0..I0) is staged as PR[t][r]; a warp takes 8 columns x 4 values of t per
+//     step, so the 16 panel values of one t are 8 broadcast double2 loads shared by 8 lanes; column blocks are paired
+//     (j, last - j) so that every warp runs the same number of steps.
+#ifndef CHS_PIPE
+#define CHS_PIPE 1
+#endif
+// Block row I0/16 of X = inv(L), formed from L[I0..I0+16)[0..I0) (read in place from the packed triangle) and the rows of
+// X above it:  X[I][0:I0] = -Di_I * ( L[I][0:I0] * X[0:I0][0:I0] ).  A warp takes the pair of 8-wide column blocks
+// (pair, last - pair) - (I0 + 8) / 4 steps of 8 columns x 4 values of t whatever the pair is - and keeps its 2 x 4 results
+// per lane in registers: the rows it overwrites are still being read by the other warps, so the store happens behind a
+// barrier (chs_inv_store).
+__device__ __forceinline__ void chs_inv_compute(const double* Ls, const double* Di, int I0, int nb, int pair, int lane, double (&res)[2][4]) {
+    const int c8 = lane & 7, tq = lane >> 3;
+    const int nblk = I0 >> 3;                       // I0 is a multiple of 16
+    const double* lrow = Ls + tri(I0, 0);           // row I0 + r starts at lrow + r * I0 + tri(r, 0)   (I0 even)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int cb = half ? nblk - 1 - pair : pair;
+        const int c = cb * 8 + c8;
+        double y[NB];
+#pragma unroll
+        for (int r = 0; r < NB; ++r) y[r] = 0.0;
+#pragma unroll 2
+        for (int t = cb * 8 + tq; t < I0; t += 4) {
+            const double xv = (t >= c) ? Ls[tri(t, c)] : 0.0;
+            const double* lt = lrow + t;
+#pragma unroll
+            for (int r = 0; r < NB; ++r) y[r] += ((r < nb) ? lt[r * I0 + tri(r, 0)] : 0.0) * xv;   // rows past k hold no data
+        }
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+            y[r] += __shfl_xor_sync(0xffffffffu, y[r], 8);
+            y[r] += __shfl_xor_sync(0xffffffffu, y[r], 16);
+        }
+        // rows tq, tq+4, tq+8, tq+12 of -Di*y: four independent chains over all 16 columns (Di is zero above its diagonal)
+        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* dr = Di + tq * (NB + 1);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s4[u] += dr[u * 4 * (NB + 1) + j] * y[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) res[half][u] = -s4[u];
+    }
+}
+__device__ __forceinline__ void chs_inv_store(double* Ls, int I0, int nb, int pair, int lane, const double (&res)[2][4]) {
+    const int c8 = lane & 7, tq = lane >> 3;
+    const int nblk = I0 >> 3;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int c = (half ? nblk - 1 - pair : pair) * 8 + c8;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (tq + 4 * u < nb) Ls[tri(I0 + tq + 4 * u, c)] = res[half][u];
+    }
+}
+
+#ifdef CHS_PROF
+// debug build only (-DCHS_PROF): cycles of thread 0 between the barriers of each phase, summed over the CTAs of the
+// 112-row variant; read back with ekfslam_debug_chs_prof
+__device__ unsigned long long g_chs_prof[16];
+extern "C" int ekfslam_debug_chs_prof(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_chs_prof, sizeof(g_chs_prof));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_chs_prof, z, sizeof(z)); }
+    return 0;
+}
+#define CHS_MARK(ph) do { if (KM == CHS_KM && KMIN == 0 && tid == 0) { const unsigned t1_ = (unsigned)clock(); atomicAdd(&g_chs_prof[ph], (unsigned long long)(t1_ - t0_)); t0_ = t1_; } } while (0)
+#else
+#define CHS_MARK(ph) do { } while (0)
+#endif
 template <int KM, int CHS_T, int KMIN, int MINB = 1>
 __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int b = blockIdx.x;
     const int k = 2 * v.ksel[b];
     if (k == 0 || k > KM || k <= KMIN) return;
@@ -372,23 +455,48 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
     const double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
     double* __restrict__ Xg = v.Li + (size_t)b * kmax * kmax;
     double* Ls = sm;                                   // packed lower triangle: L, then inv(L) in place
-    double* D = Ls + (KM * (KM + 1)) / 2;              // [NB][NB+1] diagonal block factor
+    double* D = Ls + CHS_TRI(KM);                      // [NB][NB+1] diagonal block factor
+#if CHS_PIPE
+    double* DiA = D + NB * (NB + 1);                   // [2][NB][NB+1] its inverse: this panel's and the previous one's
+    double* Pn = DiA + 2 * NB * (NB + 1);              // [KM * CHS_PRS] transposed panel of the trailing update / vectors
+#else
     double* Di = D + NB * (NB + 1);                    // [NB][NB+1] its inverse
-    double* Pn = Di + NB * (NB + 1);                   // [KM][NB+1] transposed row panel (inverse phase) / vectors
+    double* Pn = Di + NB * (NB + 1);                   // [KM * CHS_PRS] transposed panels (both phases) / vectors
+#endif
     __shared__ int s_bad;
     if (tid == 0) s_bad = 0;
+#ifdef CHS_PROF
+    unsigned t0_ = (unsigned)clock();
+    if (KM == CHS_KM && KMIN == 0 && tid == 0) atomicAdd(&g_chs_prof[15], 1ull);
+#endif
+    // every element of the lower triangle is its own 8-byte asynchronous copy (LDGSTS.64): ~20 independent copies in
+    // flight per thread instead of a dependent DRAM round trip per row (ncu: 11 % of the kernel's samples sat on the
+    // plain load loop; k_chol 1.42 -> 1.33 ms)
     for (int r = warp; r < k; r += nwarps)
-        for (int c = lane; c <= r; c += 32) Ls[tri(r, c)] = S[(size_t)r * kmax + c];
+        for (int c = lane; c <= r; c += 32) cp_async8(Ls + tri(r, c), S + (size_t)r * kmax + c);
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
+    CHS_MARK(0);
 
     for (int j0 = 0; j0 < k; j0 += NB) {
         const int nb = min(NB, k - j0);
+#if CHS_PIPE
+        double* Di = DiA + ((j0 >> 4) & 1) * NB * (NB + 1);
+        const double* Dip = DiA + (((j0 >> 4) & 1) ^ 1) * NB * (NB + 1);
+        double res[2][4];
+        // While warp 0 walks the serial pivot chain of diagonal block j, the other warps form block row j-1 of inv(L): its
+        // rows of L are final, its diagonal block inverse is Dip, the rows of X above it were stored one panel ago.
+        // At most nwarps - 1 column-block pairs exist here (block row j-1 has j-1 pairs, j <= KM/16 - 1).
+        const bool inv_prev = warp > 0 && j0 >= 2 * NB && (warp - 1) < ((j0 - NB) >> 4);
+#endif
         for (int e = tid; e < NB * NB; e += CHS_T) {
             const int r = e / NB, c = e - r * NB;
             D[r * (NB + 1) + c] = (r < nb && c <= r) ? Ls[tri(j0 + r, j0 + c)] : ((r >= nb && r == c) ? 1.0 : 0.0);
             Di[r * (NB + 1) + c] = 0.0;
         }
         __syncthreads();
+        CHS_MARK(1);
         if (warp == 0) {
             // as in k_chol: lane i holds row i of the block, pivots by rsqrt, then the triangular inverse
             const unsigned full_mask = 0xffffffffu;
@@ -413,6 +521,7 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
                 }
             }
             if (bad && lane == 0) s_bad = 1;
+            CHS_MARK(8);
             if (lane < NB) {
 #pragma unroll
                 for (int c = 0; c < NB; ++c) D[i * (NB + 1) + c] = (c <= i) ? a[c] : 0.0;
@@ -434,30 +543,47 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
                 }
             }
         }
+#if CHS_PIPE
+        else if (inv_prev) chs_inv_compute(Ls, Dip, j0 - NB, NB, warp - 1, lane, res);
         __syncthreads();
+        if (inv_prev) chs_inv_store(Ls, j0 - NB, NB, warp - 1, lane, res);
+#else
+        __syncthreads();
+#endif
+        CHS_MARK(2);
         // the diagonal block of X replaces the one of L (the panel solve and the inverse phase only use Di)
         for (int e = tid; e < nb * nb; e += CHS_T) {
             const int r = e / nb, c = e - r * nb;
             if (c <= r) Ls[tri(j0 + r, j0 + c)] = Di[r * (NB + 1) + c];
         }
-        // panel: L[i][j0+c] = sum_{t<=c} S[i][j0+t] * Di[c][t]
+        // panel: L[i][j0+c] = sum_{t<=c} S[i][j0+t] * Di[c][t]; a transposed copy PT[c][i - i1] feeds the trailing update
         const int i1 = j0 + nb;
+        const int m = k - i1;                 // m > 0 implies nb == NB
+        double* PT = Pn;                      // [NB][KM]
         for (int i = i1 + tid; i < k; i += CHS_T) {
-            double* lrow = Ls + tri(i, j0);
+            double2* lrow = reinterpret_cast<double2*>(Ls + tri(i, j0));   // j0 is a multiple of 16: 16-byte aligned
             double row[NB];
 #pragma unroll
-            for (int t = 0; t < NB; ++t) row[t] = (t < nb) ? lrow[t] : 0.0;
+            for (int t = 0; t < NB; t += 2) { const double2 p = lrow[t >> 1]; row[t] = p.x; row[t + 1] = p.y; }
+            double out[NB];
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
                 double s = 0.0;
 #pragma unroll
                 for (int t = 0; t <= c; ++t) s += row[t] * Di[c * (NB + 1) + t];
-                if (c < nb) lrow[c] = s;
+                out[c] = s;
+                PT[c * KM + (i - i1)] = s;
             }
+#pragma unroll
+            for (int c = 0; c < NB; c += 2) lrow[c >> 1] = make_double2(out[c], out[c + 1]);
+        }
+        if (m > 0 && tid < 4 && m + tid < ((m + 3) & ~3)) {   // rows of the last, partial micro tile
+#pragma unroll
+            for (int c = 0; c < NB; ++c) PT[c * KM + m + tid] = 0.0;
         }
         __syncthreads();
+        CHS_MARK(3);
         // trailing update of the lower triangle: S[i][c] -= sum_t L[i][j0+t] L[c][j0+t]   (4x4 micro tiles)
-        const int m = k - i1;
         if (m > 0) {
             const int mt = (m + 3) / 4;
             const int ntile = mt * (mt + 1) / 2;
@@ -471,80 +597,121 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-                const double* pa[4];
-                const double* pc[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    pa[a] = Ls + tri(min(i1 + ti * 4 + a, k - 1), j0);   // clamped rows are masked at the store
-                    pc[a] = Ls + tri(min(i1 + tj * 4 + a, k - 1), j0);
-                }
-                for (int t = 0; t < nb; ++t) {
-                    double ra[4], rc[4];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) { ra[a] = pa[a][t]; rc[a] = pc[a][t]; }
+                const double2* pa = reinterpret_cast<const double2*>(PT + 4 * ti);
+                const double2* pc = reinterpret_cast<const double2*>(PT + 4 * tj);
+#pragma unroll 4
+                for (int t = 0; t < NB; ++t) {
+                    const double2 a01 = pa[t * (KM / 2)], a23 = pa[t * (KM / 2) + 1];
+                    const double2 c01 = pc[t * (KM / 2)], c23 = pc[t * (KM / 2) + 1];
+                    const double ra[4] = {a01.x, a01.y, a23.x, a23.y};
+                    const double rc[4] = {c01.x, c01.y, c23.x, c23.y};
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
                         for (int c = 0; c < 4; ++c) acc[a][c] += ra[a] * rc[c];
                 }
+                if (ti != tj) {   // all four columns lie left of the diagonal: 128-bit read-modify-writes
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int ia = ti * 4 + a, ic = tj * 4 + c;
-                        if (ia < m && ic <= ia) Ls[tri(i1 + ia, i1 + ic)] -= acc[a][c];
+                    for (int a = 0; a < 4; ++a) {
+                        const int ia = ti * 4 + a;
+                        if (ia < m) {
+                            double2* p = reinterpret_cast<double2*>(Ls + tri(i1 + ia, i1 + tj * 4));
+                            double2 u0 = p[0], u1 = p[1];
+                            u0.x -= acc[a][0]; u0.y -= acc[a][1]; u1.x -= acc[a][2]; u1.y -= acc[a][3];
+                            p[0] = u0; p[1] = u1;
+                        }
                     }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int c = 0; c <= a; ++c) {
+                            const int ia = ti * 4 + a;
+                            if (ia < m) Ls[tri(i1 + ia, i1 + tj * 4 + c)] -= acc[a][c];
+                        }
+                }
             }
         }
         __syncthreads();
+        CHS_MARK(4);
     }
 
+#if CHS_PIPE
+    // the last block row of inv(L) (the others were formed under the pivot chains above): all warps, one pair each
+    if (k > NB) {
+        const int I0 = ((k - 1) >> 4) << 4;
+        const double* Dil = DiA + ((I0 >> 4) & 1) * NB * (NB + 1);
+        double res[2][4];
+        const bool act = warp < (I0 >> 4);
+        if (act) chs_inv_compute(Ls, Dil, I0, k - I0, warp, lane, res);
+        __syncthreads();
+        if (act) chs_inv_store(Ls, I0, k - I0, warp, lane, res);
+        __syncthreads();
+        CHS_MARK(6);
+    }
+#else
     // X = inv(L) in place, block row by block row:  X[I][0:I0] = -Di_I * ( L[I][0:I0] * X[0:I0][0:I0] ).
-    // Two threads per column c (even / odd t), combined by a shuffle.
+    double* PR = Pn;   // [I0][CHS_PRS]: PR[t][r] = L[I0 + r][t]
     for (int I0 = NB; I0 < k; I0 += NB) {
         const int nb = min(NB, k - I0);
-        for (int e = tid; e < nb * I0; e += CHS_T) {
-            const int r = e / I0, t = e - r * I0;
-            Pn[t * (NB + 1) + r] = Ls[tri(I0 + r, t)];
-        }
-        if (nb < NB)
-            for (int e = tid; e < (NB - nb) * I0; e += CHS_T) {
-                const int r = nb + e / I0, t = e % I0;
-                Pn[t * (NB + 1) + r] = 0.0;
-            }
+        for (int r = warp; r < NB; r += nwarps)
+            for (int t = lane; t < I0; t += 32) PR[t * CHS_PRS + r] = (r < nb) ? Ls[tri(I0 + r, t)] : 0.0;
         for (int e = tid; e < NB * NB; e += CHS_T) {
             const int r = e / NB, c = e - r * NB;
             Di[r * (NB + 1) + c] = (r < nb && c <= r) ? Ls[tri(I0 + r, I0 + c)] : 0.0;
         }
         __syncthreads();
+        CHS_MARK(5);
         {
-            const int c = tid >> 1, hh = tid & 1;
-            double y[NB];
+            // Column c needs the rows t = c .. I0-1 of X.  A warp step covers 8 columns x 4 values of t; the column blocks
+            // (8 wide) are taken in pairs (j, last - j): (I0 + 8) / 4 steps for every warp.
+            const int c8 = lane & 7, tq = lane >> 3;
+            const int nblk = I0 >> 3;   // I0 is a multiple of 16
+            for (int pair = warp; pair < (nblk >> 1); pair += nwarps) {
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    const int cb = half ? nblk - 1 - pair : pair;
+                    const int c = cb * 8 + c8;
+                    double y[NB];
 #pragma unroll
-            for (int r = 0; r < NB; ++r) y[r] = 0.0;
-            if (c < I0) {
-                for (int t = c + hh; t < I0; t += 2) {
-                    const double xv = Ls[tri(t, c)];
+                    for (int r = 0; r < NB; ++r) y[r] = 0.0;
+#pragma unroll 2
+                    for (int t = cb * 8 + tq; t < I0; t += 4) {
+                        const double xv = (t >= c) ? Ls[tri(t, c)] : 0.0;
+                        const double2* pr = reinterpret_cast<const double2*>(PR + t * CHS_PRS);
 #pragma unroll
-                    for (int r = 0; r < NB; ++r) y[r] += Pn[t * (NB + 1) + r] * xv;
-                }
-            }
+                        for (int r2 = 0; r2 < NB / 2; ++r2) {
+                            const double2 p = pr[r2];
+                            y[2 * r2] += p.x * xv;
+                            y[2 * r2 + 1] += p.y * xv;
+                        }
+                    }
 #pragma unroll
-            for (int r = 0; r < NB; ++r) y[r] += __shfl_xor_sync(0xffffffffu, y[r], 1);
-            if (c < I0) {
+                    for (int r = 0; r < NB; ++r) {
+                        y[r] += __shfl_xor_sync(0xffffffffu, y[r], 8);
+                        y[r] += __shfl_xor_sync(0xffffffffu, y[r], 16);
+                    }
+                    // rows tq, tq+4, tq+8, tq+12 of -Di*y: four independent chains over all 16 columns (Di is zero above its
+                    // diagonal), no divergence between the lanes
+                    {
+                        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+                        const double* dr = Di + tq * (NB + 1);
 #pragma unroll
-                for (int r = 0; r < NB; ++r) {
-                    if ((r & 1) == hh && r < nb) {
-                        double s = 0.0;
+                        for (int j = 0; j < NB; ++j) {
 #pragma unroll
-                        for (int j = 0; j <= r; ++j) s += Di[r * (NB + 1) + j] * y[j];
-                        Ls[tri(I0 + r, c)] = -s;
+                            for (int u = 0; u < 4; ++u) s4[u] += dr[u * 4 * (NB + 1) + j] * y[j];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (tq + 4 * u < nb) Ls[tri(I0 + tq + 4 * u, c)] = -s4[u];
                     }
                 }
             }
         }
         __syncthreads();
+        CHS_MARK(6);
     }
+#endif
     // inv(L) to global memory with explicit zeros above the diagonal (k_gemm streams it unmasked)
     for (int r = warp; r < k; r += nwarps)
         for (int c = lane; c < k; c += 32) Xg[(size_t)r * kmax + c] = (c <= r) ? Ls[tri(r, c)] : 0.0;
@@ -554,20 +721,31 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
     double* __restrict__ yv = v.yv + (size_t)b * kmax;
     for (int a = tid; a < k; a += CHS_T) nu[a] = yv[a];
     __syncthreads();
-    for (int a = warp; a < k; a += nwarps) {
+    // eight lanes per row, four rows per warp pass: the shuffle chains of the rows overlap
+    for (int a0 = warp * 4; a0 < k; a0 += nwarps * 4) {   // warp-uniform trip count: the shuffles below name all 32 lanes
+        const int a = a0 + (lane >> 3);
         double s = 0.0;
-        for (int t = lane; t <= a; t += 32) s += Ls[tri(a, t)] * nu[t];
+        if (a < k)
+            for (int t = lane & 7; t <= a; t += 8) s += Ls[tri(a, t)] * nu[t];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) { yv[a] = s; ys[a] = s; }
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (a < k && (lane & 7) == 0) { yv[a] = s; ys[a] = s; }
     }
     __syncthreads();
     double* __restrict__ cv = v.cv + (size_t)b * kmax;
     for (int t = tid; t < k; t += CHS_T) {
-        double s = 0.0;
-        for (int a = t; a < k; ++a) s += Ls[tri(a, t)] * ys[a];
-        cv[t] = s;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // four partial sums: the column is one dependent chain otherwise
+        int a = t;
+        for (; a + 3 < k; a += 4) {
+            s0 += Ls[tri(a, t)] * ys[a];
+            s1 += Ls[tri(a + 1, t)] * ys[a + 1];
+            s2 += Ls[tri(a + 2, t)] * ys[a + 2];
+            s3 += Ls[tri(a + 3, t)] * ys[a + 3];
+        }
+        for (; a < k; ++a) s0 += Ls[tri(a, t)] * ys[a];
+        cv[t] = (s0 + s1) + (s2 + s3);
     }
+    CHS_MARK(7);
     if (tid == 0 && s_bad) atomicOr(&v.stats[b].status, 2);
 }
 
@@ -975,10 +1153,10 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         if (slices > 1) { dim3 gp(slices, v.B); k_upd_pairs<<<gp, 256, 0, st>>>(v); c->launches++; }
     }
     const size_t chol_sm = sizeof(double) * (2 * NB * (NB + 1) + (size_t)v.kmax * (NB + 1));
-    const size_t chs_sm = sizeof(double) * ((CHS_K * (CHS_K + 1)) / 2 + 2 * NB * (NB + 1) + CHS_K * (NB + 1));
-    const size_t chss_sm = sizeof(double) * ((CHS_KS * (CHS_KS + 1)) / 2 + 2 * NB * (NB + 1) + CHS_KS * (NB + 1));
+    const size_t chs_sm = CHS_SMEM(CHS_K);
+    const size_t chss_sm = CHS_SMEM(CHS_KS);
     ENSURE_DYN_SMEM(k_chol, chol_sm, c->device);
-    const size_t chsm_sm = sizeof(double) * ((CHS_KM * (CHS_KM + 1)) / 2 + 2 * NB * (NB + 1) + CHS_KM * (NB + 1));
+    const size_t chsm_sm = CHS_SMEM(CHS_KM);
     ENSURE_DYN_SMEM((k_chol_sm<CHS_KM, 256, 0, 3>), chsm_sm, c->device);
     ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, CHS_KM, 2>), chs_sm, c->device);
     ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, 0, 2>), chs_sm, c->device);

@@ -1,6 +1,6 @@
 # short default-shape bench over frames 5-16 (the window the round-2 A/B numbers in DESIGN.md use); env assignments as arguments
 mkdir -p gpurun_out
-env "$@" timeout 900 python bench.py --steps 12 --warmup 4 --no-cpu-baseline --no-e2e --no-extra > gpurun_out/quick12.json 2> gpurun_out/quick12.err
+env "$@" timeout 150 python bench.py --steps 12 --warmup 4 --no-cpu-baseline --no-e2e --no-extra > gpurun_out/quick12.json 2> gpurun_out/quick12.err
 python - <<'PY'
 import json
 d=json.load(open("gpurun_out/quick12.json"))

@@ -29,7 +29,7 @@ void launch_begin_frame(ekfslam_ctx* c) {
 // place: F differs from the identity only in rows 0-6 (r and q), so only rows/columns 0-6 of P
 // change:  P[0:13,j] <- F P[0:13,j]  and  Pxx <- F Pxx F' + Q.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params prm) {
+__global__ void __launch_bounds__(256, 3) k_predict(DevView v, ekfslam_params prm) {
     const int b = blockIdx.x;
     const int n = v.nstate[b];
     const int ld = v.ld;
@@ -44,6 +44,15 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
     __shared__ double Fqq[4][4], Fqw[4][3];
 
     const int tid = threadIdx.x;
+    // The first cross-covariance column of every thread is requested BEFORE thread 0 builds F and Q, and inside the sweep
+    // the next column is requested before the current one is transformed (ncu, round 2: 60 % of the kernel's samples were
+    // long-scoreboard stalls on one DRAM round trip per column and thread, one after the other).
+    double c[13];
+    int j = 13 + tid;
+    if (j < n) {
+#pragma unroll
+        for (int r = 0; r < 13; ++r) c[r] = P[(size_t)j * ld + r];   // lower triangle (authoritative): P[r][j] = P[j][r], j >= 13 > r
+    }
     for (int e = tid; e < 169; e += blockDim.x) {
         const int r = e / 13, cc = e - r * 13;
         Pxx[r][cc] = P[(size_t)r * ld + cc];
@@ -136,14 +145,17 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
         }
     }
     // features are static: x_k_km1(14:end) = x_k_k(14:end)
-    for (int j = 13 + tid; j < n; j += blockDim.x) xp[j] = x[j];
+    for (int jj = 13 + tid; jj < n; jj += blockDim.x) xp[jj] = x[jj];
     __syncthreads();
 
     // cross-covariance panel
-    for (int j = 13 + tid; j < n; j += blockDim.x) {
-        double c[13];
+    while (j < n) {
+        const int jn = j + blockDim.x;
+        double cn[13];
+        if (jn < n) {
 #pragma unroll
-        for (int r = 0; r < 13; ++r) c[r] = P[(size_t)j * ld + r];   // lower triangle (authoritative): P[r][j] = P[j][r], j >= 13 > r
+            for (int r = 0; r < 13; ++r) cn[r] = P[(size_t)jn * ld + r];
+        }
         double o[7];
         const double dt = prm.delta_t;
         o[0] = c[0] + dt * c[7]; o[1] = c[1] + dt * c[8]; o[2] = c[2] + dt * c[9];
@@ -156,6 +168,9 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
             P[(size_t)r * ld + j] = o[r];
             P[(size_t)j * ld + r] = o[r];
         }
+#pragma unroll
+        for (int r = 0; r < 13; ++r) c[r] = cn[r];
+        j = jn;
     }
     // camera block: T = F Pxx ; Pxx' = T F' + Q, stored symmetric
     for (int e = tid; e < 169; e += blockDim.x) {
@@ -178,7 +193,7 @@ __global__ void __launch_bounds__(128, 8) k_predict(DevView v, ekfslam_params pr
 
 void launch_predict(ekfslam_ctx* c) {
     KScope ks(c, KT_PREDICT);
-    k_predict<<<c->v.B, 128, 0, c->stream>>>(c->v, c->prm);
+    k_predict<<<c->v.B, 256, 0, c->stream>>>(c->v, c->prm);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -18,8 +18,15 @@
 
 #define NB 16
 
-// S = G_sel H_sel' + I, lower triangle at feature-pair granularity: pair e -> (fa >= fb) -> one 2x2 block
-__device__ __forceinline__ void upd_S_pairs(const DevView& v, int b, int ns, int first, int stride) {
+// S = G_sel H_sel' + I, lower triangle at feature-pair granularity: pair e -> (fa >= fb) -> one 2x2 block.
+// STAGED: the per-feature operands of the pair loop (feature index, state offset, block width, compact Jacobian) come from
+// shared memory (k_upd_S stages them once per filter), so the only global loads left per pair are the 2 x 13 entries of G,
+// all independent (ncu, round 2: the loop was a chain of dependent DRAM round trips - sel -> foff / ftype -> G - and the
+// feature-block loop with its run-time width issued its loads one iteration at a time: 60 % of the kernel's samples).
+#define UPS_NMAX 128   // features per filter the staged path holds (26.6 KB of Jacobians)
+template <bool STAGED>
+__device__ __forceinline__ void upd_S_pairs(const DevView& v, int b, int ns, int first, int stride, const int* s_sel,
+                                            const int* s_off, const int* s_w, const double* s_H) {
     const int N = v.N, ld = v.ld, kmax = v.kmax;
     const int* __restrict__ sel = v.sel + (size_t)b * N;
     const double* __restrict__ G = v.G + (size_t)b * kmax * ld;
@@ -31,22 +38,35 @@ __device__ __forceinline__ void upd_S_pairs(const DevView& v, int b, int ns, int
         while ((fa + 1) * (fa + 2) / 2 <= e) ++fa;
         while (fa * (fa + 1) / 2 > e) --fa;
         const int fb = e - fa * (fa + 1) / 2;
-        const int ia = sel[fa], ib = sel[fb];
-        const size_t tb = (size_t)b * N + ib;
-        const double* __restrict__ H = v.Hc + tb * EKF_HSTRIDE;
-        const int off = v.foff[tb];
-        const int w = (v.ftype[tb] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+        int ia, off, w;
+        const double* __restrict__ H;
+        if (STAGED) {
+            ia = s_sel[fa]; off = s_off[fb]; w = s_w[fb]; H = s_H + fb * EKF_HSTRIDE;
+        } else {
+            ia = sel[fa];
+            const size_t tb = (size_t)b * N + sel[fb];
+            H = v.Hc + tb * EKF_HSTRIDE;
+            off = v.foff[tb];
+            w = (v.ftype[tb] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+        }
         const double* __restrict__ g0 = G + (size_t)(2 * ia) * ld;
         const double* __restrict__ g1 = g0 + ld;
+        // all 26 entries of G first (independent loads), then the products in the order of the reference's sparse H
+        double ga[EKF_HC], gb[EKF_HC];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) { ga[c] = g0[c]; gb[c] = g1[c]; }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const int cc = off + ((c < w) ? c : 0);
+            ga[7 + c] = g0[cc]; gb[7 + c] = g1[cc];
+        }
         double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
 #pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const double a0 = g0[c], a1 = g1[c], h0 = H[c], h1 = H[EKF_HC + c];
-            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
-        }
-        for (int c = 0; c < w; ++c) {
-            const double a0 = g0[off + c], a1 = g1[off + c], h0 = H[7 + c], h1 = H[EKF_HC + 7 + c];
-            s00 += a0 * h0; s01 += a0 * h1; s10 += a1 * h0; s11 += a1 * h1;
+        for (int c = 0; c < EKF_HC; ++c) {
+            if (c < 7 + w) {
+                const double h0 = H[c], h1 = H[EKF_HC + c];
+                s00 += ga[c] * h0; s01 += ga[c] * h1; s10 += gb[c] * h0; s11 += gb[c] * h1;
+            }
         }
         if (fa == fb) { s00 += 1.0; s11 += 1.0; }  // R = eye(length(z)), mc/ekf_update_li_inliers.m:18
         S[(size_t)(2 * fa) * kmax + 2 * fb] = s00;
@@ -116,7 +136,25 @@ __global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_pr
     }
     if (k == 0) return;
     if (!do_pairs) return;   // few filters: the pair loop runs as its own, wider launch (k_upd_pairs)
-    upd_S_pairs(v, b, ns, tid, blockDim.x);
+    if (N <= UPS_NMAX) {
+        __shared__ int s_sel[UPS_NMAX], s_off[UPS_NMAX], s_w[UPS_NMAX];
+        __shared__ double s_H[UPS_NMAX * EKF_HSTRIDE];
+        for (int f = tid; f < ns; f += blockDim.x) {
+            const int i = sel[f];
+            const size_t t = (size_t)b * N + i;
+            s_sel[f] = i;
+            s_off[f] = v.foff[t];
+            s_w[f] = (v.ftype[t] == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+        }
+        for (int e = tid; e < ns * EKF_HSTRIDE; e += blockDim.x) {
+            const int f = e / EKF_HSTRIDE;
+            s_H[e] = v.Hc[((size_t)b * N + sel[f]) * EKF_HSTRIDE + (e - f * EKF_HSTRIDE)];
+        }
+        __syncthreads();
+        upd_S_pairs<true>(v, b, ns, tid, blockDim.x, s_sel, s_off, s_w, s_H);
+    } else {
+        upd_S_pairs<false>(v, b, ns, tid, blockDim.x, nullptr, nullptr, nullptr, nullptr);
+    }
 }
 
 // S = G_sel H_sel' + I for few filters with large maps: grid = (slices, B), the pairs of a filter spread over the slices
@@ -125,7 +163,7 @@ __global__ void __launch_bounds__(256) k_upd_pairs(DevView v) {
     const int b = blockIdx.y;
     const int ns = v.ksel[b];
     if (ns == 0) return;
-    upd_S_pairs(v, b, ns, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    upd_S_pairs<false>(v, b, ns, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, nullptr, nullptr, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -362,21 +400,24 @@ __global__ void __launch_bounds__(128) k_chol(DevView v, int kskip) {
 // neighbouring columns of a row as two 128-bit accesses.
 __device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + ((r + 1) >> 1) + c; }
 #define CHS_TRI(K) (((K) * ((K) + 1)) / 2 + ((K) + 1) / 2)
-#define CHS_PRS 18  // row stride of the staged row panel of the inverse phase: 16-byte aligned rows, four consecutive rows in disjoint banks
-#define CHS_SMEM(K) (sizeof(double) * (CHS_TRI(K) + 3 * NB * (NB + 1) + (size_t)(K) * CHS_PRS))
+#define CHS_SMEM(K) (sizeof(double) * (CHS_TRI(K) + 3 * NB * (NB + 1) + (size_t)(K) * NB))
 
-// Shared-memory traffic decides this kernel (ncu, round 2: 102 M shared wavefronts per launch of 4096 filters, 39 % of
-// them in the inner loop of the inverse phase, 28 % in the trailing update, both with one 8-byte load per FMA and every
-// lane on its own row).  Both loops now read operands that are staged so that a warp's lanes either share an address
-// (broadcast) or sit next to each other, as 128-bit loads:
-//   * trailing update: the solved panel is kept TRANSPOSED (PT[t][row]), a 4x4 micro tile reads its four rows / four
-//     columns at one t as two double2 each; the tile goes back to the packed triangle as double2 read-modify-writes;
-//   * inverse phase: the row panel L[I0..I0+16)[0..I0) is staged as PR[t][r]; a warp takes 8 columns x 4 values of t per
-//     step, so the 16 panel values of one t are 8 broadcast double2 loads shared by 8 lanes; column blocks are paired
-//     (j, last - j) so that every warp runs the same number of steps.
-#ifndef CHS_PIPE
-#define CHS_PIPE 1
-#endif
+// What round 2's per-line ncu digest (tools/ncu_lines.py) and the A/B builds behind it showed about this kernel
+// (B = 4096, k ~ 103: 0.82 -> 0.60 ms for the li update, 1.77 -> 1.41 ms for both Cholesky brackets of a step):
+//   * it is a chain of LATENCY-bound phases (issue slots 35 % busy, fp64 pipe 14 %): what counts is the dependent chain
+//     of each phase, not its instruction or shared-memory volume.  Vectorised / broadcast operands alone (transposed
+//     panel PT[t][row] for the 4x4 micro tiles of the trailing update, 128-bit read-modify-writes of the packed
+//     triangle) cut the shared wavefronts by half and the time by nothing;
+//   * the biggest single loss was a DIVERGENT tail: rows of -Di*y selected per lane by `if ((r & 3) == q)` over a
+//     compile-time r ran as 16 serial predicated blocks, each its own dependent chain (-0.16 ms once the four rows of a
+//     lane became four interleaved chains over a zero-padded Di);
+//   * the S load as per-element asynchronous copies (-0.09 ms: the plain loop paid a DRAM round trip per row);
+//   * the inverse block rows need nothing from the CURRENT diagonal block, so they run in warps 1.. while warp 0 walks the
+//     serial pivot chain (-0.05 ms; what is left at the barrier behind the pivot chain, a third of the kernel, is the chain
+//     itself: shuffle -> MUFU.RSQ64H + 4 dependent fp64 operations -> multiply -> shuffle -> FMA per pivot);
+//   * rolling loops to shrink the code (13 k -> 4 k instructions; no_instruction stalls were as frequent as dependency
+//     stalls) LOST time for the pivot chain, the block inverse and the panel solve - an in-order warp stalls on every
+//     rolled dependent chain - and won only for the two halves of chs_inv_compute.
 // Block row I0/16 of X = inv(L), formed from L[I0..I0+16)[0..I0) (read in place from the packed triangle) and the rows of
 // X above it:  X[I][0:I0] = -Di_I * ( L[I][0:I0] * X[0:I0][0:I0] ).  A warp takes the pair of 8-wide column blocks
 // (pair, last - pair) - (I0 + 8) / 4 steps of 8 columns x 4 values of t whatever the pair is - and keeps its 2 x 4 results
@@ -386,7 +427,7 @@ __device__ __forceinline__ void chs_inv_compute(const double* Ls, const double* 
     const int c8 = lane & 7, tq = lane >> 3;
     const int nblk = I0 >> 3;                       // I0 is a multiple of 16
     const double* lrow = Ls + tri(I0, 0);           // row I0 + r starts at lrow + r * I0 + tri(r, 0)   (I0 even)
-#pragma unroll
+#pragma unroll 1   // rolled: half the code of the hottest loop, 1.18 -> 1.14 ms
     for (int half = 0; half < 2; ++half) {
         const int cb = half ? nblk - 1 - pair : pair;
         const int c = cb * 8 + c8;
@@ -414,7 +455,10 @@ __device__ __forceinline__ void chs_inv_compute(const double* Ls, const double* 
             for (int u = 0; u < 4; ++u) s4[u] += dr[u * 4 * (NB + 1) + j] * y[j];
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) res[half][u] = -s4[u];
+        for (int u = 0; u < 4; ++u) {
+            if (half) res[1][u] = -s4[u];
+            else res[0][u] = -s4[u];
+        }
     }
 }
 __device__ __forceinline__ void chs_inv_store(double* Ls, int I0, int nb, int pair, int lane, const double (&res)[2][4]) {
@@ -456,13 +500,8 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
     double* __restrict__ Xg = v.Li + (size_t)b * kmax * kmax;
     double* Ls = sm;                                   // packed lower triangle: L, then inv(L) in place
     double* D = Ls + CHS_TRI(KM);                      // [NB][NB+1] diagonal block factor
-#if CHS_PIPE
     double* DiA = D + NB * (NB + 1);                   // [2][NB][NB+1] its inverse: this panel's and the previous one's
-    double* Pn = DiA + 2 * NB * (NB + 1);              // [KM * CHS_PRS] transposed panel of the trailing update / vectors
-#else
-    double* Di = D + NB * (NB + 1);                    // [NB][NB+1] its inverse
-    double* Pn = Di + NB * (NB + 1);                   // [KM * CHS_PRS] transposed panels (both phases) / vectors
-#endif
+    double* Pn = DiA + 2 * NB * (NB + 1);              // [NB][KM] transposed panel of the trailing update / vectors
     __shared__ int s_bad;
     if (tid == 0) s_bad = 0;
 #ifdef CHS_PROF
@@ -481,7 +520,6 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
 
     for (int j0 = 0; j0 < k; j0 += NB) {
         const int nb = min(NB, k - j0);
-#if CHS_PIPE
         double* Di = DiA + ((j0 >> 4) & 1) * NB * (NB + 1);
         const double* Dip = DiA + (((j0 >> 4) & 1) ^ 1) * NB * (NB + 1);
         double res[2][4];
@@ -489,7 +527,6 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
         // rows of L are final, its diagonal block inverse is Dip, the rows of X above it were stored one panel ago.
         // At most nwarps - 1 column-block pairs exist here (block row j-1 has j-1 pairs, j <= KM/16 - 1).
         const bool inv_prev = warp > 0 && j0 >= 2 * NB && (warp - 1) < ((j0 - NB) >> 4);
-#endif
         for (int e = tid; e < NB * NB; e += CHS_T) {
             const int r = e / NB, c = e - r * NB;
             D[r * (NB + 1) + c] = (r < nb && c <= r) ? Ls[tri(j0 + r, j0 + c)] : ((r >= nb && r == c) ? 1.0 : 0.0);
@@ -543,13 +580,9 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
                 }
             }
         }
-#if CHS_PIPE
         else if (inv_prev) chs_inv_compute(Ls, Dip, j0 - NB, NB, warp - 1, lane, res);
         __syncthreads();
         if (inv_prev) chs_inv_store(Ls, j0 - NB, NB, warp - 1, lane, res);
-#else
-        __syncthreads();
-#endif
         CHS_MARK(2);
         // the diagonal block of X replaces the one of L (the panel solve and the inverse phase only use Di)
         for (int e = tid; e < nb * nb; e += CHS_T) {
@@ -636,7 +669,6 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
         CHS_MARK(4);
     }
 
-#if CHS_PIPE
     // the last block row of inv(L) (the others were formed under the pivot chains above): all warps, one pair each
     if (k > NB) {
         const int I0 = ((k - 1) >> 4) << 4;
@@ -649,69 +681,6 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
         __syncthreads();
         CHS_MARK(6);
     }
-#else
-    // X = inv(L) in place, block row by block row:  X[I][0:I0] = -Di_I * ( L[I][0:I0] * X[0:I0][0:I0] ).
-    double* PR = Pn;   // [I0][CHS_PRS]: PR[t][r] = L[I0 + r][t]
-    for (int I0 = NB; I0 < k; I0 += NB) {
-        const int nb = min(NB, k - I0);
-        for (int r = warp; r < NB; r += nwarps)
-            for (int t = lane; t < I0; t += 32) PR[t * CHS_PRS + r] = (r < nb) ? Ls[tri(I0 + r, t)] : 0.0;
-        for (int e = tid; e < NB * NB; e += CHS_T) {
-            const int r = e / NB, c = e - r * NB;
-            Di[r * (NB + 1) + c] = (r < nb && c <= r) ? Ls[tri(I0 + r, I0 + c)] : 0.0;
-        }
-        __syncthreads();
-        CHS_MARK(5);
-        {
-            // Column c needs the rows t = c .. I0-1 of X.  A warp step covers 8 columns x 4 values of t; the column blocks
-            // (8 wide) are taken in pairs (j, last - j): (I0 + 8) / 4 steps for every warp.
-            const int c8 = lane & 7, tq = lane >> 3;
-            const int nblk = I0 >> 3;   // I0 is a multiple of 16
-            for (int pair = warp; pair < (nblk >> 1); pair += nwarps) {
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const int cb = half ? nblk - 1 - pair : pair;
-                    const int c = cb * 8 + c8;
-                    double y[NB];
-#pragma unroll
-                    for (int r = 0; r < NB; ++r) y[r] = 0.0;
-#pragma unroll 2
-                    for (int t = cb * 8 + tq; t < I0; t += 4) {
-                        const double xv = (t >= c) ? Ls[tri(t, c)] : 0.0;
-                        const double2* pr = reinterpret_cast<const double2*>(PR + t * CHS_PRS);
-#pragma unroll
-                        for (int r2 = 0; r2 < NB / 2; ++r2) {
-                            const double2 p = pr[r2];
-                            y[2 * r2] += p.x * xv;
-                            y[2 * r2 + 1] += p.y * xv;
-                        }
-                    }
-#pragma unroll
-                    for (int r = 0; r < NB; ++r) {
-                        y[r] += __shfl_xor_sync(0xffffffffu, y[r], 8);
-                        y[r] += __shfl_xor_sync(0xffffffffu, y[r], 16);
-                    }
-                    // rows tq, tq+4, tq+8, tq+12 of -Di*y: four independent chains over all 16 columns (Di is zero above its
-                    // diagonal), no divergence between the lanes
-                    {
-                        double s4[4] = {0.0, 0.0, 0.0, 0.0};
-                        const double* dr = Di + tq * (NB + 1);
-#pragma unroll
-                        for (int j = 0; j < NB; ++j) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) s4[u] += dr[u * 4 * (NB + 1) + j] * y[j];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (tq + 4 * u < nb) Ls[tri(I0 + tq + 4 * u, c)] = -s4[u];
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        CHS_MARK(6);
-    }
-#endif
     // inv(L) to global memory with explicit zeros above the diagonal (k_gemm streams it unmasked)
     for (int r = warp; r < k; r += nwarps)
         for (int c = lane; c < k; c += 32) Xg[(size_t)r * kmax + c] = (c <= r) ? Ls[tri(r, c)] : 0.0;

@@ -14,7 +14,7 @@ zc = torch.from_numpy(seq.zc).cuda(); fl = torch.from_numpy((seq.has * pkg.F_CAN
 u = torch.from_numpy(np.ascontiguousarray(np.transpose(seq.U, (1, 0, 2)))).cuda()
 lib = bank.lib
 out = (ctypes.c_ulonglong * 16)()
-names = ["load S", "copy D", "diag block: inverse (warp 0)", "panel solve", "trailing update", "inverse: stage", "inverse: main", "store X, y, cv", "diag block: factor (warp 0)"]
+names = ["load S", "copy D", "diag block: inverse (warp 0) || inverse row p-1", "panel solve", "trailing update", "-", "last inverse row", "store X, y, cv", "diag block: factor (warp 0)"]
 for t in range(1, T + 1):
     bank.bind_frame(zc[t].data_ptr(), fl[t].data_ptr(), u[t].data_ptr(), 64)
     if t == 5: lib.ekfslam_debug_chs_prof(None, 1)

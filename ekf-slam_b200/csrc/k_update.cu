@@ -820,6 +820,26 @@ static void launch_chol_lockstep(ekfslam_ctx* c) {
 //   x+ = x + G_sel' inv(S) nu (mc/update.m:12) for its 64 columns, and column tile 0 then computes normJac(q+) and
 //   normalises the quaternion (mc/update.m:18,24) when `finalize`.
 // ---------------------------------------------------------------------------------------
+// One K chunk (TK = 16 rows of the staged panels) of k_gemm for a warp's 8-row tiles [MT0, MT1): branch-free, fully
+// unrolled.  HALF: tile MT0 sits on the diagonal and only needs K steps 0-1 (X = inv(L) has explicit zeros above it).
+template <int MT0, int MT1, bool HALF>
+__device__ __forceinline__ void gemm_chunk(const double* __restrict__ ap, const double* __restrict__ bp, double (&acc)[4][2][2]) {
+#pragma unroll
+    for (int k4 = 0; k4 < TK / 4; ++k4) {
+        double af[4], bf[2];
+#pragma unroll
+        for (int mt = MT0; mt < MT1; ++mt) af[mt] = ap[mt * 8 * APAD + k4 * 4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) bf[nt] = bp[k4 * 4 * TPAD + nt * 8];
+#pragma unroll
+        for (int mt = MT0; mt < MT1; ++mt) {
+            if (mt == MT0 && HALF && k4 >= 2) continue;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);
+        }
+    }
+}
+
 template <int mode>   // only mode 0 exists (the name k_gemm<0> is what the committed ncu profiles show)
 __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int kskip) {
     extern __shared__ __align__(16) double dsm[];
@@ -935,30 +955,38 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
         const double* ap = as + (wr * 32 + g) * APAD + q;
         const double* bp = bs + q * TPAD + wc * 16 + g;
         const int tb0 = it * TK;
-        // Every chunk a warp needs runs the same branch-free block: all four 8-row tiles x all four K steps.  A has
-        // explicit zeros above the diagonal and zero-filled rows / columns beyond k, so the products the triangular
-        // dispatch used to skip (a jump table per K step: ~20 instructions and an indirect branch for <= 8 DMMAs) are
+        // Every chunk a warp needs runs one branch-free block over its existing 8-row tiles x all four K steps.  A has
+        // explicit zeros above the diagonal and zero-filled columns beyond k, so the products a per-K-step triangular
+        // dispatch would skip (a jump table per K step: ~20 instructions and an indirect branch for <= 8 DMMAs) are
         // multiplications by zero; the tensor pipe was 37 % busy and the issue slots 63 %, so trading issue for DMMAs wins.
         if (mt_hi > 0 && tb0 < tmax_w) {
-            // d = chunk start relative to the warp's first row (a multiple of 16).  Left of the diagonal (d < 0, or any
-            // chunk of mode 1) every product is needed.  On the diagonal only part is: d = 0 -> tile 0 needs K steps 0-1;
-            // d = 16 -> tiles 0, 1 need nothing, tile 2 needs K steps 0-1.  Three compile-time blocks, one warp-uniform
-            // branch per chunk (a jump table per K step cost more than the DMMAs it saved).
+            // d = chunk start relative to the warp's first row (a multiple of 16).  Left of the diagonal (d < 0) every
+            // product is needed.  On the diagonal only part is: d = 0 -> tile 0 needs K steps 0-1; d = 16 -> tiles 0, 1
+            // need nothing, tile 2 needs K steps 0-1.  The 8-row tiles beyond the last stacked row (mt >= mt_hi: the
+            // lower warps of the last row tile, e.g. rows 96..102 of k = 103 fill ONE of their four tiles) are skipped as
+            // well: they made those warps the longest of the CTA while 3/4 of their DMMAs multiplied zeros.  All blocks are
+            // compile-time, one warp-uniform dispatch per chunk (a jump table per K step cost more than the DMMAs it saved).
             const int d = tb0 - rbase;
-#define GEMM_CHUNK(MT0, HALF)                                                                                   \
-            _Pragma("unroll") for (int k4 = 0; k4 < TK / 4; ++k4) {                                               \
-                double af[4], bf[2];                                                                              \
-                _Pragma("unroll") for (int mt = MT0; mt < 4; ++mt) af[mt] = ap[mt * 8 * APAD + k4 * 4];           \
-                _Pragma("unroll") for (int nt = 0; nt < 2; ++nt) bf[nt] = bp[k4 * 4 * TPAD + nt * 8];             \
-                _Pragma("unroll") for (int mt = MT0; mt < 4; ++mt) {                                              \
-                    if (mt == MT0 && HALF && k4 >= 2) continue;                                                   \
-                    _Pragma("unroll") for (int nt = 0; nt < 2; ++nt) dmma(acc[mt][nt], af[mt], bf[nt]);           \
-                }                                                                                                 \
+            switch (mt_hi) {
+                case 4:
+                    if (d < 0) gemm_chunk<0, 4, false>(ap, bp, acc);
+                    else if (d == 0) gemm_chunk<0, 4, true>(ap, bp, acc);
+                    else gemm_chunk<2, 4, true>(ap, bp, acc);
+                    break;
+                case 3:
+                    if (d < 0) gemm_chunk<0, 3, false>(ap, bp, acc);
+                    else if (d == 0) gemm_chunk<0, 3, true>(ap, bp, acc);
+                    else gemm_chunk<2, 3, true>(ap, bp, acc);
+                    break;
+                case 2:
+                    if (d < 0) gemm_chunk<0, 2, false>(ap, bp, acc);
+                    else if (d == 0) gemm_chunk<0, 2, true>(ap, bp, acc);
+                    break;
+                default:
+                    if (d < 0) gemm_chunk<0, 1, false>(ap, bp, acc);
+                    else if (d == 0) gemm_chunk<0, 1, true>(ap, bp, acc);
+                    break;
             }
-            if (d < 0) { GEMM_CHUNK(0, false) }
-            else if (d == 0) { GEMM_CHUNK(0, true) }
-            else { GEMM_CHUNK(2, true) }
-#undef GEMM_CHUNK
         }
         if (++it < nk) continue;
         // ---- last chunk of column tile cb: store the 64x64 tile, fold the state update, restart the accumulators

@@ -91,8 +91,8 @@ struct ekfslam_ctx {
     cudaStream_t copy_stream;
     // side stream for launches that would otherwise run nearly alone on the GPU (the large resident-Cholesky variant:
     // a handful of filters, one CTA each, ~0.15 ms of latency) - forked / joined with ev_fork / ev_join
-    cudaStream_t aux_stream;
-    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t aux_stream, aux2_stream;
+    cudaEvent_t ev_fork, ev_join, ev_join2;
     cudaEvent_t ev_in, ev_out, ev_main;
     int wait_inputs;     // ekfslam_step: make the stream wait for ev_in before the first kernel that reads zc / mflags / u
     int arm_out;         // launch_update(HI): record ev_out before the covariance downdate; cleared when recorded

@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(128) k_chol(DevView v, int kskip) {
 // k_chol above works on S in global memory (every panel / trailing update is an L2 round trip: long-scoreboard
 // stalls were half of its issue stalls) and stays as the path for larger k.  Same blocked algorithm and pivots.
 // ---------------------------------------------------------------------------------------
+#define CHS_KL 200  // largest variant (a handful of filters per frame at N = 100): 144 < k <= 200, 512 threads, 190 KB -> 1 CTA/SM, own side stream
 #define CHS_K 144   // large variant: KMIN < k <= 144, 256 threads, 2 CTAs/SM
 #define CHS_KM 112  // middle variant (li update at N = 100: k ~ 100): 256 threads, <= 85 registers, 72 KB -> 3 CTAs/SM (EKFSLAM_CHOL_MID=0 disables)
 #define CHS_KS 48   // small variant (hi update: k ~ 24): k <= 48, 128 threads, 21 KB of shared memory -> many CTAs/SM
@@ -716,6 +717,102 @@ __global__ void __launch_bounds__(CHS_T, MINB) k_chol_sm(DevView v) {
     }
     CHS_MARK(7);
     if (tid == 0 && s_bad) atomicOr(&v.stats[b].status, 2);
+}
+
+// ---------------------------------------------------------------------------------------
+// Warp-per-filter variant for k <= 32 (the usual size of the hi update: k ~ 24).  The block-per-filter kernel above spends
+// such a filter on two 16-wide panels with a dozen block barriers around a serial pivot chain that only warp 0 walks
+// (27 us per CTA, 3 CTAs per SM by registers: 0.25 ms for 4096 filters).  Here lane i holds row i of S in registers
+// for the whole factorisation (pivots by rsqrt, columns broadcast by shuffles - the diagonal-block scheme of k_chol_sm,
+// 32 wide), lane c then forms column c of X = inv(L) by forward substitution against L in shared memory, and
+// y = X nu, inv(S) nu = X' y come from the same shared tile.  No block barrier; four filters per CTA.
+// ---------------------------------------------------------------------------------------
+#define CHW_K 32
+__global__ void __launch_bounds__(128) k_chol_w32(DevView v) {
+    __shared__ double Ts[4][CHW_K][CHW_K + 1];   // S (transposing load), then L, then X
+    __shared__ double rds[4][CHW_K];             // 1 / L[c][c]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * 4 + warp;
+    if (b >= v.B) return;
+    const int k = 2 * v.ksel[b];
+    if (k == 0 || k > CHW_K) return;
+    const int kmax = v.kmax;
+    const unsigned full_mask = 0xffffffffu;
+    const double* __restrict__ S = v.Sb + (size_t)b * kmax * kmax;
+    double* __restrict__ Xg = v.Li + (size_t)b * kmax * kmax;
+    double (*T)[CHW_K + 1] = Ts[warp];
+    double* rd = rds[warp];
+    // rows of S arrive coalesced (lane = column) and leave the shared tile transposed (lane = row); rows / columns past k
+    // are padded with the identity so that the unrolled factorisation below is benign
+    for (int r = 0; r < CHW_K; ++r) {
+        double val = (r == lane) ? 1.0 : 0.0;
+        if (r < k && lane <= r) val = S[(size_t)r * kmax + lane];
+        T[r][lane] = val;
+    }
+    __syncwarp();
+    double a[CHW_K];
+#pragma unroll
+    for (int c = 0; c < CHW_K; ++c) a[c] = (c <= lane) ? T[lane][c] : 0.0;
+    __syncwarp();
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < CHW_K; ++c) {
+        const double piv = __shfl_sync(full_mask, a[c], c);
+        bad = bad || !(piv > 0.0);
+        const double rs = rsqrt(piv);
+        if (lane == c) rd[c] = rs;
+        const double lic = (lane == c) ? piv * rs : a[c] * rs;
+        a[c] = lic;
+#pragma unroll
+        for (int j = c + 1; j < CHW_K; ++j) {
+            const double ljc = __shfl_sync(full_mask, lic, j);
+            a[j] -= lic * ljc;
+        }
+    }
+    // L (lower triangle; what the updates left in the strict upper part of a lane's row is never read)
+#pragma unroll
+    for (int c = 0; c < CHW_K; ++c) T[lane][c] = a[c];
+    __syncwarp();
+    // column `lane` of X = inv(L):  X[i][c] = -(sum_{c <= t < i} L[i][t] X[t][c]) / L[i][i],  X[c][c] = 1 / L[c][c]
+    double x[CHW_K];
+#pragma unroll
+    for (int i = 0; i < CHW_K; ++i) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int t = 0; t < i; ++t) sacc += T[i][t] * x[t];
+        const double rs = rd[i];
+        x[i] = (i == lane) ? rs : ((i > lane) ? -sacc * rs : 0.0);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < CHW_K; ++i) T[i][lane] = x[i];
+    // inv(L) to global memory with explicit zeros above the diagonal, one coalesced row segment per instruction
+#pragma unroll
+    for (int i = 0; i < CHW_K; ++i)
+        if (i < k && lane < k) Xg[(size_t)i * kmax + lane] = x[i];
+    __syncwarp();
+    // y = X nu (lane = row) and inv(S) nu = X' y (lane = column)
+    double* __restrict__ yv = v.yv + (size_t)b * kmax;
+    const double nu = (lane < k) ? yv[lane] : 0.0;
+    double y = 0.0;
+#pragma unroll
+    for (int t = 0; t < CHW_K; ++t) {
+        const double nt = __shfl_sync(full_mask, nu, t);
+        if (t <= lane) y += T[lane][t] * nt;
+    }
+    if (lane >= k) y = 0.0;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < CHW_K; i += 2) {
+        const double y0 = __shfl_sync(full_mask, y, i), y1 = __shfl_sync(full_mask, y, i + 1);
+        s0 += T[i][lane] * y0;
+        s1 += T[i + 1][lane] * y1;
+    }
+    if (lane < k) {
+        yv[lane] = y;
+        v.cv[(size_t)b * kmax + lane] = s0 + s1;
+    }
+    if (bad && lane == 0) atomicOr(&v.stats[b].status, 2);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1159,6 +1256,8 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
     ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, 0, 2>), chs_sm, c->device);
     ENSURE_DYN_SMEM((k_chol_sm<CHS_K, 256, CHS_KS, 2>), chs_sm, c->device);
     ENSURE_DYN_SMEM((k_chol_sm<CHS_KM, 256, CHS_KS, 3>), chsm_sm, c->device);
+    const size_t chl_sm = CHS_SMEM(CHS_KL);
+    ENSURE_DYN_SMEM((k_chol_sm<CHS_KL, 512, CHS_K, 1>), chl_sm, c->device);
     // One block per filter fills the GPU once there are a few hundred filters (measured B=4096, k~98: block
     // 2.2 ms, lock-step 3.8 ms).  Few filters with a large stacked innovation (large maps): the single block is a
     // serial bottleneck (N=500, B=8: 7.1 of 11.5 ms per step), so every phase becomes its own launch over all
@@ -1181,6 +1280,20 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
             static int mid = -1;
             if (mid < 0) { const char* e = getenv("EKFSLAM_CHOL_MID"); mid = (e && e[0] == '0') ? 0 : 1; }
             const bool use_mid = mid && v.kmax > CHS_KM;
+            // 144 < k <= 200: the few filters of a frame with that many stacked rows used to go through k_chol (S in global
+            // memory, one 128-thread CTA each, ~0.28 ms of latency BEHIND the other variants); the resident kernel with 16
+            // warps takes them on a second side stream, under the main variant (EKFSLAM_CHOL_LARGE=0: the old path)
+            static int large_on = -1;
+            if (large_on < 0) { const char* e = getenv("EKFSLAM_CHOL_LARGE"); large_on = (e && e[0] == '0') ? 0 : 1; }
+            const bool large = large_on && use_mid && v.kmax > CHS_K;
+            auto fork_large = [&]() {   // after ev_fork has been recorded on st
+                if (!large) return;
+                cudaStreamWaitEvent(c->aux2_stream, c->ev_fork, 0);
+                k_chol_sm<CHS_KL, 512, CHS_K, 1><<<v.B, 512, chl_sm, c->aux2_stream>>>(v);
+                cudaEventRecord(c->ev_join2, c->aux2_stream);
+                c->launches++;
+            };
+            auto join_large = [&]() { if (large) cudaStreamWaitEvent(st, c->ev_join2, 0); };
             if (hi) {   // few stacked rows are the rule: k <= CHS_KS, CHS_KS < k <= CHS_KM, and the rest
                 if (use_mid) {
                     // the 144-row variant rarely has more than a few filters to do (one CTA each, ~0.1 ms of latency):
@@ -1190,11 +1303,21 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
                     k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, c->aux_stream>>>(v);
                     cudaEventRecord(c->ev_join, c->aux_stream);
                     c->launches++;
+                    fork_large();
                 }
-                k_chol_sm<CHS_KS, 128, 0><<<v.B, 128, chss_sm, st>>>(v);
+                static int w32 = -1;
+                if (w32 < 0) { const char* e = getenv("EKFSLAM_CHOL_W32"); w32 = (e && e[0] == '0') ? 0 : 1; }
+                if (w32) {   // k <= 32: a warp per filter, no block barriers; the 48-row variant keeps 32 < k <= 48
+                    k_chol_w32<<<(v.B + 3) / 4, 128, 0, st>>>(v);
+                    k_chol_sm<CHS_KS, 128, CHW_K><<<v.B, 128, chss_sm, st>>>(v);
+                    c->launches++;
+                } else {
+                    k_chol_sm<CHS_KS, 128, 0><<<v.B, 128, chss_sm, st>>>(v);
+                }
                 if (use_mid) {
                     k_chol_sm<CHS_KM, 256, CHS_KS, 3><<<v.B, 256, chsm_sm, st>>>(v);
                     cudaStreamWaitEvent(st, c->ev_join, 0);
+                    join_large();
                 } else {
                     k_chol_sm<CHS_K, 256, CHS_KS, 2><<<v.B, 256, chs_sm, st>>>(v);
                 }
@@ -1205,14 +1328,17 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
                     cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0);
                     k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, c->aux_stream>>>(v);
                     cudaEventRecord(c->ev_join, c->aux_stream);
+                    fork_large();
                     k_chol_sm<CHS_KM, 256, 0, 3><<<v.B, 256, chsm_sm, st>>>(v);
                     cudaStreamWaitEvent(st, c->ev_join, 0);
+                    join_large();
                     c->launches++;
                 } else {
                     k_chol_sm<CHS_K, 256, 0, 2><<<v.B, 256, chs_sm, st>>>(v);
                 }
             }
-            if (v.kmax > CHS_K) { k_chol<<<v.B, 128, chol_sm, st>>>(v, CHS_K); c->launches++; }
+            const int kres = large ? CHS_KL : CHS_K;   // largest k the resident variants took
+            if (v.kmax > kres) { k_chol<<<v.B, 128, chol_sm, st>>>(v, kres); c->launches++; }
         } else {
             k_chol<<<v.B, 128, chol_sm, st>>>(v, 0);
         }
@@ -1242,6 +1368,8 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         if (small < 0) { const char* e = getenv("EKFSLAM_W_SMALL"); small = (e && e[0] == '0') ? 0 : 1; }
         const int fin = (flags & 2) ? 0 : 1;
         if (small) { k_w_small<<<v.B, 128, 0, st>>>(v, fin); c->launches++; }
+        // (a persistent variant over a device-built list of the (filter, row tile) pairs with work was measured in round 2:
+        // li 1.51 -> 1.67 ms, hi 0.58 -> 0.55 ms - the CTAs that find nothing to do are not what this launch costs)
         k_gemm<0><<<gw, 256, w_sm, st>>>(v, fin, small ? WS_K : 0);
     }
     if (flags & 2) return;   // not the last iterate of an iterated update: W is recomputed

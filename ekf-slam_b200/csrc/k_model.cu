@@ -253,7 +253,7 @@ void launch_features(ekfslam_ctx* c, int which, int parts) {
 // This single pass over P feeds S_i (mc/search_IC_matches.m:8), every 1-point RANSAC gain
 // K = P H_i' inv(S_i) (mc/ransac_hypotheses.m:24-25) and P H' of the update (mc/update.m:8-9).
 // ---------------------------------------------------------------------------------------
-#define HP_CHUNK 64
+#define HP_CHUNK 64    // features per compaction round (128 = one round at N = 100 was measured: k_hp 1.41 -> 1.75 ms)
 __global__ void __launch_bounds__(128) k_hp(DevView v, int need, int forbid, int fch) {
     const int b = blockIdx.y;
     const int n = v.nstate[b];

@@ -1145,7 +1145,7 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
 // normJac(q+) and the quaternion normalisation.
 // ---------------------------------------------------------------------------------------
 #define WS_K 32
-__global__ void __launch_bounds__(128, 4) k_w_small(DevView v, int finalize) {
+__global__ void __launch_bounds__(128, 3) k_w_small(DevView v, int finalize) {
     const int b = blockIdx.x;
     const int k = 2 * v.ksel[b];
     if (k == 0 || k > WS_K) return;
@@ -1168,10 +1168,27 @@ __global__ void __launch_bounds__(128, 4) k_w_small(DevView v, int finalize) {
     }
     __syncthreads();
     double* __restrict__ x = v.x + (size_t)b * ld;
-    for (int c = tid; c < ld; c += blockDim.x) {
-        double g[WS_K];
+    // A thread walks its columns one after the other, and every column started with a DRAM round trip for its k entries of
+    // G before any arithmetic could begin (16 warps per SM, in-order issue: the launch ran at a third of the HBM rate).  Each
+    // thread now requests the entries of its NEXT column as asynchronous copies into its own slots of a double-buffered
+    // shared tile (only the thread itself reads them back: no barrier) while it works on the current one.
+    extern __shared__ __align__(16) double gsm[];   // [2][WS_K][128]
+    auto prefetch = [&](int buf, int c) {
+        double* dst = gsm + (size_t)buf * WS_K * 128 + tid;
 #pragma unroll
-        for (int t = 0; t < WS_K; ++t) g[t] = (t < k) ? G[(size_t)grow[t] * ld + c] : 0.0;
+        for (int t = 0; t < WS_K; ++t)
+            if (t < k) cp_async8(dst + t * 128, G + (size_t)grow[t] * ld + c);
+        cp_async_commit();
+    };
+    if (tid < ld) prefetch(0, tid);
+    int buf = 0;
+    for (int c = tid; c < ld; c += blockDim.x, buf ^= 1) {
+        cp_async_wait<0>();
+        if (c + (int)blockDim.x < ld) prefetch(buf ^ 1, c + blockDim.x);
+        double g[WS_K];
+        const double* src = gsm + (size_t)buf * WS_K * 128 + tid;
+#pragma unroll
+        for (int t = 0; t < WS_K; ++t) g[t] = (t < k) ? src[t * 128] : 0.0;
         const bool incol = c < n;
         double xs = 0.0;
 #pragma unroll
@@ -1367,7 +1384,12 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         static int small = -1;
         if (small < 0) { const char* e = getenv("EKFSLAM_W_SMALL"); small = (e && e[0] == '0') ? 0 : 1; }
         const int fin = (flags & 2) ? 0 : 1;
-        if (small) { k_w_small<<<v.B, 128, 0, st>>>(v, fin); c->launches++; }
+        if (small) {
+            const size_t ws_sm = sizeof(double) * 2 * WS_K * 128;
+            ENSURE_DYN_SMEM(k_w_small, ws_sm, c->device);
+            k_w_small<<<v.B, 128, ws_sm, st>>>(v, fin);
+            c->launches++;
+        }
         // (a persistent variant over a device-built list of the (filter, row tile) pairs with work was measured in round 2:
         // li 1.51 -> 1.67 ms, hi 0.58 -> 0.55 ms - the CTAs that find nothing to do are not what this launch costs)
         k_gemm<0><<<gw, 256, w_sm, st>>>(v, fin, small ? WS_K : 0);

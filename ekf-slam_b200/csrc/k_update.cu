@@ -1144,25 +1144,27 @@ __global__ void __launch_bounds__(256, 3) k_gemm(DevView v, int finalize, int ks
 // registers, inv(L) is broadcast from shared memory.  Same epilogue duties as k_gemm: x+ = x + G_sel' inv(S) nu,
 // normJac(q+) and the quaternion normalisation.
 // ---------------------------------------------------------------------------------------
-#define WS_K 32
-__global__ void __launch_bounds__(128, 3) k_w_small(DevView v, int finalize) {
+#define WS_K 32    // k <= 32 (a second launch of this kernel for 32 < k <= 48 - 152 registers, 2 CTAs per SM - lost to the DMMA tiles
+                   // of k_gemm: k_w_hi 0.47 -> 0.65 ms)
+template <int KW, int KMIN, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_w_small(DevView v, int finalize) {
     const int b = blockIdx.x;
     const int k = 2 * v.ksel[b];
-    if (k == 0 || k > WS_K) return;
+    if (k <= KMIN || k > KW) return;
     const int n = v.nstate[b], ld = v.ld, kmax = v.kmax;
     const double* __restrict__ Xg = v.Li + (size_t)b * kmax * kmax;
     const double* __restrict__ G = v.G + (size_t)b * kmax * ld;
     double* __restrict__ W = v.W + (size_t)b * v.wstride;
     const int* __restrict__ sel = v.sel + (size_t)b * v.N;
-    __shared__ double Xs[WS_K][WS_K + 1];
-    __shared__ double cs[WS_K];
-    __shared__ int grow[WS_K];
+    __shared__ double Xs[KW][KW + 1];
+    __shared__ double cs[KW];
+    __shared__ int grow[KW];
     const int tid = threadIdx.x;
-    for (int e = tid; e < WS_K * WS_K; e += blockDim.x) {
-        const int a = e / WS_K, t = e - a * WS_K;
+    for (int e = tid; e < KW * KW; e += blockDim.x) {
+        const int a = e / KW, t = e - a * KW;
         Xs[a][t] = (a < k && t <= a) ? Xg[(size_t)a * kmax + t] : 0.0;
     }
-    if (tid < WS_K) {
+    if (tid < KW) {
         cs[tid] = (tid < k) ? v.cv[(size_t)b * kmax + tid] : 0.0;
         grow[tid] = (tid < k) ? 2 * sel[tid >> 1] + (tid & 1) : 0;
     }
@@ -1172,11 +1174,11 @@ __global__ void __launch_bounds__(128, 3) k_w_small(DevView v, int finalize) {
     // G before any arithmetic could begin (16 warps per SM, in-order issue: the launch ran at a third of the HBM rate).  Each
     // thread now requests the entries of its NEXT column as asynchronous copies into its own slots of a double-buffered
     // shared tile (only the thread itself reads them back: no barrier) while it works on the current one.
-    extern __shared__ __align__(16) double gsm[];   // [2][WS_K][128]
+    extern __shared__ __align__(16) double gsm[];   // [2][KW][128]
     auto prefetch = [&](int buf, int c) {
-        double* dst = gsm + (size_t)buf * WS_K * 128 + tid;
+        double* dst = gsm + (size_t)buf * KW * 128 + tid;
 #pragma unroll
-        for (int t = 0; t < WS_K; ++t)
+        for (int t = 0; t < KW; ++t)
             if (t < k) cp_async8(dst + t * 128, G + (size_t)grow[t] * ld + c);
         cp_async_commit();
     };
@@ -1185,17 +1187,17 @@ __global__ void __launch_bounds__(128, 3) k_w_small(DevView v, int finalize) {
     for (int c = tid; c < ld; c += blockDim.x, buf ^= 1) {
         cp_async_wait<0>();
         if (c + (int)blockDim.x < ld) prefetch(buf ^ 1, c + blockDim.x);
-        double g[WS_K];
-        const double* src = gsm + (size_t)buf * WS_K * 128 + tid;
+        double g[KW];
+        const double* src = gsm + (size_t)buf * KW * 128 + tid;
 #pragma unroll
-        for (int t = 0; t < WS_K; ++t) g[t] = (t < k) ? src[t * 128] : 0.0;
+        for (int t = 0; t < KW; ++t) g[t] = (t < k) ? src[t * 128] : 0.0;
         const bool incol = c < n;
         double xs = 0.0;
 #pragma unroll
-        for (int t = 0; t < WS_K; ++t) xs += g[t] * cs[t];
+        for (int t = 0; t < KW; ++t) xs += g[t] * cs[t];
         double* __restrict__ wcol = W + w_at(v.wrows, 0, c);
 #pragma unroll
-        for (int a = 0; a < WS_K; ++a) {
+        for (int a = 0; a < KW; ++a) {
             if (a < k) {
                 double sacc = 0.0;
 #pragma unroll
@@ -1311,34 +1313,39 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
                 c->launches++;
             };
             auto join_large = [&]() { if (large) cudaStreamWaitEvent(st, c->ev_join2, 0); };
-            if (hi) {   // few stacked rows are the rule: k <= CHS_KS, CHS_KS < k <= CHS_KM, and the rest
-                if (use_mid) {
-                    // the 144-row variant rarely has more than a few filters to do (one CTA each, ~0.1 ms of latency):
-                    // it runs on the side stream, concurrently with the other two
-                    cudaEventRecord(c->ev_fork, st);
-                    cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0);
-                    k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, c->aux_stream>>>(v);
-                    cudaEventRecord(c->ev_join, c->aux_stream);
-                    c->launches++;
-                    fork_large();
-                }
+            if (hi) {   // few stacked rows are the rule: k <= 32, k <= CHS_KS, CHS_KS < k <= CHS_KM, and the rest
                 static int w32 = -1;
                 if (w32 < 0) { const char* e = getenv("EKFSLAM_CHOL_W32"); w32 = (e && e[0] == '0') ? 0 : 1; }
-                if (w32) {   // k <= 32: a warp per filter, no block barriers; the 48-row variant keeps 32 < k <= 48
-                    k_chol_w32<<<(v.B + 3) / 4, 128, 0, st>>>(v);
-                    k_chol_sm<CHS_KS, 128, CHW_K><<<v.B, 128, chss_sm, st>>>(v);
-                    c->launches++;
-                } else {
-                    k_chol_sm<CHS_KS, 128, 0><<<v.B, 128, chss_sm, st>>>(v);
-                }
                 if (use_mid) {
+                    // every variant is a chain of latencies that leaves the SMs mostly idle (one CTA per filter, a few hundred
+                    // filters each): the warp-per-filter kernel (k <= 32) and the rarely used 144-row variant run on one side
+                    // stream, the 48-row variant (and the 200-row one) on the other, the 112-row variant on the main stream -
+                    // back to back they took 0.22 ms
+                    cudaEventRecord(c->ev_fork, st);
+                    cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0);
+                    cudaStreamWaitEvent(c->aux2_stream, c->ev_fork, 0);
+                    if (w32) { k_chol_w32<<<(v.B + 3) / 4, 128, 0, c->aux_stream>>>(v); c->launches++; }
+                    k_chol_sm<CHS_K, 256, CHS_KM, 2><<<v.B, 256, chs_sm, c->aux_stream>>>(v);
+                    cudaEventRecord(c->ev_join, c->aux_stream);
+                    if (w32) k_chol_sm<CHS_KS, 128, CHW_K><<<v.B, 128, chss_sm, c->aux2_stream>>>(v);
+                    else k_chol_sm<CHS_KS, 128, 0><<<v.B, 128, chss_sm, c->aux2_stream>>>(v);
+                    if (large) { k_chol_sm<CHS_KL, 512, CHS_K, 1><<<v.B, 512, chl_sm, c->aux2_stream>>>(v); c->launches++; }
+                    cudaEventRecord(c->ev_join2, c->aux2_stream);
                     k_chol_sm<CHS_KM, 256, CHS_KS, 3><<<v.B, 256, chsm_sm, st>>>(v);
                     cudaStreamWaitEvent(st, c->ev_join, 0);
-                    join_large();
+                    cudaStreamWaitEvent(st, c->ev_join2, 0);
+                    c->launches += 2;
                 } else {
+                    if (w32) {   // k <= 32: a warp per filter, no block barriers; the 48-row variant keeps 32 < k <= 48
+                        k_chol_w32<<<(v.B + 3) / 4, 128, 0, st>>>(v);
+                        k_chol_sm<CHS_KS, 128, CHW_K><<<v.B, 128, chss_sm, st>>>(v);
+                        c->launches++;
+                    } else {
+                        k_chol_sm<CHS_KS, 128, 0><<<v.B, 128, chss_sm, st>>>(v);
+                    }
                     k_chol_sm<CHS_K, 256, CHS_KS, 2><<<v.B, 256, chs_sm, st>>>(v);
+                    c->launches++;
                 }
-                c->launches++;
             } else {
                 if (use_mid) {   // the common stacked sizes at 3 CTAs/SM, the rest in the large variant on the side stream
                     cudaEventRecord(c->ev_fork, st);
@@ -1361,11 +1368,11 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         }
     }
     // (64-row tiles, column groups, filters): the li update has work in every filter -> long CTAs that walk all column
-    // tiles; the hi update leaves few filters for this kernel (k_w_small takes k <= WS_K) -> five shorter CTAs per row tile
+    // tiles; the hi update leaves few filters for this kernel (k_w_small takes k <= WS_K) -> two shorter CTAs per row tile
     static int cg_li = -1, cg_hi = -1;
     if (cg_li < 0) {
         const char* e1 = getenv("EKFSLAM_W_CG_LI"); const char* e2 = getenv("EKFSLAM_W_CG_HI");
-        cg_li = e1 ? atoi(e1) : 1; cg_hi = e2 ? atoi(e2) : 5;
+        cg_li = e1 ? atoi(e1) : 1; cg_hi = e2 ? atoi(e2) : 2;   // hi: 2 / 3 / 5 / 10 column groups -> k_w_hi 0.43 / 0.44 / 0.47 / 0.56 ms
         if (cg_li < 1) cg_li = 1; if (cg_hi < 1) cg_hi = 1;
     }
     // few filters (large maps): split the column tiles so that the grid still fills the GPU
@@ -1386,8 +1393,8 @@ void launch_update(ekfslam_ctx* c, int mask, int which_prior, int flags) {
         const int fin = (flags & 2) ? 0 : 1;
         if (small) {
             const size_t ws_sm = sizeof(double) * 2 * WS_K * 128;
-            ENSURE_DYN_SMEM(k_w_small, ws_sm, c->device);
-            k_w_small<<<v.B, 128, ws_sm, st>>>(v, fin);
+            ENSURE_DYN_SMEM((k_w_small<WS_K, 0, 3>), ws_sm, c->device);
+            k_w_small<WS_K, 0, 3><<<v.B, 128, ws_sm, st>>>(v, fin);
             c->launches++;
         }
         // (a persistent variant over a device-built list of the (filter, row tile) pairs with work was measured in round 2:

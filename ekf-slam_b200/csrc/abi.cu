@@ -190,7 +190,15 @@ int ekfslam_create(ekfslam_ctx** out, int device, int B, int N_max, int n_max) {
     c->device = device;
     DevView& v = c->v;
     v.B = B; v.N = N_max; v.nmax = n_max;
-    v.ld = (n_max + 7) & ~7;
+    // Row pitch of x / P / G in doubles: a multiple of 32 (256 B).  With the minimal pitch (multiple of 8: 616 at n = 613) the
+    // 512-byte row segments of the 64x64 covariance tiles straddle 128-byte lines on every other row; measured on the
+    // HBM-bound hi downdate at the bench shape: pitch 616 -> 4.22 ms, 624 -> 4.08 ms, 640 -> 3.78 ms (EKFSLAM_LD_ALIGN=8|16|32...).
+    {
+        const char* e = getenv("EKFSLAM_LD_ALIGN");
+        int al = e ? atoi(e) : 32;
+        if (al < 8 || (al & 7)) al = 32;
+        v.ld = (n_max + al - 1) / al * al;
+    }
     v.kmax = 2 * N_max;
     v.n_u = 0;
     c->u_cap = 0;

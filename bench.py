@@ -80,7 +80,7 @@ def algorithmic_work(n, N, m, hyps, k_li, k_hi):
 
 def read_traffic(kernel_prefix):
     """dram__bytes_read+write per launch of a kernel from the committed ncu capture of this shape."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r2g.json")
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r2h.json")
     try:
         with open(p) as f:
             d = json.load(f)
@@ -575,7 +575,7 @@ def main():
                     "frac": dd_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": "hbm " + peaks["hbm_src"]}
         if B == 4096 and N == 100:
             roof["traffic"] = read_traffic("k_downdate")
-            roof["traffic_source"] = ("profiles/ncu_traffic_r2g.json (committed ncu --set full capture of this command at this shape, frame 3; "
+            roof["traffic_source"] = ("profiles/ncu_traffic_r2h.json (committed ncu --set full capture of this command at this shape, frame 3; "
                                       "mean of the li and hi launches) - not re-measured in this run")
         roof.update({"kernel": "k_downdate", "kernel_share_of_step": dd_ms / tot_k_ms if tot_k_ms else None,
                      "kernel_ms_per_launch": dd_ms / dd_cnt if dd_cnt else None, "launches_timed": dd_cnt,

@@ -47,11 +47,16 @@ __global__ void __launch_bounds__(256, 3) k_predict(DevView v, ekfslam_params pr
     // The first cross-covariance column of every thread is requested BEFORE thread 0 builds F and Q, and inside the sweep
     // the next column is requested before the current one is transformed (ncu, round 2: 60 % of the kernel's samples were
     // long-scoreboard stalls on one DRAM round trip per column and thread, one after the other).
+    // The columns are read from rows 0..12 (P is exactly symmetric in memory, so P[r][j] == P[j][r]): consecutive threads read
+    // consecutive addresses.  Reading the 13 entries from row j instead made every load instruction touch 32 different lines
+    // (ncu, round 2: 0.29 ms for 0.64 GB of DRAM traffic - the kernel was bound by L1 wavefronts, not by DRAM).
     double c[13];
+    const int lane = tid & 31, warp = tid >> 5;
+    __shared__ double tr[8][32][9];   // per-warp transpose of the 7 changed entries (+ entry 7) for the row-wise mirror stores
     int j = 13 + tid;
     if (j < n) {
 #pragma unroll
-        for (int r = 0; r < 13; ++r) c[r] = P[(size_t)j * ld + r];   // lower triangle (authoritative): P[r][j] = P[j][r], j >= 13 > r
+        for (int r = 0; r < 13; ++r) c[r] = P[(size_t)r * ld + j];
     }
     for (int e = tid; e < 169; e += blockDim.x) {
         const int r = e / 13, cc = e - r * 13;
@@ -149,12 +154,12 @@ __global__ void __launch_bounds__(256, 3) k_predict(DevView v, ekfslam_params pr
     __syncthreads();
 
     // cross-covariance panel
-    while (j < n) {
+    while (j - lane < n) {   // warp-uniform: the mirror stores below are a warp-wide exchange
         const int jn = j + blockDim.x;
         double cn[13];
         if (jn < n) {
 #pragma unroll
-            for (int r = 0; r < 13; ++r) cn[r] = P[(size_t)jn * ld + r];
+            for (int r = 0; r < 13; ++r) cn[r] = P[(size_t)r * ld + jn];
         }
         double o[7];
         const double dt = prm.delta_t;
@@ -163,11 +168,25 @@ __global__ void __launch_bounds__(256, 3) k_predict(DevView v, ekfslam_params pr
         for (int r = 0; r < 4; ++r)
             o[3 + r] = Fqq[r][0] * c[3] + Fqq[r][1] * c[4] + Fqq[r][2] * c[5] + Fqq[r][3] * c[6] +
                        Fqw[r][0] * c[10] + Fqw[r][1] * c[11] + Fqw[r][2] * c[12];
+        if (j < n) {
 #pragma unroll
-        for (int r = 0; r < 7; ++r) {
-            P[(size_t)r * ld + j] = o[r];
-            P[(size_t)j * ld + r] = o[r];
+            for (int r = 0; r < 7; ++r) P[(size_t)r * ld + j] = o[r];
         }
+        // mirror image: entries 0..7 of rows j (entry 7 is unchanged), eight rows of 64 bytes per warp instruction
+#pragma unroll
+        for (int r = 0; r < 7; ++r) tr[warp][lane][r] = o[r];
+        tr[warp][lane][7] = c[7];
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int row = it * 8 + (lane >> 2), part = (lane & 3) * 2;
+            const int jr = j - lane + row;
+            if (jr < n) {
+                const double2 val = make_double2(tr[warp][row][part], tr[warp][row][part + 1]);
+                *reinterpret_cast<double2*>(P + (size_t)jr * ld + part) = val;
+            }
+        }
+        __syncwarp();
 #pragma unroll
         for (int r = 0; r < 13; ++r) c[r] = cn[r];
         j = jn;

@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(128) k_innov(DevView v, ekfslam_params prm, in
 //           pass then need full rows H p_k_k (k_hp on the HI rows).
 // ---------------------------------------------------------------------------------------
 #ifndef IG_MINB
-#define IG_MINB 3   // 168 registers without spills: 0.33 vs 0.37 ms at the 128-register cap
+#define IG_MINB 2   // the whole gather lives in registers (89 doubles): ~200 registers without spills
 #endif
 __global__ void __launch_bounds__(128, IG_MINB) k_innov_gather(DevView v, ekfslam_params prm, int mode) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -447,42 +447,85 @@ __global__ void __launch_bounds__(128, IG_MINB) k_innov_gather(DevView v, ekfsla
     if (mode == 3 && !((f & EKFSLAM_F_IC) && !(f & EKFSLAM_F_LI))) return;
     const int ld = v.ld;
     const double* __restrict__ P = v.P + (size_t)b * v.nmax * ld;
-    const double* __restrict__ Hp = v.Hc + (size_t)t * EKF_HSTRIDE;
-    double H[EKF_HSTRIDE];
-#pragma unroll
-    for (int k = 0; k < EKF_HSTRIDE; ++k) H[k] = Hp[k];
     const int off = v.foff[t];
     const int w = (type == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+    // Every element of the gather is requested ONCE, up front, with 128-bit loads where the alignment allows.  A thread's
+    // rows are its own, so each load instruction of a warp touches 32 different lines = 32 L1 wavefronts whatever its width:
+    // the kernel ran at exactly that bound (ncu, round 2: 146 scattered 64-bit loads per feature - the 6x7 cross block was
+    // fetched twice, once per orientation, the 6x6 block as a full square - 0.198 ms = 4672 wavefronts per warp).
+    double H[EKF_HSTRIDE];
+    {
+        const double2* __restrict__ Hp2 = reinterpret_cast<const double2*>(v.Hc + (size_t)t * EKF_HSTRIDE);   // 208 bytes per feature
+#pragma unroll
+        for (int k = 0; k < EKF_HSTRIDE / 2; ++k) { const double2 h2 = Hp2[k]; H[2 * k] = h2.x; H[2 * k + 1] = h2.y; }
+    }
+    double A[6][7];    // A[r][j] = P[off + r][j], j < 7           (rows start on 256-byte boundaries)
+    double Lb[6][6];   // Lb[r][c] = P[off + r][off + c], c <= r  (the authoritative lower triangle of the feature's own block)
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) Lb[r][cc] = 0.0;
+    if (w == 6) {
+        const bool odd = off & 1;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const double* __restrict__ prow = P + (size_t)(off + r) * ld;
+            const double2 a01 = *reinterpret_cast<const double2*>(prow), a23 = *reinterpret_cast<const double2*>(prow + 2),
+                          a45 = *reinterpret_cast<const double2*>(prow + 4);
+            A[r][0] = a01.x; A[r][1] = a01.y; A[r][2] = a23.x; A[r][3] = a23.y; A[r][4] = a45.x; A[r][5] = a45.y; A[r][6] = prow[6];
+            const double* __restrict__ pb = prow + off;   // entries beyond c = r that ride along in a pair are valid memory, unused
+            if (odd) {
+                Lb[r][0] = pb[0];
+                if (r >= 1) { const double2 d = *reinterpret_cast<const double2*>(pb + 1); Lb[r][1] = d.x; if (r >= 2) Lb[r][2] = d.y; }
+                if (r >= 3) { const double2 d = *reinterpret_cast<const double2*>(pb + 3); Lb[r][3] = d.x; if (r >= 4) Lb[r][4] = d.y; }
+                if (r >= 5) Lb[r][5] = pb[5];
+            } else {
+                { const double2 d = *reinterpret_cast<const double2*>(pb); Lb[r][0] = d.x; if (r >= 1) Lb[r][1] = d.y; }
+                if (r >= 2) { const double2 d = *reinterpret_cast<const double2*>(pb + 2); Lb[r][2] = d.x; if (r >= 3) Lb[r][3] = d.y; }
+                if (r >= 4) { const double2 d = *reinterpret_cast<const double2*>(pb + 4); Lb[r][4] = d.x; if (r >= 5) Lb[r][5] = d.y; }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double* __restrict__ prow = P + (size_t)(off + r) * ld;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) A[r][j] = prow[j];
+#pragma unroll
+            for (int cc = 0; cc <= r; ++cc) Lb[r][cc] = prow[off + cc];
+        }
+#pragma unroll
+        for (int r = 3; r < 6; ++r)
+#pragma unroll
+            for (int j = 0; j < 7; ++j) A[r][j] = 0.0;
+    }
     double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-    // column j of the gather: t_a = sum_r H[a][r] P[c_r][c_j], then S[a][a'] += t_a H[a'][j]
+    // column j of the gather: t_a = sum_r H[a][r] P[c_r][c_j], then S[a][a'] += t_a H[a'][j]   (same order of operations as
+    // the element-by-element version)
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
         double t0 = 0.0, t1 = 0.0;
 #pragma unroll
         for (int r = 0; r < 7; ++r) {
-            const double pv = (r >= j) ? P[(size_t)r * ld + j] : P[(size_t)j * ld + r];
+            const double pv = (r >= j) ? P[(size_t)r * ld + j] : P[(size_t)j * ld + r];   // camera block: the same addresses for all features of a filter
             t0 += H[r] * pv; t1 += H[EKF_HC + r] * pv;
         }
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-            if (r < w) {
-                const double pv = P[(size_t)(off + r) * ld + j];
-                t0 += H[7 + r] * pv; t1 += H[EKF_HC + 7 + r] * pv;
-            }
+            if (r < w) { t0 += H[7 + r] * A[r][j]; t1 += H[EKF_HC + 7 + r] * A[r][j]; }
         }
         s00 += t0 * H[j]; s01 += t0 * H[EKF_HC + j]; s10 += t1 * H[j]; s11 += t1 * H[EKF_HC + j];
     }
 #pragma unroll
     for (int jj = 0; jj < 6; ++jj) {
         if (jj < w) {
-            const double* __restrict__ prow = P + (size_t)(off + jj) * ld;
             double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-            for (int r = 0; r < 7; ++r) { const double pv = prow[r]; t0 += H[r] * pv; t1 += H[EKF_HC + r] * pv; }
+            for (int r = 0; r < 7; ++r) { const double pv = A[jj][r]; t0 += H[r] * pv; t1 += H[EKF_HC + r] * pv; }
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 if (r < w) {
-                    const double pv = (r <= jj) ? prow[off + r] : P[(size_t)(off + r) * ld + off + jj];
+                    const double pv = (r <= jj) ? Lb[jj][r] : Lb[r][jj];
                     t0 += H[7 + r] * pv; t1 += H[EKF_HC + 7 + r] * pv;
                 }
             }

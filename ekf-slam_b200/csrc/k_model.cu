@@ -252,9 +252,9 @@ __global__ void __launch_bounds__(128, 6) k_features(DevView v, DevCam cam, int 
     if ((parts & 2) && (f & EKFSLAM_F_HAS_H)) {
         double Hc[EKF_HSTRIDE];
         jacobian_dev(cam, xv, R, y, type, hu, hv, Hc);
-        double* dst = v.Hc + (size_t)t * EKF_HSTRIDE;
+        double2* dst = reinterpret_cast<double2*>(v.Hc + (size_t)t * EKF_HSTRIDE);   // 208 bytes per feature: 13 128-bit stores
 #pragma unroll
-        for (int k = 0; k < EKF_HSTRIDE; ++k) dst[k] = Hc[k];
+        for (int k = 0; k < EKF_HSTRIDE / 2; ++k) dst[k] = make_double2(Hc[2 * k], Hc[2 * k + 1]);
     }
 }
 

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256, 3) k_predict(DevView v, ekfslam_params pr
         Fqq[1][0] = px; Fqq[1][1] = p0;  Fqq[1][2] = pz;  Fqq[1][3] = -py;
         Fqq[2][0] = py; Fqq[2][1] = -pz; Fqq[2][2] = p0;  Fqq[2][3] = px;
         Fqq[3][0] = pz; Fqq[3][1] = py;  Fqq[3][2] = -px; Fqq[3][3] = p0;
-        // mc/dqomegadt_by_domega.m:6-48
+        // mc/dqomegadt_by_domega.m:6-48   (giving this half of the serial work to a second warp was measured twice: no change)
         const double om = sqrt(wx * wx + wy * wy + wz * wz);
         const double sn = sin(om * dt / 2.0), cs = cos(om * dt / 2.0);
         const double w[3] = {wx, wy, wz};
@@ -237,17 +237,30 @@ __global__ void __launch_bounds__(128, 6) k_features(DevView v, DevCam cam, int 
     const int off = v.foff[t];
     double y[6];
     const int w = (type == EKFSLAM_FEAT_INVERSEDEPTH) ? 6 : 3;
+    if (w == 6) {   // 48 contiguous bytes per thread: 128-bit loads where the offset allows (every load instruction of a warp costs 32 L1 wavefronts)
+        const double* __restrict__ px = x + off;
+        if (off & 1) {
+            const double2 a = *reinterpret_cast<const double2*>(px + 1), c2 = *reinterpret_cast<const double2*>(px + 3);
+            y[0] = px[0]; y[1] = a.x; y[2] = a.y; y[3] = c2.x; y[4] = c2.y; y[5] = px[5];
+        } else {
+            const double2 a = *reinterpret_cast<const double2*>(px), c2 = *reinterpret_cast<const double2*>(px + 2),
+                          e = *reinterpret_cast<const double2*>(px + 4);
+            y[0] = a.x; y[1] = a.y; y[2] = c2.x; y[3] = c2.y; y[4] = e.x; y[5] = e.y;
+        }
+    } else {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) y[k] = (k < w) ? x[off + k] : 0.0;
+        for (int k = 0; k < 6; ++k) y[k] = (k < 3) ? x[off + k] : 0.0;
+    }
 
     uint8_t f = v.flags[t];
     double hu = 0.0, hv = 0.0;
     if ((parts & 1) && predict_h_dev(cam, xv, R, y, type, hu, hv)) {
-        v.h[2 * t] = hu; v.h[2 * t + 1] = hv;
+        *reinterpret_cast<double2*>(v.h + 2 * (size_t)t) = make_double2(hu, hv);
         f |= EKFSLAM_F_HAS_H;
         v.flags[t] = f;
     } else if (f & EKFSLAM_F_HAS_H) {
-        hu = v.h[2 * t]; hv = v.h[2 * t + 1];
+        const double2 h2 = *reinterpret_cast<const double2*>(v.h + 2 * (size_t)t);
+        hu = h2.x; hv = h2.y;
     }
     if ((parts & 2) && (f & EKFSLAM_F_HAS_H)) {
         double Hc[EKF_HSTRIDE];

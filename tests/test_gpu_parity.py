@@ -179,9 +179,17 @@ def test_downdate_filter_groups(ekf, monkeypatch):
 
 def test_n100_many_inliers_large_k(ekf):
     """No gross outliers and little pixel noise at N=100: the li update stacks more than 144 rows, i.e. the Cholesky runs in the
-    global-memory kernel (k_chol) instead of the shared-memory resident one, and the W GEMM spans three row tiles."""
+    200-row resident variant (512 threads, second side stream) and the W GEMM spans three row tiles."""
     worst, tot = _run_sequence(ekf, B=2, N=100, frames=3, seed=820, p_outlier=0.0, noise_px=0.15)
     assert tot["li"] > 2 * 3 * 72, tot
+
+
+def test_n120_more_than_200_stacked_rows(ekf):
+    """N=120 without gross outliers: 106-113 li inliers per filter (oracle), i.e. k = 212-226 stacked rows - beyond the largest
+    shared-memory resident Cholesky variant (200 rows), so the factorisation runs in the global-memory kernel (k_chol) behind
+    the resident ones, and the W GEMM spans four row tiles."""
+    worst, tot = _run_sequence(ekf, B=2, N=120, frames=2, seed=830, p_outlier=0.0, noise_px=0.15)
+    assert tot["li"] > 2 * 2 * 100, tot
 
 
 def test_blocked64_cholesky_ragged_k(ekf):

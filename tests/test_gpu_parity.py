@@ -192,6 +192,21 @@ def test_n120_more_than_200_stacked_rows(ekf):
     assert tot["li"] > 2 * 2 * 100, tot
 
 
+def test_row_pitch_knob(ekf, monkeypatch):
+    """Row pitch of x / P / G: 256 bytes by default (ld % 32 == 0), EKFSLAM_LD_ALIGN restores the minimal pitch; the partial last
+    tile column of the covariance downdate differs between the two (n = 85: ld 96 vs 88), results must not."""
+    pkg, _ = ekf
+    bank = pkg.FilterBank(1, 12, 85)
+    assert bank.ld % 32 == 0 and bank.ld >= 85
+    bank.close()
+    monkeypatch.setenv("EKFSLAM_LD_ALIGN", "8")
+    bank = pkg.FilterBank(1, 12, 85)
+    assert bank.ld == 88
+    bank.close()
+    worst, tot = _run_sequence(ekf, B=3, N=12, frames=3, seed=860)
+    assert tot["li"] > 30, tot
+
+
 def test_blocked64_cholesky_ragged_k(ekf):
     """Few filters with N_max >= 128 take the 64-wide blocked DMMA factorisation (k_chol_big.cu): three filters with
     different map sizes, so the stacked innovation sizes differ per filter and are not multiples of 64."""

@@ -79,7 +79,7 @@ __device__ __forceinline__ void upd_S_pairs(const DevView& v, int b, int ns, int
 // ---------------------------------------------------------------------------------------
 // select + S + nu.  One block per filter.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_upd_S(DevView v, int mask, int which_prior, int iter_nu, int do_pairs) {
+__global__ void __launch_bounds__(256, 4) k_upd_S(DevView v, int mask, int which_prior, int iter_nu, int do_pairs) {
     const int b = blockIdx.x;
     const int N = v.N, ld = v.ld, kmax = v.kmax;
     const int nf = v.nfeat[b];
